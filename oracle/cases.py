@@ -1,0 +1,53 @@
+"""Seeded inputs shared by oracle/make_golden.py (which runs the reference on them) and the
+tests (which run the oracle / CUDA path on them).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from diffusynth_b200 import weights as W
+
+SMALL_UNET = dict(in_dim=4, down_dims=[32, 32, 64], up_dims=[64, 64, 32], mid_depth=2,
+                  attn_type="linear_add", condition_type="natural_language_prompt", label_emb_dim=64)
+
+
+def randn(shape, seed):
+    g = torch.Generator(device="cpu"); g.manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def unet_case(name: str):
+    """-> (cfg, state_dict, x, t, cond)."""
+    if name == "deployed_w64":
+        cfg, B, Wd = W.UNET_DEPLOYED, 2, 64
+    elif name == "deployed_w24":
+        cfg, B, Wd = W.UNET_DEPLOYED, 1, 24
+    elif name == "small_w16":
+        cfg, B, Wd = SMALL_UNET, 2, 16
+    else:
+        raise KeyError(name)
+    sd = W.unet_random_state_dict(cfg, seed=0)
+    H = 128 if cfg is W.UNET_DEPLOYED else 32
+    x = randn((B, 4, H, Wd), 11) * 1.5
+    t = torch.tensor([947, 52][:B], dtype=torch.long)
+    cond = randn((B, W.unet_config(**cfg)["label_emb_dim"]), 12)
+    return cfg, sd, x, t, cond
+
+
+def toy_model(x, t, cond):
+    """A cheap stand-in eps-predictor for sampler-logic goldens (any callable works)."""
+    return 0.3 * torch.tanh(x) + 0.05 * torch.sin(t.float() / 100.0).view(-1, 1, 1, 1) \
+        + 0.1 * cond.mean(dim=1).view(-1, 1, 1, 1)
+
+
+def vq_latents(B=1, seed=21):
+    return randn((B, 4, 128, 64), seed) * 0.9
+
+
+def synthetic_wave(n=65280, seed=31, sr=16000):
+    """A decaying harmonic note plus a little noise, peak-normalised (stands in for a preset WAV)."""
+    g = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    y = sum(np.sin(2 * np.pi * 220.0 * k * t + g.uniform(0, 6.28)) / k for k in range(1, 9))
+    y = y * np.exp(-t * 1.2) + 0.01 * g.standard_normal(n)
+    return (y / np.abs(y).max()).astype(np.float64)

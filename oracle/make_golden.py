@@ -1,0 +1,140 @@
+"""Mint golden vectors from the UNMODIFIED reference (imported from /root/reference).
+Run here (the reference is absent on the GPU box):  python -m oracle.make_golden
+Outputs: tests/golden/*.npz.  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from diffusynth_b200 import weights as W            # noqa: E402
+from oracle import cases, ref_loader                # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def stats(t):
+    t = t.double()
+    return np.array([t.mean().item(), t.pow(2).mean().sqrt().item()])
+
+
+@torch.no_grad()
+def main():
+    torch.set_num_threads(8)
+    ref = ref_loader.load()
+    os.makedirs(OUT, exist_ok=True)
+
+    # ---- sampler ---------------------------------------------------------------------------
+    g = {}
+    S = ref.DiffSynthSampler(1000, device="cpu", mute=True)
+    g["betas_1000"], g["ac_1000"] = S.betas, S.alphas_cumprod
+    for steps in (10, 20):
+        S = ref.DiffSynthSampler(1000, device="cpu", mute=True)
+        S.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+        g[f"betas_{steps}"], g[f"ac_{steps}"], g[f"acp_{steps}"] = S.betas, S.alphas_cumprod, S.alphas_cumprod_prev
+        g[f"map_{steps}"] = np.array(S.timestep_map)
+    S = ref.DiffSynthSampler(1000, device="cpu", mute=True, height=2, channels=1, max_batchsize=2)
+    base = cases.randn((2, 1, 2, 64), 5)
+    for w in (17, 24, 63, 64, 65, 100, 144, 200):
+        n, pts = S.get_deterministic_noise_tensor_repeat(2, w, reference_noise=base)
+        g[f"layout_{w}"], g[f"layout_pts_{w}"] = n.numpy(), np.array(pts)
+    # full loops on a toy model: ddim / ddpm with CFG, CFG=1, img-guided, inpaint (fixed mask)
+    B, Wd = 3, 40
+    draws = cases.randn((12, B, 4, 128, 64), 6)
+    cond, uncond = W.synthetic_conditions(B, 16, seed=77)
+    for name, kw in (("ddim", dict(sampler="ddim")), ("ddpm", dict(sampler="ddpm"))):
+        S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B), draws)
+        S.activate_classifier_free_guidance(6, uncond)
+        S.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+        imgs, init = S.sample(cases.toy_model, (B, 4, 128, Wd), return_tensor=True, condition=cond,
+                              initial_noise=draws[0], **kw)
+        g[f"loop_{name}_last"], g[f"loop_{name}_mid"] = imgs[-1].numpy(), imgs[3].numpy()
+        assert len(imgs) == 9
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B), draws)
+    S.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+    imgs, _ = S.sample(cases.toy_model, (B, 4, 128, Wd), return_tensor=True, condition=cond, initial_noise=draws[0])
+    g["loop_nocfg_last"] = imgs[-1].numpy()
+    guide = cases.randn((B, 4, 128, 64), 8) * 0.5
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B), draws)
+    S.activate_classifier_free_guidance(6, uncond)
+    S.respace(list(np.linspace(0, 999, int(8 / 0.7), dtype=np.int32)))
+    # img_guided_sample requires guide width == shape width (:580) and the repeat layout requires
+    # guide width == train_width (:113): guided sampling only exists at W = 64.
+    imgs, _ = S.img_guided_sample(cases.toy_model, (B, 4, 128, 64), 0.7, guide, return_tensor=True,
+                                  condition=cond, initial_noise=draws[0])
+    g["loop_guided_first"], g["loop_guided_last"], g["loop_guided_len"] = imgs[0].numpy(), imgs[-1].numpy(), np.array(len(imgs))
+    mask = (cases.randn((B, 1, 128, Wd), 9) > 0).float()
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B), draws)
+    S.activate_classifier_free_guidance(6, uncond)
+    S.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+    imgs, _ = S.inpaint_sample(cases.toy_model, (B, 4, 128, Wd), 1.0, guide, mask, return_tensor=True,
+                               condition=cond, initial_noise=draws[0])
+    g["loop_inpaint_last"] = imgs[-1].numpy()
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), **g)
+
+    # ---- U-Net -----------------------------------------------------------------------------
+    g = {}
+    for name in ("deployed_w64", "deployed_w24", "small_w16"):
+        cfg, sd, x, t, cond = cases.unet_case(name)
+        net = ref.ConditionedUnet(**cfg).eval()
+        net.load_state_dict(sd, strict=True)
+        g[f"{name}_eps"] = net(x, t, cond).numpy()
+        if name == "deployed_w64":      # per-layer (mean, rms) to localise a mismatch
+            feats = {}
+            hooks = []
+            for mod_name, mod in net.named_modules():
+                parts = mod_name.split(".")
+                if (parts[0] in ("downs", "ups") and len(parts) == 3) or \
+                   (parts[0] in ("mid_left", "mid_right", "mid_mid", "final_conv") and len(parts) == 2) or mod_name == "init_conv":
+                    hooks.append(mod.register_forward_hook(
+                        lambda m, i, o, n=mod_name: feats.__setitem__(n, stats(o))))
+            net(x, t, cond)
+            for k, v in feats.items():
+                g[f"{name}_tap_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "unet.npz"), **g)
+
+    # ---- VQGAN -----------------------------------------------------------------------------
+    g = {}
+    vq = ref.VQGAN(**W.VQGAN_DEPLOYED).eval()
+    sd = W.vqgan_random_state_dict(seed=1)
+    vq.load_state_dict(sd, strict=True)
+    lat = cases.vq_latents()
+    q, _, _ = vq._vq_vae(lat)
+    flat = lat.permute(0, 2, 3, 1).reshape(-1, 4)
+    cb = sd["_vq_vae._embedding.weight"]
+    d = (torch.sum(flat ** 2, dim=1, keepdim=True) + torch.sum(cb ** 2, dim=1) - 2 * torch.matmul(flat, cb.t()))
+    g["vq_idx"] = torch.argmin(d, dim=1).numpy().astype(np.int16)        # VQGAN.py:107-112
+    g["vq_q"] = q.numpy()
+    dec = vq._decoder(q)
+    g["dec_sub"] = dec.flatten()[::7].numpy()
+    g["dec_stats"] = stats(dec)
+    spec = torch.from_numpy(np.stack([_spec(ref)]))
+    enc = vq._encoder(spec)
+    g["enc_lat"] = enc.numpy()
+    np.savez_compressed(os.path.join(OUT, "vqgan.npz"), **g)
+
+    # ---- STFT+ codec (tools.py) ------------------------------------------------------------
+    g = {}
+    e = cases.randn((3, 512, 6), 41).numpy()
+    e[0] = np.abs(e[0])
+    D = ref.tools.decode_stft(e)
+    g["decode_in"], g["decode_out"] = e, D
+    g["depad_out"] = ref.tools.depad_STFT(D)
+    Dc = (cases.randn((513, 5), 42) + 1j * cases.randn((513, 5), 43)).numpy()
+    g["encode_in"], g["pad_out"] = Dc, ref.tools.pad_STFT(Dc, 8)
+    g["encode_out"] = ref.tools.encode_stft(ref.tools.pad_STFT(Dc, 8))
+    np.savez_compressed(os.path.join(OUT, "codec.npz"), **g)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def _spec(ref):
+    from oracle import ds_oracle as O
+    return O.waveform_to_spectrogram(cases.synthetic_wave())
+
+
+if __name__ == "__main__":
+    main()

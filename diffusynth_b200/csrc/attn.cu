@@ -1,0 +1,200 @@
+// Linear ("efficient") attention core.
+//   U-Net  LinearCrossAttentionAdd.forward, model/diffusion_components.py:271-293
+//   VQGAN  LinearAttention.forward,         model/VQGAN.py:261-272
+// Given qkv = to_qkv(x) [N, n, 3*hidden] (bf16 NHWC, q | k | v blocks of `hidden` channels, head h owns
+// channels [32h, 32h+32) of each block; for the U-Net the label_query/label_key biases were already added
+// by the to_qkv GEMM epilogue):
+//   q' = softmax_d(q) * scale            (U-Net)      or  q' = q  (VQGAN: q is neither soft-maxed nor scaled)
+//   ctx[h][d][e] = sum_n softmax_n(k)[d,n] * v[e,n]
+//   M[c][(h,d)]  = sum_e Wout[c][(h,e)] * ctx[h][d][e]        (per sample)
+// so that  to_out(ctx^T q') = M q' + bias  is a per-sample 1x1 GEMM done by ds_conv_gemm (per_sample_weights).
+// The n x n attention matrix never exists (O(n) attention): this is not a flash-attention problem.
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+
+namespace ds {
+
+static constexpr int AT_D = 32;          // dim_head
+static constexpr int AT_PIX = 128;       // pixels per block
+static constexpr int AT_PART = AT_D * AT_D + 2 * AT_D;   // S[32][32], Z[32], m[32]
+
+// grid = (chunks, heads, N), block = 256
+__global__ void __launch_bounds__(256)
+attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
+                        __nv_bfloat16* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
+  __shared__ float s_k[AT_PIX][AT_D + 1];
+  __shared__ __align__(16) float s_v[AT_PIX][AT_D + 4];
+  __shared__ float s_red[8][AT_D];
+  __shared__ float s_m[AT_D];
+  const int chunk = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
+  const int ld = 3 * hidden;
+  const long long p0 = (long long)chunk * AT_PIX;
+  const __nv_bfloat16* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
+  const int tid = threadIdx.x;
+
+  // ---- stage k, v (fp32) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
+  {
+    const int pix = tid >> 1, half = tid & 1;   // 16 channels per thread
+    const bool ok = p0 + pix < npix;
+    const uint4* kp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + hidden + half * 16);
+    const uint4* vp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + 2 * hidden + half * 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+      if (ok) { kv = __ldg(kp + i); vv = __ldg(vp + i); }
+      const uint32_t kk[4] = {kv.x, kv.y, kv.z, kv.w}, vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = half * 16 + i * 8 + 2 * j;
+        s_k[pix][d] = ok ? bf16_lo(kk[j]) : -INFINITY;
+        s_k[pix][d + 1] = ok ? bf16_hi(kk[j]) : -INFINITY;
+        s_v[pix][d] = bf16_lo(vw[j]);
+        s_v[pix][d + 1] = bf16_hi(vw[j]);
+      }
+    }
+    // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
+    // The math runs for every thread (rows beyond npix compute on zeros) so the pair shuffles stay convergent.
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + half * 16);
+      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+      if (ok) { q0 = __ldg(qp); q1 = __ldg(qp + 1); }
+      if (q_mode == 0) {
+        const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        float f[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { f[2 * j] = bf16_lo(qq[j]); f[2 * j + 1] = bf16_hi(qq[j]); mx = fmaxf(mx, fmaxf(f[2 * j], f[2 * j + 1])); }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { f[j] = __expf(f[j] - mx); sum += f[j]; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        const float inv = scale / sum;
+        q0 = make_uint4(pack_bf16(f[0] * inv, f[1] * inv), pack_bf16(f[2] * inv, f[3] * inv), pack_bf16(f[4] * inv, f[5] * inv), pack_bf16(f[6] * inv, f[7] * inv));
+        q1 = make_uint4(pack_bf16(f[8] * inv, f[9] * inv), pack_bf16(f[10] * inv, f[11] * inv), pack_bf16(f[12] * inv, f[13] * inv), pack_bf16(f[14] * inv, f[15] * inv));
+      }
+      if (ok) {
+        uint4* qo = reinterpret_cast<uint4*>(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16);
+        qo[0] = q0;
+        qo[1] = q1;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- column max of k over the chunk
+  const int warp = tid >> 5, lane = tid & 31;
+  {
+    float mx = -INFINITY;
+    for (int p = warp * 16; p < warp * 16 + 16; ++p) mx = fmaxf(mx, s_k[p][lane]);
+    s_red[warp][lane] = mx;
+  }
+  __syncthreads();
+  if (tid < AT_D) {
+    float mx = s_red[0][tid];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w][tid]);
+    s_m[tid] = mx;
+  }
+  __syncthreads();
+  // ---- p = exp(k - m) in place; column sums Z
+  {
+    const float m = s_m[lane];
+    float z = 0.f;
+    for (int p = warp * 16; p < warp * 16 + 16; ++p) {
+      const float e = __expf(s_k[p][lane] - m);
+      s_k[p][lane] = e;
+      z += e;
+    }
+    s_red[warp][lane] = z;
+  }
+  __syncthreads();
+  // ---- S[d][e..e+3] = sum_p p[p][d] * v[p][e]
+  const int d = tid >> 3, e4 = (tid & 7) * 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+  for (int p = 0; p < AT_PIX; ++p) {
+    const float kk = s_k[p][d];
+    const float4 vv = *reinterpret_cast<const float4*>(&s_v[p][e4]);
+    a0 = fmaf(kk, vv.x, a0); a1 = fmaf(kk, vv.y, a1); a2 = fmaf(kk, vv.z, a2); a3 = fmaf(kk, vv.w, a3);
+  }
+  float* po = part + (((size_t)n * gridDim.y + head) * chunks + chunk) * AT_PART;
+  *reinterpret_cast<float4*>(po + d * AT_D + e4) = make_float4(a0, a1, a2, a3);
+  if (tid < AT_D) {
+    float z = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) z += s_red[w][tid];
+    po[AT_D * AT_D + tid] = z;
+    po[AT_D * AT_D + AT_D + tid] = s_m[tid];
+  }
+}
+
+// grid = (heads, N), block = 256: merge chunk partials (log-sum-exp style), normalise, then
+// M[n][c][head*32 + d] = sum_e Wout[c][head*32 + e] * ctx[d][e]  -> bf16 [N][Cout_pad][hidden]
+__global__ void __launch_bounds__(256)
+attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad,
+                     int hidden, __nv_bfloat16* __restrict__ M) {
+  __shared__ float s_ctx[AT_D][AT_D + 1];
+  __shared__ float s_M[AT_D], s_Z[AT_D];
+  const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const float* pb = part + ((size_t)n * gridDim.x + head) * chunks * AT_PART;
+  if (tid < AT_D) {
+    float mx = -INFINITY;
+    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + tid]);
+    float z = 0.f;
+    for (int c = 0; c < chunks; ++c)
+      z += pb[(size_t)c * AT_PART + AT_D * AT_D + tid] * __expf(pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + tid] - mx);
+    s_M[tid] = mx;
+    s_Z[tid] = z;
+  }
+  __syncthreads();
+  for (int i = tid; i < AT_D * AT_D; i += 256) {
+    const int d = i / AT_D;
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c)
+      s += pb[(size_t)c * AT_PART + i] * __expf(pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + d] - s_M[d]);
+    s_ctx[d][i % AT_D] = s / s_Z[d];
+  }
+  __syncthreads();
+  __nv_bfloat16* Mn = M + (size_t)n * Cout_pad * hidden;
+  for (int i = tid; i < Cout_pad * AT_D; i += 256) {
+    const int c = i / AT_D, d = i % AT_D;
+    float acc = 0.f;
+    if (c < C) {
+      const float* wr = wout + (size_t)c * hidden + head * AT_D;
+#pragma unroll 8
+      for (int e = 0; e < AT_D; ++e) acc = fmaf(__ldg(wr + e), s_ctx[d][e], acc);
+    }
+    Mn[(size_t)c * hidden + head * AT_D + d] = __float2bfloat16_rn(acc);
+  }
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+int ds_attn_chunks(long long npix) { return (int)((npix + AT_PIX - 1) / AT_PIX); }
+long long ds_attn_part_floats(int N, int heads, long long npix) { return (long long)N * heads * ds_attn_chunks(npix) * AT_PART; }
+
+/* q' (bf16 [N, npix, hidden]) and chunk partials of ctx.  q_mode 0: softmax over head dim * scale; 1: copy. */
+int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, int heads, long long npix, int q_mode, float scale, void* stream) {
+  DS_REQUIRE(d_qkv && d_q_out && d_part && N > 0 && heads > 0 && npix > 0, "ds_attn_ctx_partial: bad arguments");
+  const int chunks = ds_attn_chunks(npix);
+  DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_ctx_partial: grid too large");
+  attn_ctx_partial_kernel<<<dim3(chunks, heads, N), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_qkv, heads * AT_D, (int)npix,
+                                                                                   q_mode, scale, (__nv_bfloat16*)d_q_out, d_part, chunks);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+/* Merge partials and fold to_out's weight: d_M bf16 [N][Cout_pad][heads*32]. */
+int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
+  DS_REQUIRE(d_part && d_wout && d_M && N > 0 && heads > 0 && C > 0 && Cout_pad >= C, "ds_attn_finalize: bad arguments");
+  attn_finalize_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, ds_attn_chunks(npix), d_wout, C, Cout_pad, heads * AT_D,
+                                                                         (__nv_bfloat16*)d_M);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,600 @@
+// Implicit-GEMM convolution for sm_100a: TMA (tiled, zero-filled halos) -> shared memory ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> fused epilogue.  See include/diffusynth_b200.h
+// (ds_conv_gemm) for the contract and the reference lines it replaces.
+//
+// CTA = 12 warps, persistent over output tiles:
+//   warp 0      TMA producer (one elected lane): per K-block one 4-D box of the activation
+//               (BK channels x Wb x Hb pixels, shifted by the tap offset; out-of-image pixels are
+//               zero-filled by TMA = the conv's zero padding) and one box of the weights.
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN,
+//               K=16 per instruction, accumulator double-buffered in TMEM.
+//   warp 2      TMEM allocator.
+//   warps 4-11  epilogue: tcgen05.ld the accumulator (thread = pixel row), apply the folded
+//               GroupNorm(1,C) scalars / bias / GELU / residual, write bf16 NHWC (or fp32 NCHW),
+//               and emit (sum, sumsq) partials for the next GroupNorm.
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+#include <cuda.h>   // CUtensorMap (driver types only; the encode entry point is fetched at run time)
+
+namespace ds {
+
+static constexpr int kNumThreads = 384;
+static constexpr int kEpiWarp0 = 4;
+static constexpr int kEpiWarps = 8;
+static constexpr int kMaxStages = 8;
+static constexpr int BM = 128;
+
+struct __align__(16) ConvGemmDev {
+  int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
+  int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
+  int num_kb, stages, num_tiles;
+  unsigned stage_a_bytes, stage_b_bytes;
+  int Cout, Cout_pad;
+  const float2* stats_in; int stats_in_slots; float inv_count, eps;
+  const float* e1; const float* e2; int ncls;
+  const float* sbias; int sbias_stride; int act;
+  const __nv_bfloat16* residual; long long res_sn, res_sh, res_sw;
+  __nv_bfloat16* out; long long out_sn, out_sh, out_sw; long long out_goff[DS_MAX_GROUPS];
+  float* out_f32;
+  float2* stats_out; int stats_slots;
+  ds_conv_tap taps[DS_MAX_GROUPS][DS_MAX_TAPS];
+};
+
+struct TmaMaps {
+  CUtensorMap a[2][4];   // [source][view]
+  CUtensorMap b;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("ds_conv_gemm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of BK bf16 = one swizzle span
+// (64 B or 128 B), 8-row groups SBO bytes apart; version 1 (Blackwell); layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B.
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+  constexpr uint64_t row_bytes = BK * 2;
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;
+  constexpr uint64_t layout = (BK == 64) ? 2ull : 4ull;
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------------------------
+struct TileCoord { int n, g, th, tw, nt, slot; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile) {
+  TileCoord t;
+  t.nt = tile % P.n_tiles_n;
+  int r = tile / P.n_tiles_n;
+  int m = r % P.tiles_m;
+  r /= P.tiles_m;
+  t.g = r % P.groups;
+  t.n = r / P.groups;
+  t.th = m / P.tiles_w;
+  t.tw = m % P.tiles_w;
+  t.slot = (t.g * P.tiles_m + m) * P.n_tiles_n + t.nt;
+  return t;
+}
+
+template <int BK>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const unsigned stage_bytes = P.stage_a_bytes + P.stage_b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = (2 * P.BN <= 32) ? 32u : (2 * P.BN <= 64) ? 64u : (2 * P.BN <= 128) ? 128u : (2 * P.BN <= 256) ? 256u : 512u;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < 2; ++s)
+      for (int v = 0; v < 4; ++v) prefetch_tmap(&maps.a[s][v]);
+    prefetch_tmap(&maps.b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
+        const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
+        const int wz = P.per_sample_w ? t.n : t.g;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + P.stage_a_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          const ds_conv_tap tp = P.taps[t.g][tap];
+          const int src = cb < P.cblocks0 ? 0 : 1;
+          const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
+          tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
+          tma_load_3d(sb, &maps.b, &full_bar[stage], kb * BK, t.nt * P.BN, wz);
+          if (++cb == P.cblocks) { cb = 0; ++tap; }
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + P.stage_a_bytes;
+          const uint64_t adesc = make_kmajor_desc<BK>(sa);
+          const uint64_t bdesc = make_kmajor_desc<BK>(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);       // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ epilogue ====================================
+    const int ew = warp - kEpiWarp0;       // 0..7
+    const int lane_grp = warp & 3;         // TMEM lanes [32*lane_grp, +32) are the ones this warp may read
+    const int col_half = ew >> 2;          // two warps share a lane group and split the columns
+    const int row = lane_grp * 32 + lane;  // accumulator row = pixel inside the tile
+    const int chunks = P.BN / 16;          // 16-column chunks
+    const int chunk_lo = col_half == 0 ? 0 : (chunks + 1) / 2;
+    const int chunk_hi = col_half == 0 ? (chunks + 1) / 2 : chunks;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      const int ph = row / P.Wb, pw = row % P.Wb;
+      const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
+      const bool valid = (h < P.H) && (w < P.W);
+      float mean = 0.f, rstd = 1.f;
+      if (P.stats_in != nullptr) {
+        const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
+        float2 mr = reduce_stats_warp(P.stats_in + (size_t)nsrc * P.stats_in_slots, P.stats_in_slots, P.inv_count, P.eps, lane);
+        mean = mr.x;
+        rstd = mr.y;
+      }
+      int cls = 0;
+      if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
+      const float nmr = -mean * rstd;
+      const float* e1 = P.e1 ? P.e1 + (size_t)cls * P.Cout_pad : nullptr;
+      const float* e2 = P.e2 + (size_t)cls * P.Cout_pad;
+      const float* sb = P.sbias ? P.sbias + (size_t)t.n * P.sbias_stride : nullptr;
+      const long long pix_out = P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
+      const long long pix_res = (long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw;
+      float psum = 0.f, psq = 0.f;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
+      for (int ch = chunk_lo; ch < chunk_hi; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x16(t_row + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+        const int o0 = t.nt * P.BN + ch * 16;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int o = o0 + j;
+          float x = __uint_as_float(r[j]) * rstd + __ldg(e2 + o);
+          if (e1) x = fmaf(nmr, __ldg(e1 + o), x);
+          if (sb) x += __ldg(sb + o);
+          if (P.act == 1) x = gelu_erf(x);
+          v[j] = x;
+        }
+        if (valid) {
+          if (P.residual != nullptr && o0 < P.Cout) {
+            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0);
+            uint4 a = __ldg(rp), b = __ldg(rp + 1);
+            const uint32_t rr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += bf16_lo(rr[j]);
+              v[2 * j + 1] += bf16_hi(rr[j]);
+            }
+          }
+          if (P.stats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (o0 + j < P.Cout) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+          }
+          if (P.out != nullptr && o0 < P.Cout) {
+            uint4 a, b;
+            a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
+            a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
+            b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
+            b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+            uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + o0);
+            op[0] = a;
+            op[1] = b;
+          }
+          if (P.out_f32 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (o0 + j < P.Cout)
+                P.out_f32[(((size_t)t.n * P.Cout + (o0 + j)) * P.H + h) * P.W + w] = v[j];
+          }
+        }
+      }
+      // release the accumulator stage (one arrive per epilogue warp)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (P.stats_out != nullptr) {
+        psum = warp_sum(psum);
+        psq = warp_sum(psq);
+        if (lane == 0) P.stats_out[(size_t)t.n * P.stats_slots + (size_t)t.slot * kEpiWarps + ew] = make_float2(psum, psq);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int validate(const ds_conv_gemm_args* a) {
+  DS_REQUIRE(a != nullptr, "ds_conv_gemm: null args");
+  DS_REQUIRE(a->BK == 32 || a->BK == 64, "ds_conv_gemm: BK must be 32 or 64 (got %d)", a->BK);
+  DS_REQUIRE(a->C0 > 0 && a->C0 % a->BK == 0 && a->C1 >= 0 && a->C1 % a->BK == 0,
+             "ds_conv_gemm: C0=%d C1=%d must be multiples of BK=%d", a->C0, a->C1, a->BK);
+  DS_REQUIRE(a->BN >= 16 && a->BN <= 256 && a->BN % 16 == 0, "ds_conv_gemm: BN=%d must be a multiple of 16 in [16,256]", a->BN);
+  DS_REQUIRE(a->Cout_pad % a->BN == 0 && a->Cout <= a->Cout_pad && a->Cout > 0, "ds_conv_gemm: Cout=%d Cout_pad=%d BN=%d", a->Cout, a->Cout_pad, a->BN);
+  DS_REQUIRE(a->Hb * a->Wb == BM && a->Hb >= 1 && a->Wb >= 1 && a->Wb <= 256 && a->Hb <= 256, "ds_conv_gemm: tile %dx%d must cover 128 pixels", a->Hb, a->Wb);
+  DS_REQUIRE(a->ntaps >= 1 && a->ntaps <= DS_MAX_TAPS && a->groups >= 1 && a->groups <= DS_MAX_GROUPS, "ds_conv_gemm: ntaps=%d groups=%d", a->ntaps, a->groups);
+  DS_REQUIRE(a->num_views >= 1 && a->num_views <= 4, "ds_conv_gemm: num_views=%d", a->num_views);
+  DS_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->Hv > 0 && a->Wv > 0, "ds_conv_gemm: bad extents");
+  DS_REQUIRE(a->d_src0 && a->d_weight && a->d_e2, "ds_conv_gemm: src0, weight and e2 are required");
+  DS_REQUIRE(a->C1 == 0 || a->d_src1, "ds_conv_gemm: C1>0 needs src1");
+  DS_REQUIRE(a->ncls == 1 || a->ncls == 9, "ds_conv_gemm: ncls must be 1 or 9");
+  DS_REQUIRE(!(a->d_stats_in && !a->d_e1), "ds_conv_gemm: stats_in needs e1");
+  DS_REQUIRE(a->d_out || a->d_out_f32_nchw, "ds_conv_gemm: no output");
+  DS_REQUIRE(!a->d_out || a->Cout % 16 == 0, "ds_conv_gemm: bf16 output needs Cout %% 16 == 0 (got %d)", a->Cout);
+  DS_REQUIRE(!(a->per_sample_weights && a->groups != 1), "ds_conv_gemm: per-sample weights with groups");
+  for (int g = 0; g < a->groups; ++g)
+    for (int t = 0; t < a->ntaps; ++t)
+      DS_REQUIRE(a->taps[g][t].view >= 0 && a->taps[g][t].view < a->num_views, "ds_conv_gemm: tap view out of range");
+  return DS_OK;
+}
+
+static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
+  memset(&P, 0, sizeof(P));
+  P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
+  P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
+  P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
+  P.tiles_m = P.tiles_h * P.tiles_w;
+  P.n_tiles_n = a->Cout_pad / a->BN;
+  P.BN = a->BN; P.C0 = a->C0; P.C1 = a->C1;
+  P.cblocks0 = a->C0 / a->BK;
+  P.cblocks = (a->C0 + a->C1) / a->BK;
+  P.ntaps = a->ntaps; P.groups = a->groups; P.per_sample_w = a->per_sample_weights;
+  P.src_batch_mod = a->src_batch_mod;
+  P.num_kb = P.cblocks * a->ntaps;
+  P.num_tiles = a->N * a->groups * P.tiles_m * P.n_tiles_n;
+  P.stage_a_bytes = BM * a->BK * 2;
+  P.stage_b_bytes = a->BN * a->BK * 2;
+  P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
+  P.stats_in = reinterpret_cast<const float2*>(a->d_stats_in);
+  P.stats_in_slots = a->stats_in_slots; P.inv_count = a->stats_inv_count; P.eps = a->eps;
+  P.e1 = a->d_e1; P.e2 = a->d_e2; P.ncls = a->ncls;
+  P.sbias = a->d_sbias; P.sbias_stride = a->sbias_stride; P.act = a->act;
+  P.residual = reinterpret_cast<const __nv_bfloat16*>(a->d_residual);
+  P.res_sn = a->res_sn; P.res_sh = a->res_sh; P.res_sw = a->res_sw;
+  P.out = reinterpret_cast<__nv_bfloat16*>(a->d_out);
+  P.out_sn = a->out_sn; P.out_sh = a->out_sh; P.out_sw = a->out_sw;
+  for (int g = 0; g < DS_MAX_GROUPS; ++g) P.out_goff[g] = a->out_goff[g];
+  P.out_f32 = a->d_out_f32_nchw;
+  P.stats_out = reinterpret_cast<float2*>(a->d_stats_out);
+  P.stats_slots = a->groups * P.tiles_m * P.n_tiles_n * kEpiWarps;
+  memcpy(P.taps, a->taps, sizeof(P.taps));
+}
+
+static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
+  int rc = validate(a);
+  if (rc) return rc;
+  EncodeTiledFn encode = get_encode_fn();
+  DS_REQUIRE(encode != nullptr, "ds_conv_gemm: cuTensorMapEncodeTiled entry point not available");
+
+  static TmaMaps maps;   // zero-initialised; unused slots are copies of a valid map (prefetch-safe)
+  ConvGemmDev P;
+  fill_dev(a, P);
+  const CUtensorMapSwizzle swz = a->BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+
+  for (int s = 0; s < 2; ++s) {
+    const int C = s == 0 ? a->C0 : a->C1;
+    const char* base = reinterpret_cast<const char*>(s == 0 ? a->d_src0 : a->d_src1);
+    for (int v = 0; v < 4; ++v) {
+      if (C == 0 || v >= a->num_views) { maps.a[s][v] = maps.a[0][0]; continue; }
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a->Wv, (cuuint64_t)a->Hv,
+                            (cuuint64_t)(a->src_batch_mod > 0 ? a->src_batch_mod : a->N)};
+      cuuint64_t strides[3] = {(cuuint64_t)a->view_sw * C * 2, (cuuint64_t)a->view_sh * C * 2, (cuuint64_t)a->view_sn * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      void* gaddr = const_cast<char*>(base) + (size_t)a->view_off[v] * C * 2;
+      CUresult r = encode(&maps.a[s][v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gaddr, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(A src %d view %d) failed with %d (C=%d Wv=%d Hv=%d)", s, v, (int)r, C, a->Wv, a->Hv);
+    }
+  }
+  {
+    const long long K = (long long)a->ntaps * (a->C0 + a->C1);
+    const int Z = a->per_sample_weights ? a->N : a->groups;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a->Cout_pad, (cuuint64_t)Z};
+    cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * a->Cout_pad};
+    cuuint32_t box[3] = {(cuuint32_t)a->BK, (cuuint32_t)a->BN, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->d_weight), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (K=%lld Cout_pad=%d)", (int)r, K, a->Cout_pad);
+  }
+
+  const size_t stage_bytes = (size_t)P.stage_a_bytes + P.stage_b_bytes;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > P.num_kb && P.num_kb >= 2) stages = P.num_kb;
+  if (stages < 2) stages = 2;
+  P.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+
+  int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  if (a->BK == 64) {
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_gemm_kernel<64><<<grid, kNumThreads, smem, stream>>>(maps, P);
+  } else {
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_gemm_kernel<32><<<grid, kNumThreads, smem, stream>>>(maps, P);
+  }
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core cross-check of the same contract (tests only): one thread per (pixel, out channel).
+// ---------------------------------------------------------------------------------------------
+__global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const __nv_bfloat16* src0, const __nv_bfloat16* src1,
+                                     const __nv_bfloat16* weight, int Hv, int Wv, long long view_sn, long long view_sh,
+                                     long long view_sw, const long long* view_off_dev, float2* mean_rstd) {
+  const long long total = (long long)P.N * P.groups * P.H * P.W * P.Cout;
+  const long long K = (long long)P.ntaps * (P.C0 + P.C1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int o = (int)(i % P.Cout);
+    long long r = i / P.Cout;
+    int w = (int)(r % P.W); r /= P.W;
+    int h = (int)(r % P.H); r /= P.H;
+    int g = (int)(r % P.groups);
+    int n = (int)(r / P.groups);
+    const int nsrc = P.src_batch_mod > 0 ? (n % P.src_batch_mod) : n;
+    const __nv_bfloat16* wrow = weight + ((long long)(P.per_sample_w ? n : g) * P.Cout_pad + o) * K;
+    float acc = 0.f;
+    for (int t = 0; t < P.ntaps; ++t) {
+      const ds_conv_tap tp = P.taps[g][t];
+      const int y = h + tp.dy, x = w + tp.dx;
+      if (y < 0 || y >= Hv || x < 0 || x >= Wv) continue;
+      const long long pix = view_off_dev[tp.view] + nsrc * view_sn + y * view_sh + x * view_sw;
+      for (int c = 0; c < P.C0 + P.C1; ++c) {
+        const float a = c < P.C0 ? __bfloat162float(src0[pix * P.C0 + c]) : __bfloat162float(src1[pix * P.C1 + (c - P.C0)]);
+        acc = fmaf(a, __bfloat162float(wrow[(long long)t * (P.C0 + P.C1) + c]), acc);
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (mean_rstd) { mean = mean_rstd[nsrc].x; rstd = mean_rstd[nsrc].y; }
+    int cls = 0;
+    if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
+    float v = acc * rstd + P.e2[(size_t)cls * P.Cout_pad + o];
+    if (P.e1) v = fmaf(-mean * rstd, P.e1[(size_t)cls * P.Cout_pad + o], v);
+    if (P.sbias) v += P.sbias[(size_t)n * P.sbias_stride + o];
+    if (P.act == 1) v = gelu_erf(v);
+    if (P.residual) v += __bfloat162float(P.residual[n * P.res_sn + h * P.res_sh + w * P.res_sw + o]);
+    if (P.out) P.out[P.out_goff[g] + n * P.out_sn + h * P.out_sh + w * P.out_sw + o] = __float2bfloat16_rn(v);
+    if (P.out_f32) P.out_f32[(((size_t)n * P.Cout + o) * P.H + h) * P.W + w] = v;
+  }
+}
+
+__global__ void stats_finalize_kernel(const float2* part, int slots, float inv_count, float eps, float2* mean_rstd) {
+  float2 mr = reduce_stats_warp(part + (size_t)blockIdx.x * slots, slots, inv_count, eps, threadIdx.x);
+  if (threadIdx.x == 0) mean_rstd[blockIdx.x] = mr;
+}
+
+static int conv_gemm_reference_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
+  int rc = validate(a);
+  if (rc) return rc;
+  ConvGemmDev P;
+  fill_dev(a, P);
+  long long* voff = nullptr;
+  float2* mr = nullptr;
+  DS_CHECK_CUDA(cudaMallocAsync(&voff, 4 * sizeof(long long), stream));
+  DS_CHECK_CUDA(cudaMemcpyAsync(voff, a->view_off, 4 * sizeof(long long), cudaMemcpyHostToDevice, stream));
+  const int nsrc = a->src_batch_mod > 0 ? a->src_batch_mod : a->N;
+  if (a->d_stats_in) {
+    DS_CHECK_CUDA(cudaMallocAsync(&mr, nsrc * sizeof(float2), stream));
+    stats_finalize_kernel<<<nsrc, 32, 0, stream>>>(P.stats_in, P.stats_in_slots, P.inv_count, P.eps, mr);
+  }
+  conv_gemm_ref_kernel<<<num_sms() * 8, 256, 0, stream>>>(P, reinterpret_cast<const __nv_bfloat16*>(a->d_src0),
+                                                          reinterpret_cast<const __nv_bfloat16*>(a->d_src1),
+                                                          reinterpret_cast<const __nv_bfloat16*>(a->d_weight), a->Hv, a->Wv,
+                                                          a->view_sn, a->view_sh, a->view_sw, voff, mr);
+  DS_CHECK_CUDA(cudaGetLastError());
+  DS_CHECK_CUDA(cudaFreeAsync(voff, stream));
+  if (mr) DS_CHECK_CUDA(cudaFreeAsync(mr, stream));
+  return DS_OK;
+}
+
+}  // namespace ds
+
+extern "C" int ds_conv_gemm(const ds_conv_gemm_args* args, void* stream) {
+  return ds::conv_gemm_launch(args, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int ds_conv_gemm_reference(const ds_conv_gemm_args* args, void* stream) {
+  return ds::conv_gemm_reference_launch(args, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int ds_conv_gemm_stats_slots(const ds_conv_gemm_args* a) {
+  if (!a || a->Hb <= 0 || a->Wb <= 0 || a->BN <= 0) return -1;
+  const int tiles = ((a->H + a->Hb - 1) / a->Hb) * ((a->W + a->Wb - 1) / a->Wb);
+  return a->groups * tiles * (a->Cout_pad / a->BN) * ds::kEpiWarps;
+}

@@ -1,0 +1,215 @@
+// Depthwise 7x7 convolution (ConvNextBlock.ds_conv, model/diffusion_components.py:118,131) fused with the
+// per-sample time-embedding bias (:133-136) and the (sum, sumsq) partials of the GroupNorm(1,C) that
+// follows (:121), and the 7x7 stem convolution (init_conv, model/diffusion.py:82).
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+
+namespace ds {
+
+// ---------------------------------------------------------------------------------------------
+// dwconv7: bf16 NHWC in (one or two channel-concatenated sources), bf16 NHWC out.
+// block = 256 threads = 16 channel pairs x 16 pixel-threads; tile = 8 rows x 16 cols x 32 channels.
+// The (8+6) x (16+6) halo tile is staged in shared memory (row pitch padded to 23 pixels so the two
+// pixel-threads of a warp hit different banks); each thread slides a 7-wide window over 8 outputs.
+// ---------------------------------------------------------------------------------------------
+static constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 32;
+static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6, DW_PITCH = 23;
+
+__global__ void __launch_bounds__(256)
+dwconv7_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __restrict__ src1, int C0, int C1, int src_batch_mod,
+               const float* __restrict__ weight,   // [49][C] (tap-major)
+               const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
+               __nv_bfloat16* __restrict__ out, float2* __restrict__ stats, int H, int W, int tiles_w, int tiles) {
+  __shared__ __align__(16) uint32_t s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // bf16 pairs
+  __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
+  __shared__ float s_red[16];
+  const int C = C0 + C1;
+  const int tile = blockIdx.x, cblk = blockIdx.y, n = blockIdx.z;
+  const int h0 = (tile / tiles_w) * DW_TH, w0 = (tile % tiles_w) * DW_TW;
+  const int c0 = cblk * DW_CB;
+  const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
+  const __nv_bfloat16* src;
+  int Cs, cs0;
+  if (c0 < C0) { src = src0; Cs = C0; cs0 = c0; } else { src = src1; Cs = C1; cs0 = c0 - C0; }
+  src += (size_t)nsrc * H * W * Cs;
+
+  // stage weights: s_w[tap][cp] = (w[tap][c0+2cp], w[tap][c0+2cp+1])
+  for (int i = threadIdx.x; i < 49 * (DW_CB / 2); i += 256) {
+    const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
+    s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
+  }
+  // stage the halo tile: 16-byte pieces (8 channels); 4 pieces per pixel
+  for (int i = threadIdx.x; i < DW_HH * DW_HW * 4; i += 256) {
+    const int piece = i & 3, pix = i >> 2;
+    const int r = pix / DW_HW, cc = pix % DW_HW;
+    const int y = h0 + r - 3, x = w0 + cc - 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * W + x) * Cs + cs0 + piece * 8));
+    *reinterpret_cast<uint4*>(&s_in[(r * DW_PITCH + cc) * (DW_CB / 2) + piece * 4]) = v;
+  }
+  __syncthreads();
+
+  const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
+  const int row = pt & 7, col0 = (pt >> 3) * 8;
+  float acc0[8], acc1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky) {
+    float2 wv[7];
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) wv[kx] = s_w[(ky * 7 + kx) * (DW_CB / 2) + cp];
+    const uint32_t* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
+#pragma unroll
+    for (int j = 0; j < 14; ++j) {
+      const uint32_t v = rowp[j * (DW_CB / 2)];
+      const float a = bf16_lo(v), b = bf16_hi(v);
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ow = j - kx;
+        if (ow >= 0 && ow < 8) {
+          acc0[ow] = fmaf(a, wv[kx].x, acc0[ow]);
+          acc1[ow] = fmaf(b, wv[kx].y, acc1[ow]);
+        }
+      }
+    }
+  }
+  const int c = c0 + 2 * cp;
+  const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
+  const float b0 = __ldg(tb + c), b1 = __ldg(tb + c + 1);
+  const int y = h0 + row;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int x = w0 + col0 + j;
+    if (y < H && x < W) {
+      const float v0 = acc0[j] + b0, v1 = acc1[j] + b1;
+      s += v0 + v1;
+      q = fmaf(v0, v0, fmaf(v1, v1, q));
+      *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack_bf16(v0, v1);
+    }
+  }
+  if (stats != nullptr) {
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_red[warp] = s; s_red[8 + warp] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float ts = 0.f, tq = 0.f;
+      for (int i = 0; i < 8; ++i) { ts += s_red[i]; tq += s_red[8 + i]; }
+      stats[(size_t)n * (tiles * gridDim.y) + (size_t)cblk * tiles + tile] = make_float2(ts, tq);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: 7x7 conv, Cin (<=4) -> Cout (multiple of 32, <= 128), fp32 NCHW in, bf16 NHWC out.
+// block = 256 threads; tile = 4 rows x 32 cols; thread = (pixel, half of the output channels).
+// Weights live in shared memory as [tap*Cin + ci][Cout] fp32 and are read as broadcast float4.
+// ---------------------------------------------------------------------------------------------
+static constexpr int ST_TH = 4, ST_TW = 32;
+
+template <int CO_PER_THREAD>
+__global__ void __launch_bounds__(256)
+stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __restrict__ weight /* [49*Cin][Cout] */,
+                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N, int Cin, int Cout, int H, int W,
+                  int tiles_w, int tiles_per_sample, int total_tiles) {
+  extern __shared__ __align__(16) float s_mem[];
+  float* s_w = s_mem;                                   // [49*Cin][Cout]
+  float* s_in = s_mem + 49 * Cin * Cout;                // [Cin][ST_TH+6][ST_TW+6 (+1 pad)]
+  const int IW = ST_TW + 7;
+  for (int i = threadIdx.x; i < 49 * Cin * Cout; i += 256) s_w[i] = __ldg(weight + i);
+  const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int pr = p / ST_TW, pc = p % ST_TW;
+  const int co0 = half * CO_PER_THREAD;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int n = tile / tiles_per_sample, t = tile % tiles_per_sample;
+    const int h0 = (t / tiles_w) * ST_TH, w0 = (t % tiles_w) * ST_TW;
+    const int nsrc = x_batch_mod > 0 ? n % x_batch_mod : n;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cin * (ST_TH + 6) * (ST_TW + 6); i += 256) {
+      const int cc = i % (ST_TW + 6), r = (i / (ST_TW + 6)) % (ST_TH + 6), ci = i / ((ST_TW + 6) * (ST_TH + 6));
+      const int y = h0 + r - 3, xx = w0 + cc - 3;
+      float v = 0.f;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)nsrc * Cin + ci) * H + y) * W + xx);
+      s_in[(ci * (ST_TH + 6) + r) * IW + cc] = v;
+    }
+    __syncthreads();
+    float acc[CO_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < CO_PER_THREAD; ++j) acc[j] = __ldg(bias + co0 + j);
+    for (int ky = 0; ky < 7; ++ky)
+      for (int kx = 0; kx < 7; ++kx)
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = s_in[(ci * (ST_TH + 6) + pr + ky) * IW + pc + kx];
+          const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 7 + kx) * Cin + ci) * Cout + co0);
+#pragma unroll
+          for (int j = 0; j < CO_PER_THREAD / 4; ++j) {
+            const float4 w4 = wr[j];
+            acc[4 * j] = fmaf(v, w4.x, acc[4 * j]);
+            acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+          }
+        }
+    const int y = h0 + pr, xx = w0 + pc;
+    if (y < H && xx < W) {
+      uint4* op = reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + xx) * Cout + co0);
+#pragma unroll
+      for (int j = 0; j < CO_PER_THREAD / 8; ++j)
+        op[j] = make_uint4(pack_bf16(acc[8 * j], acc[8 * j + 1]), pack_bf16(acc[8 * j + 2], acc[8 * j + 3]),
+                           pack_bf16(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16(acc[8 * j + 6], acc[8 * j + 7]));
+    }
+  }
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+/* Depthwise 7x7 + time bias + GroupNorm partials.  d_weight fp32 [49][C0+C1] (tap-major);
+   d_tbias fp32 [N][tbias_stride] (or one row when tbias_stride == 0) holding ds_conv.bias + mlp(time_emb).
+   d_stats (nullable) float2 [N][ds_dwconv7_stats_slots(...)]. */
+int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight, const float* d_tbias,
+               long long tbias_stride, void* d_out, void* d_stats, int N, int H, int W, void* stream) {
+  DS_REQUIRE(d_src0 && d_weight && d_tbias && d_out && N > 0 && H > 0 && W > 0, "ds_dwconv7: bad arguments");
+  DS_REQUIRE(C0 > 0 && C0 % DW_CB == 0 && C1 >= 0 && C1 % DW_CB == 0 && (C1 == 0 || d_src1), "ds_dwconv7: C0=%d C1=%d must be multiples of 32", C0, C1);
+  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
+  const int tiles = tiles_w * tiles_h;
+  DS_REQUIRE(N <= 65535 && (C0 + C1) / DW_CB <= 65535, "ds_dwconv7: grid too large");
+  dwconv7_kernel<<<dim3(tiles, (C0 + C1) / DW_CB, N), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d_src0, (const __nv_bfloat16*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
+      (__nv_bfloat16*)d_out, (float2*)d_stats, H, W, tiles_w, tiles);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_dwconv7_stats_slots(int C, int H, int W) {
+  return ((W + DW_TW - 1) / DW_TW) * ((H + DW_TH - 1) / DW_TH) * (C / DW_CB);
+}
+
+/* Stem 7x7 conv (init_conv).  d_x fp32 NCHW [x_batch_mod or N, Cin, H, W]; d_weight fp32 [49*Cin][Cout]
+   ((ky,kx,ci)-major); output bf16 NHWC [N,H,W,Cout]. */
+int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out, int N, int Cin, int Cout,
+                  int H, int W, void* stream) {
+  DS_REQUIRE(d_x && d_weight && d_bias && d_out && N > 0 && Cin > 0 && Cin <= 4 && H > 0 && W > 0, "ds_stem_conv7: bad arguments");
+  DS_REQUIRE(Cout == 96 || Cout == 64 || Cout == 32 || Cout == 128, "ds_stem_conv7: Cout=%d unsupported (32/64/96/128)", Cout);
+  const int tiles_w = (W + ST_TW - 1) / ST_TW, tiles_h = (H + ST_TH - 1) / ST_TH;
+  const int tps = tiles_w * tiles_h, total = tps * N;
+  const size_t smem = (size_t)(49 * Cin * Cout + Cin * (ST_TH + 6) * (ST_TW + 7)) * sizeof(float);
+  int grid = total < 2 * num_sms() ? total : 2 * num_sms();
+#define LAUNCH_STEM(CPT)                                                                                                    \
+  DS_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+  stem_conv7_kernel<CPT><<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, x_batch_mod, d_weight, d_bias, (__nv_bfloat16*)d_out, N, \
+                                                                     Cin, Cout, H, W, tiles_w, tps, total);
+  if (Cout == 96) { LAUNCH_STEM(48) } else if (Cout == 64) { LAUNCH_STEM(32) } else if (Cout == 32) { LAUNCH_STEM(16) } else { LAUNCH_STEM(64) }
+#undef LAUNCH_STEM
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+// Bandwidth-bound elementwise kernels of the sampling path: the fused CFG + DDIM/DDPM update,
+// q_sample, inpaint mask blend, layout/precision conversions, GroupNorm apply (+residual),
+// GroupNorm(16) statistics + activation for the VQGAN, and the tiny time/condition linears.
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+
+namespace ds {
+
+// ---------------------------------------------------------------------------------------------
+// K11: eps = eps_u + s (eps_c - eps_u);  x0 = (x - c0 eps) / c1;  x_prev = c2 x0 + c3 eps + c4 z
+// model/DiffSynthSampler.py:320,327,337,343 -- same operation order, fp32.
+// coef (device): {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev-sigma^2), sigma, cfg_scale, -, -}
+// ---------------------------------------------------------------------------------------------
+__global__ void ddim_step_kernel(const float4* __restrict__ eps_u, const float4* __restrict__ eps_c,
+                                 const float4* __restrict__ x, const float4* __restrict__ z,
+                                 const float* __restrict__ coef, float4* __restrict__ out, long long n4) {
+  const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], c4 = coef[4], s = coef[5];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 ec = __ldg(eps_c + i), xv = __ldg(x + i);
+    float e[4] = {ec.x, ec.y, ec.z, ec.w};
+    if (eps_u != nullptr) {
+      float4 eu = __ldg(eps_u + i);
+      const float u[4] = {eu.x, eu.y, eu.z, eu.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = __fadd_rn(u[j], __fmul_rn(s, __fsub_rn(e[j], u[j])));
+    }
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (z != nullptr) { float4 zv = __ldg(z + i); zz[0] = zv.x; zz[1] = zv.y; zz[2] = zv.z; zz[3] = zv.w; }
+    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x0 = __fdiv_rn(__fsub_rn(xx[j], __fmul_rn(c0, e[j])), c1);
+      o[j] = __fadd_rn(__fadd_rn(__fmul_rn(c2, x0), __fmul_rn(c3, e[j])), __fmul_rn(c4, zz[j]));
+    }
+    out[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// q_sample: a*x0 + b*noise (model/DiffSynthSampler.py:290-294); coef = {a, b}
+__global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, const float* __restrict__ coef,
+                                float4* __restrict__ out, long long n4) {
+  const float a = coef[0], b = coef[1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = __ldg(x0 + i), q = __ldg(noise + i);
+    out[i] = make_float4(__fadd_rn(__fmul_rn(a, p.x), __fmul_rn(b, q.x)), __fadd_rn(__fmul_rn(a, p.y), __fmul_rn(b, q.y)),
+                         __fadd_rn(__fmul_rn(a, p.z), __fmul_rn(b, q.z)), __fadd_rn(__fmul_rn(a, p.w), __fmul_rn(b, q.w)));
+  }
+}
+
+// inpaint blend: img = m*(a*guide + b*noise) + (1-m)*img   (model/DiffSynthSampler.py:502-510);
+// mask is [B,1,H,W] broadcast over C channels; coef = {a, b} (a=1,b=0 reproduces the i==0 branch).
+__global__ void mask_blend_kernel(const float* __restrict__ guide, const float* __restrict__ noise, const float* __restrict__ mask,
+                                  const float* __restrict__ coef, float* __restrict__ img, int C, long long hw, long long total) {
+  const float a = coef[0], b = coef[1];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / (C * hw), p = i % hw;
+    const float m = __ldg(mask + n * hw + p);
+    const float g = b == 0.f ? __fmul_rn(a, guide[i]) : __fadd_rn(__fmul_rn(a, guide[i]), __fmul_rn(b, noise[i]));
+    img[i] = __fadd_rn(__fmul_rn(m, g), __fmul_rn(__fsub_rn(1.0f, m), img[i]));
+  }
+}
+
+// fp32 NCHW -> bf16 NHWC with the channel count padded to Cp (zeros); and back.
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+                                             long long hw, long long total_pix) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix * Cp; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const long long pix = i / Cp, n = pix / hw, p = pix % hw;
+    out[i] = __float2bfloat16_rn(c < C ? in[(n * C + c) * hw + p] : 0.f);
+  }
+}
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int Cp,
+                                             long long hw, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i % hw, r = i / hw;
+    const int c = (int)(r % C);
+    const long long n = r / C;
+    out[i] = __bfloat162float(in[(n * hw + p) * Cp + c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(1,C) apply + residual:  out = (y - mean) * rstd * gamma[c] + beta[c] + x
+// (the to_out[1] GroupNorm and the Residual of the attention block, diffusion_components.py:264,22-29)
+// grid = (chunks, N); y/x/out bf16 NHWC with C % 8 == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x, uint4* __restrict__ out,
+                                         const float2* __restrict__ stats, int slots, float inv_count, float eps,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
+                                         long long vec_per_sample) {
+  __shared__ float2 s_mr;
+  const int n = blockIdx.y;
+  if (threadIdx.x < 32) {
+    float2 mr = reduce_stats_warp(stats + (size_t)n * slots, slots, inv_count, eps, threadIdx.x);
+    if (threadIdx.x == 0) s_mr = mr;
+  }
+  __syncthreads();
+  const float mean = s_mr.x, rstd = s_mr.y;
+  const uint4* yb = y + (size_t)n * vec_per_sample;
+  const uint4* xb = x ? x + (size_t)n * vec_per_sample : nullptr;
+  uint4* ob = out + (size_t)n * vec_per_sample;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vec_per_sample; i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % C8) * 8;
+    const uint4 yv = __ldg(yb + i);
+    uint4 xv = make_uint4(0, 0, 0, 0);
+    if (xb) xv = __ldg(xb + i);
+    const uint32_t yy[4] = {yv.x, yv.y, yv.z, yv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g0 = __ldg(gamma + c0 + 2 * j), g1 = __ldg(gamma + c0 + 2 * j + 1);
+      const float b0 = __ldg(beta + c0 + 2 * j), b1 = __ldg(beta + c0 + 2 * j + 1);
+      const float a = (bf16_lo(yy[j]) - mean) * rstd * g0 + b0 + bf16_lo(xx[j]);
+      const float b = (bf16_hi(yy[j]) - mean) * rstd * g1 + b1 + bf16_hi(xx[j]);
+      oo[j] = pack_bf16(a, b);
+    }
+    ob[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// VQGAN GroupNorm(G groups, eps 1e-6) + activation as two passes (model/VQGAN.py:12-27,223-226):
+//   group_stats: per (sample, chunk) partial (sum, sumsq) per group       grid = (chunks, N)
+//   gn_act:      out = act((x - mean_g) * rstd_g * gamma + beta)          act: 0 none, 1 relu, 2 swish
+// x bf16 NHWC with Cp channels stored (C real, Cp - C zero padding), C % G == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void group_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
+                                   long long hw, int chunks) {
+  extern __shared__ float s_acc[];   // [2*G]
+  const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G;
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const long long per = (hw + chunks - 1) / chunks;
+  const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
+  const __nv_bfloat16* xb = x + (size_t)n * hw * Cp;
+  // thread handles a fixed channel (so a fixed group) across pixels
+  const int tc = threadIdx.x % Cp;
+  const int tp = threadIdx.x / Cp, pstride = blockDim.x / Cp;
+  float s = 0.f, q = 0.f;
+  if (tc < C && tp < pstride) {
+    for (long long p = p0 + tp; p < p1; p += pstride) {
+      const float v = __bfloat162float(xb[p * Cp + tc]);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+    atomicAdd(&s_acc[2 * (tc / cpg)], s);
+    atomicAdd(&s_acc[2 * (tc / cpg) + 1], q);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x)
+    part[((size_t)n * G + g) * chunks + chunk] = make_float2(s_acc[2 * g], s_acc[2 * g + 1]);
+}
+
+__global__ void gn_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float2* __restrict__ part,
+                              int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int C, int Cp, int G,
+                              long long hw, float eps, int act) {
+  extern __shared__ float s_ab[];   // per channel scale, shift  [2*Cp]
+  const int n = blockIdx.y, cpg = C / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nwarps) {
+    float2 mr = reduce_stats_warp(part + ((size_t)n * G + g) * chunks, chunks, 1.0f / (float)(cpg * hw), eps, lane);
+    for (int c = g * cpg + lane; c < (g + 1) * cpg; c += 32) {
+      const float a = mr.y * gamma[c];
+      s_ab[2 * c] = a;
+      s_ab[2 * c + 1] = beta[c] - mr.x * a;
+    }
+  }
+  for (int c = C + threadIdx.x; c < Cp; c += blockDim.x) { s_ab[2 * c] = 0.f; s_ab[2 * c + 1] = 0.f; }
+  __syncthreads();
+  const long long total = hw * Cp;
+  const __nv_bfloat16* xb = x + (size_t)n * total;
+  __nv_bfloat16* ob = out + (size_t)n * total;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < total; i += (long long)gridDim.x * blockDim.x * 2) {
+    const int c = (int)(i % Cp);
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(xb + i);
+    float a = bf16_lo(v) * s_ab[2 * c] + s_ab[2 * c + 1];
+    float b = bf16_hi(v) * s_ab[2 * c + 2] + s_ab[2 * c + 3];
+    if (act == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    else if (act == 2) { a = a / (1.f + __expf(-a)); b = b / (1.f + __expf(-b)); }
+    *reinterpret_cast<uint32_t*>(ob + i) = pack_bf16(a, b);
+  }
+}
+
+// out = a + b (bf16 NHWC), used for the VQGAN residual adds that are not fused into a conv epilogue
+__global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 x = __ldg(a + i), y = __ldg(b + i);
+    const uint32_t xx[4] = {x.x, x.y, x.z, x.w}, yy[4] = {y.x, y.y, y.z, y.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = pack_bf16(bf16_lo(xx[j]) + bf16_lo(yy[j]), bf16_hi(xx[j]) + bf16_hi(yy[j]));
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// VQGAN decoder head (model/VQGAN.py:394-398): ch0 softplus, ch1/ch2 tanh on (a + b); fp32 NCHW [N,3,H,W] in and out
+// (a = final ResnetBlock conv, b = its nin_shortcut; both written as fp32 by the conv epilogue).
+__global__ void decoder_head_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long hw, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / hw) % 3);
+    const float v = a[i] + (b ? b[i] : 0.f);
+    out[i] = c == 0 ? (v > 20.f ? v : log1pf(expf(v))) : tanhf(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiny linears (time MLP, per-block time projections, condition projections):
+//   out[n][o] = bias[o] + sum_k act(in[n][k]) * W[o][k]        act_in: 0 none, 1 GELU(erf)
+// One warp per output feature, looping over samples (the weight row stays in registers/L1).
+// SinusoidalPositionEmbeddings (diffusion_components.py:42-56) is a separate small kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void linear_kernel(const float* __restrict__ in, long long in_stride, const float* __restrict__ W, const float* __restrict__ bias,
+                              float* __restrict__ out, long long out_stride, int N, int K, int O, int act_in, int act_out) {
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  const float* wr = W + (size_t)o * K;
+  const float b = bias ? bias[o] : 0.f;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const float* xr = in + (size_t)n * in_stride;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float v = xr[k];
+      if (act_in == 1) v = gelu_erf(v);
+      acc = fmaf(v, __ldg(wr + k), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float r = acc + b;
+      if (act_out == 1) r = gelu_erf(r);
+      out[(size_t)n * out_stride + o] = r;
+    }
+  }
+}
+
+__global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __restrict__ out, int N, int dim) {
+  const int half = dim / 2;
+  const float k = logf(10000.0f) / (float)(half - 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * half; i += gridDim.x * blockDim.x) {
+    const int n = i / half, j = i % half;
+    const float f = expf((float)j * -k);
+    const float a = (float)t[n] * f;
+    out[(size_t)n * dim + j] = sinf(a);
+    out[(size_t)n * dim + half + j] = cosf(a);
+  }
+}
+
+static inline int grid_for(long long n, int block, int per_sm = 8) {
+  long long g = (n + block - 1) / block;
+  long long cap = (long long)num_sms() * per_sm;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+/* Fused CFG combine + DDIM/DDPM update (K11).  Replaces model/DiffSynthSampler.py:320-343.
+   d_eps_u may be NULL (CFG == 1.0, :311-312); d_z may be NULL when sigma == 0.  n = elements. */
+int ds_ddim_step(const float* d_eps_u, const float* d_eps_c, const float* d_x, const float* d_z, const float* d_coef,
+                 float* d_out, long long n, void* stream) {
+  DS_REQUIRE(d_eps_c && d_x && d_coef && d_out && n > 0 && n % 4 == 0, "ds_ddim_step: bad arguments (n=%lld must be a positive multiple of 4)", n);
+  ddim_step_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)d_eps_u, (const float4*)d_eps_c, (const float4*)d_x, (const float4*)d_z, d_coef, (float4*)d_out, n / 4);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, float* d_out, long long n, void* stream) {
+  DS_REQUIRE(d_x0 && d_noise && d_coef && d_out && n > 0 && n % 4 == 0, "ds_q_sample: bad arguments");
+  q_sample_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_x0, (const float4*)d_noise, d_coef,
+                                                                          (float4*)d_out, n / 4);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mask, const float* d_coef, float* d_img, int B, int C,
+                  long long hw, void* stream) {
+  DS_REQUIRE(d_guide && d_noise && d_mask && d_coef && d_img && B > 0 && C > 0 && hw > 0, "ds_mask_blend: bad arguments");
+  const long long total = (long long)B * C * hw;
+  mask_blend_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_guide, d_noise, d_mask, d_coef, d_img, C, hw, total);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int Cp, long long hw, void* stream) {
+  DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nchw_f32_to_nhwc_bf16: bad arguments");
+  nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)N * hw * Cp, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_in, (__nv_bfloat16*)d_out, C, Cp, hw, (long long)N * hw);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_nhwc_bf16_to_nchw_f32(const void* d_in, float* d_out, int N, int C, int Cp, long long hw, void* stream) {
+  DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nhwc_bf16_to_nchw_f32: bad arguments");
+  const long long total = (long long)N * C * hw;
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in, d_out, C, Cp, hw, total);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots, float inv_count, float eps,
+                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream) {
+  DS_REQUIRE(d_y && d_out && d_stats && d_gamma && d_beta && N > 0 && C % 8 == 0 && hw > 0 && slots > 0, "ds_gn_apply_residual: bad arguments");
+  const long long vps = hw * C / 8;
+  int gx = (int)((vps + 255) / 256);
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  gn_apply_residual_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
+                                                                          (const float2*)d_stats, slots, inv_count, eps, d_gamma,
+                                                                          d_beta, C / 8, vps);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, long long hw, int chunks, void* stream) {
+  DS_REQUIRE(d_x && d_part && N > 0 && C > 0 && Cp >= C && Cp <= 1024 && G > 0 && C % G == 0 && chunks > 0, "ds_group_stats: bad arguments");
+  const int block = (1024 / Cp) * Cp;
+  group_stats_kernel<<<dim3(chunks, N), block, 2 * G * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)d_x, (float2*)d_part,
+                                                                                              C, Cp, G, hw, chunks);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_gn_act(const void* d_x, void* d_out, const void* d_part, int chunks, const float* d_gamma, const float* d_beta, int N, int C,
+              int Cp, int G, long long hw, float eps, int act, void* stream) {
+  DS_REQUIRE(d_x && d_out && d_part && d_gamma && d_beta && N > 0 && Cp % 2 == 0 && C % G == 0, "ds_gn_act: bad arguments");
+  const long long total = hw * Cp / 2;
+  int gx = (int)((total + 255) / 256);
+  const int cap = (num_sms() * 8 + N - 1) / N;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  gn_act_kernel<<<dim3(gx, N), 256, (2 * Cp + 4) * sizeof(float), (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d_x, (__nv_bfloat16*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_add_bf16(const void* d_a, const void* d_b, void* d_out, long long n, void* stream) {
+  DS_REQUIRE(d_a && d_b && d_out && n > 0 && n % 8 == 0, "ds_add_bf16: bad arguments");
+  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n / 8);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_decoder_head(const float* d_a, const float* d_b, float* d_out, int N, long long hw, void* stream) {
+  DS_REQUIRE(d_a && d_out && N > 0 && hw > 0, "ds_decoder_head: bad arguments");
+  const long long total = (long long)N * 3 * hw;
+  decoder_head_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, d_out, hw, total);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_linear(const float* d_in, long long in_stride, const float* d_w, const float* d_bias, float* d_out, long long out_stride, int N,
+              int K, int O, int act_in, int act_out, void* stream) {
+  DS_REQUIRE(d_in && d_w && d_out && N > 0 && K > 0 && O > 0, "ds_linear: bad arguments");
+  const int wpb = 8;
+  int gy = N < 16 ? N : 16;
+  linear_kernel<<<dim3((O + wpb - 1) / wpb, gy), wpb * 32, 0, (cudaStream_t)stream>>>(d_in, in_stride, d_w, d_bias, d_out, out_stride, N, K,
+                                                                                      O, act_in, act_out);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_sinusoidal_embedding(const long long* d_t, float* d_out, int N, int dim, void* stream) {
+  DS_REQUIRE(d_t && d_out && N > 0 && dim >= 4 && dim % 2 == 0, "ds_sinusoidal_embedding: bad arguments");
+  sinusoidal_kernel<<<grid_for((long long)N * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(d_t, d_out, N, dim);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// STFT+ decode fused with the inverse STFT, and the forward STFT fused with the STFT+ encode.
+//   decode_stft, depad_STFT          tools.py:334-345, 185-191
+//   librosa.istft(D, hop_length=256, win_length=1024) call   webUI/natural_language_guided_4/utils.py:241
+//   librosa.stft(y, n_fft=1024, hop_length=256, win_length=1024) + pad_STFT + encode_stft
+//                                    webUI/natural_language_guided_4/sound2sound_with_text.py:85-94; tools.py:170-182,320-331
+// n_fft = 1024 (fixed by the 512 (+DC) frequency rows of the spectral representation), hop = 256,
+// periodic Hann window.  Real transforms run as 512-point complex FFTs (even/odd packing) with
+// radix-2 Stockham passes in shared memory; everything is fp32 (the reference runs float64 on the CPU).
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+
+namespace ds {
+
+static constexpr int NFFT = 1024, NH = 512, HOP = 256;
+static constexpr int FR = 8;   // frames per block
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// In-place-by-ping-pong 512-point complex DFT of FR frames held in smem: out[n] = sum_k in[k] e^{sign*2*pi*i*k*n/512}.
+// buf[2][FR][NH]; returns which buffer holds the result.  blockDim.x == 256.
+template <int SIGN>
+__device__ __forceinline__ int fft512_block(float2 (*buf)[FR][NH], const float2* __restrict__ tw /* e^{+2 pi i j/512}, j<256 */) {
+  int cur = 0;
+  // Stockham autosort, decimation in frequency: Ns = 1, 2, 4, ..., 256
+#pragma unroll 1
+  for (int Ns = 1; Ns < NH; Ns <<= 1) {
+    for (int i = threadIdx.x; i < FR * (NH / 2); i += blockDim.x) {
+      const int f = i / (NH / 2), j = i % (NH / 2);
+      const int k = j % Ns;                       // position inside the current sub-transform
+      const float2 a = buf[cur][f][j];
+      float2 b = buf[cur][f][j + NH / 2];
+      float2 w = tw[k * (NH / 2 / Ns)];           // e^{+2 pi i k / (2 Ns)}
+      if (SIGN < 0) w.y = -w.y;
+      b = cmul(b, w);
+      const int o = (j / Ns) * 2 * Ns + k;
+      buf[cur ^ 1][f][o] = make_float2(a.x + b.x, a.y + b.y);
+      buf[cur ^ 1][f][o + Ns] = make_float2(a.x - b.x, a.y - b.y);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// ---- inverse: spec [B,3,512,T] fp32 -> windowed frames [B][T][1024] fp32 -------------------------
+__global__ void __launch_bounds__(256)
+istft_frames_kernel(const float* __restrict__ spec, float* __restrict__ frames, int T, const float2* __restrict__ tw512,
+                    const float2* __restrict__ tw1024 /* e^{+2 pi i k/1024}, k<512 */) {
+  extern __shared__ __align__(16) uint8_t is_smem[];
+  float2 (*buf)[FR][NH] = reinterpret_cast<float2 (*)[FR][NH]>(is_smem);          // [2][FR][NH]
+  float2 (*X)[NH + 1] = reinterpret_cast<float2 (*)[NH + 1]>(is_smem + 2 * FR * NH * sizeof(float2));   // [FR][513]
+  const int b = blockIdx.y, t0 = blockIdx.x * FR;
+  const float* sp = spec + (size_t)b * 3 * NH * T;
+  // decode: bin f (1..512) <- row f-1 of the representation; bin 0 (DC) = 0
+  for (int i = threadIdx.x; i < NH * FR; i += blockDim.x) {
+    const int fr = i % FR, row = i / FR, t = t0 + fr;
+    float2 v = make_float2(0.f, 0.f);
+    if (t < T) {
+      const float lm = __ldg(sp + (size_t)row * T + t);
+      const float c = __ldg(sp + ((size_t)NH + row) * T + t), s = __ldg(sp + ((size_t)2 * NH + row) * T + t);
+      const float mag = expm1f(lm);
+      const float nrm = sqrtf(c * c + s * s);
+      // atan2(s, c) -> (cos, sin) = (c, s)/|(c, s)|; atan2(0, 0) = 0 -> (1, 0)
+      const float cc = nrm > 0.f ? c / nrm : 1.f, ss = nrm > 0.f ? s / nrm : 0.f;
+      v = make_float2(mag * cc, mag * ss);
+    }
+    X[fr][row + 1] = v;
+  }
+  if (threadIdx.x < FR) X[threadIdx.x][0] = make_float2(0.f, 0.f);
+  __syncthreads();
+  // Z[k] = (X[k] + conj(X[512-k])) + i * w^k * (X[k] - conj(X[512-k])),  w = e^{2 pi i/1024}; c2r ignores Im of DC/Nyquist
+  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
+    const int fr = i / NH, k = i % NH;
+    float2 a = X[fr][k], c = X[fr][NH - k];
+    if (k == 0) { a.y = 0.f; c.y = 0.f; }
+    const float2 e = make_float2(a.x + c.x, a.y - c.y);
+    const float2 o = cmul(make_float2(a.x - c.x, a.y + c.y), __ldg(tw1024 + k));
+    buf[0][fr][k] = make_float2(e.x - o.y, e.y + o.x);
+  }
+  __syncthreads();
+  const int cur = fft512_block<+1>(buf, tw512);
+  // x[2n] = Re z[n] / 1024, x[2n+1] = Im z[n] / 1024; times the periodic Hann window
+  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
+    const int fr = i / NH, n = i % NH, t = t0 + fr;
+    if (t >= T) continue;
+    const float2 z = buf[cur][fr][n];
+    const float w0 = 0.5f - 0.5f * cospif((float)(2 * n) / 512.0f), w1 = 0.5f - 0.5f * cospif((float)(2 * n + 1) / 512.0f);
+    reinterpret_cast<float2*>(frames + ((size_t)b * T + t) * NFFT)[n] = make_float2(z.x * (1.0f / NFFT) * w0, z.y * (1.0f / NFFT) * w1);
+  }
+}
+
+// ---- overlap-add, window-sum-square normalisation, centre trim: wave [B][256*(T-1)] --------------
+__global__ void istft_ola_kernel(const float* __restrict__ frames, float* __restrict__ wave, int T, long long out_len) {
+  const int b = blockIdx.y;
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < out_len; j += (long long)gridDim.x * blockDim.x) {
+    const long long jj = j + NFFT / 2;
+    int t_hi = (int)(jj / HOP);
+    if (t_hi > T - 1) t_hi = T - 1;
+    float acc = 0.f, wss = 0.f;
+    for (int t = t_hi; t >= 0 && jj - (long long)t * HOP < NFFT; --t) {
+      const int m = (int)(jj - (long long)t * HOP);
+      const float w = 0.5f - 0.5f * cospif((float)m / 512.0f);
+      acc += __ldg(frames + ((size_t)b * T + t) * NFFT + m);
+      wss = fmaf(w, w, wss);
+    }
+    wave[(size_t)b * out_len + j] = wss > 1.17549435e-38f ? acc / wss : acc;
+  }
+}
+
+// ---- forward: wave [B][L] fp32 (zero-padded 512 each side, "constant" centre padding) -> STFT+ [B,3,512,Tpad] ----
+__global__ void __launch_bounds__(256)
+stft_encode_kernel(const float* __restrict__ wave, long long L, float* __restrict__ spec, int T, int Tpad, const float2* __restrict__ tw512,
+                   const float2* __restrict__ tw1024) {
+  extern __shared__ __align__(16) uint8_t st_smem[];
+  float2 (*buf)[FR][NH] = reinterpret_cast<float2 (*)[FR][NH]>(st_smem);
+  const int b = blockIdx.y, t0 = blockIdx.x * FR;
+  const float* wv = wave + (size_t)b * L;
+  // z[n] = x[2n] + i x[2n+1] of the windowed frame
+  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
+    const int fr = i / NH, n = i % NH, t = t0 + fr;
+    const long long s0 = (long long)t * HOP - NFFT / 2 + 2 * n;
+    float a = 0.f, c = 0.f;
+    if (t < T) {
+      if (s0 >= 0 && s0 < L) a = __ldg(wv + s0);
+      if (s0 + 1 >= 0 && s0 + 1 < L) c = __ldg(wv + s0 + 1);
+    }
+    const float w0 = 0.5f - 0.5f * cospif((float)(2 * n) / 512.0f), w1 = 0.5f - 0.5f * cospif((float)(2 * n + 1) / 512.0f);
+    buf[0][fr][n] = make_float2(a * w0, c * w1);
+  }
+  __syncthreads();
+  const int cur = fft512_block<-1>(buf, tw512);
+  // X[k] = (Z[k] + conj Z[512-k])/2 - i/2 * e^{-2 pi i k/1024} (Z[k] - conj Z[512-k]),  k = 1..512 (row k-1); DC row dropped (pad_STFT)
+  float* sp = spec + (size_t)b * 3 * NH * Tpad;
+  for (int i = threadIdx.x; i < NH * FR; i += blockDim.x) {
+    const int fr = i % FR, row = i / FR, t = t0 + fr, k = row + 1;
+    if (t >= Tpad) continue;
+    float lm = 0.f, co = 1.f, si = 0.f;      // padded frames: |D| = 0 -> log1p 0 = 0, angle(0) = 0 -> cos 1, sin 0
+    if (t < T) {
+      const float2 zk = buf[cur][fr][k & (NH - 1)], zc = buf[cur][fr][(NH - k) & (NH - 1)];
+      const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
+      const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
+      float2 w = k < NH ? __ldg(tw1024 + k) : make_float2(-1.f, 0.f);
+      w.y = -w.y;
+      const float2 o = cmul(d, w);            // then multiply by -i: (x, y) -> (y, -x)
+      const float re = e.x + o.y, im = e.y - o.x;
+      const float mag = sqrtf(re * re + im * im);
+      lm = log1pf(mag);
+      if (mag > 0.f) { co = re / mag; si = im / mag; }
+    }
+    sp[(size_t)row * Tpad + t] = lm;
+    sp[((size_t)NH + row) * Tpad + t] = co;
+    sp[((size_t)2 * NH + row) * Tpad + t] = si;
+  }
+}
+
+__global__ void twiddle_init_kernel(float2* tw512, float2* tw1024) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 256) { double s, c; sincospi((double)i / 256.0, &s, &c); tw512[i] = make_float2((float)c, (float)s); }
+  if (i < 512) { double s, c; sincospi((double)i / 512.0, &s, &c); tw1024[i] = make_float2((float)c, (float)s); }
+}
+
+struct Twiddles { float2* tw512 = nullptr; float2* tw1024 = nullptr; int dev = -1; };
+static Twiddles g_tw[16];
+
+static int get_twiddles(cudaStream_t stream, float2** a, float2** b) {
+  int dev = 0;
+  DS_CHECK_CUDA(cudaGetDevice(&dev));
+  DS_REQUIRE(dev >= 0 && dev < 16, "istft: device index %d out of range", dev);
+  Twiddles& t = g_tw[dev];
+  if (t.tw512 == nullptr) {
+    // one-time table build on the legacy stream (must not happen inside a graph capture: callers warm up first)
+    DS_CHECK_CUDA(cudaMalloc(&t.tw512, 256 * sizeof(float2)));
+    DS_CHECK_CUDA(cudaMalloc(&t.tw1024, 512 * sizeof(float2)));
+    twiddle_init_kernel<<<2, 256, 0, stream>>>(t.tw512, t.tw1024);
+    DS_CHECK_CUDA(cudaGetLastError());
+  }
+  *a = t.tw512;
+  *b = t.tw1024;
+  return DS_OK;
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+long long ds_istft_length(int T) { return (long long)HOP * (T - 1); }
+
+/* d_spec fp32 [B,3,512,T] (decoder output) -> d_wave fp32 [B, 256*(T-1)].  d_frames: scratch fp32 [B*T*1024]. */
+int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, int B, int T, void* stream) {
+  DS_REQUIRE(d_spec && d_frames && d_wave && B > 0 && T > 1, "ds_stft_decode_istft: bad arguments");
+  float2 *tw512, *tw1024;
+  int rc = get_twiddles((cudaStream_t)stream, &tw512, &tw1024);
+  if (rc) return rc;
+  const size_t smem = 2 * FR * NH * sizeof(float2) + FR * (NH + 1) * sizeof(float2);
+  DS_CHECK_CUDA(cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  istft_frames_kernel<<<dim3((T + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_spec, d_frames, T, tw512, tw1024);
+  DS_CHECK_CUDA(cudaGetLastError());
+  const long long out_len = ds_istft_length(T);
+  istft_ola_kernel<<<dim3((unsigned)((out_len + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d_frames, d_wave, T, out_len);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+/* d_wave fp32 [B, L] -> d_spec fp32 [B,3,512,Tpad] with T = 1 + L/256 frames, zero-padded in time to Tpad (pad_STFT). */
+int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int Tpad, void* stream) {
+  DS_REQUIRE(d_wave && d_spec && B > 0 && L > 0 && Tpad > 0, "ds_stft_encode: bad arguments");
+  const int T = 1 + (int)(L / HOP);
+  DS_REQUIRE(T <= Tpad, "ds_stft_encode: %d frames exceed the time resolution %d", T, Tpad);
+  float2 *tw512, *tw1024;
+  int rc = get_twiddles((cudaStream_t)stream, &tw512, &tw1024);
+  if (rc) return rc;
+  const size_t smem = 2 * FR * NH * sizeof(float2);
+  DS_CHECK_CUDA(cudaFuncSetAttribute(stft_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stft_encode_kernel<<<dim3((Tpad + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_wave, L, d_spec, T, Tpad, tw512, tw1024);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

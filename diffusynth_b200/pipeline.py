@@ -1,0 +1,93 @@
+"""Text-to-timbre pipeline (the hot path of webUI/natural_language_guided_4/text2sound.py:45-179, without the UI):
+condition vectors -> DiffSynthSampler.sample (CFG, respaced DDIM/DDPM) -> VectorQuantizerEMA -> Decoder ->
+STFT+ decode + iSTFT -> waveforms, and its data-parallel form (prompts sharded over ranks, one all-gather)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import weights as W
+from .codec import spectrogram_to_waveform
+from .sampler import DiffSynthSampler
+from .unet import ConditionedUnet
+from .vqgan import VQGAN
+
+
+@dataclass
+class Timbres:
+    latents: torch.Tensor        # [B,4,128,W]     final continuous latent (imgs[-1])
+    quantized: torch.Tensor      # [B,4,128,W]
+    spectrograms: torch.Tensor   # [B,3,512,4W]
+    waveforms: torch.Tensor      # [B, 256*(4W-1)]
+
+
+class TextToTimbre:
+    def __init__(self, unet: ConditionedUnet, vqgan: VQGAN, timesteps: int = 1000, height: int = 128, channels: int = 4,
+                 noise_strategy: str = "repeat", device=None):
+        self.unet, self.vqgan = unet, vqgan
+        self.timesteps, self.height, self.channels, self.noise_strategy = timesteps, height, channels, noise_strategy
+        self.device = torch.device(device if device is not None else unet.device)
+        self._samplers = {}
+
+    @classmethod
+    def random_init(cls, device="cuda", seed: int = 0, perturb_norm: bool = False) -> "TextToTimbre":
+        """Deployed architecture (app.py:32-40) with deterministic synthetic weights (no checkpoints offline)."""
+        unet = ConditionedUnet(**{k: v for k, v in W.UNET_DEPLOYED.items() if k not in ("out_dim", "time_dim")}, device=device)
+        unet.load_state_dict(W.unet_random_state_dict(seed=seed, perturb_norm=perturb_norm))
+        vq = VQGAN(**W.VQGAN_DEPLOYED, device=device)
+        vq.load_state_dict(W.vqgan_random_state_dict(seed=seed + 1, perturb_norm=perturb_norm))
+        return cls(unet, vq, device=device)
+
+    def sampler_for(self, batch: int, steps: int, cfg_scale: float, uncond: Optional[torch.Tensor]) -> DiffSynthSampler:
+        """text2sound.py:96-106: fresh sampler, CFG activated, respaced to ``steps`` (cached per (batch, steps))."""
+        key = (batch, steps)
+        s = self._samplers.get(key)
+        if s is None:
+            s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy=self.noise_strategy,
+                                 mute=True, device=str(self.device), max_batchsize=batch)
+            s.respace(list(np.linspace(0, self.timesteps - 1, steps, dtype=np.int32)))
+            self._samplers[key] = s
+        s.activate_classifier_free_guidance(cfg_scale, uncond)
+        return s
+
+    @torch.no_grad()
+    def generate(self, cond: torch.Tensor, uncond: Optional[torch.Tensor], steps: int = 20, cfg_scale: float = 6, width: int = 64,
+                 sampler: str = "ddim", seed: Optional[int] = None, noise_feed: Optional[torch.Tensor] = None,
+                 decode: bool = True) -> Timbres:
+        B = cond.shape[0]
+        s = self.sampler_for(B, steps, cfg_scale, uncond)
+        s.noise_feed = noise_feed
+        init = None
+        if noise_feed is not None:
+            init = noise_feed[0][:B].to(self.device, torch.float32)
+            s.noise_feed = noise_feed[1:]
+        imgs, _ = s.sample(self.unet, (B, self.channels, self.height, width), return_tensor=True, condition=cond.to(self.device),
+                           sampler=sampler, initial_noise=init, seed=seed)
+        latents = imgs[-1]
+        if not decode:
+            return Timbres(latents, None, None, None)
+        q, _, _ = self.vqgan._vq_vae(latents)                              # text2sound.py:128
+        spec = self.vqgan._decoder(q)                                      # utils.py:224
+        wave = spectrogram_to_waveform(spec)                               # utils.py:229-241
+        return Timbres(latents, q, spec, wave)
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of ``total`` prompts: rank r owns [lo, hi); per = ceil(total/world)."""
+    per = -(-total // world)
+    lo = min(rank * per, total)
+    return lo, min(lo + per, total)
+
+
+def all_gather_waveforms(local: torch.Tensor, total: int, world: int) -> torch.Tensor:
+    """One equal-count all-gather of [per, L] waveforms (NCCL on GPUs, gloo in CPU tests) -> [total, L] on every rank."""
+    import torch.distributed as dist
+    per = -(-total // world)
+    if local.shape[0] < per:
+        local = torch.cat([local, local.new_zeros((per - local.shape[0],) + tuple(local.shape[1:]))])
+    out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, local.contiguous())
+    return out[:total]

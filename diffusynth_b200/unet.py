@@ -1,0 +1,401 @@
+"""ConditionedUnet -- B200 drop-in for the reference's epsilon-predictor
+(model/diffusion.py:21-258: ``ConditionedUnet(**unetConfig)``, ``.load_state_dict``, ``model(x, time, condition)``).
+
+Same constructor arguments, same ``state_dict`` key names, same call signature and result
+(fp32 NCHW epsilon).  The forward pass is a fixed sequence of calls into the C ABI
+(ds_stem_conv7, ds_dwconv7, ds_conv_gemm, ds_attn_*, ds_gn_apply_residual, ds_linear ...);
+activations live in HBM as bf16 NHWC and GroupNorm(1,C) never runs as its own pass -- its
+statistics come out of the producing kernel's epilogue and its affine is folded into the
+consuming convolution.  The call sequence for a given (N, H, W) is built once
+("plan") and then replayed, which is what makes it capturable in a CUDA graph."""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops, weights as W
+from ._lib import check
+from .ops import PackedConv, Stats, conv_args, pack_conv_down, pack_conv_s1, pack_conv_up, run_conv
+
+HEADS, DHEAD = W.ATTN_HEADS, W.ATTN_DIM_HEAD
+HID = HEADS * DHEAD
+
+
+class _Block:
+    """Packed constants of one ConvNextBlock (diffusion_components.py:107-139)."""
+
+    def __init__(self, sd, p, dim, dim_out, has_time):
+        self.p, self.dim, self.dim_out = p, dim, dim_out
+        self.dw = sd[p + "ds_conv.weight"].float().reshape(dim, 49).t().contiguous()      # [49][C]
+        self.dw_bias = sd[p + "ds_conv.bias"].float()
+        self.has_time = has_time
+        self.conv1 = pack_conv_s1(sd[p + "net.1.weight"], sd[p + "net.1.bias"], sd[p + "net.0.weight"].float(), sd[p + "net.0.bias"].float())
+        self.conv2 = pack_conv_s1(sd[p + "net.4.weight"], sd[p + "net.4.bias"], sd[p + "net.3.weight"].float(), sd[p + "net.3.bias"].float())
+        self.res = pack_conv_s1(sd[p + "res_conv.weight"], sd[p + "res_conv.bias"]) if (p + "res_conv.weight") in sd else None
+        self.t_off = 0   # column offset of this block's time projection in the fused [N, sum(dim)] buffer
+
+    def to(self, dev):
+        self.dw = self.dw.to(dev)
+        for c in (self.conv1, self.conv2, self.res):
+            if c is not None:
+                c.to(dev)
+        return self
+
+
+class _Attn:
+    """Packed constants of Residual(PreNorm(LinearCrossAttentionAdd)) (diffusion_components.py:252-293,142-152)."""
+
+    def __init__(self, sd, p, dim):
+        self.p, self.dim = p, dim
+        self.qkv = pack_conv_s1(sd[p + "fn.fn.to_qkv.weight"], None, sd[p + "fn.norm.weight"].float(), sd[p + "fn.norm.bias"].float())
+        self.wout = sd[p + "fn.fn.to_out.0.weight"].float().reshape(dim, HID).contiguous()
+        cout_pad = ops.pad16(dim)
+        # the per-sample matrix M = Wout . ctx is produced on the device; this PackedConv only carries e2 (= bias), taps, sizes
+        e2 = torch.zeros(1, cout_pad)
+        e2[0, :dim] = sd[p + "fn.fn.to_out.0.bias"].float()
+        self.out = PackedConv(weight=torch.zeros(1, dtype=torch.bfloat16), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=HID, cout=dim,
+                              cout_pad=cout_pad, ncls=1, kind="s1")
+        self.gamma = sd[p + "fn.fn.to_out.1.weight"].float().contiguous()
+        self.beta = sd[p + "fn.fn.to_out.1.bias"].float().contiguous()
+        self.c_off = 0   # column offset of this site's [label_query | label_key | 0] bias in the fused cond buffer
+
+    def to(self, dev):
+        self.qkv.to(dev)
+        self.out.to(dev)
+        self.wout, self.gamma, self.beta = self.wout.to(dev), self.gamma.to(dev), self.beta.to(dev)
+        return self
+
+
+class ConditionedUnet:
+    def __init__(self, in_dim, out_dim=None, down_dims=None, up_dims=None, mid_depth=3, with_time_emb=True, time_dim=None,
+                 resnet_block_groups=8, use_convnext=True, convnext_mult=2, attn_type="linear_cat", n_label_class=11,
+                 condition_type="instrument_family", label_emb_dim=128, device=None):
+        if attn_type not in ("linear_cat", "linear_add"):
+            raise NotImplementedError()                       # diffusion.py:96
+        if condition_type not in ("instrument_family", "natural_language_prompt"):
+            raise NotImplementedError()                       # diffusion_components.py:165
+        if not use_convnext or attn_type != "linear_add" or condition_type != "natural_language_prompt" or not with_time_emb:
+            raise NotImplementedError("diffusynth_b200 implements the deployed variant: ConvNeXt blocks, "
+                                      "attn_type='linear_add', condition_type='natural_language_prompt' (app.py:40)")
+        if up_dims is None:
+            up_dims = [128, 128, 64, 32]
+        if down_dims is None:
+            down_dims = [32, 32, 64, 128]
+        assert len(down_dims) == len(up_dims), "len(down_dims) != len(up_dims)"
+        assert down_dims[0] == up_dims[-1], "down_dims[0] != up_dims[-1]"
+        assert up_dims[0] == down_dims[-1], "up_dims[0] != down_dims[-1]"
+        self.cfg = W.unet_config(in_dim=in_dim, out_dim=out_dim, down_dims=list(down_dims), up_dims=list(up_dims), mid_depth=mid_depth,
+                                 time_dim=time_dim, convnext_mult=convnext_mult, attn_type=attn_type, condition_type=condition_type,
+                                 label_emb_dim=label_emb_dim)
+        for d in set(self.cfg["down_dims"] + self.cfg["up_dims"]):
+            if d % 32:
+                raise NotImplementedError(f"channel widths must be multiples of 32 (got {d})")
+        self.device = torch.device(device if device is not None else "cuda")
+        self._sd: Optional[OrderedDict] = None
+        self._plans: Dict[Tuple, "_Plan"] = {}
+        self.training = False
+
+    # ---- nn.Module-like surface ------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True):
+        spec = W.unet_param_spec(self.cfg)
+        missing = [k for k, _ in spec if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in dict(spec)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
+        for k, shp in spec:
+            if k in state_dict and tuple(state_dict[k].shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: {tuple(state_dict[k].shape)} vs {shp}")
+        self._sd = OrderedDict((k, state_dict[k].detach().float().cpu().contiguous()) for k, _ in spec)
+        self._pack()
+        self._plans.clear()
+        return self
+
+    def state_dict(self):
+        return OrderedDict(self._sd)
+
+    def parameters(self):
+        return iter([self._probe])
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device != self.device:
+            self.device = device
+            if self._sd is not None:
+                self._pack()
+                self._plans.clear()
+        return self
+
+    def __call__(self, x, time, condition=None):
+        return self.forward(x, time, condition)
+
+    # ---- packing -----------------------------------------------------------------------------
+    def _pack(self):
+        sd, cfg, dev = self._sd, self.cfg, self.device
+        dd, ud, td, L = cfg["down_dims"], cfg["up_dims"], cfg["time_dim"], cfg["label_emb_dim"]
+        self._probe = torch.zeros(1, device=dev)
+        self.blocks: "OrderedDict[str, _Block]" = OrderedDict()
+        self.attns: "OrderedDict[str, _Attn]" = OrderedDict()
+        self.samplers: Dict[str, PackedConv] = {}
+
+        def blk(p, dim, dim_out, has_time=True):
+            self.blocks[p] = _Block(sd, p, dim, dim_out, has_time)
+
+        def att(p, dim):
+            self.attns[p] = _Attn(sd, p, dim)
+
+        skips = []
+        for i, (cin, cout) in enumerate(zip(dd[:-1], dd[1:])):
+            p = f"downs.{i}."
+            blk(p + "0.", cin, cout); att(p + "1.", cout); blk(p + "2.", cout, cout); att(p + "3.", cout)
+            self.samplers[p + "4."] = pack_conv_down(sd[p + "4.weight"], sd[p + "4.bias"].float())
+            skips.append(cout)
+        mid = dd[-1]
+        for j in range(cfg["mid_depth"] - 1):
+            blk(f"mid_left.{j}.", mid, mid)
+        blk("mid_mid.0.", mid, mid); att("mid_mid.1.", mid); blk("mid_mid.2.", mid, mid)
+        for j in range(cfg["mid_depth"] - 1):
+            blk(f"mid_right.{j}.", 2 * mid, mid)
+        for i, (cin, cout) in enumerate(zip(ud[:-1], ud[1:])):
+            s = skips.pop()
+            p = f"ups.{i}."
+            blk(p + "0.", cin + s, cin); att(p + "1.", cin)
+            self.samplers[p + "2."] = pack_conv_up(sd[p + "2.weight"], sd[p + "2.bias"].float())
+            blk(p + "3.", cin + s, cout); att(p + "4.", cout)
+            blk(p + "5.", cout + s, cout); att(p + "6.", cout)
+        blk("final_conv.0.", dd[0] + ud[-1], ud[-1], has_time=False)
+        self.final = pack_conv_s1(sd["final_conv.1.weight"], sd["final_conv.1.bias"].float())
+
+        # fused time projection: rows = concat over blocks of mlp.1 (GELU on the input); bias += ds_conv.bias.
+        rows, biases, off = [], [], 0
+        for b in self.blocks.values():
+            b.t_off = off
+            if b.has_time:
+                rows.append(sd[b.p + "mlp.1.weight"].float())
+                biases.append(sd[b.p + "mlp.1.bias"].float() + b.dw_bias)
+            else:
+                rows.append(torch.zeros(b.dim, td))
+                biases.append(b.dw_bias.clone())
+            off += b.dim
+        self.t_total = off
+        self.t_w, self.t_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
+        # fused condition projection: per attention site [label_query | label_key | zeros(v)]
+        rows, biases, off = [], [], 0
+        for a in self.attns.values():
+            a.c_off = off
+            rows += [sd[a.p + "fn.fn.label_query.weight"].float(), sd[a.p + "fn.fn.label_key.weight"].float(), torch.zeros(HID, L)]
+            biases += [sd[a.p + "fn.fn.label_query.bias"].float(), sd[a.p + "fn.fn.label_key.bias"].float(), torch.zeros(HID)]
+            off += 3 * HID
+        self.c_total = off
+        self.c_w, self.c_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
+        self.lab_w = sd["label_embedding.embedding.weight"].float().contiguous().to(dev)
+        self.lab_b = sd["label_embedding.embedding.bias"].float().contiguous().to(dev)
+        self.tm1_w, self.tm1_b = sd["time_mlp.1.weight"].float().contiguous().to(dev), sd["time_mlp.1.bias"].float().contiguous().to(dev)
+        self.tm3_w, self.tm3_b = sd["time_mlp.3.weight"].float().contiguous().to(dev), sd["time_mlp.3.bias"].float().contiguous().to(dev)
+        # stem: [96,4,7,7] -> [(ky,kx,ci)][Cout]
+        self.stem_w = sd["init_conv.weight"].float().permute(2, 3, 1, 0).reshape(-1, dd[0]).contiguous().to(dev)
+        self.stem_b = sd["init_conv.bias"].float().contiguous().to(dev)
+        for m in list(self.blocks.values()) + list(self.attns.values()):
+            m.to(dev)
+        for s in self.samplers.values():
+            s.to(dev)
+        self.final.to(dev)
+
+    # ---- forward -----------------------------------------------------------------------------
+    def plan(self, N: int, H: int, Wd: int, x_batch_mod: int = 0, uniform_time: bool = False) -> "_Plan":
+        key = (N, H, Wd, x_batch_mod, uniform_time)
+        if key not in self._plans:
+            if self._sd is None:
+                raise RuntimeError("ConditionedUnet: load_state_dict() has not been called")
+            self._plans[key] = _Plan(self, N, H, Wd, x_batch_mod, uniform_time)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def forward(self, x, time, condition=None, taps: Optional[dict] = None):
+        """x [N,4,H,W] fp32, time [N] int64, condition [N, label_emb_dim] fp32 -> eps [N,4,H,W] fp32 (diffusion.py:187-258)."""
+        if condition is None:
+            raise NotImplementedError("unconditional call (condition=None) is not implemented; the sampling path always conditions")
+        N, Cin, H, Wd = x.shape
+        assert Cin == self.cfg["in_dim"]
+        n_stage = len(self.cfg["down_dims"]) - 1
+        if H % (1 << n_stage) or Wd % (1 << n_stage):
+            raise NotImplementedError(f"H={H}, W={Wd} must be divisible by {1 << n_stage} (pad_to_match path not implemented)")
+        pl = self.plan(N, H, Wd)
+        pl.x.copy_(x.to(self.device, torch.float32))
+        pl.t.copy_(time.to(self.device, torch.long))
+        pl.cond.copy_(condition.to(self.device, torch.float32))
+        pl.run_cond()
+        pl.run()
+        if taps is not None:
+            pl.export_taps(taps)
+        return pl.eps.clone()
+
+
+class _Plan:
+    """The static call sequence + buffers of one (N, H, W) U-Net evaluation."""
+
+    def __init__(self, net: ConditionedUnet, N: int, H: int, Wd: int, x_batch_mod: int, uniform_time: bool):
+        self.net, self.N, self.H, self.W = net, N, H, Wd
+        dev, cfg = net.device, net.cfg
+        lib = _lib.load()
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.keep: list = []
+        self.ops: List[Tuple[str, Callable[[], None]]] = []
+        self.cond_ops: List[Tuple[str, Callable[[], None]]] = []
+        self.named: Dict[str, Tuple[torch.Tensor, int]] = {}
+        nb = x_batch_mod if x_batch_mod > 0 else N
+        self.x = torch.zeros((nb, cfg["in_dim"], H, Wd), **f32)
+        self.t = torch.zeros((N,), dtype=torch.long, device=dev)
+        self.cond = torch.zeros((N, cfg["label_emb_dim"]), **f32)
+        self.eps = torch.zeros((N, cfg["out_dim"], H, Wd), **f32)
+        dd, td = cfg["down_dims"], cfg["time_dim"]
+        self.uniform_time = uniform_time
+        NT = 1 if uniform_time else N          # all samples share t inside the sampling loop
+        self.t_stride = 0 if uniform_time else net.t_total
+        stream = ops._stream
+
+        def act(n, h, w, c):
+            return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+
+        scratch: Dict[Tuple, torch.Tensor] = {}
+
+        def scr(role, n, h, w, c):
+            k = (role, n, h, w, c)
+            if k not in scratch:
+                scratch[k] = act(n, h, w, c)
+            return scratch[k]
+
+        def add(name, fn):
+            self.ops.append((name, fn))
+
+        # ---- condition path (step-invariant: run once per sample() call) ----
+        cemb = torch.empty((N, cfg["label_emb_dim"]), **f32)
+        self.sbias = torch.empty((N, net.c_total), **f32)
+        self.cond_ops.append(("label_embedding", lambda: ops.linear(self.cond, net.lab_w, net.lab_b, cemb)))
+        self.cond_ops.append(("label_qk", lambda: ops.linear(cemb, net.c_w, net.c_b, self.sbias)))
+        # ---- time path ----
+        sin = torch.empty((NT, dd[0]), **f32)
+        t1 = torch.empty((NT, td), **f32)
+        temb = torch.empty((NT, td), **f32)
+        self.tbias = torch.empty((NT, net.t_total), **f32)
+        add("time_sin", lambda: check(lib.ds_sinusoidal_embedding(self.t.data_ptr(), sin.data_ptr(), NT, dd[0], stream()), "sinusoidal"))
+        add("time_mlp1", lambda: ops.linear(sin, net.tm1_w, net.tm1_b, t1, act_out=1))
+        add("time_mlp3", lambda: ops.linear(t1, net.tm3_w, net.tm3_b, temb))
+        add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1))
+        self.named["time_emb"] = (temb, -1)
+
+        def conv(name, pc, s0, s1, h, w, **kw):
+            a, st, keep = conv_args(pc, s0, s1, N, h, w, **kw)
+            self.keep += keep + [a]
+            add(name, lambda a=a: run_conv(a))
+            return st
+
+        def block(p, s0, s1, h, w):
+            b = net.blocks[p]
+            hbuf = scr("dw", N, h, w, b.dim)
+            tb = self.tbias[:, b.t_off:]
+            st_h = ops.dwconv7_stats(N, b.dim, h, w, dev)
+            add(p + "ds_conv", lambda: ops.dwconv7(s0, s1, b.dw, tb, self.t_stride, hbuf, N, h, w, stats=st_h))
+            y = scr("hid", N, h, w, b.conv1.cout)
+            st_y = conv(p + "net.1", b.conv1, hbuf, None, h, w, out=y, stats_in=st_h, act=1, want_stats=True)
+            if b.res is not None:
+                r = scr("res", N, h, w, b.dim_out)
+                conv(p + "res_conv", b.res, s0, s1, h, w, out=r)
+            else:
+                assert s1 is None
+                r = s0
+            o = act(N, h, w, b.dim_out)
+            st_o = conv(p + "net.4", b.conv2, y, None, h, w, out=o, stats_in=st_y, residual=r, want_stats=True)
+            self.named[p[:-1]] = (o, b.dim_out)
+            return o, st_o
+
+        def attn(p, x, st_x, h, w):
+            a = net.attns[p]
+            npix = h * w
+            qkv = scr("qkv", N, h, w, 3 * HID)
+            sb = self.sbias[:, a.c_off:a.c_off + 3 * HID]
+            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=sb)
+            qp = scr("qp", N, h, w, HID)
+            part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
+            M = torch.empty((N, a.out.cout_pad, HID), dtype=torch.bfloat16, device=dev)
+            add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
+                                                                  float(DHEAD ** -0.5), stream()), "attn_ctx_partial"))
+            add(p + "fin", lambda: check(lib.ds_attn_finalize(part.data_ptr(), a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim,
+                                                               a.out.cout_pad, stream()), "attn_finalize"))
+            y = scr("atty", N, h, w, a.dim)
+            st_y = conv(p + "to_out", a.out, qp, None, h, w, out=y, want_stats=True, weight_override=M, per_sample_weights=True)
+            o = act(N, h, w, a.dim)
+            add(p + "gn_res", lambda: check(lib.ds_gn_apply_residual(y.data_ptr(), x.data_ptr(), o.data_ptr(), st_y.buf.data_ptr(), st_y.slots,
+                                                                      1.0 / st_y.count, 1e-5, a.gamma.data_ptr(), a.beta.data_ptr(), N,
+                                                                      a.dim, npix, stream()), "gn_apply_residual"))
+            self.keep += [part, M]
+            self.named[p[:-1]] = (o, a.dim)
+            return o
+
+        # ---- network (diffusion.py:187-258) ----
+        n_stage = len(dd) - 1
+        h, w = H, Wd
+        x0 = act(N, h, w, dd[0])
+        add("init_conv", lambda: check(lib.ds_stem_conv7(self.x.data_ptr(), x_batch_mod, net.stem_w.data_ptr(), net.stem_b.data_ptr(),
+                                                         x0.data_ptr(), N, cfg["in_dim"], dd[0], H, Wd, stream()), "stem_conv7"))
+        self.named["init_conv"] = (x0, dd[0])
+        hs = [x0]
+        x = x0
+        for i in range(n_stage):
+            p = f"downs.{i}."
+            x, st = block(p + "0.", x, None, h, w)
+            x = attn(p + "1.", x, st, h, w); hs.append(x)
+            x, st = block(p + "2.", x, None, h, w)
+            x = attn(p + "3.", x, st, h, w); hs.append(x)
+            pc = net.samplers[p + "4."]
+            d = act(N, h // 2, w // 2, pc.cout)
+            conv(p + "4", pc, x, None, h, w, out=d)
+            self.named[p + "4"] = (d, pc.cout)
+            x = d; h //= 2; w //= 2; hs.append(x)
+        for j in range(cfg["mid_depth"] - 1):
+            x, _ = block(f"mid_left.{j}.", x, None, h, w); hs.append(x)
+        x, st = block("mid_mid.0.", x, None, h, w)
+        x = attn("mid_mid.1.", x, st, h, w)
+        x, _ = block("mid_mid.2.", x, None, h, w)
+        for j in range(cfg["mid_depth"] - 1):
+            x, _ = block(f"mid_right.{j}.", hs.pop(), x, h, w)
+        for i in range(n_stage):
+            p = f"ups.{i}."
+            x, st = block(p + "0.", hs.pop(), x, h, w)
+            x = attn(p + "1.", x, st, h, w)
+            pc = net.samplers[p + "2."]
+            u = act(N, 2 * h, 2 * w, pc.cout)
+            conv(p + "2", pc, x, None, h, w, out=u)
+            self.named[p + "2"] = (u, pc.cout)
+            x = u; h *= 2; w *= 2
+            x, st = block(p + "3.", hs.pop(), x, h, w)
+            x = attn(p + "4.", x, st, h, w)
+            x, st = block(p + "5.", hs.pop(), x, h, w)
+            x = attn(p + "6.", x, st, h, w)
+        x, _ = block("final_conv.0.", hs.pop(), x, h, w)
+        conv("final_conv.1", net.final, x, None, h, w, out_f32=self.eps)
+        self.keep.append(scratch)
+
+    def run_cond(self):
+        for _, fn in self.cond_ops:
+            fn()
+
+    def run(self):
+        for _, fn in self.ops:
+            fn()
+
+    def num_launches(self) -> int:
+        return len(self.ops)
+
+    def export_taps(self, taps: dict):
+        """Named intermediates as fp32 NCHW (for per-layer parity tests)."""
+        for name, (t, c) in self.named.items():
+            if c < 0:
+                taps[name] = t.clone()
+            else:
+                taps[name] = t.float().permute(0, 3, 1, 2).contiguous()

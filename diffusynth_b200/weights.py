@@ -7,7 +7,7 @@ checkpoint (``torch.load(...)['model_state_dict']``, reference
 B200 classes unchanged, and so that the very same tensors can be handed to the
 reference, the oracle and the CUDA path in the parity tests.
 
-Nothing here reads ``/root/reference``; ``tests/test_oracle_vs_reference.py``
+Nothing here reads the reference tree; ``tests/test_oracle_vs_reference.py``
 checks this inventory against the reference constructors when the reference is
 available.
 """

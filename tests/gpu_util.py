@@ -1,0 +1,26 @@
+"""Helpers for the GPU parity tests (torch is used only to move/convert test data)."""
+import torch
+
+
+def nhwc(x_nchw: torch.Tensor, cp: int = None) -> torch.Tensor:
+    """fp32 NCHW (CPU) -> bf16 NHWC on cuda, channels zero-padded to cp."""
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    if cp is not None and cp > x.shape[-1]:
+        x = torch.nn.functional.pad(x, (0, cp - x.shape[-1]))
+    return x.to(torch.bfloat16).cuda().contiguous()
+
+
+def nchw(x_nhwc: torch.Tensor, c: int = None) -> torch.Tensor:
+    x = x_nhwc.float().cpu()
+    if c is not None:
+        x = x[..., :c]
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(x: torch.Tensor) -> torch.Tensor:
+    return x.bfloat16().float()

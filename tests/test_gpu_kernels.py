@@ -1,0 +1,207 @@
+"""Bandwidth-bound kernels through the C ABI against the CPU oracle on the same seeded inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusynth_b200 import weights as W
+from oracle import cases, ds_oracle as O
+from tests.gpu_util import bf, nchw, nhwc, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def lib():
+    from diffusynth_b200 import _lib
+    return _lib.load()
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_device_is_blackwell():
+    assert lib().ds_check_device(0) == 0 and lib().ds_version() >= 100
+
+
+@pytest.mark.parametrize("eta", [0.0, 1.0])
+def test_ddim_step_matches_reference_formula(eta):
+    from diffusynth_b200 import ops
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, 20, dtype=np.int32)))
+    x, eu, ec, z = (cases.randn((3, 4, 128, 64), s) for s in (1, 2, 3, 4))
+    for t in (19, 7, 0):
+        co = O.ddim_coefficients(sch, t, eta)
+        ref = O.ddim_update(x, eu, ec, 6, co, z)
+        coef = torch.tensor([co["sqrt_one_minus_at"], co["sqrt_at"], co["sqrt_ap"], co["dir_coef"], co["sigma"], 6.0, 0, 0], dtype=torch.float32).cuda()
+        out = torch.empty_like(x).cuda()
+        ops.ddim_step(eu.cuda(), ec.cuda(), x.cuda(), z.cuda(), coef, out)
+        assert rel(out, ref) < 1e-6          # fp32, same operation order: differences are last-bit only
+        ref1 = O.ddim_update(x, None, ec, 1.0, co, z)
+        ops.ddim_step(None, ec.cuda(), x.cuda(), z.cuda() if eta else None, coef, out)
+        assert rel(out, ref1) < 1e-6
+
+
+def test_sampler_coefficients_match_oracle():
+    from diffusynth_b200.sampler import DiffSynthSampler
+    s = DiffSynthSampler(1000, device="cuda", mute=True)
+    s.respace(list(np.linspace(0, 999, 20, dtype=np.int32)))
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, 20, dtype=np.int32)))
+    assert s.timestep_map == sch.timestep_map and np.array_equal(s.alphas_cumprod, sch.alphas_cumprod)
+    for eta in (0.0, 1.0):
+        for t in range(20):
+            co = O.ddim_coefficients(sch, t, eta)
+            mine = s._coef(t, eta)
+            assert mine[:5] == [co["sqrt_one_minus_at"], co["sqrt_at"], co["sqrt_ap"], co["dir_coef"], co["sigma"]]
+
+
+def test_q_sample_and_mask_blend():
+    from diffusynth_b200 import ops
+    sch = O.Schedule(1000)
+    x0, nz, img = (cases.randn((2, 4, 128, 40), s) for s in (5, 6, 7))
+    mask = (cases.randn((2, 1, 128, 40), 8) > 0).float()
+    ref = O.q_sample(sch, x0, 500, nz)
+    coef = torch.tensor([np.float32(sch.sqrt_alphas_cumprod[500]), np.float32(sch.sqrt_one_minus_alphas_cumprod[500])], dtype=torch.float32).cuda()
+    out = torch.empty_like(x0).cuda()
+    ops.q_sample(x0.cuda(), nz.cuda(), coef, out)
+    assert rel(out, ref) < 1e-7
+    blended = img.clone().cuda()
+    ops.mask_blend(x0.cuda(), nz.cuda(), mask.cuda(), coef, blended)
+    assert rel(blended, mask * ref + (1 - mask) * img) < 1e-7
+
+
+@pytest.mark.parametrize("C0,C1,H,W,N", [(96, 0, 128, 64, 2), (96, 192, 32, 16, 2), (384, 384, 16, 8, 3), (32, 0, 20, 24, 1)])
+def test_dwconv7(C0, C1, H, W, N):
+    from diffusynth_b200 import ops
+    Cc = C0 + C1
+    x = cases.randn((N, Cc, H, W), 9)
+    w, tb = cases.randn((Cc, 1, 7, 7), 10) * 0.1, cases.randn((N, Cc + 5), 11)
+    out = torch.zeros((N, H, W, Cc), dtype=torch.bfloat16, device="cuda")
+    st = ops.dwconv7_stats(N, Cc, H, W, "cuda")
+    s0 = nhwc(x[:, :C0])
+    s1 = nhwc(x[:, C0:]) if C1 else None
+    ops.dwconv7(s0, s1, w.reshape(Cc, 49).t().contiguous().cuda(), tb.cuda(), tb.shape[1], out, N, H, W, stats=st)
+    ref = F.conv2d(bf(x), w, None, padding=3, groups=Cc) + tb[:, :Cc, None, None]
+    assert rel(nchw(out), ref) < 4e-3
+    s = st.buf.double().sum(dim=1).cpu()
+    assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=1e-3, atol=1.0)
+    assert torch.allclose(s[:, 1], (ref.double() ** 2).sum(dim=(1, 2, 3)), rtol=1e-3)
+
+
+def test_stem_conv7():
+    x = cases.randn((2, 4, 128, 64), 12) * 3
+    w, b = cases.randn((96, 4, 7, 7), 13) * 0.07, cases.randn((96,), 14)
+    out = torch.zeros((4, 128, 64, 96), dtype=torch.bfloat16, device="cuda")
+    xd, wd, bd = x.cuda(), w.permute(2, 3, 1, 0).reshape(-1, 96).contiguous().cuda(), b.cuda()
+    assert lib().ds_stem_conv7(xd.data_ptr(), 2, wd.data_ptr(), bd.data_ptr(), out.data_ptr(), 4, 4, 96, 128, 64, S()) == 0
+    ref = F.conv2d(x, w, b, padding=3)
+    assert rel(nchw(out)[:2], ref) < 4e-3 and torch.equal(out[:2], out[2:])
+
+
+def test_time_and_condition_linears():
+    from diffusynth_b200 import ops
+    sd = W.unet_random_state_dict(seed=0)
+    t = torch.tensor([947, 52, 0, 999], dtype=torch.long)
+    ref = O.time_embedding(sd, t, 96)
+    sin = torch.empty((4, 96), device="cuda")
+    assert lib().ds_sinusoidal_embedding(t.cuda().data_ptr(), sin.data_ptr(), 4, 96, S()) == 0
+    t1, te = torch.empty((4, 384), device="cuda"), torch.empty((4, 384), device="cuda")
+    ops.linear(sin, sd["time_mlp.1.weight"].cuda(), sd["time_mlp.1.bias"].cuda(), t1, act_out=1)
+    ops.linear(t1, sd["time_mlp.3.weight"].cuda(), sd["time_mlp.3.bias"].cuda(), te)
+    assert rel(te, ref) < 2e-4       # sin/cos of arguments up to ~1000 rad in fp32
+
+
+def _attn_ref(qkv, heads, softmax_q):
+    B, n, _ = qkv.shape
+    q, k, v = (qkv[..., i * heads * 32:(i + 1) * heads * 32].reshape(B, n, heads, 32).permute(0, 2, 3, 1) for i in range(3))
+    if softmax_q:
+        q = q.softmax(dim=-2) * 32 ** -0.5
+    ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
+    return q, ctx
+
+
+@pytest.mark.parametrize("heads,n,mode", [(4, 8192, 0), (4, 128, 0), (1, 2048 + 40, 1)])
+def test_linear_attention_core(heads, n, mode):
+    B, hid, Cc = 2, heads * 32, 96
+    qkv = cases.randn((B, n, 3 * hid), 15) * 1.5
+    wout = cases.randn((Cc, hid), 16) * 0.1
+    qd = qkv.to(torch.bfloat16).cuda()
+    qp = torch.zeros((B, n, hid), dtype=torch.bfloat16, device="cuda")
+    part = torch.empty((lib().ds_attn_part_floats(B, heads, n),), device="cuda")
+    M = torch.zeros((B, Cc, hid), dtype=torch.bfloat16, device="cuda")
+    assert lib().ds_attn_ctx_partial(qd.data_ptr(), qp.data_ptr(), part.data_ptr(), B, heads, n, mode, C.c_float(32 ** -0.5), S()) == 0
+    assert lib().ds_attn_finalize(part.data_ptr(), wout.cuda().data_ptr(), M.data_ptr(), B, heads, n, Cc, Cc, S()) == 0
+    q_ref, ctx = _attn_ref(bf(qkv), heads, mode == 0)
+    assert rel(qp.float().cpu().reshape(B, n, heads, 32).permute(0, 2, 3, 1), q_ref) < 4e-3
+    M_ref = torch.einsum("che,bhde->bchd", wout.view(Cc, heads, 32), ctx).reshape(B, Cc, hid)
+    assert rel(M, M_ref) < 4e-3
+
+
+def test_gn_apply_residual():
+    N, H, Wd, Cc = 2, 16, 8, 96
+    y, x = cases.randn((N, Cc, H, Wd), 17) * 2 + 1, cases.randn((N, Cc, H, Wd), 18)
+    g, b = 1 + 0.1 * cases.randn((Cc,), 19), 0.1 * cases.randn((Cc,), 20)
+    yb = bf(y)
+    st = torch.stack([yb.sum(dim=(1, 2, 3)), (yb * yb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous()
+    out = torch.zeros((N, H, Wd, Cc), dtype=torch.bfloat16, device="cuda")
+    yd, xd = nhwc(y), nhwc(x)
+    assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.data_ptr(), 1, C.c_float(1.0 / (Cc * H * Wd)), C.c_float(1e-5),
+                                      g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, S()) == 0
+    assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)) < 4e-3
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_group_norm16_act(act):
+    N, H, Wd, Cc, Cp, G = 2, 32, 16, 80, 96, 16
+    x = cases.randn((N, Cc, H, Wd), 21) * 2 + 0.5
+    g, b = 1 + 0.1 * cases.randn((Cc,), 22), 0.1 * cases.randn((Cc,), 23)
+    xd = nhwc(x, Cp)
+    part = torch.empty((N, G, 64, 2), device="cuda")
+    out = torch.zeros_like(xd)
+    assert lib().ds_group_stats(xd.data_ptr(), part.data_ptr(), N, Cc, Cp, G, H * Wd, 64, S()) == 0
+    assert lib().ds_gn_act(xd.data_ptr(), out.data_ptr(), part.data_ptr(), 64, g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, Cp, G, H * Wd,
+                           C.c_float(1e-6), act, S()) == 0
+    r = F.group_norm(bf(x), G, g, b, 1e-6)
+    r = F.relu(r) if act == 1 else r * torch.sigmoid(r)
+    assert rel(nchw(out, Cc), r) < 4e-3 and float(out[..., Cc:].abs().max()) == 0.0
+
+
+def test_vq_indices_bit_exact(golden):
+    sd = W.vqgan_random_state_dict(seed=1)
+    cb = sd["_vq_vae._embedding.weight"]
+    for lat in (cases.vq_latents(), cases.randn((3, 4, 128, 24), 77) * 2):
+        q_ref, idx_ref = O.vq_quantize(lat, cb)
+        x = lat.cuda()
+        out = torch.empty_like(x)
+        idx = torch.empty((lat.numel() // 4,), dtype=torch.long, device="cuda")
+        assert lib().ds_vq_quantize(x.data_ptr(), cb.cuda().data_ptr(), 8192, out.data_ptr(), idx.data_ptr(), lat.shape[0], lat.shape[2] * lat.shape[3], S()) == 0
+        assert torch.equal(idx.cpu(), idx_ref), int((idx.cpu() != idx_ref).sum())
+        assert torch.equal(out.cpu(), q_ref)
+    assert np.array_equal(O.vq_quantize(cases.vq_latents(), cb)[1].numpy()[:100], golden["vqgan"]["vq_idx"][:100].astype(np.int64))
+
+
+def test_istft_and_stft_kernels():
+    from diffusynth_b200 import codec
+    spec = cases.randn((2, 3, 512, 256), 24)
+    spec[:, 0] = spec[:, 0].abs() * 0.8
+    wave = codec.spectrogram_to_waveform(spec.cuda()).cpu()
+    assert tuple(wave.shape) == (2, 65280)
+    for b in range(2):
+        ref = O.spectrogram_to_waveform(spec[b].numpy().astype(np.float64))
+        assert rel(wave[b], torch.from_numpy(ref)) < 1e-5
+    short = codec.spectrogram_to_waveform(spec[:, :, :, :37].contiguous().cuda()).cpu()      # ragged frame count
+    assert rel(short[1], torch.from_numpy(O.spectrogram_to_waveform(spec[1, :, :, :37].numpy().astype(np.float64)))) < 1e-5
+    w = torch.from_numpy(np.stack([cases.synthetic_wave(seed=31), cases.synthetic_wave(seed=32)])).float()
+    enc = codec.waveform_to_spectrogram(w.cuda()).cpu()
+    for b in range(2):
+        ref = O.waveform_to_spectrogram(w[b].numpy().astype(np.float64))
+        assert rel(enc[b, 0], torch.from_numpy(ref[0])) < 1e-4
+        strong = torch.from_numpy(ref[0]) > 1e-2          # phase is ill-conditioned where the magnitude vanishes
+        assert float((enc[b, 1] - torch.from_numpy(ref[1]))[strong].abs().max()) < 5e-3
+        assert float((enc[b, 2] - torch.from_numpy(ref[2]))[strong].abs().max()) < 5e-3
+    # encode -> decode round trip at full size
+    back = codec.spectrogram_to_waveform(enc.cuda()).cpu()
+    assert float((back[:, 2048:-2048] - (w - w.mean(dim=1, keepdim=True))[:, 2048:-2048]).abs().max()) < 5e-3

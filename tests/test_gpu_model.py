@@ -1,0 +1,175 @@
+"""Model-level parity on the GPU: U-Net forward, VQGAN decoder/encoder, the sampling loop (teacher-forced and
+free-running) and the full text-to-timbre pipeline, CUDA path (through the C ABI) vs the CPU oracle.
+Tolerance for everything that passes through bf16 tensor-core math: relative L2 <= 1e-2 against the fp32
+oracle (BASELINE.json north_star); fp32 kernels: <= 1e-5; codebook indices: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from diffusynth_b200 import weights as W
+from oracle import cases, ds_oracle as O
+from tests.gpu_util import rel
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+def _unet(cfg, sd):
+    from diffusynth_b200 import ConditionedUnet
+    net = ConditionedUnet(**{k: v for k, v in cfg.items() if k not in ("out_dim", "time_dim")}, device="cuda")
+    net.load_state_dict(sd)
+    return net
+
+
+@pytest.mark.parametrize("name", ["small_w16", "deployed_w64", "deployed_w24"])
+def test_unet_forward_parity(name, golden):
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    net = _unet(cfg, sd)
+    taps, ref_taps = {}, {}
+    eps = net.forward(x.cuda(), t.cuda(), cond.cuda(), taps=taps).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, cond, ref_taps)
+    report = [(k, rel(taps[k], ref_taps[k])) for k in ref_taps if k in taps]
+    worst = max(report, key=lambda kv: kv[1])
+    print(f"\n[{name}] eps rel-L2 {rel(eps, ref):.3e}; worst layer {worst[0]} {worst[1]:.3e}")
+    for k, v in report:
+        print(f"    {k:16s} {v:.3e}")
+    assert rel(eps, ref) < BF16_TOL
+    assert all(v < 2 * BF16_TOL for _, v in report), worst
+    assert rel(eps, torch.from_numpy(golden["unet"][f"{name}_eps"])) < BF16_TOL       # the reference's own output
+
+
+def test_unet_rejects_unsupported_variants():
+    from diffusynth_b200 import ConditionedUnet
+    with pytest.raises(NotImplementedError):
+        ConditionedUnet(in_dim=4, attn_type="bogus")
+    with pytest.raises(NotImplementedError):
+        ConditionedUnet(in_dim=4, attn_type="linear_add", condition_type="bogus")
+
+
+def test_vqgan_decoder_encoder_parity(golden):
+    from diffusynth_b200 import VQGAN
+    sd = W.vqgan_random_state_dict(seed=1)
+    vq = VQGAN(**W.VQGAN_DEPLOYED, device="cuda")
+    vq.load_state_dict(sd)
+    enc_plan, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
+    lat = cases.vq_latents(B=2)
+    q, loss, (perp, _, _) = vq._vq_vae(lat.cuda())
+    q_ref, _ = O.vq_quantize(lat, sd["_vq_vae._embedding.weight"])
+    assert torch.equal(q.cpu(), q_ref) and torch.isfinite(loss) and torch.isfinite(perp)
+    dec = vq._decoder(q).cpu()
+    with torch.no_grad():
+        dec_ref = O.vqgan_decode(sd, dec_plan, q_ref)
+    print(f"\ndecoder rel-L2 {rel(dec, dec_ref):.3e} (mag {rel(dec[:, 0], dec_ref[:, 0]):.3e}, cos {rel(dec[:, 1], dec_ref[:, 1]):.3e})")
+    assert tuple(dec.shape) == (2, 3, 512, 256) and rel(dec, dec_ref) < BF16_TOL
+    assert rel(dec[:1].flatten()[::7], torch.from_numpy(golden["vqgan"]["dec_sub"])) < BF16_TOL
+    spec = torch.from_numpy(O.waveform_to_spectrogram(cases.synthetic_wave())[None])
+    enc = vq._encoder(spec.cuda()).cpu()
+    with torch.no_grad():
+        enc_ref = O.vqgan_encode(sd, enc_plan, spec)
+    print(f"encoder rel-L2 {rel(enc, enc_ref):.3e}")
+    assert tuple(enc.shape) == (1, 4, 128, 64) and rel(enc, enc_ref) < BF16_TOL
+    assert rel(enc, torch.from_numpy(golden["vqgan"]["enc_lat"])) < BF16_TOL
+
+
+@pytest.mark.parametrize("kind", ["ddim", "ddpm", "nocfg", "guided", "inpaint"])
+def test_sampler_generic_model_matches_reference_golden(kind, golden):
+    """Drop-in behaviour with an arbitrary callable model: same loops, same outputs as the reference (fp32 kernels)."""
+    from diffusynth_b200 import DiffSynthSampler
+    g = golden["sampler"]
+    B, Wd = 3, 40
+    draws = cases.randn((12, B, 4, 128, 64), 6)
+    cond, uncond = W.synthetic_conditions(B, 16, seed=77)
+    guide = cases.randn((B, 4, 128, 64), 8) * 0.5
+    s = DiffSynthSampler(1000, device="cuda", mute=True, max_batchsize=B)
+    s.noise_feed = draws[1:]
+    model = lambda x, t, c: cases.toy_model(x, t, c)
+    if kind != "nocfg":
+        s.activate_classifier_free_guidance(6, uncond.cuda())
+    if kind == "guided":
+        s.respace(list(np.linspace(0, 999, int(8 / 0.7), dtype=np.int32)))
+        imgs, _ = s.img_guided_sample(model, (B, 4, 128, 64), 0.7, guide.cuda(), return_tensor=True, condition=cond.cuda(), initial_noise=draws[0].cuda())
+        assert len(imgs) == int(g["loop_guided_len"]) and rel(imgs[0], torch.from_numpy(g["loop_guided_first"])) < 1e-6
+    else:
+        s.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+        if kind == "inpaint":
+            mask = (cases.randn((B, 1, 128, Wd), 9) > 0).float()
+            imgs, _ = s.inpaint_sample(model, (B, 4, 128, Wd), 1.0, guide.cuda(), mask.cuda(), return_tensor=True, condition=cond.cuda(), initial_noise=draws[0].cuda())
+        else:
+            imgs, _ = s.sample(model, (B, 4, 128, Wd), return_tensor=True, condition=cond.cuda(), initial_noise=draws[0].cuda(),
+                               sampler="ddpm" if kind == "ddpm" else "ddim")
+            assert len(imgs) == 9
+    assert rel(imgs[-1], torch.from_numpy(g[f"loop_{kind}_last"])) < 1e-5
+    with pytest.raises(NotImplementedError):
+        s.sample(model, (B, 4, 128, Wd), condition=cond.cuda(), sampler="euler")
+
+
+@pytest.mark.parametrize("sampler_kind", ["ddim", "ddpm"])
+def test_graph_sampling_loop_parity(sampler_kind):
+    """CUDA-graph loop with the B200 U-Net vs the oracle loop on the same host noise: free-running latents per
+    step, and teacher-forced eps / x_{t-1} (feed the oracle's x_t into one step)."""
+    from diffusynth_b200 import DiffSynthSampler
+    cfg, sd, _, _, _ = cases.unet_case("deployed_w64")
+    net = _unet(cfg, sd)
+    B, steps = 2, 4
+    draws = W.host_noise(3, 1 + steps, B)
+    cond, uncond = W.synthetic_conditions(B, 512)
+    s = DiffSynthSampler(1000, device="cuda", mute=True, max_batchsize=B)
+    s.activate_classifier_free_guidance(6, uncond.cuda())
+    s.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    s.noise_feed = draws[1:]
+    imgs, init = s.sample(net, (B, 4, 128, 64), return_tensor=True, condition=cond.cuda(), sampler=sampler_kind, initial_noise=draws[0].cuda())
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    trace = []
+    with torch.no_grad():
+        ref = O.sample_loop(lambda x, t, c: O.unet_forward(sd, x, t, c), sch, (B, 4, 128, 64), cond, uncond, 6, draws, sampler=sampler_kind, trace=trace)
+    assert len(imgs) == len(ref) == steps + 1 and torch.equal(imgs[0].cpu(), ref[0])
+    errs = [rel(a, b) for a, b in zip(imgs, ref)]
+    print(f"\n[{sampler_kind}] free-running latent rel-L2 per step: {['%.2e' % e for e in errs]}")
+    assert max(errs) < BF16_TOL
+    # teacher-forced: one step from the oracle's x_t
+    for k, tr in enumerate(trace):
+        t_mapped = torch.full((2 * B,), sch.timestep_map[tr["t"]], dtype=torch.long)
+        u = uncond.unsqueeze(0).repeat(B, 1)
+        eps = net(torch.cat([tr["x"], tr["x"]]).cuda(), t_mapped.cuda(), torch.cat([u, cond]).cuda()).cpu()
+        e_u, e_c = rel(eps[:B], tr["eps_u"]), rel(eps[B:], tr["eps_c"])
+        print(f"    step {k} (t={tr['t']}): teacher-forced eps_u {e_u:.2e} eps_c {e_c:.2e}")
+        assert e_u < BF16_TOL and e_c < BF16_TOL
+    # replaying the cached graph with the same inputs is deterministic
+    s.noise_feed = draws[1:]
+    imgs2, _ = s.sample(net, (B, 4, 128, 64), return_tensor=True, condition=cond.cuda(), sampler=sampler_kind, initial_noise=draws[0].cuda())
+    assert all(torch.equal(a, b) for a, b in zip(imgs, imgs2))
+
+
+def test_text_to_timbre_pipeline_parity():
+    """sampling -> VQ -> decoder -> iSTFT at B=2, 3 steps: spectrogram and waveform vs the oracle pipeline; VQ indices
+    bit-exact given identical quantiser inputs."""
+    from diffusynth_b200 import TextToTimbre
+    from diffusynth_b200 import ConditionedUnet, VQGAN
+    usd, vsd = W.unet_random_state_dict(seed=0), W.vqgan_random_state_dict(seed=1)
+    unet = _unet(W.UNET_DEPLOYED, usd)
+    vq = VQGAN(**W.VQGAN_DEPLOYED, device="cuda")
+    vq.load_state_dict(vsd)
+    pipe = TextToTimbre(unet, vq)
+    B, steps = 2, 3
+    draws = W.host_noise(5, 1 + steps, B)
+    cond, uncond = W.synthetic_conditions(B, 512)
+    out = pipe.generate(cond.cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws)
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    _, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
+    with torch.no_grad():
+        lat_ref = O.sample_loop(lambda x, t, c: O.unet_forward(usd, x, t, c), sch, (B, 4, 128, 64), cond, uncond, 6, draws)[-1]
+        # quantiser: identical inputs (the CUDA latents) -> identical indices
+        q_same, idx_same = O.vq_quantize(out.latents.cpu(), vsd["_vq_vae._embedding.weight"])
+        assert torch.equal(q_same, out.quantized.cpu()) and torch.equal(idx_same, pipe.vqgan._vq_vae.last_indices.cpu())
+        spec_ref = O.vqgan_decode(vsd, dec_plan, q_same)
+    wave_ref = np.stack([O.spectrogram_to_waveform(s.numpy().astype(np.float64)) for s in spec_ref])
+    e_lat, e_spec, e_wave = rel(out.latents, lat_ref), rel(out.spectrograms, spec_ref), rel(out.waveforms, torch.from_numpy(wave_ref))
+    # the fp32 iSTFT alone, on the CUDA spectrogram
+    wave_own = np.stack([O.spectrogram_to_waveform(s.numpy().astype(np.float64)) for s in out.spectrograms.cpu()])
+    e_istft = rel(out.waveforms, torch.from_numpy(wave_own))
+    print(f"\npipeline: latent {e_lat:.2e}  spectrogram {e_spec:.2e}  waveform {e_wave:.2e}  (iSTFT alone {e_istft:.2e})")
+    assert tuple(out.waveforms.shape) == (B, 65280)
+    assert e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL and e_istft < 1e-5

@@ -48,6 +48,7 @@ _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SIGNATURES = {
     "ds_last_error": (C.c_char_p, []),
     "ds_version": (_I, []),
+    "ds_operand_dtype": (_I, []),
     "ds_check_device": (_I, [_I]),
     "ds_conv_gemm": (_I, [C.POINTER(ConvGemmArgs), _P]),
     "ds_conv_gemm_reference": (_I, [C.POINTER(ConvGemmArgs), _P]),

@@ -17,6 +17,7 @@ const char* get_error() { return g_err; }
 extern "C" {
 const char* ds_last_error(void) { return ds::get_error(); }
 int ds_version(void) { return 100; }
+int ds_operand_dtype(void) { return ds::kOperandIsFp16; }
 int ds_check_device(int dev) {
   cudaDeviceProp p;
   DS_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));

@@ -20,8 +20,8 @@ static constexpr int AT_PART = AT_D * AT_D + 2 * AT_D;   // S[32][32], Z[32], m[
 
 // grid = (chunks, heads, N), block = 256
 __global__ void __launch_bounds__(256)
-attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
-                        __nv_bfloat16* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
+attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
+                        act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
   __shared__ float s_k[AT_PIX][AT_D + 1];
   __shared__ __align__(16) float s_v[AT_PIX][AT_D + 4];
   __shared__ float s_red[8][AT_D];
@@ -29,7 +29,7 @@ attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int n
   const int chunk = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
   const int ld = 3 * hidden;
   const long long p0 = (long long)chunk * AT_PIX;
-  const __nv_bfloat16* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
+  const act_t* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
   const int tid = threadIdx.x;
 
   // ---- stage k, v (fp32) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
@@ -46,10 +46,10 @@ attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int n
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int d = half * 16 + i * 8 + 2 * j;
-        s_k[pix][d] = ok ? bf16_lo(kk[j]) : -INFINITY;
-        s_k[pix][d + 1] = ok ? bf16_hi(kk[j]) : -INFINITY;
-        s_v[pix][d] = bf16_lo(vw[j]);
-        s_v[pix][d + 1] = bf16_hi(vw[j]);
+        s_k[pix][d] = ok ? lo16(kk[j]) : -INFINITY;
+        s_k[pix][d + 1] = ok ? hi16(kk[j]) : -INFINITY;
+        s_v[pix][d] = lo16(vw[j]);
+        s_v[pix][d + 1] = hi16(vw[j]);
       }
     }
     // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
@@ -63,15 +63,15 @@ attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int n
         float f[16];
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { f[2 * j] = bf16_lo(qq[j]); f[2 * j + 1] = bf16_hi(qq[j]); mx = fmaxf(mx, fmaxf(f[2 * j], f[2 * j + 1])); }
+        for (int j = 0; j < 8; ++j) { f[2 * j] = lo16(qq[j]); f[2 * j + 1] = hi16(qq[j]); mx = fmaxf(mx, fmaxf(f[2 * j], f[2 * j + 1])); }
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) { f[j] = __expf(f[j] - mx); sum += f[j]; }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
         const float inv = scale / sum;
-        q0 = make_uint4(pack_bf16(f[0] * inv, f[1] * inv), pack_bf16(f[2] * inv, f[3] * inv), pack_bf16(f[4] * inv, f[5] * inv), pack_bf16(f[6] * inv, f[7] * inv));
-        q1 = make_uint4(pack_bf16(f[8] * inv, f[9] * inv), pack_bf16(f[10] * inv, f[11] * inv), pack_bf16(f[12] * inv, f[13] * inv), pack_bf16(f[14] * inv, f[15] * inv));
+        q0 = make_uint4(pack16(f[0] * inv, f[1] * inv), pack16(f[2] * inv, f[3] * inv), pack16(f[4] * inv, f[5] * inv), pack16(f[6] * inv, f[7] * inv));
+        q1 = make_uint4(pack16(f[8] * inv, f[9] * inv), pack16(f[10] * inv, f[11] * inv), pack16(f[12] * inv, f[13] * inv), pack16(f[14] * inv, f[15] * inv));
       }
       if (ok) {
         uint4* qo = reinterpret_cast<uint4*>(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16);
@@ -132,7 +132,7 @@ attn_ctx_partial_kernel(const __nv_bfloat16* __restrict__ qkv, int hidden, int n
 // M[n][c][head*32 + d] = sum_e Wout[c][head*32 + e] * ctx[d][e]  -> bf16 [N][Cout_pad][hidden]
 __global__ void __launch_bounds__(256)
 attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad,
-                     int hidden, __nv_bfloat16* __restrict__ M) {
+                     int hidden, act_t* __restrict__ M) {
   __shared__ float s_ctx[AT_D][AT_D + 1];
   __shared__ float s_M[AT_D], s_Z[AT_D];
   const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
@@ -155,7 +155,7 @@ attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __
     s_ctx[d][i % AT_D] = s / s_Z[d];
   }
   __syncthreads();
-  __nv_bfloat16* Mn = M + (size_t)n * Cout_pad * hidden;
+  act_t* Mn = M + (size_t)n * Cout_pad * hidden;
   for (int i = tid; i < Cout_pad * AT_D; i += 256) {
     const int c = i / AT_D, d = i % AT_D;
     float acc = 0.f;
@@ -164,7 +164,7 @@ attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __
 #pragma unroll 8
       for (int e = 0; e < AT_D; ++e) acc = fmaf(__ldg(wr + e), s_ctx[d][e], acc);
     }
-    Mn[(size_t)c * hidden + head * AT_D + d] = __float2bfloat16_rn(acc);
+    Mn[(size_t)c * hidden + head * AT_D + d] = f2act(acc);
   }
 }
 
@@ -182,8 +182,8 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
   DS_REQUIRE(d_qkv && d_q_out && d_part && N > 0 && heads > 0 && npix > 0, "ds_attn_ctx_partial: bad arguments");
   const int chunks = ds_attn_chunks(npix);
   DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_ctx_partial: grid too large");
-  attn_ctx_partial_kernel<<<dim3(chunks, heads, N), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_qkv, heads * AT_D, (int)npix,
-                                                                                   q_mode, scale, (__nv_bfloat16*)d_q_out, d_part, chunks);
+  attn_ctx_partial_kernel<<<dim3(chunks, heads, N), 256, 0, (cudaStream_t)stream>>>((const act_t*)d_qkv, heads * AT_D, (int)npix,
+                                                                                   q_mode, scale, (act_t*)d_q_out, d_part, chunks);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -192,7 +192,7 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
 int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
   DS_REQUIRE(d_part && d_wout && d_M && N > 0 && heads > 0 && C > 0 && Cout_pad >= C, "ds_attn_finalize: bad arguments");
   attn_finalize_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, ds_attn_chunks(npix), d_wout, C, Cout_pad, heads * AT_D,
-                                                                         (__nv_bfloat16*)d_M);
+                                                                         (act_t*)d_M);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

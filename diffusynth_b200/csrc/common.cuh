@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -42,12 +43,34 @@ inline int num_sms() {
 }
 
 // ---- device helpers ---------------------------------------------------------------------------
-__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+// 16-bit storage / tensor-core operand type of activations and weights.
+// Default: IEEE fp16 (tcgen05 kind::f16 with f16 inputs, fp32 accumulate).  bf16 activations cannot hold the
+// classifier-free-guidance difference eps_c - eps_u (0.5% of |eps| at random init, below bf16 resolution), see
+// DESIGN.md "Operand precision"; -DDS_OPERANDS_BF16 builds the bf16 variant for comparison.
+#ifdef DS_OPERANDS_BF16
+typedef __nv_bfloat16 act_t;
+static constexpr int kOperandIsFp16 = 0;
+__device__ __forceinline__ float lo16(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float hi16(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
+__device__ __forceinline__ float act2f(act_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ act_t f2act(float v) { return __float2bfloat16_rn(v); }
+#else
+typedef __half act_t;
+static constexpr int kOperandIsFp16 = 1;
+__device__ __forceinline__ float lo16(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v & 0xffffu))); }
+__device__ __forceinline__ float hi16(uint32_t v) { return __half2float(__ushort_as_half((unsigned short)(v >> 16))); }
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }   // finite saturation
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  __half2 p = __floats2half2_rn(sat16(lo), sat16(hi));
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
+__device__ __forceinline__ act_t f2act(float v) { return __float2half_rn(sat16(v)); }
+#endif
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -33,8 +33,8 @@ struct __align__(16) ConvGemmDev {
   const float2* stats_in; int stats_in_slots; float inv_count, eps;
   const float* e1; const float* e2; int ncls;
   const float* sbias; int sbias_stride; int act;
-  const __nv_bfloat16* residual; long long res_sn, res_sh, res_sw;
-  __nv_bfloat16* out; long long out_sn, out_sh, out_sw; long long out_goff[DS_MAX_GROUPS];
+  const act_t* residual; long long res_sn, res_sh, res_sw;
+  act_t* out; long long out_sn, out_sh, out_sw; long long out_goff[DS_MAX_GROUPS];
   float* out_f32;
   float2* stats_out; int stats_slots;
   ds_conv_tap taps[DS_MAX_GROUPS][DS_MAX_TAPS];
@@ -111,7 +111,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -243,8 +243,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
-      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // instruction descriptor: D=f32 (bit 4), A/B format (bits 7-9, 10-12), K-major both, N>>3 at 17, M>>4 at 24
+      const uint32_t fmt = kOperandIsFp16 ? 0u : 1u;   // F16F32Format: 0 = f16, 1 = bf16
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -263,7 +264,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
           if (++stage == P.stages) { stage = 0; phase ^= 1u; }
@@ -330,8 +331,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             const uint32_t rr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              v[2 * j] += bf16_lo(rr[j]);
-              v[2 * j + 1] += bf16_hi(rr[j]);
+              v[2 * j] += lo16(rr[j]);
+              v[2 * j + 1] += hi16(rr[j]);
             }
           }
           if (P.stats_out != nullptr) {
@@ -341,10 +342,10 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           }
           if (P.out != nullptr && o0 < P.Cout) {
             uint4 a, b;
-            a.x = pack_bf16(v[0], v[1]);   a.y = pack_bf16(v[2], v[3]);
-            a.z = pack_bf16(v[4], v[5]);   a.w = pack_bf16(v[6], v[7]);
-            b.x = pack_bf16(v[8], v[9]);   b.y = pack_bf16(v[10], v[11]);
-            b.z = pack_bf16(v[12], v[13]); b.w = pack_bf16(v[14], v[15]);
+            a.x = pack16(v[0], v[1]);   a.y = pack16(v[2], v[3]);
+            a.z = pack16(v[4], v[5]);   a.w = pack16(v[6], v[7]);
+            b.x = pack16(v[8], v[9]);   b.y = pack16(v[10], v[11]);
+            b.z = pack16(v[12], v[13]); b.w = pack16(v[14], v[15]);
             uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + o0);
             op[0] = a;
             op[1] = b;
@@ -441,9 +442,9 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.stats_in_slots = a->stats_in_slots; P.inv_count = a->stats_inv_count; P.eps = a->eps;
   P.e1 = a->d_e1; P.e2 = a->d_e2; P.ncls = a->ncls;
   P.sbias = a->d_sbias; P.sbias_stride = a->sbias_stride; P.act = a->act;
-  P.residual = reinterpret_cast<const __nv_bfloat16*>(a->d_residual);
+  P.residual = reinterpret_cast<const act_t*>(a->d_residual);
   P.res_sn = a->res_sn; P.res_sh = a->res_sh; P.res_sw = a->res_sw;
-  P.out = reinterpret_cast<__nv_bfloat16*>(a->d_out);
+  P.out = reinterpret_cast<act_t*>(a->d_out);
   P.out_sn = a->out_sn; P.out_sh = a->out_sh; P.out_sw = a->out_sw;
   for (int g = 0; g < DS_MAX_GROUPS; ++g) P.out_goff[g] = a->out_goff[g];
   P.out_f32 = a->d_out_f32_nchw;
@@ -474,7 +475,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
       cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       void* gaddr = const_cast<char*>(base) + (size_t)a->view_off[v] * C * 2;
-      CUresult r = encode(&maps.a[s][v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, gaddr, dims, strides, box, estr,
+      CUresult r = encode(&maps.a[s][v], (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, gaddr, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(A src %d view %d) failed with %d (C=%d Wv=%d Hv=%d)", s, v, (int)r, C, a->Wv, a->Hv);
@@ -487,7 +488,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * a->Cout_pad};
     cuuint32_t box[3] = {(cuuint32_t)a->BK, (cuuint32_t)a->BN, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->d_weight), dims, strides, box, estr,
+    CUresult r = encode(&maps.b, (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 3, const_cast<void*>(a->d_weight), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (K=%lld Cout_pad=%d)", (int)r, K, a->Cout_pad);
@@ -517,8 +518,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 // CUDA-core cross-check of the same contract (tests only): one thread per (pixel, out channel).
 // ---------------------------------------------------------------------------------------------
-__global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const __nv_bfloat16* src0, const __nv_bfloat16* src1,
-                                     const __nv_bfloat16* weight, int Hv, int Wv, long long view_sn, long long view_sh,
+__global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, const act_t* src1,
+                                     const act_t* weight, int Hv, int Wv, long long view_sn, long long view_sh,
                                      long long view_sw, const long long* view_off_dev, float2* mean_rstd) {
   const long long total = (long long)P.N * P.groups * P.H * P.W * P.Cout;
   const long long K = (long long)P.ntaps * (P.C0 + P.C1);
@@ -530,7 +531,7 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const __nv_bfloat16* s
     int g = (int)(r % P.groups);
     int n = (int)(r / P.groups);
     const int nsrc = P.src_batch_mod > 0 ? (n % P.src_batch_mod) : n;
-    const __nv_bfloat16* wrow = weight + ((long long)(P.per_sample_w ? n : g) * P.Cout_pad + o) * K;
+    const act_t* wrow = weight + ((long long)(P.per_sample_w ? n : g) * P.Cout_pad + o) * K;
     float acc = 0.f;
     for (int t = 0; t < P.ntaps; ++t) {
       const ds_conv_tap tp = P.taps[g][t];
@@ -538,8 +539,8 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const __nv_bfloat16* s
       if (y < 0 || y >= Hv || x < 0 || x >= Wv) continue;
       const long long pix = view_off_dev[tp.view] + nsrc * view_sn + y * view_sh + x * view_sw;
       for (int c = 0; c < P.C0 + P.C1; ++c) {
-        const float a = c < P.C0 ? __bfloat162float(src0[pix * P.C0 + c]) : __bfloat162float(src1[pix * P.C1 + (c - P.C0)]);
-        acc = fmaf(a, __bfloat162float(wrow[(long long)t * (P.C0 + P.C1) + c]), acc);
+        const float a = c < P.C0 ? act2f(src0[pix * P.C0 + c]) : act2f(src1[pix * P.C1 + (c - P.C0)]);
+        acc = fmaf(a, act2f(wrow[(long long)t * (P.C0 + P.C1) + c]), acc);
       }
     }
     float mean = 0.f, rstd = 1.f;
@@ -550,8 +551,8 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const __nv_bfloat16* s
     if (P.e1) v = fmaf(-mean * rstd, P.e1[(size_t)cls * P.Cout_pad + o], v);
     if (P.sbias) v += P.sbias[(size_t)n * P.sbias_stride + o];
     if (P.act == 1) v = gelu_erf(v);
-    if (P.residual) v += __bfloat162float(P.residual[n * P.res_sn + h * P.res_sh + w * P.res_sw + o]);
-    if (P.out) P.out[P.out_goff[g] + n * P.out_sn + h * P.out_sh + w * P.out_sw + o] = __float2bfloat16_rn(v);
+    if (P.residual) v += act2f(P.residual[n * P.res_sn + h * P.res_sh + w * P.res_sw + o]);
+    if (P.out) P.out[P.out_goff[g] + n * P.out_sn + h * P.out_sh + w * P.out_sw + o] = f2act(v);
     if (P.out_f32) P.out_f32[(((size_t)n * P.Cout + o) * P.H + h) * P.W + w] = v;
   }
 }
@@ -575,9 +576,9 @@ static int conv_gemm_reference_launch(const ds_conv_gemm_args* a, cudaStream_t s
     DS_CHECK_CUDA(cudaMallocAsync(&mr, nsrc * sizeof(float2), stream));
     stats_finalize_kernel<<<nsrc, 32, 0, stream>>>(P.stats_in, P.stats_in_slots, P.inv_count, P.eps, mr);
   }
-  conv_gemm_ref_kernel<<<num_sms() * 8, 256, 0, stream>>>(P, reinterpret_cast<const __nv_bfloat16*>(a->d_src0),
-                                                          reinterpret_cast<const __nv_bfloat16*>(a->d_src1),
-                                                          reinterpret_cast<const __nv_bfloat16*>(a->d_weight), a->Hv, a->Wv,
+  conv_gemm_ref_kernel<<<num_sms() * 8, 256, 0, stream>>>(P, reinterpret_cast<const act_t*>(a->d_src0),
+                                                          reinterpret_cast<const act_t*>(a->d_src1),
+                                                          reinterpret_cast<const act_t*>(a->d_weight), a->Hv, a->Wv,
                                                           a->view_sn, a->view_sh, a->view_sw, voff, mr);
   DS_CHECK_CUDA(cudaGetLastError());
   DS_CHECK_CUDA(cudaFreeAsync(voff, stream));

@@ -16,10 +16,10 @@ static constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 32;
 static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6, DW_PITCH = 23;
 
 __global__ void __launch_bounds__(256)
-dwconv7_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __restrict__ src1, int C0, int C1, int src_batch_mod,
+dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, int C0, int C1, int src_batch_mod,
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
-               __nv_bfloat16* __restrict__ out, float2* __restrict__ stats, int H, int W, int tiles_w, int tiles) {
+               act_t* __restrict__ out, float2* __restrict__ stats, int H, int W, int tiles_w, int tiles) {
   __shared__ __align__(16) uint32_t s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // bf16 pairs
   __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
   __shared__ float s_red[16];
@@ -28,7 +28,7 @@ dwconv7_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __re
   const int h0 = (tile / tiles_w) * DW_TH, w0 = (tile % tiles_w) * DW_TW;
   const int c0 = cblk * DW_CB;
   const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
-  const __nv_bfloat16* src;
+  const act_t* src;
   int Cs, cs0;
   if (c0 < C0) { src = src0; Cs = C0; cs0 = c0; } else { src = src1; Cs = C1; cs0 = c0 - C0; }
   src += (size_t)nsrc * H * W * Cs;
@@ -64,7 +64,7 @@ dwconv7_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __re
 #pragma unroll
     for (int j = 0; j < 14; ++j) {
       const uint32_t v = rowp[j * (DW_CB / 2)];
-      const float a = bf16_lo(v), b = bf16_hi(v);
+      const float a = lo16(v), b = hi16(v);
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
         const int ow = j - kx;
@@ -87,7 +87,7 @@ dwconv7_kernel(const __nv_bfloat16* __restrict__ src0, const __nv_bfloat16* __re
       const float v0 = acc0[j] + b0, v1 = acc1[j] + b1;
       s += v0 + v1;
       q = fmaf(v0, v0, fmaf(v1, v1, q));
-      *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack_bf16(v0, v1);
+      *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
     }
   }
   if (stats != nullptr) {
@@ -114,7 +114,7 @@ static constexpr int ST_TH = 4, ST_TW = 32;
 template <int CO_PER_THREAD>
 __global__ void __launch_bounds__(256)
 stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __restrict__ weight /* [49*Cin][Cout] */,
-                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N, int Cin, int Cout, int H, int W,
+                  const float* __restrict__ bias, act_t* __restrict__ out, int N, int Cin, int Cout, int H, int W,
                   int tiles_w, int tiles_per_sample, int total_tiles) {
   extern __shared__ __align__(16) float s_mem[];
   float* s_w = s_mem;                                   // [49*Cin][Cout]
@@ -159,8 +159,8 @@ stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __r
       uint4* op = reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + xx) * Cout + co0);
 #pragma unroll
       for (int j = 0; j < CO_PER_THREAD / 8; ++j)
-        op[j] = make_uint4(pack_bf16(acc[8 * j], acc[8 * j + 1]), pack_bf16(acc[8 * j + 2], acc[8 * j + 3]),
-                           pack_bf16(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16(acc[8 * j + 6], acc[8 * j + 7]));
+        op[j] = make_uint4(pack16(acc[8 * j], acc[8 * j + 1]), pack16(acc[8 * j + 2], acc[8 * j + 3]),
+                           pack16(acc[8 * j + 4], acc[8 * j + 5]), pack16(acc[8 * j + 6], acc[8 * j + 7]));
     }
   }
 }
@@ -182,8 +182,8 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
   const int tiles = tiles_w * tiles_h;
   DS_REQUIRE(N <= 65535 && (C0 + C1) / DW_CB <= 65535, "ds_dwconv7: grid too large");
   dwconv7_kernel<<<dim3(tiles, (C0 + C1) / DW_CB, N), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)d_src0, (const __nv_bfloat16*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-      (__nv_bfloat16*)d_out, (float2*)d_stats, H, W, tiles_w, tiles);
+      (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
+      (act_t*)d_out, (float2*)d_stats, H, W, tiles_w, tiles);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -204,7 +204,7 @@ int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, cons
   int grid = total < 2 * num_sms() ? total : 2 * num_sms();
 #define LAUNCH_STEM(CPT)                                                                                                    \
   DS_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-  stem_conv7_kernel<CPT><<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, x_batch_mod, d_weight, d_bias, (__nv_bfloat16*)d_out, N, \
+  stem_conv7_kernel<CPT><<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, x_batch_mod, d_weight, d_bias, (act_t*)d_out, N, \
                                                                      Cin, Cout, H, W, tiles_w, tps, total);
   if (Cout == 96) { LAUNCH_STEM(48) } else if (Cout == 64) { LAUNCH_STEM(32) } else if (Cout == 32) { LAUNCH_STEM(16) } else { LAUNCH_STEM(64) }
 #undef LAUNCH_STEM

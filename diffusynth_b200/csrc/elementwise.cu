@@ -62,21 +62,21 @@ __global__ void mask_blend_kernel(const float* __restrict__ guide, const float* 
 }
 
 // fp32 NCHW -> bf16 NHWC with the channel count padded to Cp (zeros); and back.
-__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int Cp,
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, act_t* __restrict__ out, int C, int Cp,
                                              long long hw, long long total_pix) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix * Cp; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cp);
     const long long pix = i / Cp, n = pix / hw, p = pix % hw;
-    out[i] = __float2bfloat16_rn(c < C ? in[(n * C + c) * hw + p] : 0.f);
+    out[i] = f2act(c < C ? in[(n * C + c) * hw + p] : 0.f);
   }
 }
-__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C, int Cp,
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const act_t* __restrict__ in, float* __restrict__ out, int C, int Cp,
                                              long long hw, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i % hw, r = i / hw;
     const int c = (int)(r % C);
     const long long n = r / C;
-    out[i] = __bfloat162float(in[(n * hw + p) * Cp + c]);
+    out[i] = act2f(in[(n * hw + p) * Cp + c]);
   }
 }
 
@@ -111,9 +111,9 @@ __global__ void gn_apply_residual_kernel(const uint4* __restrict__ y, const uint
     for (int j = 0; j < 4; ++j) {
       const float g0 = __ldg(gamma + c0 + 2 * j), g1 = __ldg(gamma + c0 + 2 * j + 1);
       const float b0 = __ldg(beta + c0 + 2 * j), b1 = __ldg(beta + c0 + 2 * j + 1);
-      const float a = (bf16_lo(yy[j]) - mean) * rstd * g0 + b0 + bf16_lo(xx[j]);
-      const float b = (bf16_hi(yy[j]) - mean) * rstd * g1 + b1 + bf16_hi(xx[j]);
-      oo[j] = pack_bf16(a, b);
+      const float a = (lo16(yy[j]) - mean) * rstd * g0 + b0 + lo16(xx[j]);
+      const float b = (hi16(yy[j]) - mean) * rstd * g1 + b1 + hi16(xx[j]);
+      oo[j] = pack16(a, b);
     }
     ob[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
   }
@@ -125,7 +125,7 @@ __global__ void gn_apply_residual_kernel(const uint4* __restrict__ y, const uint
 //   gn_act:      out = act((x - mean_g) * rstd_g * gamma + beta)          act: 0 none, 1 relu, 2 swish
 // x bf16 NHWC with Cp channels stored (C real, Cp - C zero padding), C % G == 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void group_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
+__global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
                                    long long hw, int chunks) {
   extern __shared__ float s_acc[];   // [2*G]
   const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G;
@@ -133,14 +133,14 @@ __global__ void group_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* 
   __syncthreads();
   const long long per = (hw + chunks - 1) / chunks;
   const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
-  const __nv_bfloat16* xb = x + (size_t)n * hw * Cp;
+  const act_t* xb = x + (size_t)n * hw * Cp;
   // thread handles a fixed channel (so a fixed group) across pixels
   const int tc = threadIdx.x % Cp;
   const int tp = threadIdx.x / Cp, pstride = blockDim.x / Cp;
   float s = 0.f, q = 0.f;
   if (tc < C && tp < pstride) {
     for (long long p = p0 + tp; p < p1; p += pstride) {
-      const float v = __bfloat162float(xb[p * Cp + tc]);
+      const float v = act2f(xb[p * Cp + tc]);
       s += v;
       q = fmaf(v, v, q);
     }
@@ -152,7 +152,7 @@ __global__ void group_stats_kernel(const __nv_bfloat16* __restrict__ x, float2* 
     part[((size_t)n * G + g) * chunks + chunk] = make_float2(s_acc[2 * g], s_acc[2 * g + 1]);
 }
 
-__global__ void gn_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float2* __restrict__ part,
+__global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ out, const float2* __restrict__ part,
                               int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int C, int Cp, int G,
                               long long hw, float eps, int act) {
   extern __shared__ float s_ab[];   // per channel scale, shift  [2*Cp]
@@ -169,16 +169,16 @@ __global__ void gn_act_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
   for (int c = C + threadIdx.x; c < Cp; c += blockDim.x) { s_ab[2 * c] = 0.f; s_ab[2 * c + 1] = 0.f; }
   __syncthreads();
   const long long total = hw * Cp;
-  const __nv_bfloat16* xb = x + (size_t)n * total;
-  __nv_bfloat16* ob = out + (size_t)n * total;
+  const act_t* xb = x + (size_t)n * total;
+  act_t* ob = out + (size_t)n * total;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < total; i += (long long)gridDim.x * blockDim.x * 2) {
     const int c = (int)(i % Cp);
     const uint32_t v = *reinterpret_cast<const uint32_t*>(xb + i);
-    float a = bf16_lo(v) * s_ab[2 * c] + s_ab[2 * c + 1];
-    float b = bf16_hi(v) * s_ab[2 * c + 2] + s_ab[2 * c + 3];
+    float a = lo16(v) * s_ab[2 * c] + s_ab[2 * c + 1];
+    float b = hi16(v) * s_ab[2 * c + 2] + s_ab[2 * c + 3];
     if (act == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
     else if (act == 2) { a = a / (1.f + __expf(-a)); b = b / (1.f + __expf(-b)); }
-    *reinterpret_cast<uint32_t*>(ob + i) = pack_bf16(a, b);
+    *reinterpret_cast<uint32_t*>(ob + i) = pack16(a, b);
   }
 }
 
@@ -189,7 +189,7 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
     const uint32_t xx[4] = {x.x, x.y, x.z, x.w}, yy[4] = {y.x, y.y, y.z, y.w};
     uint32_t o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = pack_bf16(bf16_lo(xx[j]) + bf16_lo(yy[j]), bf16_hi(xx[j]) + bf16_hi(yy[j]));
+    for (int j = 0; j < 4; ++j) o[j] = pack16(lo16(xx[j]) + lo16(yy[j]), hi16(xx[j]) + hi16(yy[j]));
     out[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -289,7 +289,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
 int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int Cp, long long hw, void* stream) {
   DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nchw_f32_to_nhwc_bf16: bad arguments");
   nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)N * hw * Cp, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_in, (__nv_bfloat16*)d_out, C, Cp, hw, (long long)N * hw);
+      d_in, (act_t*)d_out, C, Cp, hw, (long long)N * hw);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -297,7 +297,7 @@ int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int C
 int ds_nhwc_bf16_to_nchw_f32(const void* d_in, float* d_out, int N, int C, int Cp, long long hw, void* stream) {
   DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nhwc_bf16_to_nchw_f32: bad arguments");
   const long long total = (long long)N * C * hw;
-  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)d_in, d_out, C, Cp, hw, total);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const act_t*)d_in, d_out, C, Cp, hw, total);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -319,7 +319,7 @@ int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const vo
 int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, long long hw, int chunks, void* stream) {
   DS_REQUIRE(d_x && d_part && N > 0 && C > 0 && Cp >= C && Cp <= 1024 && G > 0 && C % G == 0 && chunks > 0, "ds_group_stats: bad arguments");
   const int block = (1024 / Cp) * Cp;
-  group_stats_kernel<<<dim3(chunks, N), block, 2 * G * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)d_x, (float2*)d_part,
+  group_stats_kernel<<<dim3(chunks, N), block, 2 * G * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
                                                                                               C, Cp, G, hw, chunks);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
@@ -333,7 +333,7 @@ int ds_gn_act(const void* d_x, void* d_out, const void* d_part, int chunks, cons
   const int cap = (num_sms() * 8 + N - 1) / N;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   gn_act_kernel<<<dim3(gx, N), 256, (2 * Cp + 4) * sizeof(float), (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)d_x, (__nv_bfloat16*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act);
+      (const act_t*)d_x, (act_t*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -15,7 +15,14 @@ import torch
 from . import _lib
 from ._lib import ConvGemmArgs, check
 
-BF16 = torch.bfloat16
+
+
+def _act_dtype():
+    return torch.float16 if _lib.load().ds_operand_dtype() == 1 else torch.bfloat16
+
+
+ACT = _act_dtype()      # 16-bit storage / MMA operand dtype the library was built with (fp16 by default)
+BF16 = ACT              # (historical alias)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:

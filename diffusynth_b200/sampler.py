@@ -113,11 +113,11 @@ class DiffSynthSampler:
 
     def _coef(self, t: int, eta: float) -> List[float]:
         """Per-step scalars of :323-337, evaluated as the reference does: f64 table -> fp32 -> fp32 math."""
-        at, ap = np.float32(self.alphas_cumprod[t]), np.float32(self.alphas_cumprod_prev[t])
-        one = np.float32(1.0)
-        sigma = np.float32(eta) * np.sqrt((one - ap) / (one - at), dtype=np.float32) * np.sqrt(one - at / ap, dtype=np.float32)
-        return [float(np.sqrt(one - at, dtype=np.float32)), float(np.sqrt(at, dtype=np.float32)), float(np.sqrt(ap, dtype=np.float32)),
-                float(np.sqrt(one - ap - sigma * sigma, dtype=np.float32)), float(sigma), float(self.CFG), 0.0, 0.0]
+        at = torch.tensor(self.alphas_cumprod[t]).float()
+        ap = torch.tensor(self.alphas_cumprod_prev[t]).float()
+        sigma = eta * torch.sqrt((1 - ap) / (1 - at)) * torch.sqrt(1 - at / ap)
+        return [float(torch.sqrt(1. - at)), float(torch.sqrt(at)), float(torch.sqrt(ap)), float(torch.sqrt(1 - ap - sigma ** 2)),
+                float(sigma), float(self.CFG), 0.0, 0.0]
 
     # ---- noise --------------------------------------------------------------------------------
     def _draw(self, batchsize: int) -> torch.Tensor:

@@ -56,7 +56,7 @@ class _Attn:
         # the per-sample matrix M = Wout . ctx is produced on the device; this PackedConv only carries e2 (= bias), taps, sizes
         e2 = torch.zeros(1, cout_pad)
         e2[0, :dim] = sd[p + "fn.fn.to_out.0.bias"].float()
-        self.out = PackedConv(weight=torch.zeros(1, dtype=torch.bfloat16), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=HID, cout=dim,
+        self.out = PackedConv(weight=torch.zeros(1, dtype=ops.ACT), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=HID, cout=dim,
                               cout_pad=cout_pad, ncls=1, kind="s1")
         self.gamma = sd[p + "fn.fn.to_out.1.weight"].float().contiguous()
         self.beta = sd[p + "fn.fn.to_out.1.bias"].float().contiguous()
@@ -260,7 +260,7 @@ class _Plan:
         stream = ops._stream
 
         def act(n, h, w, c):
-            return torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+            return torch.empty((n, h, w, c), dtype=ops.ACT, device=dev)
 
         scratch: Dict[Tuple, torch.Tensor] = {}
 
@@ -322,7 +322,7 @@ class _Plan:
             conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=sb)
             qp = scr("qp", N, h, w, HID)
             part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
-            M = torch.empty((N, a.out.cout_pad, HID), dtype=torch.bfloat16, device=dev)
+            M = torch.empty((N, a.out.cout_pad, HID), dtype=ops.ACT, device=dev)
             add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
                                                                   float(DHEAD ** -0.5), stream()), "attn_ctx_partial"))
             add(p + "fin", lambda: check(lib.ds_attn_finalize(part.data_ptr(), a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim,

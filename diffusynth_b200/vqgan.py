@@ -96,7 +96,7 @@ class _Stack:
                 cout_pad = ops.pad16(cin)
                 e2 = torch.zeros(1, cout_pad)
                 e2[0, :cin] = sd[p + "to_out.bias"].float()
-                L["out"] = PackedConv(weight=torch.zeros(1, dtype=torch.bfloat16), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=DH, cout=cin,
+                L["out"] = PackedConv(weight=torch.zeros(1, dtype=ops.ACT), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=DH, cout=cin,
                                       cout_pad=cout_pad, ncls=1, kind="s1")
                 if (p + "nin_shortcut.weight") in sd:
                     L["short"] = pack_conv_s1(sd[p + "nin_shortcut.weight"], sd[p + "nin_shortcut.bias"].float(), cin_pad=_cp(cin))
@@ -132,7 +132,7 @@ class _StackPlan:
         self.inp = torch.zeros((B, first_c, H, Wd), **f32)
 
         def act(h, w, c):      # zero-initialised: padded channels must stay zero
-            return torch.zeros((B, h, w, _cp(c)), dtype=torch.bfloat16, device=dev)
+            return torch.zeros((B, h, w, _cp(c)), dtype=ops.ACT, device=dev)
 
         def add(name, fn):
             self.ops.append((name, fn))
@@ -196,7 +196,7 @@ class _StackPlan:
                 conv(name + ".to_qkv", L["qkv"], x, h, w, out=qkv)
                 qp = act(h, w, DH)
                 part = torch.empty((lib.ds_attn_part_floats(B, 1, npix),), **f32)
-                M = torch.empty((B, L["out"].cout_pad, DH), dtype=torch.bfloat16, device=dev)
+                M = torch.empty((B, L["out"].cout_pad, DH), dtype=ops.ACT, device=dev)
                 add(name + ".ctx", lambda qkv=qkv, qp=qp, part=part, npix=npix: check(
                     lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), B, 1, npix, 1, 1.0, stream()), "attn_ctx_partial"))
                 add(name + ".fin", lambda part=part, M=M, L=L, npix=npix, cin=cin: check(

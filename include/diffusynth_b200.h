@@ -13,7 +13,7 @@
  * that stream and capturable into a CUDA graph; return value 0 = ok, <0 = error
  * (-1 invalid argument/shape, -2 CUDA error, -3 NCCL error, -4 unsupported);
  * ds_last_error() returns the message of the calling thread's last failure.
- * Activation tensors are bf16 channels-last ("NHWC") unless a name says f32/nchw.
+ * Activation tensors are 16-bit ("act16", see ds_operand_dtype) channels-last ("NHWC") unless a name says f32/nchw.
  */
 #ifndef DIFFUSYNTH_B200_H
 #define DIFFUSYNTH_B200_H
@@ -26,6 +26,9 @@ extern "C" {
 
 const char* ds_last_error(void);
 int ds_version(void);
+/* 16-bit storage / tensor-core operand format the library was built with: 1 = IEEE fp16 (default),
+   0 = bf16 (-DDS_OPERANDS_BF16).  "act16" below means this type. */
+int ds_operand_dtype(void);
 /* Device sanity: returns 0 when device `dev` is compute capability 10.x. */
 int ds_check_device(int dev);
 
@@ -55,7 +58,7 @@ typedef struct ds_conv_tap {
 } ds_conv_tap;
 
 typedef struct ds_conv_gemm_args {
-  /* sources: bf16 NHWC [N, Hs, Ws, C]; source 1 optional (C1 = 0), concatenated after source 0 along C.
+  /* sources: act16 NHWC [N, Hs, Ws, C]; source 1 optional (C1 = 0), concatenated after source 0 along C.
      A "view" v of a source is a strided pixel window, given in PIXEL units so that it applies to both
      sources: pixel(n, y, x) = view_off[v] + n*view_sn + y*view_sh + x*view_sw, extent Hv x Wv; the
      element offset in a source with C channels is pixel*C + c.  Stride-1 convs use the identity view,
@@ -72,7 +75,7 @@ typedef struct ds_conv_gemm_args {
   /* GEMM pixel grid (per sample) and tile shape */
   int32_t H, W;             /* output-tile grid extent */
   int32_t Hb, Wb;           /* Hb*Wb == 128 */
-  /* weights: bf16 [Z, Cout_pad, K] K-major, K = ntaps*(C0+C1) ordered tap-major then channel
+  /* weights: act16 [Z, Cout_pad, K] K-major, K = ntaps*(C0+C1) ordered tap-major then channel
      (source 0 channels first).  Z = groups, or N when per_sample_weights. */
   const void* d_weight;
   int32_t Cout_pad;         /* multiple of BN */
@@ -93,9 +96,9 @@ typedef struct ds_conv_gemm_args {
   const float* d_sbias;     /* per-sample bias [N][sbias_stride] or NULL */
   int32_t sbias_stride;
   int32_t act;              /* 0 none, 1 GELU(erf) */
-  const void* d_residual;   /* bf16, pixel strides below, or NULL */
+  const void* d_residual;   /* act16, pixel strides below, or NULL */
   int64_t res_sn, res_sh, res_sw;      /* in elements */
-  void* d_out;              /* bf16 out, or NULL */
+  void* d_out;              /* act16 out, or NULL */
   int64_t out_sn, out_sh, out_sw;      /* in elements */
   int64_t out_goff[DS_MAX_GROUPS];     /* element offset per group (sub-pixel phase of ConvTranspose) */
   float* d_out_f32_nchw;    /* optional fp32 [N, Cout, H, W] output (final conv) */
@@ -129,7 +132,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
 int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight,
                const float* d_tbias, long long tbias_stride, void* d_out, void* d_stats, int N, int H, int W, void* stream);
 int ds_dwconv7_stats_slots(int C, int H, int W);
-/* init_conv 7x7 (model/diffusion.py:82,208): fp32 NCHW in, bf16 NHWC out. */
+/* init_conv 7x7 (model/diffusion.py:82,208): fp32 NCHW in, act16 NHWC out. */
 int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out,
                   int N, int Cin, int Cout, int H, int W, void* stream);
 /* SinusoidalPositionEmbeddings (:42-56) and the small Linear layers (time_mlp, per-block mlp,

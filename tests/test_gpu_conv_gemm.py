@@ -5,13 +5,13 @@ import torch
 import torch.nn.functional as F
 
 from oracle import cases
-from tests.gpu_util import bf, nchw, nhwc, rel
+from tests.gpu_util import EPS16, bf, nchw, nhwc, rel
 from tests.test_host_packing import contract
 
 pytestmark = pytest.mark.gpu
 
-# bf16 output rounding: 2^-9 relative per element
-TOL = 4e-3
+# output rounding of the 16-bit storage type: EPS16/2 relative per element (fp16: 2^-12, bf16: 2^-9)
+TOL = EPS16
 
 
 def _run(pc, srcs, N, H, W, reference=False, **kw):
@@ -38,14 +38,14 @@ def test_plain_conv(cin, cout, k, H, W, N):
     x = cases.randn((N, cin, H, W), 1)
     w, b = cases.randn((cout, cin, k, k), 2) * (1.0 / (cin * k * k) ** 0.5), cases.randn((cout,), 3)
     pc = ops.pack_conv_s1(w, b)
-    out = torch.zeros((N, H, W, cout), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H, W, cout), dtype=ops.ACT, device="cuda")
     _run(pc, [nhwc(x)], N, H, W, out=out)
     ref = F.conv2d(bf(x), bf(w), b, padding=k // 2)
     assert rel(nchw(out), ref) < TOL
     out2 = torch.zeros_like(out)
     _run(pc, [nhwc(x)], N, H, W, reference=True, out=out2)
     assert rel(nchw(out2), ref) < TOL
-    assert rel(nchw(out), nchw(out2)) < 1e-3
+    assert rel(nchw(out), nchw(out2)) < TOL
 
 
 def test_convnext_conv1_fold_gelu_stats_concat():
@@ -59,14 +59,14 @@ def test_convnext_conv1_fold_gelu_stats_concat():
     xb = torch.cat([bf(x0), bf(x1)], 1)
     # statistics of the (bf16-stored) source as one partial slot per sample
     st = ops.Stats(torch.stack([xb.sum(dim=(1, 2, 3)), (xb * xb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous(), 1, 288 * H * W)
-    out = torch.zeros((N, H, W, 192), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H, W, 192), dtype=ops.ACT, device="cuda")
     so = _run(pc, [nhwc(x0), nhwc(x1)], N, H, W, out=out, stats_in=st, act=1, want_stats=True)
     ref = F.gelu(F.conv2d(F.group_norm(xb, 1, gamma, beta, 1e-5), w, b, padding=1))
     got = nchw(out)
-    assert rel(got, ref) < 6e-3
+    assert rel(got, ref) < 1.5 * TOL
     # partials: sum over slots == sums of the fp32 (pre-rounding) outputs
     s = so.buf.double().sum(dim=1).cpu()
-    assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=2e-3, atol=2.0)
+    assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=2e-3, atol=4.0)
     assert torch.allclose(s[:, 1], (ref.double() ** 2).sum(dim=(1, 2, 3)), rtol=4e-3)
     assert so.count == 192 * H * W
 
@@ -80,10 +80,10 @@ def test_conv2_residual_and_contract_cross_check():
     pc = ops.pack_conv_s1(w, b, gamma, beta)
     xb = bf(x)
     st = ops.Stats(torch.stack([xb.sum(dim=(1, 2, 3)), (xb * xb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous(), 1, 128 * H * W)
-    out = torch.zeros((N, H, W, 64), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H, W, 64), dtype=ops.ACT, device="cuda")
     _run(pc, [nhwc(x)], N, H, W, out=out, stats_in=st, residual=nhwc(r))
     ref = F.conv2d(F.group_norm(xb, 1, gamma, beta, 1e-5), w, b, padding=1) + bf(r)
-    assert rel(nchw(out), ref) < 6e-3
+    assert rel(nchw(out), ref) < 1.5 * TOL
     pc_cpu = ops.pack_conv_s1(w, b, gamma, beta)
     for n in range(N):
         mean, var = xb[n].mean(), xb[n].var(unbiased=False)
@@ -97,13 +97,13 @@ def test_downsample_and_upsample():
     x = cases.randn((N, 96, H, W), 16)
     w, b = cases.randn((96, 96, 4, 4), 17) * 0.03, cases.randn((96,), 18)
     pc = ops.pack_conv_down(w, b)
-    out = torch.zeros((N, H // 2, W // 2, 96), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H // 2, W // 2, 96), dtype=ops.ACT, device="cuda")
     _run(pc, [nhwc(x)], N, H, W, out=out)
     assert rel(nchw(out), F.conv2d(bf(x), bf(w), b, stride=2, padding=1)) < TOL
     wt = cases.randn((96, 64, 4, 4), 19) * 0.05
     bt = cases.randn((64,), 20)
     pcu = ops.pack_conv_up(wt, bt)
-    outu = torch.zeros((N, 2 * H, 2 * W, 64), dtype=torch.bfloat16, device="cuda")
+    outu = torch.zeros((N, 2 * H, 2 * W, 64), dtype=ops.ACT, device="cuda")
     _run(pcu, [nhwc(x)], N, H, W, out=outu)
     assert rel(nchw(outu), F.conv_transpose2d(bf(x), bf(wt), bt, stride=2, padding=1)) < TOL
 
@@ -127,9 +127,9 @@ def test_per_sample_weights_and_sample_bias():
     M = cases.randn((N, 96, 128), 25) * 0.1
     bias, sb = cases.randn((96,), 26), cases.randn((N, 96), 27)
     e2 = torch.zeros(1, 96); e2[0] = bias
-    pc = ops.PackedConv(weight=torch.zeros(1, dtype=torch.bfloat16), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=128, cout=96, cout_pad=96, ncls=1, kind="s1")
-    out = torch.zeros((N, H, W, 96), dtype=torch.bfloat16, device="cuda")
-    _run(pc, [nhwc(x)], N, H, W, out=out, weight_override=M.to(torch.bfloat16).cuda().contiguous(), per_sample_weights=True, sbias=sb.cuda())
+    pc = ops.PackedConv(weight=torch.zeros(1, dtype=ops.ACT), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=128, cout=96, cout_pad=96, ncls=1, kind="s1")
+    out = torch.zeros((N, H, W, 96), dtype=ops.ACT, device="cuda")
+    _run(pc, [nhwc(x)], N, H, W, out=out, weight_override=M.to(ops.ACT).cuda().contiguous(), per_sample_weights=True, sbias=sb.cuda())
     ref = torch.einsum("nok,nkhw->nohw", bf(M), bf(x)) + bias.view(1, -1, 1, 1) + sb.view(N, -1, 1, 1)
     assert rel(nchw(out), ref) < TOL
 
@@ -137,7 +137,7 @@ def test_per_sample_weights_and_sample_bias():
 def test_invalid_arguments_are_rejected():
     from diffusynth_b200 import _lib, ops
     pc = ops.pack_conv_s1(cases.randn((32, 40, 1, 1), 1), None)     # 40 input channels: not a multiple of 32
-    x = torch.zeros((1, 8, 16, 40), dtype=torch.bfloat16, device="cuda")
-    out = torch.zeros((1, 8, 16, 32), dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros((1, 8, 16, 40), dtype=ops.ACT, device="cuda")
+    out = torch.zeros((1, 8, 16, 32), dtype=ops.ACT, device="cuda")
     with pytest.raises(_lib.DsError):
         _run(pc, [x], 1, 8, 16, out=out)

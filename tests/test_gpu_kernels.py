@@ -8,7 +8,8 @@ import torch.nn.functional as F
 
 from diffusynth_b200 import weights as W
 from oracle import cases, ds_oracle as O
-from tests.gpu_util import bf, nchw, nhwc, rel
+from tests.gpu_util import EPS16, bf, nchw, nhwc, rel
+from diffusynth_b200 import ops
 
 pytestmark = pytest.mark.gpu
 
@@ -79,13 +80,13 @@ def test_dwconv7(C0, C1, H, W, N):
     Cc = C0 + C1
     x = cases.randn((N, Cc, H, W), 9)
     w, tb = cases.randn((Cc, 1, 7, 7), 10) * 0.1, cases.randn((N, Cc + 5), 11)
-    out = torch.zeros((N, H, W, Cc), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H, W, Cc), dtype=ops.ACT, device="cuda")
     st = ops.dwconv7_stats(N, Cc, H, W, "cuda")
     s0 = nhwc(x[:, :C0])
     s1 = nhwc(x[:, C0:]) if C1 else None
     ops.dwconv7(s0, s1, w.reshape(Cc, 49).t().contiguous().cuda(), tb.cuda(), tb.shape[1], out, N, H, W, stats=st)
     ref = F.conv2d(bf(x), w, None, padding=3, groups=Cc) + tb[:, :Cc, None, None]
-    assert rel(nchw(out), ref) < 4e-3
+    assert rel(nchw(out), ref) < EPS16
     s = st.buf.double().sum(dim=1).cpu()
     assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=1e-3, atol=1.0)
     assert torch.allclose(s[:, 1], (ref.double() ** 2).sum(dim=(1, 2, 3)), rtol=1e-3)
@@ -94,11 +95,11 @@ def test_dwconv7(C0, C1, H, W, N):
 def test_stem_conv7():
     x = cases.randn((2, 4, 128, 64), 12) * 3
     w, b = cases.randn((96, 4, 7, 7), 13) * 0.07, cases.randn((96,), 14)
-    out = torch.zeros((4, 128, 64, 96), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((4, 128, 64, 96), dtype=ops.ACT, device="cuda")
     xd, wd, bd = x.cuda(), w.permute(2, 3, 1, 0).reshape(-1, 96).contiguous().cuda(), b.cuda()
     assert lib().ds_stem_conv7(xd.data_ptr(), 2, wd.data_ptr(), bd.data_ptr(), out.data_ptr(), 4, 4, 96, 128, 64, S()) == 0
     ref = F.conv2d(x, w, b, padding=3)
-    assert rel(nchw(out)[:2], ref) < 4e-3 and torch.equal(out[:2], out[2:])
+    assert rel(nchw(out)[:2], ref) < EPS16 and torch.equal(out[:2], out[2:])
 
 
 def test_time_and_condition_linears():
@@ -128,16 +129,16 @@ def test_linear_attention_core(heads, n, mode):
     B, hid, Cc = 2, heads * 32, 96
     qkv = cases.randn((B, n, 3 * hid), 15) * 1.5
     wout = cases.randn((Cc, hid), 16) * 0.1
-    qd = qkv.to(torch.bfloat16).cuda()
-    qp = torch.zeros((B, n, hid), dtype=torch.bfloat16, device="cuda")
+    qd = qkv.to(ops.ACT).cuda()
+    qp = torch.zeros((B, n, hid), dtype=ops.ACT, device="cuda")
     part = torch.empty((lib().ds_attn_part_floats(B, heads, n),), device="cuda")
-    M = torch.zeros((B, Cc, hid), dtype=torch.bfloat16, device="cuda")
+    M = torch.zeros((B, Cc, hid), dtype=ops.ACT, device="cuda")
     assert lib().ds_attn_ctx_partial(qd.data_ptr(), qp.data_ptr(), part.data_ptr(), B, heads, n, mode, C.c_float(32 ** -0.5), S()) == 0
     assert lib().ds_attn_finalize(part.data_ptr(), wout.cuda().data_ptr(), M.data_ptr(), B, heads, n, Cc, Cc, S()) == 0
     q_ref, ctx = _attn_ref(bf(qkv), heads, mode == 0)
-    assert rel(qp.float().cpu().reshape(B, n, heads, 32).permute(0, 2, 3, 1), q_ref) < 4e-3
+    assert rel(qp.float().cpu().reshape(B, n, heads, 32).permute(0, 2, 3, 1), q_ref) < EPS16
     M_ref = torch.einsum("che,bhde->bchd", wout.view(Cc, heads, 32), ctx).reshape(B, Cc, hid)
-    assert rel(M, M_ref) < 4e-3
+    assert rel(M, M_ref) < EPS16
 
 
 def test_gn_apply_residual():
@@ -146,11 +147,11 @@ def test_gn_apply_residual():
     g, b = 1 + 0.1 * cases.randn((Cc,), 19), 0.1 * cases.randn((Cc,), 20)
     yb = bf(y)
     st = torch.stack([yb.sum(dim=(1, 2, 3)), (yb * yb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous()
-    out = torch.zeros((N, H, Wd, Cc), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros((N, H, Wd, Cc), dtype=ops.ACT, device="cuda")
     yd, xd = nhwc(y), nhwc(x)
     assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.data_ptr(), 1, C.c_float(1.0 / (Cc * H * Wd)), C.c_float(1e-5),
                                       g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, S()) == 0
-    assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)) < 4e-3
+    assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)) < EPS16
 
 
 @pytest.mark.parametrize("act", [1, 2])
@@ -166,7 +167,7 @@ def test_group_norm16_act(act):
                            C.c_float(1e-6), act, S()) == 0
     r = F.group_norm(bf(x), G, g, b, 1e-6)
     r = F.relu(r) if act == 1 else r * torch.sigmoid(r)
-    assert rel(nchw(out, Cc), r) < 4e-3 and float(out[..., Cc:].abs().max()) == 0.0
+    assert rel(nchw(out, Cc), r) < EPS16 and float(out[..., Cc:].abs().max()) == 0.0
 
 
 def test_vq_indices_bit_exact(golden):

@@ -127,7 +127,6 @@ def test_graph_sampling_loop_parity(sampler_kind):
     assert len(imgs) == len(ref) == steps + 1 and torch.equal(imgs[0].cpu(), ref[0])
     errs = [rel(a, b) for a, b in zip(imgs, ref)]
     print(f"\n[{sampler_kind}] free-running latent rel-L2 per step: {['%.2e' % e for e in errs]}")
-    assert max(errs) < BF16_TOL
     # teacher-forced: one step from the oracle's x_t
     for k, tr in enumerate(trace):
         t_mapped = torch.full((2 * B,), sch.timestep_map[tr["t"]], dtype=torch.long)
@@ -136,6 +135,7 @@ def test_graph_sampling_loop_parity(sampler_kind):
         e_u, e_c = rel(eps[:B], tr["eps_u"]), rel(eps[B:], tr["eps_c"])
         print(f"    step {k} (t={tr['t']}): teacher-forced eps_u {e_u:.2e} eps_c {e_c:.2e}")
         assert e_u < BF16_TOL and e_c < BF16_TOL
+    assert max(errs) < BF16_TOL
     # replaying the cached graph with the same inputs is deterministic
     s.noise_feed = draws[1:]
     imgs2, _ = s.sample(net, (B, 4, 128, 64), return_tensor=True, condition=cond.cuda(), sampler=sampler_kind, initial_noise=draws[0].cuda())

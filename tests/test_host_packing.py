@@ -11,7 +11,7 @@ from oracle import cases
 
 def contract(pc, srcs, kind, mean_rstd=None, act=0, residual=None):
     """ds_conv_gemm's contract restated: srcs = list of NCHW fp32 tensors (channel-concatenated)."""
-    x = torch.cat(srcs, dim=1).bfloat16().float()
+    x = torch.cat(srcs, dim=1).to(ops.ACT).float()
     N, C, Hin, Win = x.shape
     w = pc.weight.float()                                    # [G, Cout_pad, ntaps*C]
     G, ntaps = len(pc.taps), len(pc.taps[0])
@@ -59,7 +59,7 @@ def test_conv3x3_with_folded_groupnorm():
     w, b = cases.randn((48, 96, 3, 3), 3) * 0.05, cases.randn((48,), 4)
     gamma, beta = 1 + 0.2 * cases.randn((96,), 5), 0.3 * cases.randn((96,), 6)
     pc = ops.pack_conv_s1(w, b, gamma, beta)
-    xb = torch.cat([x0, x1], 1).bfloat16().float()
+    xb = torch.cat([x0, x1], 1).to(ops.ACT).float()
     out = torch.empty(2, 48, 8, 16)
     ref = torch.empty_like(out)
     for n in range(2):       # GroupNorm(1, C): per-sample scalars
@@ -76,7 +76,7 @@ def test_plain_conv(k):
     w, b = cases.randn((20, 64, k, k), 8) * 0.1, cases.randn((20,), 9)
     pc = ops.pack_conv_s1(w, b)
     assert pc.cout_pad == 32 and pc.e1 is None
-    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, padding=k // 2)
+    ref = F.conv2d(x.to(ops.ACT).float(), w.to(ops.ACT).float(), b, padding=k // 2)
     assert rel(contract(pc, [x], "s1"), ref) < 1e-5
 
 
@@ -84,7 +84,7 @@ def test_downsample_as_parity_views():
     x = cases.randn((2, 32, 8, 12), 10)
     w, b = cases.randn((32, 32, 4, 4), 11) * 0.1, cases.randn((32,), 12)
     pc = ops.pack_conv_down(w, b)
-    ref = F.conv2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=2, padding=1)
+    ref = F.conv2d(x.to(ops.ACT).float(), w.to(ops.ACT).float(), b, stride=2, padding=1)
     assert rel(contract(pc, [x], "down"), ref) < 1e-5
 
 
@@ -92,7 +92,7 @@ def test_transposed_conv_as_four_phases():
     x = cases.randn((2, 32, 5, 6), 13)
     w, b = cases.randn((32, 48, 4, 4), 14) * 0.1, cases.randn((48,), 15)
     pc = ops.pack_conv_up(w, b)
-    ref = F.conv_transpose2d(x.bfloat16().float(), w.bfloat16().float(), b, stride=2, padding=1)
+    ref = F.conv_transpose2d(x.to(ops.ACT).float(), w.to(ops.ACT).float(), b, stride=2, padding=1)
     assert rel(contract(pc, [x], "up"), ref) < 1e-5
 
 

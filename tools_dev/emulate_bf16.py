@@ -6,7 +6,13 @@ import torch, torch.nn.functional as F
 from oracle import cases, ds_oracle as O
 
 RES_FP32 = os.environ.get("RES_FP32", "0") == "1"
-def r(x): return x.bfloat16().float()
+RA = os.environ.get("RA", "bf16"); RW = os.environ.get("RW", "bf16")
+def _rnd(x, kind):
+    if kind == "bf16": return x.bfloat16().float()
+    if kind == "fp16": return x.half().float()
+    return x
+def r(x): return _rnd(x, RA)
+def rw(x): return _rnd(x, RW)
 def rs(x): return x if RES_FP32 else r(x)      # residual stream storage
 
 def gn_fold_conv(h_b, sd, pn, pc, pad):
@@ -15,7 +21,7 @@ def gn_fold_conv(h_b, sd, pn, pc, pad):
     g, be = sd[pn + "weight"], sd[pn + "bias"]
     mu = h_b.mean(dim=(1, 2, 3), keepdim=True); var = h_b.var(dim=(1, 2, 3), keepdim=True, unbiased=False)
     rstd = (var + 1e-5).rsqrt()
-    wg = r(w * g.view(1, -1, 1, 1))
+    wg = rw(w * g.view(1, -1, 1, 1))
     acc = F.conv2d(h_b, wg, None, padding=pad)
     ones = torch.ones_like(h_b[:1, :1])
     e1 = F.conv2d(ones.expand(1, w.shape[1], -1, -1), wg, None, padding=pad)
@@ -31,7 +37,7 @@ def block(sd, p, x, temb):
     y = r(F.gelu(gn_fold_conv(h, sd, p + "net.0.", p + "net.1.", 1)))
     o = gn_fold_conv(y, sd, p + "net.3.", p + "net.4.", 1)
     if (p + "res_conv.weight") in sd:
-        res = F.conv2d(xb, r(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"])
+        res = F.conv2d(xb, rw(sd[p + "res_conv.weight"]), sd[p + "res_conv.bias"])
     else:
         res = x
     return rs(o + res)
@@ -47,7 +53,7 @@ def attn(sd, p, x, cemb, heads=4, dh=32):
     k = r(k); v = r(v)
     ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(dim=-1), v)
     wo = sd[p + "fn.fn.to_out.0.weight"].view(C, heads, dh)
-    M = r(torch.einsum("che,bhde->bchd", wo, ctx).reshape(B, C, heads * dh))
+    M = rw(torch.einsum("che,bhde->bchd", wo, ctx).reshape(B, C, heads * dh))
     y = torch.einsum("bck,bkn->bcn", M, q.reshape(B, heads * dh, n)).reshape(B, C, H, W) + sd[p + "fn.fn.to_out.0.bias"].view(1, -1, 1, 1)
     y = r(y)
     return rs(F.group_norm(y, 1, sd[p + "fn.fn.to_out.1.weight"], sd[p + "fn.fn.to_out.1.bias"], 1e-5) + x)
@@ -59,7 +65,7 @@ def unet(sd, x, t, cond):
     hs = []
     x = rs(F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)); hs.append(x)
     temb = O.time_embedding(sd, t, sd["init_conv.weight"].shape[0])
-    conv = lambda x, p, **kw: rs(F.conv2d(r(x), r(sd[p + "weight"]), sd[p + "bias"], **kw))
+    conv = lambda x, p, **kw: rs(F.conv2d(r(x), rw(sd[p + "weight"]), sd[p + "bias"], **kw))
     for i in range(n_stage):
         p = f"downs.{i}."
         x = block(sd, p + "0.", x, temb); x = attn(sd, p + "1.", x, cemb); hs.append(x)
@@ -73,11 +79,11 @@ def unet(sd, x, t, cond):
     for i in range(n_stage):
         p = f"ups.{i}."
         x = block(sd, p + "0.", torch.cat([hs.pop(), x], 1), temb); x = attn(sd, p + "1.", x, cemb)
-        x = rs(F.conv_transpose2d(r(x), r(sd[p + "2.weight"]), sd[p + "2.bias"], stride=2, padding=1))
+        x = rs(F.conv_transpose2d(r(x), rw(sd[p + "2.weight"]), sd[p + "2.bias"], stride=2, padding=1))
         x = block(sd, p + "3.", torch.cat([hs.pop(), x], 1), temb); x = attn(sd, p + "4.", x, cemb)
         x = block(sd, p + "5.", torch.cat([hs.pop(), x], 1), temb); x = attn(sd, p + "6.", x, cemb)
     x = block(sd, "final_conv.0.", torch.cat([hs.pop(), x], 1), None)
-    return F.conv2d(r(x), r(sd["final_conv.1.weight"]), sd["final_conv.1.bias"], padding=1)
+    return F.conv2d(r(x), rw(sd["final_conv.1.weight"]), sd["final_conv.1.bias"], padding=1)
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
@@ -86,4 +92,18 @@ if __name__ == "__main__":
     with torch.no_grad():
         ref = O.unet_forward(sd, x, t, cond)
         em = unet(sd, x, t, cond)
-    print(name, "RES_FP32", RES_FP32, "rel-L2", float((em - ref).norm() / ref.norm()))
+    print(name, "RA", RA, "RW", RW, "eps rel-L2", float((em - ref).norm() / ref.norm()))
+    # CFG-combined one-step latent error at t=999 (first sampling step), two conditions
+    B = 1
+    from diffusynth_b200 import weights as W
+    import numpy as np
+    cond, uncond = W.synthetic_conditions(B, 512)
+    x0 = cases.randn((B, 4, 128, 64), 3)
+    xin = torch.cat([x0, x0]); tt = torch.full((2,), 999, dtype=torch.long); cc = torch.cat([uncond[None], cond])
+    with torch.no_grad():
+        er = O.unet_forward(sd, xin, tt, cc); ee = unet(sd, xin, tt, cc)
+    sch = O.Schedule(1000); sch.respace(list(np.linspace(0, 999, 4, dtype=np.int32)))
+    co = O.ddim_coefficients(sch, 3, 0.0)
+    a = O.ddim_update(x0, er[:1], er[1:], 6, co, torch.zeros_like(x0)); b = O.ddim_update(x0, ee[:1], ee[1:], 6, co, torch.zeros_like(x0))
+    print("   eps_u", float((ee[:1]-er[:1]).norm()/er[:1].norm()), "eps_c", float((ee[1:]-er[1:]).norm()/er[1:].norm()), "latent(CFG=6)", float((a-b).norm()/a.norm()),
+          "  |eps_c-eps_u|/|eps|", float((er[1:]-er[:1]).norm()/er[1:].norm()))

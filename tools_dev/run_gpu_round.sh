@@ -1,0 +1,24 @@
+# usage: bash tools_dev/run_gpu_round.sh [tests] [bench] [ncu]
+mkdir -p gpurun_out; rm -f gpurun_out/rc.txt
+for what in "$@"; do
+case $what in
+tests)
+  timeout 900 python -m pytest tests/test_gpu_conv_gemm.py tests/test_gpu_kernels.py -q -m gpu --tb=short > gpurun_out/t_kern.log 2>&1; echo "kern rc=$?" >> gpurun_out/rc.txt
+  timeout 1500 python -m pytest tests/test_gpu_model.py -q -m gpu --tb=short -s > gpurun_out/t_model.log 2>&1; echo "model rc=$?" >> gpurun_out/rc.txt
+  tail -4 gpurun_out/t_kern.log; tail -12 gpurun_out/t_model.log ;;
+bench)
+  timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
+  tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+ncu)
+  timeout 600 python bench.py --steps 1 --warmup 1 --sample-steps 2 > gpurun_out/plain.log 2>&1 && \
+  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 1 --warmup 1 --sample-steps 2 > gpurun_out/ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/rc.txt
+  tail -3 gpurun_out/plain.log; tail -3 gpurun_out/ncu.log ;;
+ncufull)
+  timeout 600 python tools_dev/unet_once.py > gpurun_out/plain_full.log 2>&1 && \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 30 -c 4 -o gpurun_out/prof_conv -f \
+      python tools_dev/unet_once.py > gpurun_out/ncu_full.log 2>&1; echo "ncufull rc=$?" >> gpurun_out/rc.txt
+  tail -3 gpurun_out/ncu_full.log ;;
+esac
+done
+cat gpurun_out/rc.txt

@@ -289,7 +289,7 @@ def run_b200(args):
         launches = loop.launches + len(plan.cond_ops) + 1 + len(dec_plan.ops) + 2
         cpu = cpu_arm(args.sample_steps, unet_evals=2) if world == 1 else None
         line = dict(metric=METRIC, value=value, unit="timbres/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
-                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+                    ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp16", data="synthetic",
                     config=workload_config(args, world), clocks=clocks,
                     e2e=dict(value=e2e_value, unit="timbres/s", h2d_bytes_per_step=int(cond_host.numel() * 4),
                              d2h_bytes_per_step=int(wave_host.numel() * 4), ms_per_step=ms_e2e / args.steps),

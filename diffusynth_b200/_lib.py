@@ -34,7 +34,7 @@ class ConvGemmArgs(C.Structure):
         ("Cout_pad", C.c_int32), ("Cout", C.c_int32), ("BN", C.c_int32), ("BK", C.c_int32),
         ("ntaps", C.c_int32), ("groups", C.c_int32), ("per_sample_weights", C.c_int32),
         ("taps", (ConvTap * DS_MAX_TAPS) * DS_MAX_GROUPS),
-        ("d_stats_in", C.c_void_p), ("stats_in_slots", C.c_int32), ("stats_inv_count", C.c_float), ("eps", C.c_float),
+        ("d_stats_in", C.c_void_p), ("stats_in_slots", C.c_int32), ("stats_out_inv_count", C.c_float), ("eps", C.c_float),
         ("d_e1", C.c_void_p), ("d_e2", C.c_void_p), ("ncls", C.c_int32),
         ("d_sbias", C.c_void_p), ("sbias_stride", C.c_int32), ("act", C.c_int32),
         ("d_residual", C.c_void_p), ("res_sn", C.c_int64), ("res_sh", C.c_int64), ("res_sw", C.c_int64),
@@ -56,7 +56,7 @@ _SIGNATURES = {
     "ds_ddim_step": (_I, [_P, _P, _P, _P, _P, _P, _L, _P]),
     "ds_q_sample": (_I, [_P, _P, _P, _P, _L, _P]),
     "ds_mask_blend": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
-    "ds_dwconv7": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _I, _I, _I, _P]),
+    "ds_dwconv7": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _F, _I, _I, _I, _P]),
     "ds_dwconv7_stats_slots": (_I, [_I, _I, _I]),
     "ds_stem_conv7": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ds_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _P]),
@@ -65,7 +65,7 @@ _SIGNATURES = {
     "ds_attn_part_floats": (_L, [_I, _I, _L]),
     "ds_attn_ctx_partial": (_I, [_P, _P, _P, _I, _I, _L, _I, _F, _P]),
     "ds_attn_finalize": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _P]),
-    "ds_gn_apply_residual": (_I, [_P, _P, _P, _P, _I, _F, _F, _P, _P, _I, _I, _L, _P]),
+    "ds_gn_apply_residual": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _L, _P]),
     "ds_vq_quantize": (_I, [_P, _P, _I, _P, _P, _I, _L, _P]),
     "ds_group_stats": (_I, [_P, _P, _I, _I, _I, _I, _L, _I, _P]),
     "ds_gn_act": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _L, _F, _I, _P]),

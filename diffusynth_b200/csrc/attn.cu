@@ -22,7 +22,7 @@ static constexpr int AT_PART = AT_D * AT_D + 2 * AT_D;   // S[32][32], Z[32], m[
 __global__ void __launch_bounds__(256)
 attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
                         act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
-  __shared__ float s_k[AT_PIX][AT_D + 1];
+  __shared__ __align__(16) float s_k[AT_PIX][AT_D + 4];
   __shared__ __align__(16) float s_v[AT_PIX][AT_D + 4];
   __shared__ float s_red[8][AT_D];
   __shared__ float s_m[AT_D];
@@ -108,15 +108,38 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     s_red[warp][lane] = z;
   }
   __syncthreads();
-  // ---- S[d][e..e+3] = sum_p p[p][d] * v[p][e]
-  const int d = tid >> 3, e4 = (tid & 7) * 4;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-  for (int p = 0; p < AT_PIX; ++p) {
-    const float kk = s_k[p][d];
-    const float4 vv = *reinterpret_cast<const float4*>(&s_v[p][e4]);
-    a0 = fmaf(kk, vv.x, a0); a1 = fmaf(kk, vv.y, a1); a2 = fmaf(kk, vv.z, a2); a3 = fmaf(kk, vv.w, a3);
+  // ---- S[d][e] = sum_p p[p][d] * v[p][e]: 4x4 register tile per thread (packed FFMA2), 4 pixel groups of 32
+  const int pg = tid >> 6, d0 = ((tid >> 3) & 7) * 4, e0 = (tid & 7) * 4;
+  float2 acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+#pragma unroll 4
+  for (int p = pg * 32; p < pg * 32 + 32; ++p) {
+    const float4 kk = *reinterpret_cast<const float4*>(&s_k[p][d0]);
+    const float4 vv = *reinterpret_cast<const float4*>(&s_v[p][e0]);
+    const float2 v01 = make_float2(vv.x, vv.y), v23 = make_float2(vv.z, vv.w);
+    const float kd[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 kb = make_float2(kd[i], kd[i]);
+      ffma2(acc[i][0], kb, v01);
+      ffma2(acc[i][1], kb, v23);
+    }
   }
+  __syncthreads();                       // everyone is done reading s_k / s_v: reuse s_v as the cross-group buffer
+  float* s_part = &s_v[0][0];            // [4][32][32] floats = 16 KB <= sizeof(s_v) (128*36*4 = 18 KB)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(&s_part[(pg * AT_D + d0 + i) * AT_D + e0]) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+  __syncthreads();
+  const int d = tid >> 3, e4 = (tid & 7) * 4;
+  float4 s4 = *reinterpret_cast<const float4*>(&s_part[d * AT_D + e4]);
+#pragma unroll
+  for (int g = 1; g < 4; ++g) {
+    const float4 t4 = *reinterpret_cast<const float4*>(&s_part[(g * AT_D + d) * AT_D + e4]);
+    s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
+  }
+  const float a0 = s4.x, a1 = s4.y, a2 = s4.z, a3 = s4.w;
   float* po = part + (((size_t)n * gridDim.y + head) * chunks + chunk) * AT_PART;
   *reinterpret_cast<float4*>(po + d * AT_D + e4) = make_float4(a0, a1, a2, a3);
   if (tid < AT_D) {

@@ -71,6 +71,17 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi) {
 __device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
 __device__ __forceinline__ act_t f2act(float v) { return __float2half_rn(sat16(v)); }
 #endif
+// Packed fp32x2 FMA (sm_100 FFMA2): acc = a * b + acc on both halves with one instruction.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+__device__ __forceinline__ float2 cvt16x2(uint32_t v) { return make_float2(lo16(v), hi16(v)); }
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -89,8 +100,8 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// Reduce the per-tile (sum, sumsq) partials of one sample to (mean, rstd).  Called by a full warp;
-// every lane returns the result.  Deterministic (fixed order), accumulates in double.
+// Reduce (sum, sumsq) partials to (mean, rstd).  Called by a full warp; every lane returns the result.
+// Deterministic (fixed order), accumulates in double.  (VQGAN GroupNorm(16) two-pass path.)
 __device__ __forceinline__ float2 reduce_stats_warp(const float2* __restrict__ part, int slots, float inv_count,
                                                     float eps, int lane) {
   double s = 0.0, q = 0.0;
@@ -105,6 +116,58 @@ __device__ __forceinline__ float2 reduce_stats_warp(const float2* __restrict__ p
   double var = q * (double)inv_count - mean * mean;
   if (var < 0.0) var = 0.0;
   return make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// ---- GroupNorm(1,C) statistics buffers ---------------------------------------------------------------------
+// One buffer per normalised tensor: per sample `2 + slots` float2 entries
+//   [0]            (mean, rstd)       -- final, written by the LAST producer tile of that sample
+//   [1]            arrival counter (uint32 in .x; zero between launches: the last arriver resets it)
+//   [2, 2+slots)   (sum, sumsq) partials, one per producer tile-warp
+// The last arriver reduces the partials in slot order (double accumulation), so the result is deterministic
+// whatever the arrival order.  Consumers read entry [0] only.
+__device__ __forceinline__ const float2* stats_sample(const float2* base, int slots, int n) { return base + (size_t)n * (slots + 2); }
+__device__ __forceinline__ float2* stats_sample(float2* base, int slots, int n) { return base + (size_t)n * (slots + 2); }
+
+// Called by a full, converged warp; lane 0 carries this warp's (s, q).
+__device__ __forceinline__ void stats_publish(float2* sb, int slots, int slot, float s, float q, float inv_count, float eps, int lane) {
+  unsigned old = 0;
+  if (lane == 0) {
+    sb[2 + slot] = make_float2(s, q);
+    __threadfence();
+    old = atomicAdd(reinterpret_cast<unsigned*>(&sb[1]), 1u);
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old == (unsigned)(slots - 1)) {
+    __threadfence();
+    double ds = 0.0, dq = 0.0;
+    for (int i = lane; i < slots; i += 32) {
+      const float2 v = __ldcg(sb + 2 + i);
+      ds += (double)v.x;
+      dq += (double)v.y;
+    }
+    ds = warp_sum(ds);
+    dq = warp_sum(dq);
+    if (lane == 0) {
+      const double mean = ds * (double)inv_count;
+      double var = dq * (double)inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sb[0] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      *reinterpret_cast<unsigned*>(&sb[1]) = 0u;
+    }
+  }
+}
+
+// Branch-free GELU(erf): erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), straight-line code so the
+// 16 independent elements of an epilogue chunk interleave.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);      // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
 }  // namespace ds

@@ -30,7 +30,7 @@ struct __align__(16) ConvGemmDev {
   int num_kb, stages, num_tiles;
   unsigned stage_a_bytes, stage_b_bytes;
   int Cout, Cout_pad;
-  const float2* stats_in; int stats_in_slots; float inv_count, eps;
+  const float2* stats_in; int stats_in_slots; float out_inv_count, eps;
   const float* e1; const float* e2; int ncls;
   const float* sbias; int sbias_stride; int act;
   const act_t* residual; long long res_sn, res_sh, res_sw;
@@ -135,7 +135,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -292,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       float mean = 0.f, rstd = 1.f;
       if (P.stats_in != nullptr) {
         const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
-        float2 mr = reduce_stats_warp(P.stats_in + (size_t)nsrc * P.stats_in_slots, P.stats_in_slots, P.inv_count, P.eps, lane);
+        const float2 mr = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc));
         mean = mr.x;
         rstd = mr.y;
       }
@@ -309,54 +309,100 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
-      for (int ch = chunk_lo; ch < chunk_hi; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x16(t_row + (uint32_t)(ch * 16), r);
-        tmem_ld_wait();
+      const bool has_res = P.residual != nullptr && valid;
+      // one 16-column chunk: folded-GroupNorm scalars, bias, activation, residual, statistics, store
+      auto finish_chunk = [&](int ch, const uint32_t (&r)[16], const uint4& ra, const uint4& rb) {
         const int o0 = t.nt * P.BN + ch * 16;
         float v[16];
+        const float4* e2v = reinterpret_cast<const float4*>(e2 + o0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int o = o0 + j;
-          float x = __uint_as_float(r[j]) * rstd + __ldg(e2 + o);
-          if (e1) x = fmaf(nmr, __ldg(e1 + o), x);
-          if (sb) x += __ldg(sb + o);
-          if (P.act == 1) x = gelu_erf(x);
-          v[j] = x;
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 b4 = __ldg(e2v + q4);
+          v[4 * q4 + 0] = fmaf(__uint_as_float(r[4 * q4 + 0]), rstd, b4.x);
+          v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), rstd, b4.y);
+          v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, b4.z);
+          v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, b4.w);
         }
-        if (valid) {
-          if (P.residual != nullptr && o0 < P.Cout) {
-            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0);
-            uint4 a = __ldg(rp), b = __ldg(rp + 1);
-            const uint32_t rr[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (e1) {
+          const float4* e1v = reinterpret_cast<const float4*>(e1 + o0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[2 * j] += lo16(rr[j]);
-              v[2 * j + 1] += hi16(rr[j]);
-            }
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 a4 = __ldg(e1v + q4);
+            v[4 * q4 + 0] = fmaf(nmr, a4.x, v[4 * q4 + 0]);
+            v[4 * q4 + 1] = fmaf(nmr, a4.y, v[4 * q4 + 1]);
+            v[4 * q4 + 2] = fmaf(nmr, a4.z, v[4 * q4 + 2]);
+            v[4 * q4 + 3] = fmaf(nmr, a4.w, v[4 * q4 + 3]);
           }
-          if (P.stats_out != nullptr) {
+        }
+        if (sb) {
+          const float4* sbv = reinterpret_cast<const float4*>(sb + o0);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 a4 = __ldg(sbv + q4);
+            v[4 * q4 + 0] += a4.x; v[4 * q4 + 1] += a4.y; v[4 * q4 + 2] += a4.z; v[4 * q4 + 3] += a4.w;
+          }
+        }
+        if (P.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(v[j]);
+        }
+        if (!valid) return;
+        if (has_res && o0 < P.Cout) {
+          const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[2 * j] += lo16(rr[j]);
+            v[2 * j + 1] += hi16(rr[j]);
+          }
+        }
+        if (P.stats_out != nullptr) {
+          if (o0 + 16 <= P.Cout) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+          } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
               if (o0 + j < P.Cout) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
           }
-          if (P.out != nullptr && o0 < P.Cout) {
-            uint4 a, b;
-            a.x = pack16(v[0], v[1]);   a.y = pack16(v[2], v[3]);
-            a.z = pack16(v[4], v[5]);   a.w = pack16(v[6], v[7]);
-            b.x = pack16(v[8], v[9]);   b.y = pack16(v[10], v[11]);
-            b.z = pack16(v[12], v[13]); b.w = pack16(v[14], v[15]);
-            uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + o0);
-            op[0] = a;
-            op[1] = b;
-          }
-          if (P.out_f32 != nullptr) {
+        }
+        if (P.out != nullptr && o0 < P.Cout) {
+          uint4 a, b;
+          a.x = pack16(v[0], v[1]);   a.y = pack16(v[2], v[3]);
+          a.z = pack16(v[4], v[5]);   a.w = pack16(v[6], v[7]);
+          b.x = pack16(v[8], v[9]);   b.y = pack16(v[10], v[11]);
+          b.z = pack16(v[12], v[13]); b.w = pack16(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + o0);
+          op[0] = a;
+          op[1] = b;
+        }
+        if (P.out_f32 != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (o0 + j < P.Cout)
-                P.out_f32[(((size_t)t.n * P.Cout + (o0 + j)) * P.H + h) * P.W + w] = v[j];
+          for (int j = 0; j < 16; ++j)
+            if (o0 + j < P.Cout)
+              P.out_f32[(((size_t)t.n * P.Cout + (o0 + j)) * P.H + h) * P.W + w] = v[j];
+        }
+      };
+      // two chunks in flight: both TMEM loads and both residual fetches are issued before the wait
+      for (int ch = chunk_lo; ch < chunk_hi; ch += 2) {
+        const bool two = ch + 1 < chunk_hi;
+        uint32_t r0[16], r1[16];
+        tmem_ld_32x32b_x16(t_row + (uint32_t)(ch * 16), r0);
+        if (two) tmem_ld_32x32b_x16(t_row + (uint32_t)((ch + 1) * 16), r1);
+        uint4 ra0 = make_uint4(0, 0, 0, 0), rb0 = ra0, ra1 = ra0, rb1 = ra0;
+        if (has_res) {
+          const int o0 = t.nt * P.BN + ch * 16;
+          if (o0 < P.Cout) {
+            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0);
+            ra0 = __ldg(rp); rb0 = __ldg(rp + 1);
+          }
+          if (two && o0 + 16 < P.Cout) {
+            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0 + 16);
+            ra1 = __ldg(rp); rb1 = __ldg(rp + 1);
           }
         }
+        tmem_ld_wait();
+        finish_chunk(ch, r0, ra0, rb0);
+        if (two) finish_chunk(ch + 1, r1, ra1, rb1);
       }
       // release the accumulator stage (one arrive per epilogue warp)
       tcgen05_fence_before();
@@ -365,7 +411,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (P.stats_out != nullptr) {
         psum = warp_sum(psum);
         psq = warp_sum(psq);
-        if (lane == 0) P.stats_out[(size_t)t.n * P.stats_slots + (size_t)t.slot * kEpiWarps + ew] = make_float2(psum, psq);
+        stats_publish(stats_sample(P.stats_out, P.stats_slots, t.n), P.stats_slots, t.slot * kEpiWarps + ew, psum, psq, P.out_inv_count, P.eps, lane);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -439,7 +485,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.stage_b_bytes = a->BN * a->BK * 2;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.stats_in = reinterpret_cast<const float2*>(a->d_stats_in);
-  P.stats_in_slots = a->stats_in_slots; P.inv_count = a->stats_inv_count; P.eps = a->eps;
+  P.stats_in_slots = a->stats_in_slots; P.out_inv_count = a->stats_out_inv_count; P.eps = a->eps;
   P.e1 = a->d_e1; P.e2 = a->d_e2; P.ncls = a->ncls;
   P.sbias = a->d_sbias; P.sbias_stride = a->sbias_stride; P.act = a->act;
   P.residual = reinterpret_cast<const act_t*>(a->d_residual);
@@ -520,7 +566,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------
 __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, const act_t* src1,
                                      const act_t* weight, int Hv, int Wv, long long view_sn, long long view_sh,
-                                     long long view_sw, const long long* view_off_dev, float2* mean_rstd) {
+                                     long long view_sw, const long long* view_off_dev) {
   const long long total = (long long)P.N * P.groups * P.H * P.W * P.Cout;
   const long long K = (long long)P.ntaps * (P.C0 + P.C1);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -544,22 +590,17 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, con
       }
     }
     float mean = 0.f, rstd = 1.f;
-    if (mean_rstd) { mean = mean_rstd[nsrc].x; rstd = mean_rstd[nsrc].y; }
+    if (P.stats_in) { const float2 mr = *stats_sample(P.stats_in, P.stats_in_slots, nsrc); mean = mr.x; rstd = mr.y; }
     int cls = 0;
     if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
     float v = acc * rstd + P.e2[(size_t)cls * P.Cout_pad + o];
     if (P.e1) v = fmaf(-mean * rstd, P.e1[(size_t)cls * P.Cout_pad + o], v);
     if (P.sbias) v += P.sbias[(size_t)n * P.sbias_stride + o];
-    if (P.act == 1) v = gelu_erf(v);
+    if (P.act == 1) v = gelu_erf(v);   // exact erf here: cross-checks the fast form used by the tcgen05 epilogue
     if (P.residual) v += act2f(P.residual[n * P.res_sn + h * P.res_sh + w * P.res_sw + o]);
     if (P.out) P.out[P.out_goff[g] + n * P.out_sn + h * P.out_sh + w * P.out_sw + o] = f2act(v);
     if (P.out_f32) P.out_f32[(((size_t)n * P.Cout + o) * P.H + h) * P.W + w] = v;
   }
-}
-
-__global__ void stats_finalize_kernel(const float2* part, int slots, float inv_count, float eps, float2* mean_rstd) {
-  float2 mr = reduce_stats_warp(part + (size_t)blockIdx.x * slots, slots, inv_count, eps, threadIdx.x);
-  if (threadIdx.x == 0) mean_rstd[blockIdx.x] = mr;
 }
 
 static int conv_gemm_reference_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
@@ -568,21 +609,14 @@ static int conv_gemm_reference_launch(const ds_conv_gemm_args* a, cudaStream_t s
   ConvGemmDev P;
   fill_dev(a, P);
   long long* voff = nullptr;
-  float2* mr = nullptr;
   DS_CHECK_CUDA(cudaMallocAsync(&voff, 4 * sizeof(long long), stream));
   DS_CHECK_CUDA(cudaMemcpyAsync(voff, a->view_off, 4 * sizeof(long long), cudaMemcpyHostToDevice, stream));
-  const int nsrc = a->src_batch_mod > 0 ? a->src_batch_mod : a->N;
-  if (a->d_stats_in) {
-    DS_CHECK_CUDA(cudaMallocAsync(&mr, nsrc * sizeof(float2), stream));
-    stats_finalize_kernel<<<nsrc, 32, 0, stream>>>(P.stats_in, P.stats_in_slots, P.inv_count, P.eps, mr);
-  }
   conv_gemm_ref_kernel<<<num_sms() * 8, 256, 0, stream>>>(P, reinterpret_cast<const act_t*>(a->d_src0),
                                                           reinterpret_cast<const act_t*>(a->d_src1),
                                                           reinterpret_cast<const act_t*>(a->d_weight), a->Hv, a->Wv,
-                                                          a->view_sn, a->view_sh, a->view_sw, voff, mr);
+                                                          a->view_sn, a->view_sh, a->view_sw, voff);
   DS_CHECK_CUDA(cudaGetLastError());
   DS_CHECK_CUDA(cudaFreeAsync(voff, stream));
-  if (mr) DS_CHECK_CUDA(cudaFreeAsync(mr, stream));
   return DS_OK;
 }
 

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256)
 dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, int C0, int C1, int src_batch_mod,
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
-               act_t* __restrict__ out, float2* __restrict__ stats, int H, int W, int tiles_w, int tiles) {
+               act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w, int tiles) {
   __shared__ __align__(16) uint32_t s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // bf16 pairs
   __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
   __shared__ float s_red[16];
@@ -52,9 +52,9 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
 
   const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
   const int row = pt & 7, col0 = (pt >> 3) * 8;
-  float acc0[8], acc1[8];
+  float2 acc[8];       // (channel 2cp, channel 2cp+1) of 8 consecutive output columns: packed FFMA2 lanes
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int ky = 0; ky < 7; ++ky) {
     float2 wv[7];
@@ -63,15 +63,11 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
     const uint32_t* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
 #pragma unroll
     for (int j = 0; j < 14; ++j) {
-      const uint32_t v = rowp[j * (DW_CB / 2)];
-      const float a = lo16(v), b = hi16(v);
+      const float2 in = cvt16x2(rowp[j * (DW_CB / 2)]);
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
         const int ow = j - kx;
-        if (ow >= 0 && ow < 8) {
-          acc0[ow] = fmaf(a, wv[kx].x, acc0[ow]);
-          acc1[ow] = fmaf(b, wv[kx].y, acc1[ow]);
-        }
+        if (ow >= 0 && ow < 8) ffma2(acc[ow], in, wv[kx]);
       }
     }
   }
@@ -84,7 +80,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   for (int j = 0; j < 8; ++j) {
     const int x = w0 + col0 + j;
     if (y < H && x < W) {
-      const float v0 = acc0[j] + b0, v1 = acc1[j] + b1;
+      const float v0 = acc[j].x + b0, v1 = acc[j].y + b1;
       s += v0 + v1;
       q = fmaf(v0, v0, fmaf(v1, v1, q));
       *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
@@ -96,10 +92,12 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) { s_red[warp] = s; s_red[8 + warp] = q; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
       float ts = 0.f, tq = 0.f;
-      for (int i = 0; i < 8; ++i) { ts += s_red[i]; tq += s_red[8 + i]; }
-      stats[(size_t)n * (tiles * gridDim.y) + (size_t)cblk * tiles + tile] = make_float2(ts, tq);
+      if (threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) { ts += s_red[i]; tq += s_red[8 + i]; }
+      const int slots = tiles * gridDim.y;
+      stats_publish(stats_sample(stats, slots, n), slots, cblk * tiles + tile, ts, tq, stats_inv_count, eps, threadIdx.x);
     }
   }
 }
@@ -137,23 +135,25 @@ stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __r
       s_in[(ci * (ST_TH + 6) + r) * IW + cc] = v;
     }
     __syncthreads();
-    float acc[CO_PER_THREAD];
+    float2 acc2[CO_PER_THREAD / 2];
 #pragma unroll
-    for (int j = 0; j < CO_PER_THREAD; ++j) acc[j] = __ldg(bias + co0 + j);
+    for (int j = 0; j < CO_PER_THREAD / 2; ++j) acc2[j] = make_float2(__ldg(bias + co0 + 2 * j), __ldg(bias + co0 + 2 * j + 1));
     for (int ky = 0; ky < 7; ++ky)
       for (int kx = 0; kx < 7; ++kx)
         for (int ci = 0; ci < Cin; ++ci) {
           const float v = s_in[(ci * (ST_TH + 6) + pr + ky) * IW + pc + kx];
+          const float2 vv = make_float2(v, v);
           const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 7 + kx) * Cin + ci) * Cout + co0);
 #pragma unroll
           for (int j = 0; j < CO_PER_THREAD / 4; ++j) {
             const float4 w4 = wr[j];
-            acc[4 * j] = fmaf(v, w4.x, acc[4 * j]);
-            acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+            ffma2(acc2[2 * j], vv, make_float2(w4.x, w4.y));
+            ffma2(acc2[2 * j + 1], vv, make_float2(w4.z, w4.w));
           }
         }
+    float acc[CO_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < CO_PER_THREAD / 2; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
     const int y = h0 + pr, xx = w0 + pc;
     if (y < H && xx < W) {
       uint4* op = reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + xx) * Cout + co0);
@@ -173,9 +173,9 @@ extern "C" {
 
 /* Depthwise 7x7 + time bias + GroupNorm partials.  d_weight fp32 [49][C0+C1] (tap-major);
    d_tbias fp32 [N][tbias_stride] (or one row when tbias_stride == 0) holding ds_conv.bias + mlp(time_emb).
-   d_stats (nullable) float2 [N][ds_dwconv7_stats_slots(...)]. */
+   d_stats (nullable): statistics buffer float2 [N][2 + ds_dwconv7_stats_slots(...)], zero-initialised once (see ds_conv_gemm). */
 int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight, const float* d_tbias,
-               long long tbias_stride, void* d_out, void* d_stats, int N, int H, int W, void* stream) {
+               long long tbias_stride, void* d_out, void* d_stats, float eps, int N, int H, int W, void* stream) {
   DS_REQUIRE(d_src0 && d_weight && d_tbias && d_out && N > 0 && H > 0 && W > 0, "ds_dwconv7: bad arguments");
   DS_REQUIRE(C0 > 0 && C0 % DW_CB == 0 && C1 >= 0 && C1 % DW_CB == 0 && (C1 == 0 || d_src1), "ds_dwconv7: C0=%d C1=%d must be multiples of 32", C0, C1);
   const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
@@ -183,7 +183,7 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
   DS_REQUIRE(N <= 65535 && (C0 + C1) / DW_CB <= 65535, "ds_dwconv7: grid too large");
   dwconv7_kernel<<<dim3(tiles, (C0 + C1) / DW_CB, N), 256, 0, (cudaStream_t)stream>>>(
       (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-      (act_t*)d_out, (float2*)d_stats, H, W, tiles_w, tiles);
+      (act_t*)d_out, (float2*)d_stats, 1.0f / ((float)H * (float)W * (float)(C0 + C1)), eps, H, W, tiles_w, tiles);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -86,17 +86,12 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const act_t* __restrict__ in, float
 // grid = (chunks, N); y/x/out bf16 NHWC with C % 8 == 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x, uint4* __restrict__ out,
-                                         const float2* __restrict__ stats, int slots, float inv_count, float eps,
+                                         const float2* __restrict__ stats, int slots,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
                                          long long vec_per_sample) {
-  __shared__ float2 s_mr;
   const int n = blockIdx.y;
-  if (threadIdx.x < 32) {
-    float2 mr = reduce_stats_warp(stats + (size_t)n * slots, slots, inv_count, eps, threadIdx.x);
-    if (threadIdx.x == 0) s_mr = mr;
-  }
-  __syncthreads();
-  const float mean = s_mr.x, rstd = s_mr.y;
+  const float2 mr = __ldg(stats_sample(stats, slots, n));
+  const float mean = mr.x, rstd = mr.y;
   const uint4* yb = y + (size_t)n * vec_per_sample;
   const uint4* xb = x ? x + (size_t)n * vec_per_sample : nullptr;
   uint4* ob = out + (size_t)n * vec_per_sample;
@@ -302,15 +297,15 @@ int ds_nhwc_bf16_to_nchw_f32(const void* d_in, float* d_out, int N, int C, int C
   return DS_OK;
 }
 
-int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots, float inv_count, float eps,
+int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots,
                          const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream) {
-  DS_REQUIRE(d_y && d_out && d_stats && d_gamma && d_beta && N > 0 && C % 8 == 0 && hw > 0 && slots > 0, "ds_gn_apply_residual: bad arguments");
+  DS_REQUIRE(d_y && d_out && d_stats && d_gamma && d_beta && N > 0 && C % 8 == 0 && hw > 0 && slots >= 0, "ds_gn_apply_residual: bad arguments");
   const long long vps = hw * C / 8;
   int gx = (int)((vps + 255) / 256);
   const int cap = (num_sms() * 8 + N - 1) / N;
   if (gx > cap) gx = cap < 1 ? 1 : cap;
   gn_apply_residual_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
-                                                                          (const float2*)d_stats, slots, inv_count, eps, d_gamma,
+                                                                          (const float2*)d_stats, slots, d_gamma,
                                                                           d_beta, C / 8, vps);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;

@@ -172,10 +172,23 @@ def pack_conv_up(w: torch.Tensor, bias: torch.Tensor, cin_pad: Optional[int] = N
 # ------------------------------------------------------------------------------------------
 @dataclass
 class Stats:
-    """(sum, sumsq) partials of one tensor: float2 [N][slots]; count = elements per sample."""
+    """GroupNorm(1,C) statistics buffer of one tensor: float2 [N][2 + slots] (see csrc/common.cuh):
+    [n][0] = (mean, rstd) published by the producer's last tile, [n][1] = arrival counter, then the partials.
+    count = elements per sample."""
     buf: torch.Tensor
     slots: int
     count: int
+
+
+def new_stats(N: int, slots: int, count: int, device) -> Stats:
+    return Stats(torch.zeros((N, slots + 2, 2), dtype=torch.float32, device=device), slots, count)
+
+
+def given_stats(mean: torch.Tensor, rstd: torch.Tensor, count: int, device="cuda") -> Stats:
+    """A statistics buffer carrying externally computed (mean, rstd) per sample (tests)."""
+    buf = torch.zeros((mean.shape[0], 2, 2), dtype=torch.float32)
+    buf[:, 0, 0], buf[:, 0, 1] = mean, rstd
+    return Stats(buf.to(device), 0, count)
 
 
 def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], N: int, Hin: int, Win: int,
@@ -220,7 +233,7 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
             a.taps[g][t].dy, a.taps[g][t].dx, a.taps[g][t].view = dy, dx, v
     if stats_in is not None:
         assert pc.e1 is not None
-        a.d_stats_in, a.stats_in_slots, a.stats_inv_count = _ptr(stats_in.buf), stats_in.slots, 1.0 / stats_in.count
+        a.d_stats_in, a.stats_in_slots = _ptr(stats_in.buf), stats_in.slots
         a.d_e1 = _ptr(pc.e1)
     a.eps = eps
     a.d_e2, a.ncls = _ptr(pc.e2), pc.ncls
@@ -244,10 +257,10 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
     st = None
     if want_stats:
         slots = _lib.load().ds_conv_gemm_stats_slots(C.byref(a))
-        buf = torch.empty((N, slots, 2), dtype=torch.float32, device=src0.device)
-        a.d_stats_out = _ptr(buf)
-        st = Stats(buf, slots, Ho * Wo * pc.cout)
-        keep.append(buf)
+        st = new_stats(N, slots, Ho * Wo * pc.cout, src0.device)
+        a.d_stats_out = _ptr(st.buf)
+        a.stats_out_inv_count = 1.0 / st.count
+        keep.append(st)
     return a, st, keep
 
 
@@ -276,15 +289,14 @@ def mask_blend(guide, noise, mask, coef, img):
 
 
 def dwconv7_stats(N, C, H, W, device) -> Stats:
-    slots = _lib.load().ds_dwconv7_stats_slots(C, H, W)
-    return Stats(torch.empty((N, slots, 2), dtype=torch.float32, device=device), slots, H * W * C)
+    return new_stats(N, _lib.load().ds_dwconv7_stats_slots(C, H, W), H * W * C, device)
 
 
-def dwconv7(src0, src1, weight, tbias, tbias_stride, out, N, H, W, stats: Optional[Stats] = None, src_batch_mod=0) -> None:
+def dwconv7(src0, src1, weight, tbias, tbias_stride, out, N, H, W, stats: Optional[Stats] = None, src_batch_mod=0, eps=1e-5) -> None:
     C0 = src0.shape[-1]
     C1 = 0 if src1 is None else src1.shape[-1]
     check(_lib.load().ds_dwconv7(_ptr(src0), _ptr(src1), C0, C1, src_batch_mod, _ptr(weight), _ptr(tbias), tbias_stride, _ptr(out),
-                                 _ptr(stats.buf) if stats else None, N, H, W, _stream()), "ds_dwconv7")
+                                 _ptr(stats.buf) if stats else None, eps, N, H, W, _stream()), "ds_dwconv7")
 
 
 def linear(inp, w, bias, out, act_in=0, act_out=0):

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 import torch
 
@@ -421,9 +423,11 @@ class _GraphLoop:
         # warm-up run outside capture (lazy one-time initialisations, kernel attribute sets), then capture
         self._body(first_only=True)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        self.graph = None
+        if os.environ.get("DS_NO_GRAPH", "0") != "1":      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
 
     def _body(self, first_only: bool = False):
         pl, B = self.plan, self.B
@@ -438,4 +442,7 @@ class _GraphLoop:
                 ops.mask_blend(self.guide, self.init_noise, self.masks[k], self.blend_coef[k], self.imgs[k + 1])
 
     def launch(self):
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()

@@ -331,8 +331,8 @@ class _Plan:
             st_y = conv(p + "to_out", a.out, qp, None, h, w, out=y, want_stats=True, weight_override=M, per_sample_weights=True)
             o = act(N, h, w, a.dim)
             add(p + "gn_res", lambda: check(lib.ds_gn_apply_residual(y.data_ptr(), x.data_ptr(), o.data_ptr(), st_y.buf.data_ptr(), st_y.slots,
-                                                                      1.0 / st_y.count, 1e-5, a.gamma.data_ptr(), a.beta.data_ptr(), N,
-                                                                      a.dim, npix, stream()), "gn_apply_residual"))
+                                                                      a.gamma.data_ptr(), a.beta.data_ptr(), N, a.dim, npix, stream()),
+                                            "gn_apply_residual"))
             self.keep += [part, M]
             self.named[p[:-1]] = (o, a.dim)
             return o

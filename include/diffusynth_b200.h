@@ -86,10 +86,11 @@ typedef struct ds_conv_gemm_args {
   int32_t per_sample_weights;
   ds_conv_tap taps[DS_MAX_GROUPS][DS_MAX_TAPS];
   /* epilogue:  v = rstd*acc - rstd*mean*e1[cls][o] + e2[cls][o] + sbias[n][o];  act;  + residual */
-  const void* d_stats_in;   /* float2 [N][stats_in_slots] partial (sum, sumsq) of the source, or NULL */
+  const void* d_stats_in;   /* statistics buffer of the (GroupNorm(1,C)-normalised) source, or NULL: float2
+                               [N][2 + stats_in_slots], entry [n][0] = (mean, rstd) published by the producer */
   int32_t stats_in_slots;
-  float stats_inv_count;    /* 1 / (elements per sample of the normalised tensor) */
-  float eps;
+  float stats_out_inv_count; /* 1 / (elements per sample of THIS call's output), used when d_stats_out is set */
+  float eps;                /* GroupNorm eps used when publishing (mean, rstd) of the output */
   const float* d_e1;        /* [ncls][Cout_pad] or NULL */
   const float* d_e2;        /* [ncls][Cout_pad]: bias (+ folded GroupNorm beta term) */
   int32_t ncls;             /* 1, or 9 = (top/mid/bottom) x (left/mid/right) border classes of a 3x3 */
@@ -102,11 +103,13 @@ typedef struct ds_conv_gemm_args {
   int64_t out_sn, out_sh, out_sw;      /* in elements */
   int64_t out_goff[DS_MAX_GROUPS];     /* element offset per group (sub-pixel phase of ConvTranspose) */
   float* d_out_f32_nchw;    /* optional fp32 [N, Cout, H, W] output (final conv) */
-  void* d_stats_out;        /* float2 [N][ds_conv_gemm_stats_slots()] or NULL */
+  void* d_stats_out;        /* statistics buffer of the output, float2 [N][2 + ds_conv_gemm_stats_slots()], zero-initialised
+                               once by the caller (entry [n][1] is an arrival counter that resets itself), or NULL:
+                               [n][2+i] = (sum, sumsq) partial of tile-warp i, [n][0] = (mean, rstd) written by the last arriver */
 } ds_conv_gemm_args;
 
 int ds_conv_gemm(const ds_conv_gemm_args* args, void* stream);
-/* number of (sum, sumsq) partial slots per sample the call writes to d_stats_out */
+/* number of (sum, sumsq) partial slots per sample the call writes to d_stats_out (buffer holds 2 more entries) */
 int ds_conv_gemm_stats_slots(const ds_conv_gemm_args* args);
 /* Same contract on plain CUDA cores; exists only to cross-check the tcgen05 kernel in tests. */
 int ds_conv_gemm_reference(const ds_conv_gemm_args* args, void* stream);
@@ -130,7 +133,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
  * -------------------------------------------------------------------------------------- */
 /* ConvNextBlock.ds_conv (:118,131) + time-embedding bias (:133-136) + partials of net[0] GroupNorm (:121). */
 int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight,
-               const float* d_tbias, long long tbias_stride, void* d_out, void* d_stats, int N, int H, int W, void* stream);
+               const float* d_tbias, long long tbias_stride, void* d_out, void* d_stats, float eps, int N, int H, int W, void* stream);
 int ds_dwconv7_stats_slots(int C, int H, int W);
 /* init_conv 7x7 (model/diffusion.py:82,208): fp32 NCHW in, act16 NHWC out. */
 int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out,
@@ -149,8 +152,7 @@ int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N,
                      int C, int Cout_pad, void* stream);
 /* to_out[1] GroupNorm(1,C) + Residual (:264, :22-29): out = GN(y)*gamma+beta + x. */
 int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots,
-                         float inv_count, float eps, const float* d_gamma, const float* d_beta,
-                         int N, int C, long long hw, void* stream);
+                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * VQGAN (model/VQGAN.py) and the spectrogram <-> waveform transforms (tools.py + librosa call sites).

@@ -58,17 +58,28 @@ def test_convnext_conv1_fold_gelu_stats_concat():
     pc = ops.pack_conv_s1(w, b, gamma, beta)
     xb = torch.cat([bf(x0), bf(x1)], 1)
     # statistics of the (bf16-stored) source as one partial slot per sample
-    st = ops.Stats(torch.stack([xb.sum(dim=(1, 2, 3)), (xb * xb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous(), 1, 288 * H * W)
+    st = ops.given_stats(xb.mean(dim=(1, 2, 3)), (xb.var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), 288 * H * W)
     out = torch.zeros((N, H, W, 192), dtype=ops.ACT, device="cuda")
     so = _run(pc, [nhwc(x0), nhwc(x1)], N, H, W, out=out, stats_in=st, act=1, want_stats=True)
     ref = F.gelu(F.conv2d(F.group_norm(xb, 1, gamma, beta, 1e-5), w, b, padding=1))
     got = nchw(out)
     assert rel(got, ref) < 1.5 * TOL
-    # partials: sum over slots == sums of the fp32 (pre-rounding) outputs
-    s = so.buf.double().sum(dim=1).cpu()
+    # published statistics of the output: partial slots sum to the fp32 totals; entry 0 = (mean, rstd); counter reset
+    buf = so.buf.double().cpu()
+    s = buf[:, 2:].sum(dim=1)
     assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=2e-3, atol=4.0)
     assert torch.allclose(s[:, 1], (ref.double() ** 2).sum(dim=(1, 2, 3)), rtol=4e-3)
     assert so.count == 192 * H * W
+    assert torch.allclose(buf[:, 0, 0], ref.double().mean(dim=(1, 2, 3)), rtol=2e-3, atol=1e-4)
+    assert torch.allclose(buf[:, 0, 1], (ref.double().var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=2e-3)
+    assert float(so.buf[:, 1].abs().max()) == 0.0
+    # second launch into the same buffer (counter must have reset itself): identical statistics
+    first = so.buf.clone()
+    a2, so2, _ = ops.conv_args(pc, nhwc(x0), nhwc(x1), N, H, W, out=out, stats_in=st, act=1, want_stats=True)
+    a2.d_stats_out = so.buf.data_ptr()
+    ops.run_conv(a2)
+    torch.cuda.synchronize()
+    assert torch.equal(first, so.buf)
 
 
 def test_conv2_residual_and_contract_cross_check():
@@ -79,7 +90,7 @@ def test_conv2_residual_and_contract_cross_check():
     gamma, beta = 1 + 0.2 * cases.randn((128,), 14), 0.2 * cases.randn((128,), 15)
     pc = ops.pack_conv_s1(w, b, gamma, beta)
     xb = bf(x)
-    st = ops.Stats(torch.stack([xb.sum(dim=(1, 2, 3)), (xb * xb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous(), 1, 128 * H * W)
+    st = ops.given_stats(xb.mean(dim=(1, 2, 3)), (xb.var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), 128 * H * W)
     out = torch.zeros((N, H, W, 64), dtype=ops.ACT, device="cuda")
     _run(pc, [nhwc(x)], N, H, W, out=out, stats_in=st, residual=nhwc(r))
     ref = F.conv2d(F.group_norm(xb, 1, gamma, beta, 1e-5), w, b, padding=1) + bf(r)

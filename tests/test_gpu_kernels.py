@@ -87,9 +87,12 @@ def test_dwconv7(C0, C1, H, W, N):
     ops.dwconv7(s0, s1, w.reshape(Cc, 49).t().contiguous().cuda(), tb.cuda(), tb.shape[1], out, N, H, W, stats=st)
     ref = F.conv2d(bf(x), w, None, padding=3, groups=Cc) + tb[:, :Cc, None, None]
     assert rel(nchw(out), ref) < EPS16
-    s = st.buf.double().sum(dim=1).cpu()
+    buf = st.buf.double().cpu()
+    s = buf[:, 2:].sum(dim=1)
     assert torch.allclose(s[:, 0], ref.double().sum(dim=(1, 2, 3)), rtol=1e-3, atol=1.0)
     assert torch.allclose(s[:, 1], (ref.double() ** 2).sum(dim=(1, 2, 3)), rtol=1e-3)
+    assert torch.allclose(buf[:, 0, 0], ref.double().mean(dim=(1, 2, 3)), rtol=1e-3, atol=1e-4)
+    assert torch.allclose(buf[:, 0, 1], (ref.double().var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=1e-3)
 
 
 def test_stem_conv7():
@@ -146,10 +149,10 @@ def test_gn_apply_residual():
     y, x = cases.randn((N, Cc, H, Wd), 17) * 2 + 1, cases.randn((N, Cc, H, Wd), 18)
     g, b = 1 + 0.1 * cases.randn((Cc,), 19), 0.1 * cases.randn((Cc,), 20)
     yb = bf(y)
-    st = torch.stack([yb.sum(dim=(1, 2, 3)), (yb * yb).sum(dim=(1, 2, 3))], dim=1).view(N, 1, 2).cuda().contiguous()
+    st = ops.given_stats(yb.mean(dim=(1, 2, 3)), (yb.var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), Cc * H * Wd)
     out = torch.zeros((N, H, Wd, Cc), dtype=ops.ACT, device="cuda")
     yd, xd = nhwc(y), nhwc(x)
-    assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.data_ptr(), 1, C.c_float(1.0 / (Cc * H * Wd)), C.c_float(1e-5),
+    assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.buf.data_ptr(), st.slots,
                                       g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, S()) == 0
     assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)) < EPS16
 

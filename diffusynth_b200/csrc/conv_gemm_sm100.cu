@@ -175,18 +175,69 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile)
   return t;
 }
 
+// tcgen05.wait::ld with the destination registers as in/out operands, so that no use of them can be scheduled
+// above the wait.
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16_lo(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// GELU(x) = relu(x) - 0.5 |x| q(|x|),  q = poly(t) t exp(-x^2/2),  t = 1/(1 + p |x|/sqrt2)   (Abramowitz-Stegun 7.1.26,
+// |erf error| <= 1.5e-7; the 0.5 is folded into the coefficients).  Straight-line, 2 MUFU + 13 FP32 ops.
+__device__ __forceinline__ float gelu_epi(float x) {
+  const float ax = fabsf(x);
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
+  const float w = ax * 0.84932180028801904f;          // sqrt(log2(e)/2): exp(-x^2/2) = 2^(-w^2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-w * w));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return fmaxf(x, 0.0f) - ax * (p * t * e);
+}
+
+#ifdef DS_OPERANDS_BF16
+__device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) { return pack16(lo, hi); }
+#else
+__device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2FP.SATFINITE instead of clamp + convert
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+#endif
+
 template <int BK>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B)] then barriers
+  // carve: [stages x (A | B)] | barriers | stats partials | epilogue tables e2, e1 ([ncls][Cout_pad] fp32 each)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const unsigned stage_bytes = P.stage_a_bytes + P.stage_b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* stats_full = tmem_empty + 2;
+  uint64_t* stats_empty = stats_full + 2;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(stats_empty + 2);
+  float2* s_stats = reinterpret_cast<float2*>(tmem_base_smem + 4);          // [2][kEpiWarps]
+  float* s_e2 = reinterpret_cast<float*>(s_stats + 2 * kEpiWarps);
+  float* s_e1 = s_e2 + P.ncls * P.Cout_pad;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,10 +256,16 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&stats_full[a], kEpiWarps);
+      mbar_init(&stats_empty[a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
+  for (int i = threadIdx.x; i < P.ncls * P.Cout_pad; i += kNumThreads) {
+    s_e2[i] = __ldg(P.e2 + i);
+    s_e1[i] = P.e1 ? __ldg(P.e1 + i) : 0.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -273,6 +330,27 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
+  } else if (warp == 3) {
+    // ================================ statistics publisher =========================
+    // Sums the 8 epilogue-warp partials of each tile (fixed order), writes one slot per tile and runs the
+    // last-arriver reduction, so the epilogue warps never wait on a memory fence or an atomic.
+    if (P.stats_out != nullptr) {
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile);
+        mbar_wait(&stats_full[acc], acc_phase);
+        float s = 0.f, q = 0.f;
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < kEpiWarps; ++i) { const float2 v = s_stats[acc * kEpiWarps + i]; s += v.x; q += v.y; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stats_empty[acc]);
+        stats_publish(stats_sample(P.stats_out, P.stats_slots, t.n), P.stats_slots, t.slot, s, q, P.out_inv_count, P.eps, lane);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
   } else if (warp >= kEpiWarp0) {
     // ================================ epilogue ====================================
     const int ew = warp - kEpiWarp0;       // 0..7
@@ -282,11 +360,12 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const int chunks = P.BN / 16;          // 16-column chunks
     const int chunk_lo = col_half == 0 ? 0 : (chunks + 1) / 2;
     const int chunk_hi = col_half == 0 ? (chunks + 1) / 2 : chunks;
+    const int npairs = (chunk_hi - chunk_lo + 1) / 2;
+    const int ph = row / P.Wb, pw = row % P.Wb;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int ph = row / P.Wb, pw = row % P.Wb;
       const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
       const bool valid = (h < P.H) && (w < P.W);
       float mean = 0.f, rstd = 1.f;
@@ -299,35 +378,36 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       int cls = 0;
       if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
       const float nmr = -mean * rstd;
-      const float* e1 = P.e1 ? P.e1 + (size_t)cls * P.Cout_pad : nullptr;
-      const float* e2 = P.e2 + (size_t)cls * P.Cout_pad;
-      const float* sb = P.sbias ? P.sbias + (size_t)t.n * P.sbias_stride : nullptr;
-      const long long pix_out = P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
-      const long long pix_res = (long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw;
+      const bool use_e1 = P.e1 != nullptr;
+      const float* e1 = s_e1 + cls * P.Cout_pad + t.nt * P.BN;
+      const float* e2 = s_e2 + cls * P.Cout_pad + t.nt * P.BN;
+      const float* sb = P.sbias ? P.sbias + (size_t)t.n * P.sbias_stride + t.nt * P.BN : nullptr;
+      const int col0 = t.nt * P.BN;
+      const long long pix_out = P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw + col0;
+      const long long pix_res = (long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw + col0;
+      const bool has_res = P.residual != nullptr && valid;
       float psum = 0.f, psq = 0.f;
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
-      const bool has_res = P.residual != nullptr && valid;
-      // one 16-column chunk: folded-GroupNorm scalars, bias, activation, residual, statistics, store
-      auto finish_chunk = [&](int ch, const uint32_t (&r)[16], const uint4& ra, const uint4& rb) {
-        const int o0 = t.nt * P.BN + ch * 16;
+      // one 16-column chunk (ch = chunk index inside the tile): folded-GroupNorm scalars, bias, activation, residual,
+      // statistics, store.  r = accumulator values, ra/rb = prefetched residual.
+      auto finish_chunk = [&](int ch, const uint32_t* r, const uint4& ra, const uint4& rb) {
+        const int c0 = ch * 16;                 // column inside the tile
+        const int o0 = col0 + c0;               // global output channel
         float v[16];
-        const float4* e2v = reinterpret_cast<const float4*>(e2 + o0);
+        const float4* e2v = reinterpret_cast<const float4*>(e2 + c0);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 b4 = __ldg(e2v + q4);
+          const float4 b4 = e2v[q4];
           v[4 * q4 + 0] = fmaf(__uint_as_float(r[4 * q4 + 0]), rstd, b4.x);
           v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), rstd, b4.y);
           v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, b4.z);
           v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, b4.w);
         }
-        if (e1) {
-          const float4* e1v = reinterpret_cast<const float4*>(e1 + o0);
+        if (use_e1) {
+          const float4* e1v = reinterpret_cast<const float4*>(e1 + c0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 a4 = __ldg(e1v + q4);
+            const float4 a4 = e1v[q4];
             v[4 * q4 + 0] = fmaf(nmr, a4.x, v[4 * q4 + 0]);
             v[4 * q4 + 1] = fmaf(nmr, a4.y, v[4 * q4 + 1]);
             v[4 * q4 + 2] = fmaf(nmr, a4.z, v[4 * q4 + 2]);
@@ -335,7 +415,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           }
         }
         if (sb) {
-          const float4* sbv = reinterpret_cast<const float4*>(sb + o0);
+          const float4* sbv = reinterpret_cast<const float4*>(sb + c0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             const float4 a4 = __ldg(sbv + q4);
@@ -344,7 +424,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
         if (P.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = gelu_erf_fast(v[j]);
+          for (int j = 0; j < 16; ++j) v[j] = gelu_epi(v[j]);
         }
         if (!valid) return;
         if (has_res && o0 < P.Cout) {
@@ -367,11 +447,11 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
         if (P.out != nullptr && o0 < P.Cout) {
           uint4 a, b;
-          a.x = pack16(v[0], v[1]);   a.y = pack16(v[2], v[3]);
-          a.z = pack16(v[4], v[5]);   a.w = pack16(v[6], v[7]);
-          b.x = pack16(v[8], v[9]);   b.y = pack16(v[10], v[11]);
-          b.z = pack16(v[12], v[13]); b.w = pack16(v[14], v[15]);
-          uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + o0);
+          a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
+          a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
+          b.x = pack16_epi(v[8], v[9]);   b.y = pack16_epi(v[10], v[11]);
+          b.z = pack16_epi(v[12], v[13]); b.w = pack16_epi(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + c0);
           op[0] = a;
           op[1] = b;
         }
@@ -382,27 +462,46 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
               P.out_f32[(((size_t)t.n * P.Cout + (o0 + j)) * P.H + h) * P.W + w] = v[j];
         }
       };
-      // two chunks in flight: both TMEM loads and both residual fetches are issued before the wait
-      for (int ch = chunk_lo; ch < chunk_hi; ch += 2) {
-        const bool two = ch + 1 < chunk_hi;
-        uint32_t r0[16], r1[16];
-        tmem_ld_32x32b_x16(t_row + (uint32_t)(ch * 16), r0);
-        if (two) tmem_ld_32x32b_x16(t_row + (uint32_t)((ch + 1) * 16), r1);
-        uint4 ra0 = make_uint4(0, 0, 0, 0), rb0 = ra0, ra1 = ra0, rb1 = ra0;
+      const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
+      // pair p covers chunks chunk_lo + 2p (and + 2p + 1 when it exists)
+      auto issue_pair = [&](int p, uint32_t (&r)[32]) {
+        const int ch = chunk_lo + 2 * p;
+        if (ch + 1 < chunk_hi) tmem_ld_32x32b_x32(t_row + (uint32_t)(ch * 16), r);
+        else tmem_ld_x16_lo(t_row + (uint32_t)(ch * 16), r);
+      };
+      auto fetch_res = [&](int p, uint4 (&rr)[4]) {
+        const int ch = chunk_lo + 2 * p;
+        rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0, 0, 0, 0);
         if (has_res) {
-          const int o0 = t.nt * P.BN + ch * 16;
-          if (o0 < P.Cout) {
-            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0);
-            ra0 = __ldg(rp); rb0 = __ldg(rp + 1);
-          }
-          if (two && o0 + 16 < P.Cout) {
-            const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + o0 + 16);
-            ra1 = __ldg(rp); rb1 = __ldg(rp + 1);
-          }
+          const int o0 = col0 + ch * 16;
+          const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + ch * 16);
+          if (o0 < P.Cout) { rr[0] = __ldg(rp); rr[1] = __ldg(rp + 1); }
+          if (ch + 1 < chunk_hi && o0 + 16 < P.Cout) { rr[2] = __ldg(rp + 2); rr[3] = __ldg(rp + 3); }
         }
-        tmem_ld_wait();
-        finish_chunk(ch, r0, ra0, rb0);
-        if (two) finish_chunk(ch + 1, r1, ra1, rb1);
+      };
+      auto finish_pair = [&](int p, uint32_t (&r)[32], const uint4 (&rr)[4]) {
+        const int ch = chunk_lo + 2 * p;
+        finish_chunk(ch, &r[0], rr[0], rr[1]);
+        if (ch + 1 < chunk_hi) finish_chunk(ch + 1, &r[16], rr[2], rr[3]);
+      };
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      // software pipeline: while pair p is being finished, the TMEM load of pair p+1 is in flight
+      uint32_t ra_[32], rb_[32];
+      uint4 q[4];
+      if (npairs > 0) issue_pair(0, ra_);
+      for (int p = 0; p < npairs; p += 2) {
+        fetch_res(p, q);
+        tmem_ld_wait32(ra_);
+        if (p + 1 < npairs) issue_pair(p + 1, rb_);
+        finish_pair(p, ra_, q);
+        if (p + 1 < npairs) {
+          fetch_res(p + 1, q);
+          tmem_ld_wait32(rb_);
+          if (p + 2 < npairs) issue_pair(p + 2, ra_);
+          finish_pair(p + 1, rb_, q);
+        }
       }
       // release the accumulator stage (one arrive per epilogue warp)
       tcgen05_fence_before();
@@ -411,7 +510,12 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (P.stats_out != nullptr) {
         psum = warp_sum(psum);
         psq = warp_sum(psq);
-        stats_publish(stats_sample(P.stats_out, P.stats_slots, t.n), P.stats_slots, t.slot * kEpiWarps + ew, psum, psq, P.out_inv_count, P.eps, lane);
+        if (lane == 0) {
+          mbar_wait(&stats_empty[acc], acc_phase ^ 1u);
+          s_stats[acc * kEpiWarps + ew] = make_float2(psum, psq);
+          mbar_arrive(&stats_full[acc]);
+        }
+        __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -495,7 +599,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   for (int g = 0; g < DS_MAX_GROUPS; ++g) P.out_goff[g] = a->out_goff[g];
   P.out_f32 = a->d_out_f32_nchw;
   P.stats_out = reinterpret_cast<float2*>(a->d_stats_out);
-  P.stats_slots = a->groups * P.tiles_m * P.n_tiles_n * kEpiWarps;
+  P.stats_slots = a->groups * P.tiles_m * P.n_tiles_n;
   memcpy(P.taps, a->taps, sizeof(P.taps));
 }
 
@@ -541,13 +645,15 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   }
 
   const size_t stage_bytes = (size_t)P.stage_a_bytes + P.stage_b_bytes;
-  const size_t budget = 200 * 1024;
+  const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float);
+  const size_t fixed_bytes = 1024 + (2 * kMaxStages + 8) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + table_bytes + 64;
+  const size_t budget = 226 * 1024 - fixed_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages > P.num_kb && P.num_kb >= 2) stages = P.num_kb;
-  if (stages < 2) stages = 2;
+  DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables (%zu B) leave no room for a 2-stage pipeline", table_bytes);
   P.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem = fixed_bytes + stages * stage_bytes;
 
   int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
   if (a->BK == 64) {
@@ -631,5 +737,5 @@ extern "C" int ds_conv_gemm_reference(const ds_conv_gemm_args* args, void* strea
 extern "C" int ds_conv_gemm_stats_slots(const ds_conv_gemm_args* a) {
   if (!a || a->Hb <= 0 || a->Wb <= 0 || a->BN <= 0) return -1;
   const int tiles = ((a->H + a->Hb - 1) / a->Hb) * ((a->W + a->Wb - 1) / a->Wb);
-  return a->groups * tiles * (a->Cout_pad / a->BN) * ds::kEpiWarps;
+  return a->groups * tiles * (a->Cout_pad / a->BN);
 }

@@ -15,9 +15,14 @@ ncu)
       python bench.py --steps 1 --warmup 1 --sample-steps 2 > gpurun_out/ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/rc.txt
   tail -3 gpurun_out/plain.log; tail -3 gpurun_out/ncu.log ;;
 ncufull)
+  export REPS=1
   timeout 600 python tools_dev/unet_once.py > gpurun_out/plain_full.log 2>&1 && \
-  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 30 -c 4 -o gpurun_out/prof_conv -f \
-      python tools_dev/unet_once.py > gpurun_out/ncu_full.log 2>&1; echo "ncufull rc=$?" >> gpurun_out/rc.txt
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 0 -c 3 -o gpurun_out/prof_conv -f \
+      python tools_dev/unet_once.py > gpurun_out/ncu_full.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:dwconv7 -s 0 -c 1 -o gpurun_out/prof_dw -f \
+      python tools_dev/unet_once.py >> gpurun_out/ncu_full.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_ctx -s 0 -c 1 -o gpurun_out/prof_attn -f \
+      python tools_dev/unet_once.py >> gpurun_out/ncu_full.log 2>&1; echo "ncufull rc=$?" >> gpurun_out/rc.txt
   tail -3 gpurun_out/ncu_full.log ;;
 esac
 done

@@ -22,8 +22,9 @@ static constexpr int AT_PART = AT_D * AT_D + 2 * AT_D;   // S[32][32], Z[32], m[
 __global__ void __launch_bounds__(256)
 attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
                         act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
-  __shared__ __align__(16) float s_k[AT_PIX][AT_D + 4];
-  __shared__ __align__(16) float s_v[AT_PIX][AT_D + 4];
+  __shared__ __align__(16) float s_kv[2][AT_PIX][AT_D + 4];
+  float (*s_k)[AT_D + 4] = s_kv[0];
+  float (*s_v)[AT_D + 4] = s_kv[1];
   __shared__ float s_red[8][AT_D];
   __shared__ float s_m[AT_D];
   const int chunk = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
@@ -42,15 +43,15 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     for (int i = 0; i < 2; ++i) {
       uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
       if (ok) { kv = __ldg(kp + i); vv = __ldg(vp + i); }
-      const uint32_t kk[4] = {kv.x, kv.y, kv.z, kv.w}, vw[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int d = half * 16 + i * 8 + 2 * j;
-        s_k[pix][d] = ok ? lo16(kk[j]) : -INFINITY;
-        s_k[pix][d + 1] = ok ? hi16(kk[j]) : -INFINITY;
-        s_v[pix][d] = lo16(vw[j]);
-        s_v[pix][d + 1] = hi16(vw[j]);
-      }
+      const float2 k0 = cvt16x2(kv.x), k1 = cvt16x2(kv.y), k2 = cvt16x2(kv.z), k3 = cvt16x2(kv.w);
+      const float2 v0 = cvt16x2(vv.x), v1 = cvt16x2(vv.y), v2 = cvt16x2(vv.z), v3 = cvt16x2(vv.w);
+      const float ninf = -INFINITY;
+      float4* kd = reinterpret_cast<float4*>(&s_k[pix][half * 16 + i * 8]);     // 128-bit stores: conflict-free at pitch 36
+      float4* vd = reinterpret_cast<float4*>(&s_v[pix][half * 16 + i * 8]);
+      kd[0] = ok ? make_float4(k0.x, k0.y, k1.x, k1.y) : make_float4(ninf, ninf, ninf, ninf);
+      kd[1] = ok ? make_float4(k2.x, k2.y, k3.x, k3.y) : make_float4(ninf, ninf, ninf, ninf);
+      vd[0] = make_float4(v0.x, v0.y, v1.x, v1.y);
+      vd[1] = make_float4(v2.x, v2.y, v3.x, v3.y);
     }
     // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
     // The math runs for every thread (rows beyond npix compute on zeros) so the pair shuffles stay convergent.
@@ -108,34 +109,35 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     s_red[warp][lane] = z;
   }
   __syncthreads();
-  // ---- S[d][e] = sum_p p[p][d] * v[p][e]: 4x4 register tile per thread (packed FFMA2), 4 pixel groups of 32
-  const int pg = tid >> 6, d0 = ((tid >> 3) & 7) * 4, e0 = (tid & 7) * 4;
-  float2 acc[4][2];
+  // ---- S[d][e] = sum_p p[p][d] * v[p][e]: 8x4 register tile per thread (packed FFMA2), 8 pixel groups of 16
+  const int pg = tid >> 5, d0 = ((tid >> 3) & 3) * 8, e0 = (tid & 7) * 4;
+  float2 acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
+  for (int i = 0; i < 8; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
 #pragma unroll 4
-  for (int p = pg * 32; p < pg * 32 + 32; ++p) {
-    const float4 kk = *reinterpret_cast<const float4*>(&s_k[p][d0]);
+  for (int p = pg * 16; p < pg * 16 + 16; ++p) {
+    const float4 ka = *reinterpret_cast<const float4*>(&s_k[p][d0]);
+    const float4 kb4 = *reinterpret_cast<const float4*>(&s_k[p][d0 + 4]);
     const float4 vv = *reinterpret_cast<const float4*>(&s_v[p][e0]);
     const float2 v01 = make_float2(vv.x, vv.y), v23 = make_float2(vv.z, vv.w);
-    const float kd[4] = {kk.x, kk.y, kk.z, kk.w};
+    const float kd[8] = {ka.x, ka.y, ka.z, ka.w, kb4.x, kb4.y, kb4.z, kb4.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float2 kb = make_float2(kd[i], kd[i]);
       ffma2(acc[i][0], kb, v01);
       ffma2(acc[i][1], kb, v23);
     }
   }
-  __syncthreads();                       // everyone is done reading s_k / s_v: reuse s_v as the cross-group buffer
-  float* s_part = &s_v[0][0];            // [4][32][32] floats = 16 KB <= sizeof(s_v) (128*36*4 = 18 KB)
+  __syncthreads();                       // everyone is done reading s_k / s_v: reuse them as the cross-group buffer
+  float* s_part = &s_k[0][0];            // [8][32][32] floats = 32 KB <= s_k + s_v (2 x 128*36*4 = 36 KB, contiguous)
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
     *reinterpret_cast<float4*>(&s_part[(pg * AT_D + d0 + i) * AT_D + e0]) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
   __syncthreads();
   const int d = tid >> 3, e4 = (tid & 7) * 4;
   float4 s4 = *reinterpret_cast<const float4*>(&s_part[d * AT_D + e4]);
 #pragma unroll
-  for (int g = 1; g < 4; ++g) {
+  for (int g = 1; g < 8; ++g) {
     const float4 t4 = *reinterpret_cast<const float4*>(&s_part[(g * AT_D + d) * AT_D + e4]);
     s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
   }

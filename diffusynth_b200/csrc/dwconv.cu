@@ -9,8 +9,8 @@ namespace ds {
 // ---------------------------------------------------------------------------------------------
 // dwconv7: bf16 NHWC in (one or two channel-concatenated sources), bf16 NHWC out.
 // block = 256 threads = 16 channel pairs x 16 pixel-threads; tile = 8 rows x 16 cols x 32 channels.
-// The (8+6) x (16+6) halo tile is staged in shared memory (row pitch padded to 23 pixels so the two
-// pixel-threads of a warp hit different banks); each thread slides a 7-wide window over 8 outputs.
+// The (8+6) x (16+6) halo tile is staged in shared memory as fp32 (row pitch padded to 23 pixels so the two
+// pixel-threads of a warp hit different banks); each thread slides a 7-wide window over 8 outputs with packed FFMA2.
 // ---------------------------------------------------------------------------------------------
 static constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 32;
 static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6, DW_PITCH = 23;
@@ -20,7 +20,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
                act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w, int tiles) {
-  __shared__ __align__(16) uint32_t s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // bf16 pairs
+  __shared__ __align__(16) float2 s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // fp32 channel pairs (converted once at staging)
   __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
   __shared__ float s_red[16];
   const int C = C0 + C1;
@@ -38,15 +38,18 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
     const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
     s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
   }
-  // stage the halo tile: 16-byte pieces (8 channels); 4 pieces per pixel
+  // stage the halo tile: 16-byte pieces (8 channels) per thread, converted to fp32 once; 4 pieces per pixel
   for (int i = threadIdx.x; i < DW_HH * DW_HW * 4; i += 256) {
     const int piece = i & 3, pix = i >> 2;
-    const int r = pix / DW_HW, cc = pix % DW_HW;
+    const int r = pix / DW_HW, cc = pix - r * DW_HW;
     const int y = h0 + r - 3, x = w0 + cc - 3;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < H && x >= 0 && x < W)
       v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * W + x) * Cs + cs0 + piece * 8));
-    *reinterpret_cast<uint4*>(&s_in[(r * DW_PITCH + cc) * (DW_CB / 2) + piece * 4]) = v;
+    float4* dst = reinterpret_cast<float4*>(&s_in[(r * DW_PITCH + cc) * (DW_CB / 2) + piece * 4]);
+    const float2 a = cvt16x2(v.x), b = cvt16x2(v.y), c = cvt16x2(v.z), d = cvt16x2(v.w);
+    dst[0] = make_float4(a.x, a.y, b.x, b.y);
+    dst[1] = make_float4(c.x, c.y, d.x, d.y);
   }
   __syncthreads();
 
@@ -55,15 +58,15 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   float2 acc[8];       // (channel 2cp, channel 2cp+1) of 8 consecutive output columns: packed FFMA2 lanes
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll
   for (int ky = 0; ky < 7; ++ky) {
     float2 wv[7];
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) wv[kx] = s_w[(ky * 7 + kx) * (DW_CB / 2) + cp];
-    const uint32_t* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
+    const float2* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
 #pragma unroll
     for (int j = 0; j < 14; ++j) {
-      const float2 in = cvt16x2(rowp[j * (DW_CB / 2)]);
+      const float2 in = rowp[j * (DW_CB / 2)];
 #pragma unroll
       for (int kx = 0; kx < 7; ++kx) {
         const int ow = j - kx;

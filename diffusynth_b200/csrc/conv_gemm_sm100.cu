@@ -236,7 +236,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   uint64_t* stats_empty = stats_full + 2;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(stats_empty + 2);
   float2* s_stats = reinterpret_cast<float2*>(tmem_base_smem + 4);          // [2][kEpiWarps]
-  float* s_e2 = reinterpret_cast<float*>(s_stats + 2 * kEpiWarps);
+  float* s_sb = reinterpret_cast<float*>(s_stats + 2 * kEpiWarps);           // [kEpiWarps][128] per-sample bias of the current tile
+  float* s_e2 = s_sb + kEpiWarps * 128;
   float* s_e1 = s_e2 + P.ncls * P.Cout_pad;
 
   const int warp = threadIdx.x >> 5;
@@ -364,9 +365,29 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const int ph = row / P.Wb, pw = row % P.Wb;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // per-sample bias (to_qkv's label_query/label_key): this warp's column range, fetched one tile ahead into
+    // registers and parked in shared memory while the tile is processed
+    float* my_sb = s_sb + ew * 128;
+    const int sb_cols = (chunk_hi - chunk_lo) * 16;
+    float sb_next[4] = {0.f, 0.f, 0.f, 0.f};
+    auto fetch_sbias = [&](int tile_idx) {
+      if (P.sbias == nullptr || tile_idx >= P.num_tiles) return;
+      const TileCoord tt = decode_tile(P, tile_idx);
+      const float* src = P.sbias + (size_t)tt.n * P.sbias_stride + tt.nt * P.BN + chunk_lo * 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
+    };
+    fetch_sbias(blockIdx.x);
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
       const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
+      if (P.sbias != nullptr) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) my_sb[lane + 32 * i] = sb_next[i];
+        __syncwarp();
+        fetch_sbias(tile + gridDim.x);
+      }
       const bool valid = (h < P.H) && (w < P.W);
       float mean = 0.f, rstd = 1.f;
       if (P.stats_in != nullptr) {
@@ -381,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const bool use_e1 = P.e1 != nullptr;
       const float* e1 = s_e1 + cls * P.Cout_pad + t.nt * P.BN;
       const float* e2 = s_e2 + cls * P.Cout_pad + t.nt * P.BN;
-      const float* sb = P.sbias ? P.sbias + (size_t)t.n * P.sbias_stride + t.nt * P.BN : nullptr;
+      const float* sb = P.sbias ? my_sb - chunk_lo * 16 : nullptr;      // indexed by the column inside the tile
       const int col0 = t.nt * P.BN;
       const long long pix_out = P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw + col0;
       const long long pix_res = (long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw + col0;
@@ -418,7 +439,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           const float4* sbv = reinterpret_cast<const float4*>(sb + c0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 a4 = __ldg(sbv + q4);
+            const float4 a4 = sbv[q4];
             v[4 * q4 + 0] += a4.x; v[4 * q4 + 1] += a4.y; v[4 * q4 + 2] += a4.z; v[4 * q4 + 3] += a4.w;
           }
         }
@@ -646,7 +667,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
 
   const size_t stage_bytes = (size_t)P.stage_a_bytes + P.stage_b_bytes;
   const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float);
-  const size_t fixed_bytes = 1024 + (2 * kMaxStages + 8) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + table_bytes + 64;
+  const size_t fixed_bytes = 1024 + (2 * kMaxStages + 8) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + kEpiWarps * 128 * sizeof(float) + table_bytes + 64;
   const size_t budget = 226 * 1024 - fixed_bytes;
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

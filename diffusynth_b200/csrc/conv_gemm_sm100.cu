@@ -29,6 +29,8 @@ struct __align__(16) ConvGemmDev {
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;
   unsigned stage_a_bytes, stage_b_bytes;
+  int halo, Wp, halo_rows;          // halo mode (3x3 stride 1): one (halo_rows x Wp)-pixel activation box per channel block
+  unsigned halo_a_bytes;
   int Cout, Cout_pad;
   const float2* stats_in; int stats_in_slots; float out_inv_count, eps;
   const float* e1; const float* e2; int ncls;
@@ -221,16 +223,25 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 }
 #endif
 
-template <int BK>
+// HALO = false: generic mode, one (A tap tile | B) pair per pipeline stage.
+// HALO = true : 3x3 stride-1 convs.  M rows are 128 consecutive positions q = h*Wp + w' of the width-padded image
+//               (Wp = W + 2; w' >= W rows are discarded), so that the input of tap (ky,kx) for row q is the padded-linear
+//               pixel q + ky*Wp + kx: ONE TMA box of halo_rows full padded rows per channel block serves all 9 taps through
+//               row-shifted UMMA descriptors (the swizzle is a function of the absolute shared-memory address, so any
+//               row offset is a valid operand start; tools_dev/umma_shift_test.cu).  Activation traffic drops ~3.4x.
+template <int BK, bool HALO>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B)] | barriers | stats partials | epilogue tables e2, e1 ([ncls][Cout_pad] fp32 each)
+  // carve: generic [stages x (A | B)]  /  halo [2 x A-halo][stages x B]  | barriers | stats partials | sbias | tables e2, e1
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const unsigned stage_bytes = P.stage_a_bytes + P.stage_b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+  const unsigned stage_bytes = HALO ? P.stage_b_bytes : P.stage_a_bytes + P.stage_b_bytes;
+  uint8_t* smem_b0 = HALO ? smem + 2 * (size_t)P.halo_a_bytes : smem;          // start of the per-stage ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b0 + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tmem_full = empty_bar + kMaxStages;
+  uint64_t* full_a = empty_bar + kMaxStages;        // halo ring (2 stages)
+  uint64_t* empty_a = full_a + 2;
+  uint64_t* tmem_full = empty_a + 2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* stats_full = tmem_empty + 2;
   uint64_t* stats_empty = stats_full + 2;
@@ -255,6 +266,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&full_a[a], 1);
+      mbar_init(&empty_a[a], 1);
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps);
       mbar_init(&stats_full[a], kEpiWarps);
@@ -277,24 +290,44 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
-        const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
         const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
         const int wz = P.per_sample_w ? t.n : t.g;
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < P.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + P.stage_a_bytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
-          const ds_conv_tap tp = P.taps[t.g][tap];
-          const int src = cb < P.cblocks0 ? 0 : 1;
-          const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
-          tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
-          tma_load_3d(sb, &maps.b, &full_bar[stage], kb * BK, t.nt * P.BN, wz);
-          if (++cb == P.cblocks) { cb = 0; ++tap; }
-          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        if (HALO) {
+          const int pr0 = ((t.th * P.tiles_w + t.tw) * BM) / P.Wp;      // first padded row of the halo box
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            mbar_wait(&empty_a[as], aphase ^ 1u);
+            mbar_expect_tx(&full_a[as], P.halo_a_bytes);
+            const int src = cb < P.cblocks0 ? 0 : 1;
+            const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
+            tma_load_4d(smem + (size_t)as * P.halo_a_bytes, &maps.a[src][0], &full_a[as], c, -1, pr0 - 1, nsrc);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_expect_tx(&full_bar[stage], P.stage_b_bytes);
+              tma_load_3d(smem_b0 + (size_t)stage * stage_bytes, &maps.b, &full_bar[stage], (tap * P.cblocks + cb) * BK, t.nt * P.BN, wz);
+              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+            }
+            if (++as == 2) { as = 0; aphase ^= 1u; }
+          }
+        } else {
+          const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
+          int tap = 0, cb = 0;
+          for (int kb = 0; kb < P.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + P.stage_a_bytes;
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            const ds_conv_tap tp = P.taps[t.g][tap];
+            const int src = cb < P.cblocks0 ? 0 : 1;
+            const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
+            tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
+            tma_load_3d(sb, &maps.b, &full_bar[stage], kb * BK, t.nt * P.BN, wz);
+            if (++cb == P.cblocks) { cb = 0; ++tap; }
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -306,26 +339,56 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
-        for (int kb = 0; kb < P.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + P.stage_a_bytes;
-          const uint64_t adesc = make_kmajor_desc<BK>(sa);
-          const uint64_t bdesc = make_kmajor_desc<BK>(sb);
+        if (HALO) {
+          const TileCoord t = decode_tile(P, tile);
+          const int p0 = (t.th * P.tiles_w + t.tw) * BM;
+          const int base_row = p0 - (p0 / P.Wp) * P.Wp;      // row of position q = p0 inside the box for tap (0,0)
+          uint32_t accum = 0;
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            mbar_wait(&full_a[as], aphase);
+            tcgen05_fence_after();
+            const uint32_t sa0 = smem_u32(smem + (size_t)as * P.halo_a_bytes);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const int off = base_row + (tap / 3) * P.Wp + (tap % 3);
+              const uint64_t adesc = make_kmajor_desc<BK>(sa0 + (uint32_t)off * (BK * 2));
+              const uint64_t bdesc = make_kmajor_desc<BK>(smem_u32(smem_b0 + (size_t)stage * stage_bytes));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                accum = 1u;
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(&empty_a[as]);        // the halo box is free once the MMAs of its 9 taps retire
+            if (++as == 2) { as = 0; aphase ^= 1u; }
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+        } else {
+          for (int kb = 0; kb < P.num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+            const uint32_t sb = sa + P.stage_a_bytes;
+            const uint64_t adesc = make_kmajor_desc<BK>(sa);
+            const uint64_t bdesc = make_kmajor_desc<BK>(sb);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+          }
         }
         umma_commit(&tmem_full[acc]);       // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -380,7 +443,15 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     fetch_sbias(blockIdx.x);
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
+      int h, w;
+      if (HALO) {
+        const int q = (t.th * P.tiles_w + t.tw) * BM + row;
+        h = q / P.Wp;
+        w = q - h * P.Wp;
+      } else {
+        h = t.th * P.Hb + ph;
+        w = t.tw * P.Wb + pw;
+      }
       if (P.sbias != nullptr) {
         __syncwarp();
 #pragma unroll
@@ -592,11 +663,51 @@ static int validate(const ds_conv_gemm_args* a) {
   return DS_OK;
 }
 
+// Halo mode applies to plain 3x3 stride-1 'same' convolutions on images at least DS_CONV_HALO_MINW (default 32) wide.
+static bool use_halo(const ds_conv_gemm_args* a) {
+  static int minw = -1;
+  if (minw < 0) {
+    const char* e = getenv("DS_CONV_HALO_MINW");
+    minw = e ? atoi(e) : 32;
+  }
+  if (a->ntaps != 9 || a->groups != 1 || a->num_views != 1 || a->H != a->Hv || a->W != a->Wv) return false;
+  if (a->W < minw || a->W + 2 > 256 || a->view_sw != 1 || a->view_sh != a->Wv || a->view_off[0] != 0) return false;
+  for (int t = 0; t < 9; ++t)
+    if (a->taps[0][t].dy != t / 3 - 1 || a->taps[0][t].dx != t % 3 - 1 || a->taps[0][t].view != 0) return false;
+  return true;
+}
+
+static size_t smem_fixed_bytes(const ds_conv_gemm_args* a) {
+  const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float);
+  return 1024 + (2 * kMaxStages + 12) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + kEpiWarps * 128 * sizeof(float) + table_bytes + 64;
+}
+static size_t smem_budget(const ds_conv_gemm_args* a) {
+  const size_t f = smem_fixed_bytes(a);
+  return f < 226 * 1024 ? 226 * 1024 - f : 0;
+}
+
 static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   memset(&P, 0, sizeof(P));
   P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
-  P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
-  P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
+  P.stage_a_bytes = BM * a->BK * 2;
+  P.stage_b_bytes = a->BN * a->BK * 2;
+  P.halo = use_halo(a) ? 1 : 0;
+  if (P.halo) {
+    P.Wp = a->W + 2;
+    P.halo_rows = (3 * P.Wp + BM + 1 + P.Wp - 1) / P.Wp;
+    P.halo_a_bytes = (unsigned)(((size_t)P.halo_rows * P.Wp * a->BK * 2 + 1023) / 1024 * 1024);
+    const size_t budget = smem_budget(a);
+    if (budget < 2 * (size_t)P.halo_a_bytes + 3 * (size_t)P.stage_b_bytes) P.halo = 0;   // no room for two halo boxes + a weight ring
+  }
+  if (P.halo) {
+    P.Hb = 1; P.Wb = BM;
+    P.tiles_h = 1;
+    P.tiles_w = (a->H * P.Wp + BM - 1) / BM;
+  } else {
+    P.Wp = 0; P.halo_rows = 0; P.halo_a_bytes = 0;
+    P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
+    P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
+  }
   P.tiles_m = P.tiles_h * P.tiles_w;
   P.n_tiles_n = a->Cout_pad / a->BN;
   P.BN = a->BN; P.C0 = a->C0; P.C1 = a->C1;
@@ -606,8 +717,6 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.src_batch_mod = a->src_batch_mod;
   P.num_kb = P.cblocks * a->ntaps;
   P.num_tiles = a->N * a->groups * P.tiles_m * P.n_tiles_n;
-  P.stage_a_bytes = BM * a->BK * 2;
-  P.stage_b_bytes = a->BN * a->BK * 2;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.stats_in = reinterpret_cast<const float2*>(a->d_stats_in);
   P.stats_in_slots = a->stats_in_slots; P.out_inv_count = a->stats_out_inv_count; P.eps = a->eps;
@@ -643,7 +752,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a->Wv, (cuuint64_t)a->Hv,
                             (cuuint64_t)(a->src_batch_mod > 0 ? a->src_batch_mod : a->N)};
       cuuint64_t strides[3] = {(cuuint64_t)a->view_sw * C * 2, (cuuint64_t)a->view_sh * C * 2, (cuuint64_t)a->view_sn * C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
+      cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)(P.halo ? P.Wp : a->Wb), (cuuint32_t)(P.halo ? P.halo_rows : a->Hb), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       void* gaddr = const_cast<char*>(base) + (size_t)a->view_off[v] * C * 2;
       CUresult r = encode(&maps.a[s][v], (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, gaddr, dims, strides, box, estr,
@@ -665,25 +774,25 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (K=%lld Cout_pad=%d)", (int)r, K, a->Cout_pad);
   }
 
-  const size_t stage_bytes = (size_t)P.stage_a_bytes + P.stage_b_bytes;
-  const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float);
-  const size_t fixed_bytes = 1024 + (2 * kMaxStages + 8) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + kEpiWarps * 128 * sizeof(float) + table_bytes + 64;
-  const size_t budget = 226 * 1024 - fixed_bytes;
-  int stages = (int)(budget / stage_bytes);
+  const size_t fixed_bytes = smem_fixed_bytes(a);
+  const size_t budget = smem_budget(a);
+  const size_t stage_bytes = P.halo ? (size_t)P.stage_b_bytes : (size_t)P.stage_a_bytes + P.stage_b_bytes;
+  int stages = (int)((budget - (P.halo ? 2 * (size_t)P.halo_a_bytes : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > P.num_kb && P.num_kb >= 2) stages = P.num_kb;
-  DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables (%zu B) leave no room for a 2-stage pipeline", table_bytes);
+  if (!P.halo && stages > P.num_kb && P.num_kb >= 2) stages = P.num_kb;
+  DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables leave no room for a 2-stage pipeline (Cout_pad=%d ncls=%d)", a->Cout_pad, a->ncls);
   P.stages = stages;
-  const size_t smem = fixed_bytes + stages * stage_bytes;
+  const size_t smem = fixed_bytes + (P.halo ? 2 * (size_t)P.halo_a_bytes : 0) + stages * stage_bytes;
 
   int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-  if (a->BK == 64) {
-    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_gemm_kernel<64><<<grid, kNumThreads, smem, stream>>>(maps, P);
-  } else {
-    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_gemm_kernel<32><<<grid, kNumThreads, smem, stream>>>(maps, P);
-  }
+#define DS_LAUNCH_CONV(BKV, HALOV)                                                                                                   \
+  do {                                                                                                                               \
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV, HALOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    conv_gemm_kernel<BKV, HALOV><<<grid, kNumThreads, smem, stream>>>(maps, P);                                                     \
+  } while (0)
+  if (a->BK == 64) { if (P.halo) DS_LAUNCH_CONV(64, true); else DS_LAUNCH_CONV(64, false); }
+  else             { if (P.halo) DS_LAUNCH_CONV(32, true); else DS_LAUNCH_CONV(32, false); }
+#undef DS_LAUNCH_CONV
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -757,6 +866,7 @@ extern "C" int ds_conv_gemm_reference(const ds_conv_gemm_args* args, void* strea
 }
 extern "C" int ds_conv_gemm_stats_slots(const ds_conv_gemm_args* a) {
   if (!a || a->Hb <= 0 || a->Wb <= 0 || a->BN <= 0) return -1;
-  const int tiles = ((a->H + a->Hb - 1) / a->Hb) * ((a->W + a->Wb - 1) / a->Wb);
-  return a->groups * tiles * (a->Cout_pad / a->BN);
+  ds::ConvGemmDev P;
+  ds::fill_dev(a, P);
+  return P.stats_slots;
 }

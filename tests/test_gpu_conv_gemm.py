@@ -32,6 +32,9 @@ def _run(pc, srcs, N, H, W, reference=False, **kw):
     (96, 96, 3, 128, 64, 2),      # full-resolution level-0 shape, 64 m-tiles per sample (persistent loop)
     (32, 32, 3, 128, 24, 1),      # width not a multiple of the preferred tile
     (64, 48, 3, 20, 12, 2),       # ragged: partial tiles in both directions
+    (96, 192, 3, 64, 32, 2),      # halo mode (W >= 32): BK=32, padded width 34
+    (64, 64, 3, 20, 40, 3),       # halo mode, ragged: 20 x 42 padded positions = 6.56 tiles
+    (128, 256, 3, 128, 64, 1),    # halo mode, BK=64, BN=256, 66 tiles per sample
 ])
 def test_plain_conv(cin, cout, k, H, W, N):
     from diffusynth_b200 import ops
@@ -51,7 +54,7 @@ def test_plain_conv(cin, cout, k, H, W, N):
 def test_convnext_conv1_fold_gelu_stats_concat():
     """Two concatenated sources, GroupNorm(1,C) folded, GELU, and the (sum, sumsq) partials for the next norm."""
     from diffusynth_b200 import ops
-    N, H, W = 2, 32, 16
+    N, H, W = 2, 16, 32          # W = 32: halo mode
     x0, x1 = cases.randn((N, 96, H, W), 4) + 0.5, cases.randn((N, 192, H, W), 5) * 1.7
     w, b = cases.randn((192, 288, 3, 3), 6) * 0.02, cases.randn((192,), 7) * 0.1
     gamma, beta = 1 + 0.2 * cases.randn((288,), 8), 0.2 * cases.randn((288,), 9)
@@ -82,9 +85,10 @@ def test_convnext_conv1_fold_gelu_stats_concat():
     assert torch.equal(first, so.buf)
 
 
-def test_conv2_residual_and_contract_cross_check():
+@pytest.mark.parametrize("H,W", [(16, 8), (8, 64)])
+def test_conv2_residual_and_contract_cross_check(H, W):
     from diffusynth_b200 import ops
-    N, H, W = 2, 16, 8
+    N = 2
     x, r = cases.randn((N, 128, H, W), 10) * 2 + 1, cases.randn((N, 64, H, W), 11)
     w, b = cases.randn((64, 128, 3, 3), 12) * 0.03, cases.randn((64,), 13) * 0.1
     gamma, beta = 1 + 0.2 * cases.randn((128,), 14), 0.2 * cases.randn((128,), 15)

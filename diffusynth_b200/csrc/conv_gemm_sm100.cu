@@ -30,7 +30,8 @@ struct __align__(16) ConvGemmDev {
   int num_kb, stages, num_tiles;
   unsigned stage_a_bytes, stage_b_bytes;
   int halo, Wp, halo_rows;          // halo mode (3x3 stride 1): one (halo_rows x Wp)-pixel activation box per channel block
-  unsigned halo_a_bytes;
+  unsigned halo_a_bytes;            // smem stride of one halo box (rounded to 1 KB)
+  unsigned halo_box_bytes;          // bytes one halo TMA box delivers
   int Cout, Cout_pad;
   const float2* stats_in; int stats_in_slots; float out_inv_count, eps;
   const float* e1; const float* e2; int ncls;
@@ -300,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           const int pr0 = ((t.th * P.tiles_w + t.tw) * BM) / P.Wp;      // first padded row of the halo box
           for (int cb = 0; cb < P.cblocks; ++cb) {
             mbar_wait(&empty_a[as], aphase ^ 1u);
-            mbar_expect_tx(&full_a[as], P.halo_a_bytes);
+            mbar_expect_tx(&full_a[as], P.halo_box_bytes);
             const int src = cb < P.cblocks0 ? 0 : 1;
             const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
             tma_load_4d(smem + (size_t)as * P.halo_a_bytes, &maps.a[src][0], &full_a[as], c, -1, pr0 - 1, nsrc);
@@ -695,7 +696,8 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   if (P.halo) {
     P.Wp = a->W + 2;
     P.halo_rows = (3 * P.Wp + BM + 1 + P.Wp - 1) / P.Wp;
-    P.halo_a_bytes = (unsigned)(((size_t)P.halo_rows * P.Wp * a->BK * 2 + 1023) / 1024 * 1024);
+    P.halo_box_bytes = (unsigned)((size_t)P.halo_rows * P.Wp * a->BK * 2);
+    P.halo_a_bytes = (P.halo_box_bytes + 1023u) / 1024u * 1024u;
     const size_t budget = smem_budget(a);
     if (budget < 2 * (size_t)P.halo_a_bytes + 3 * (size_t)P.stage_b_bytes) P.halo = 0;   // no room for two halo boxes + a weight ring
   }
@@ -704,7 +706,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
     P.tiles_h = 1;
     P.tiles_w = (a->H * P.Wp + BM - 1) / BM;
   } else {
-    P.Wp = 0; P.halo_rows = 0; P.halo_a_bytes = 0;
+    P.Wp = 0; P.halo_rows = 0; P.halo_a_bytes = 0; P.halo_box_bytes = 0;
     P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
     P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
   }

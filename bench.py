@@ -193,6 +193,19 @@ def profile_unet_eval(plan):
         fam[key] = fam.get(key, 0.0) + e0.elapsed_time(e1)
     flops = sum(conv_flops(k) for k in plan.keep if isinstance(k, ConvGemmArgs))
     launches = sum(1 for k in plan.keep if isinstance(k, ConvGemmArgs))
+    if os.environ.get("DS_DUMP_OPS"):
+        convs = [k for k in plan.keep if isinstance(k, ConvGemmArgs)]
+        ci, rows = 0, []
+        for name, e0, e1 in evs:
+            ms = e0.elapsed_time(e1)
+            row = dict(op=name, ms=round(ms, 4))
+            is_conv = name.endswith(("net.1", "net.4", "final_conv.1", "res_conv", "to_qkv", "to_out")) or name.split(".")[-1] in ("2", "4") and name.count(".") == 2
+            if is_conv and ci < len(convs):
+                a = convs[ci]; ci += 1
+                row.update(tflops=round(conv_flops(a) / (ms / 1e3) / 1e12, 1), H=a.H, W=a.W, Cin=a.C0 + a.C1, Cout=a.Cout, taps=a.ntaps, BN=a.BN, BK=a.BK)
+            rows.append(row)
+        with open(os.environ["DS_DUMP_OPS"], "w") as f:
+            json.dump(rows, f, indent=0)
     return fam, flops, launches
 
 

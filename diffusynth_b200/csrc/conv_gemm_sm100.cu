@@ -28,6 +28,7 @@ struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;
+  int sps;                          // K-blocks per pipeline stage (generic mode): keeps >= ~384 MMA cycles behind every barrier round trip
   unsigned stage_a_bytes, stage_b_bytes;
   int halo, Wp, halo_rows;          // halo mode (3x3 stride 1): one (halo_rows x Wp)-pixel activation box per channel block
   unsigned halo_a_bytes;            // smem stride of one halo box (rounded to 1 KB)
@@ -236,7 +237,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: generic [stages x (A | B)]  /  halo [2 x A-halo][stages x B]  | barriers | stats partials | sbias | tables e2, e1
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const unsigned stage_bytes = HALO ? P.stage_b_bytes : P.stage_a_bytes + P.stage_b_bytes;
+  const unsigned stage_bytes = HALO ? P.stage_b_bytes : (unsigned)P.sps * (P.stage_a_bytes + P.stage_b_bytes);
   uint8_t* smem_b0 = HALO ? smem + 2 * (size_t)P.halo_a_bytes : smem;          // start of the per-stage ring
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b0 + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -315,18 +316,22 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           }
         } else {
           const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
+          const unsigned sub_bytes = P.stage_a_bytes + P.stage_b_bytes;
           int tap = 0, cb = 0;
-          for (int kb = 0; kb < P.num_kb; ++kb) {
+          for (int kb = 0; kb < P.num_kb; kb += P.sps) {
+            const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
             mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            uint8_t* sb = sa + P.stage_a_bytes;
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
-            const ds_conv_tap tp = P.taps[t.g][tap];
-            const int src = cb < P.cblocks0 ? 0 : 1;
-            const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
-            tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
-            tma_load_3d(sb, &maps.b, &full_bar[stage], kb * BK, t.nt * P.BN, wz);
-            if (++cb == P.cblocks) { cb = 0; ++tap; }
+            mbar_expect_tx(&full_bar[stage], (unsigned)nsub * sub_bytes);
+            for (int j = 0; j < nsub; ++j) {
+              uint8_t* sa = smem + (size_t)stage * stage_bytes + (size_t)j * sub_bytes;
+              uint8_t* sb = sa + P.stage_a_bytes;
+              const ds_conv_tap tp = P.taps[t.g][tap];
+              const int src = cb < P.cblocks0 ? 0 : 1;
+              const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
+              tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
+              tma_load_3d(sb, &maps.b, &full_bar[stage], (kb + j) * BK, t.nt * P.BN, wz);
+              if (++cb == P.cblocks) { cb = 0; ++tap; }
+            }
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -375,17 +380,23 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             if (++as == 2) { as = 0; aphase ^= 1u; }
           }
         } else {
-          for (int kb = 0; kb < P.num_kb; ++kb) {
+          const unsigned sub_bytes = P.stage_a_bytes + P.stage_b_bytes;
+          uint32_t accum = 0;
+          for (int kb = 0; kb < P.num_kb; kb += P.sps) {
+            const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-            const uint32_t sb = sa + P.stage_a_bytes;
-            const uint64_t adesc = make_kmajor_desc<BK>(sa);
-            const uint64_t bdesc = make_kmajor_desc<BK>(sb);
+            const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
+            for (int j = 0; j < nsub; ++j) {
+              const uint32_t sa = s0 + (uint32_t)j * sub_bytes;
+              const uint64_t adesc = make_kmajor_desc<BK>(sa);
+              const uint64_t bdesc = make_kmajor_desc<BK>(sa + P.stage_a_bytes);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-              umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) {
+                // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
+                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                accum = 1u;
+              }
             }
             umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
             if (++stage == P.stages) { stage = 0; phase ^= 1u; }
@@ -664,13 +675,10 @@ static int validate(const ds_conv_gemm_args* a) {
   return DS_OK;
 }
 
-// Halo mode applies to plain 3x3 stride-1 'same' convolutions on images at least DS_CONV_HALO_MINW (default 32) wide.
+// Halo mode (opt-in, DS_CONV_HALO_MINW=<min width>) applies to plain 3x3 stride-1 'same' convolutions.
 static bool use_halo(const ds_conv_gemm_args* a) {
-  static int minw = -1;
-  if (minw < 0) {
-    const char* e = getenv("DS_CONV_HALO_MINW");
-    minw = e ? atoi(e) : 32;
-  }
+  const char* e = getenv("DS_CONV_HALO_MINW");
+  const int minw = e ? atoi(e) : (1 << 30);     // measured ~10% slower than the generic mode on B200 (profiles/r01_notes.md): off by default
   if (a->ntaps != 9 || a->groups != 1 || a->num_views != 1 || a->H != a->Hv || a->W != a->Wv) return false;
   if (a->W < minw || a->W + 2 > 256 || a->view_sw != 1 || a->view_sh != a->Wv || a->view_off[0] != 0) return false;
   for (int t = 0; t < 9; ++t)
@@ -778,10 +786,21 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
 
   const size_t fixed_bytes = smem_fixed_bytes(a);
   const size_t budget = smem_budget(a);
-  const size_t stage_bytes = P.halo ? (size_t)P.stage_b_bytes : (size_t)P.stage_a_bytes + P.stage_b_bytes;
+  // K-blocks per stage: one barrier round trip per stage costs a few hundred cycles on the single MMA-issuing thread, so every
+  // stage should carry >= ~384 cycles of tensor work (BK/16 MMAs of BN/2 cycles each per K-block) while >= 4 stages still fit.
+  P.sps = 1;
+  if (!P.halo) {
+    const size_t sub = (size_t)P.stage_a_bytes + P.stage_b_bytes;
+    const int cyc = (a->BK / 16) * (a->BN / 2);
+    const char* e = getenv("DS_CONV_MAX_SPS");
+    const int max_sps = e ? atoi(e) : 4;
+    while (P.sps < max_sps && P.sps * cyc < 384 && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * 4 <= budget) ++P.sps;
+  }
+  const size_t stage_bytes = P.halo ? (size_t)P.stage_b_bytes : (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
   int stages = (int)((budget - (P.halo ? 2 * (size_t)P.halo_a_bytes : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (!P.halo && stages > P.num_kb && P.num_kb >= 2) stages = P.num_kb;
+  const int stage_iters = (P.num_kb + P.sps - 1) / P.sps;
+  if (!P.halo && stages > stage_iters && stage_iters >= 2) stages = stage_iters;
   DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables leave no room for a 2-stage pipeline (Cout_pad=%d ncls=%d)", a->Cout_pad, a->ncls);
   P.stages = stages;
   const size_t smem = fixed_bytes + (P.halo ? 2 * (size_t)P.halo_a_bytes : 0) + stages * stage_bytes;

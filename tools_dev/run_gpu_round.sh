@@ -7,7 +7,7 @@ tests)
   timeout 1500 python -m pytest tests/test_gpu_model.py -q -m gpu --tb=short -s > gpurun_out/t_model.log 2>&1; echo "model rc=$?" >> gpurun_out/rc.txt
   tail -4 gpurun_out/t_kern.log; tail -12 gpurun_out/t_model.log ;;
 bench)
-  timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
+  DS_DUMP_OPS=gpurun_out/ops.json timeout 1200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/rc.txt
   tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
 ncu)
   timeout 600 python bench.py --steps 1 --warmup 1 --sample-steps 2 > gpurun_out/plain.log 2>&1 && \

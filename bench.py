@@ -217,6 +217,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     from diffusynth_b200 import TextToTimbre, weights as W
     from diffusynth_b200.pipeline import all_gather_waveforms, shard_range

@@ -7,42 +7,24 @@
 namespace ds {
 
 // ---------------------------------------------------------------------------------------------
-// dwconv7: 16-bit NHWC in (one or two channel-concatenated sources), 16-bit NHWC out, fp32 accumulation.
-//
-// A depthwise conv has no channel reduction, so it cannot fill a tcgen05 tile; on the fp32 pipe it is bound by FMA
-// issue (49 MAC per element; measured 24 TFLOP/s = 67% of the register-operand FFMA/FFMA2 rate, 6.4 ms per U-Net
-// evaluation).  Here it runs on the warp-level tensor-core path instead: mma.sync.m16n8k16 with
-//   M = 16 output pixels of one image row,  N = 8 channels,  K = 2 horizontal taps x 8 channels,
-//   A[m][(t,c)] = x[row+ky][m + kx0 + t][c]          -- ldmatrix.x4 straight from the NHWC halo tile in smem
-//   B[(t,c)][n] = w[ky][kx0+t][n] if c == n else 0     -- per-thread constant fragments (block-diagonal weights)
-// i.e. 28 MMAs (7 rows x 4 tap pairs, the 8th tap is a zero weight) per 16x8 output block; 1/8 of the MMA lanes are
-// useful, which still leaves the kernel bound by shared-memory / HBM traffic rather than by math.
-// block = 256 threads = 8 warps; tile = 8 rows x 16 cols x 32 channels; warp = (channel group of 8) x (4 rows).
+// dwconv7: bf16 NHWC in (one or two channel-concatenated sources), bf16 NHWC out.
+// block = 256 threads = 16 channel pairs x 16 pixel-threads; tile = 8 rows x 16 cols x 32 channels.
+// (A warp-level tensor-core formulation -- mma.sync m16n8k16 with block-diagonal weight fragments, 1/8 of the lanes
+// useful -- was measured on B200 at 9.6 ms per U-Net evaluation against 6.4 ms for this kernel: legacy HMMA is too slow
+// on sm_100a to pay for the 8x redundancy.  See profiles/r01_notes.md.)
+// The (8+6) x (16+6) halo tile is staged in shared memory as fp32 (row pitch padded to 23 pixels so the two
+// pixel-threads of a warp hit different banks); each thread slides a 7-wide window over 8 outputs with packed FFMA2.
 // ---------------------------------------------------------------------------------------------
 static constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 32;
-static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6;
-static constexpr int DW_PIX = 40;     // halves per staged pixel: 32 channels + 8 pad -> conflict-free ldmatrix rows (80 B pitch)
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t smem_addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr));
-}
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-#ifdef DS_OPERANDS_BF16
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-#else
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-#endif
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
+static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6, DW_PITCH = 23;
 
 __global__ void __launch_bounds__(256)
 dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, int C0, int C1, int src_batch_mod,
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
                act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w, int tiles) {
-  __shared__ __align__(16) act_t s_in[(DW_HH * DW_HW + 2) * DW_PIX];
+  __shared__ __align__(16) float2 s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // fp32 channel pairs (converted once at staging)
+  __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
   __shared__ float s_red[16];
   const int C = C0 + C1;
   const int tile = blockIdx.x, cblk = blockIdx.y, n = blockIdx.z;
@@ -54,81 +36,67 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   if (c0 < C0) { src = src0; Cs = C0; cs0 = c0; } else { src = src1; Cs = C1; cs0 = c0 - C0; }
   src += (size_t)nsrc * H * W * Cs;
 
-  // stage the halo tile (zero outside the image = the conv's padding); 16-byte pieces, 4 per pixel
-  for (int i = threadIdx.x; i < (DW_HH * DW_HW + 2) * 4; i += 256) {
+  // stage weights: s_w[tap][cp] = (w[tap][c0+2cp], w[tap][c0+2cp+1])
+  for (int i = threadIdx.x; i < 49 * (DW_CB / 2); i += 256) {
+    const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
+    s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
+  }
+  // stage the halo tile: 16-byte pieces (8 channels) per thread, converted to fp32 once; 4 pieces per pixel
+  for (int i = threadIdx.x; i < DW_HH * DW_HW * 4; i += 256) {
     const int piece = i & 3, pix = i >> 2;
     const int r = pix / DW_HW, cc = pix - r * DW_HW;
     const int y = h0 + r - 3, x = w0 + cc - 3;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < DW_HH && y >= 0 && y < H && x >= 0 && x < W)
+    if (y >= 0 && y < H && x >= 0 && x < W)
       v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)y * W + x) * Cs + cs0 + piece * 8));
-    *reinterpret_cast<uint4*>(&s_in[pix * DW_PIX + piece * 8]) = v;
+    float4* dst = reinterpret_cast<float4*>(&s_in[(r * DW_PITCH + cc) * (DW_CB / 2) + piece * 4]);
+    const float2 a = cvt16x2(v.x), b = cvt16x2(v.y), c = cvt16x2(v.z), d = cvt16x2(v.w);
+    dst[0] = make_float4(a.x, a.y, b.x, b.y);
+    dst[1] = make_float4(c.x, c.y, d.x, d.y);
   }
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cg = warp & 3, rbase = (warp >> 2) * 4;      // channel group (8 channels), first of this warp's 4 tile rows
-  // B fragments: thread (k0 = 2*(lane%4), n = lane/4) holds B[k0..k0+1][n] and B[k0+8..k0+9][n]; only c == n is non-zero
-  const int bn = lane >> 2;
-  const bool b_active = (lane & 3) == (bn >> 1);
-  const int bch = c0 + cg * 8 + bn;
-  uint32_t bfrag[7][4][2];
-#pragma unroll
-  for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-    for (int kp = 0; kp < 4; ++kp) {
-      const float wa = b_active ? __ldg(weight + (size_t)(ky * 7 + 2 * kp) * C + bch) : 0.f;
-      const float wb = (b_active && kp < 3) ? __ldg(weight + (size_t)(ky * 7 + 2 * kp + 1) * C + bch) : 0.f;
-      bfrag[ky][kp][0] = (bn & 1) ? pack16(0.f, wa) : pack16(wa, 0.f);
-      bfrag[ky][kp][1] = (bn & 1) ? pack16(0.f, wb) : pack16(wb, 0.f);
-    }
   __syncthreads();
 
-  // ldmatrix row address of this lane: matrix j = lane/8 -> (m0 = 8*(j&1), tap t = j>>1), row i = lane%8
-  const int lj = lane >> 3, li = lane & 7;
-  const uint32_t a_lane = (uint32_t)__cvta_generic_to_shared(s_in) + (uint32_t)(((lj & 1) * 8 + li + (lj >> 1)) * DW_PIX + cg * 8) * 2u;
-  float acc[4][4];
+  const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
+  const int row = pt & 7, col0 = (pt >> 3) * 8;
+  float2 acc[8];       // (channel 2cp, channel 2cp+1) of 8 consecutive output columns: packed FFMA2 lanes
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+  for (int ky = 0; ky < 7; ++ky) {
+    float2 wv[7];
 #pragma unroll
-  for (int hrl = 0; hrl < 10; ++hrl) {                    // halo row rbase + hrl feeds output rows lr with ky = hrl - lr
-    uint32_t a[4][4];
+    for (int kx = 0; kx < 7; ++kx) wv[kx] = s_w[(ky * 7 + kx) * (DW_CB / 2) + cp];
+    const float2* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
 #pragma unroll
-    for (int kp = 0; kp < 4; ++kp)
-      ldmatrix_x4(a[kp], a_lane + (uint32_t)(((rbase + hrl) * DW_HW + 2 * kp) * DW_PIX) * 2u);
+    for (int j = 0; j < 14; ++j) {
+      const float2 in = rowp[j * (DW_CB / 2)];
 #pragma unroll
-    for (int lr = 0; lr < 4; ++lr) {
-      const int ky = hrl - lr;
-      if (ky >= 0 && ky < 7) {
-#pragma unroll
-        for (int kp = 0; kp < 4; ++kp) mma16816(acc[lr], a[kp], bfrag[ky][kp][0], bfrag[ky][kp][1]);
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ow = j - kx;
+        if (ow >= 0 && ow < 8) ffma2(acc[ow], in, wv[kx]);
       }
     }
   }
-  // D fragment: acc[.][0,1] -> pixel column lane/4, channels 2*(lane%4)+{0,1}; acc[.][2,3] -> column lane/4 + 8
-  const int c = c0 + cg * 8 + (lane & 3) * 2;
+  const int c = c0 + 2 * cp;
   const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
   const float b0 = __ldg(tb + c), b1 = __ldg(tb + c + 1);
+  const int y = h0 + row;
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int lr = 0; lr < 4; ++lr) {
-    const int y = h0 + rbase + lr;
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int x = w0 + (lane >> 2) + hf * 8;
-      if (y < H && x < W) {
-        const float v0 = acc[lr][2 * hf] + b0, v1 = acc[lr][2 * hf + 1] + b1;
-        s += v0 + v1;
-        q = fmaf(v0, v0, fmaf(v1, v1, q));
-        *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
-      }
+  for (int j = 0; j < 8; ++j) {
+    const int x = w0 + col0 + j;
+    if (y < H && x < W) {
+      const float v0 = acc[j].x + b0, v1 = acc[j].y + b1;
+      s += v0 + v1;
+      q = fmaf(v0, v0, fmaf(v1, v1, q));
+      *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
     }
   }
   if (stats != nullptr) {
     s = warp_sum(s);
     q = warp_sum(q);
-    if (lane == 0) { s_red[warp] = s; s_red[8 + warp] = q; }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_red[warp] = s; s_red[8 + warp] = q; }
     __syncthreads();
     if (threadIdx.x < 32) {
       float ts = 0.f, tq = 0.f;

@@ -200,6 +200,17 @@ __device__ __forceinline__ void tmem_ld_x16_lo(uint32_t taddr, uint32_t (&r)[32]
       : "memory");
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {          // read-only tables: may be scheduled freely
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4_volatile(uint32_t addr) { // per-tile buffers rewritten by the same warp
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // GELU(x) = relu(x) - 0.5 |x| q(|x|),  q = poly(t) t exp(-x^2/2),  t = 1/(1 + p |x|/sqrt2)   (Abramowitz-Stegun 7.1.26,
 // |erf error| <= 1.5e-7; the 0.5 is folded into the coefficients).  Straight-line, 2 MUFU + 13 FP32 ops.
 __device__ __forceinline__ float gelu_epi(float x) {
@@ -482,47 +493,47 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       int cls = 0;
       if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
       const float nmr = -mean * rstd;
-      const bool use_e1 = P.e1 != nullptr;
-      const float* e1 = s_e1 + cls * P.Cout_pad + t.nt * P.BN;
-      const float* e2 = s_e2 + cls * P.Cout_pad + t.nt * P.BN;
-      const float* sb = P.sbias ? my_sb - chunk_lo * 16 : nullptr;      // indexed by the column inside the tile
-      const int col0 = t.nt * P.BN;
-      const long long pix_out = P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw + col0;
-      const long long pix_res = (long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw + col0;
-      const bool has_res = P.residual != nullptr && valid;
+      const bool use_e1 = P.e1 != nullptr, use_sb = P.sbias != nullptr, do_stats = P.stats_out != nullptr;
+      const int col0 = t.nt * P.BN + chunk_lo * 16;        // first global output channel of this warp's column range
+      // running addresses, advanced by one 16-column chunk at a time: 32-bit shared-space addresses for the tables (so the
+      // loads are LDS with immediate offsets, not generic LD), element pointers for the tensors
+      uint32_t e2_s = smem_u32(s_e2) + (uint32_t)(cls * P.Cout_pad + col0) * 4u;
+      uint32_t e1_s = smem_u32(s_e1) + (uint32_t)(cls * P.Cout_pad + col0) * 4u;
+      uint32_t sb_s = smem_u32(my_sb);
+      act_t* out_p = P.out ? P.out + (P.out_goff[t.g] + (long long)t.n * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw + col0) : nullptr;
+      const act_t* res_p = P.residual ? P.residual + ((long long)t.n * P.res_sn + (long long)h * P.res_sh + (long long)w * P.res_sw + col0) : nullptr;
+      float* o32_p = P.out_f32 ? P.out_f32 + (((size_t)t.n * P.Cout + col0) * P.H + h) * P.W + w : nullptr;
+      const size_t o32_stride = (size_t)P.H * P.W;
+      const bool has_res = res_p != nullptr && valid;
+      int cols_left = P.Cout - col0;                       // real (unpadded) output channels from col0 on
       float psum = 0.f, psq = 0.f;
 
-      // one 16-column chunk (ch = chunk index inside the tile): folded-GroupNorm scalars, bias, activation, residual,
-      // statistics, store.  r = accumulator values, ra/rb = prefetched residual.
-      auto finish_chunk = [&](int ch, const uint32_t* r, const uint4& ra, const uint4& rb) {
-        const int c0 = ch * 16;                 // column inside the tile
-        const int o0 = col0 + c0;               // global output channel
+      // one 16-column chunk: folded-GroupNorm scalars, bias, activation, residual, statistics, store.
+      // r = accumulator values, ra/rb = prefetched residual.  Advances the running addresses.
+      auto finish_chunk = [&](const uint32_t* r, const uint4& ra, const uint4& rb) {
         float v[16];
-        const float4* e2v = reinterpret_cast<const float4*>(e2 + c0);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 b4 = e2v[q4];
+          const float4 b4 = lds_f4(e2_s + 16u * q4);
           v[4 * q4 + 0] = fmaf(__uint_as_float(r[4 * q4 + 0]), rstd, b4.x);
           v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), rstd, b4.y);
           v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, b4.z);
           v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, b4.w);
         }
         if (use_e1) {
-          const float4* e1v = reinterpret_cast<const float4*>(e1 + c0);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 a4 = e1v[q4];
+            const float4 a4 = lds_f4(e1_s + 16u * q4);
             v[4 * q4 + 0] = fmaf(nmr, a4.x, v[4 * q4 + 0]);
             v[4 * q4 + 1] = fmaf(nmr, a4.y, v[4 * q4 + 1]);
             v[4 * q4 + 2] = fmaf(nmr, a4.z, v[4 * q4 + 2]);
             v[4 * q4 + 3] = fmaf(nmr, a4.w, v[4 * q4 + 3]);
           }
         }
-        if (sb) {
-          const float4* sbv = reinterpret_cast<const float4*>(sb + c0);
+        if (use_sb) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            const float4 a4 = sbv[q4];
+            const float4 a4 = lds_f4_volatile(sb_s + 16u * q4);
             v[4 * q4 + 0] += a4.x; v[4 * q4 + 1] += a4.y; v[4 * q4 + 2] += a4.z; v[4 * q4 + 3] += a4.w;
           }
         }
@@ -530,41 +541,44 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = gelu_epi(v[j]);
         }
-        if (!valid) return;
-        if (has_res && o0 < P.Cout) {
-          const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        if (valid && cols_left > 0) {
+          if (has_res) {
+            const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[2 * j] += lo16(rr[j]);
-            v[2 * j + 1] += hi16(rr[j]);
+            for (int j = 0; j < 8; ++j) {
+              v[2 * j] += lo16(rr[j]);
+              v[2 * j + 1] += hi16(rr[j]);
+            }
           }
-        }
-        if (P.stats_out != nullptr) {
-          if (o0 + 16 <= P.Cout) {
+          if (do_stats) {
+            if (cols_left >= 16) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
-          } else {
+              for (int j = 0; j < 16; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < cols_left) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+            }
+          }
+          if (out_p != nullptr) {           // Cout % 16 == 0 is enforced for 16-bit outputs
+            uint4 a, b;
+            a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
+            a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
+            b.x = pack16_epi(v[8], v[9]);   b.y = pack16_epi(v[10], v[11]);
+            b.z = pack16_epi(v[12], v[13]); b.w = pack16_epi(v[14], v[15]);
+            reinterpret_cast<uint4*>(out_p)[0] = a;
+            reinterpret_cast<uint4*>(out_p)[1] = b;
+          }
+          if (o32_p != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (o0 + j < P.Cout) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+              if (j < cols_left) o32_p[(size_t)j * o32_stride] = v[j];
           }
         }
-        if (P.out != nullptr && o0 < P.Cout) {
-          uint4 a, b;
-          a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
-          a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
-          b.x = pack16_epi(v[8], v[9]);   b.y = pack16_epi(v[10], v[11]);
-          b.z = pack16_epi(v[12], v[13]); b.w = pack16_epi(v[14], v[15]);
-          uint4* op = reinterpret_cast<uint4*>(P.out + pix_out + c0);
-          op[0] = a;
-          op[1] = b;
-        }
-        if (P.out_f32 != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (o0 + j < P.Cout)
-              P.out_f32[(((size_t)t.n * P.Cout + (o0 + j)) * P.H + h) * P.W + w] = v[j];
-        }
+        e2_s += 64u; e1_s += 64u; sb_s += 64u;
+        if (out_p) out_p += 16;
+        if (o32_p) o32_p += 16 * o32_stride;
+        cols_left -= 16;
       };
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
       // pair p covers chunks chunk_lo + 2p (and + 2p + 1 when it exists)
@@ -574,19 +588,18 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         else tmem_ld_x16_lo(t_row + (uint32_t)(ch * 16), r);
       };
       auto fetch_res = [&](int p, uint4 (&rr)[4]) {
-        const int ch = chunk_lo + 2 * p;
         rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0, 0, 0, 0);
         if (has_res) {
-          const int o0 = col0 + ch * 16;
-          const uint4* rp = reinterpret_cast<const uint4*>(P.residual + pix_res + ch * 16);
-          if (o0 < P.Cout) { rr[0] = __ldg(rp); rr[1] = __ldg(rp + 1); }
-          if (ch + 1 < chunk_hi && o0 + 16 < P.Cout) { rr[2] = __ldg(rp + 2); rr[3] = __ldg(rp + 3); }
+          const int ch = chunk_lo + 2 * p;
+          const int left = P.Cout - (t.nt * P.BN + ch * 16);
+          const uint4* rp = reinterpret_cast<const uint4*>(res_p + 32 * p);
+          if (left > 0) { rr[0] = __ldg(rp); rr[1] = __ldg(rp + 1); }
+          if (ch + 1 < chunk_hi && left > 16) { rr[2] = __ldg(rp + 2); rr[3] = __ldg(rp + 3); }
         }
       };
       auto finish_pair = [&](int p, uint32_t (&r)[32], const uint4 (&rr)[4]) {
-        const int ch = chunk_lo + 2 * p;
-        finish_chunk(ch, &r[0], rr[0], rr[1]);
-        if (ch + 1 < chunk_hi) finish_chunk(ch + 1, &r[16], rr[2], rr[3]);
+        finish_chunk(&r[0], rr[0], rr[1]);
+        if (chunk_lo + 2 * p + 1 < chunk_hi) finish_chunk(&r[16], rr[2], rr[3]);
       };
 
       mbar_wait(&tmem_full[acc], acc_phase);

@@ -812,8 +812,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   const size_t stage_bytes = P.halo ? (size_t)P.stage_b_bytes : (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
   int stages = (int)((budget - (P.halo ? 2 * (size_t)P.halo_a_bytes : 0)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  const int stage_iters = (P.num_kb + P.sps - 1) / P.sps;
-  if (!P.halo && stages > stage_iters && stage_iters >= 2) stages = stage_iters;
+  // (the ring spans tiles of the persistent loop: small-K convs prefetch several tiles ahead, so it is never clamped to K)
   DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables leave no room for a 2-stage pipeline (Cout_pad=%d ncls=%d)", a->Cout_pad, a->ncls);
   P.stages = stages;
   const size_t smem = fixed_bytes + (P.halo ? 2 * (size_t)P.halo_a_bytes : 0) + stages * stage_bytes;

@@ -185,7 +185,9 @@ def profile_unet_eval(plan):
         elif name.endswith("gn_res"):
             key = "gn_apply_residual"
         elif name == "init_conv":
-            key = "stem_conv7"
+            key = "conv_gemm(1x1)"
+        elif name == "init_im2col":
+            key = "stem_im2col"
         elif name.startswith("time_"):
             key = "time_mlp"
         else:
@@ -199,7 +201,7 @@ def profile_unet_eval(plan):
         for name, e0, e1 in evs:
             ms = e0.elapsed_time(e1)
             row = dict(op=name, ms=round(ms, 4))
-            is_conv = name.endswith(("net.1", "net.4", "final_conv.1", "res_conv", "to_qkv", "to_out")) or name.split(".")[-1] in ("2", "4") and name.count(".") == 2
+            is_conv = name == "init_conv" or name.endswith(("net.1", "net.4", "final_conv.1", "res_conv", "to_qkv", "to_out")) or name.split(".")[-1] in ("2", "4") and name.count(".") == 2
             if is_conv and ci < len(convs):
                 a = convs[ci]; ci += 1
                 row.update(tflops=round(conv_flops(a) / (ms / 1e3) / 1e12, 1), H=a.H, W=a.W, Cin=a.C0 + a.C1, Cout=a.Cout, taps=a.ntaps, BN=a.BN, BK=a.BK)

@@ -59,6 +59,7 @@ _SIGNATURES = {
     "ds_dwconv7": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _F, _I, _I, _I, _P]),
     "ds_dwconv7_stats_slots": (_I, [_I, _I, _I]),
     "ds_stem_conv7": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ds_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ds_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _P]),
     "ds_linear": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "ds_attn_chunks": (_I, [_L]),

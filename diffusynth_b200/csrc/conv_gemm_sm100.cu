@@ -28,6 +28,7 @@ struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;
+  int dbg;                          // DS_CONV_DBG bitmask (profiling experiments): 1 = no global stores, 2 = no TMEM loads, 4 = no MMA issue
   int sps;                          // K-blocks per pipeline stage (generic mode): keeps >= ~384 MMA cycles behind every barrier round trip
   unsigned stage_a_bytes, stage_b_bytes;
   int halo, Wp, halo_rows;          // halo mode (3x3 stride 1): one (halo_rows x Wp)-pixel activation box per channel block
@@ -405,7 +406,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
+                if (!(P.dbg & 4)) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
                 accum = 1u;
               }
             }
@@ -560,7 +561,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
                 if (j < cols_left) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
             }
           }
-          if (out_p != nullptr) {           // Cout % 16 == 0 is enforced for 16-bit outputs
+          if (out_p != nullptr && !(P.dbg & 1)) {           // Cout % 16 == 0 is enforced for 16-bit outputs
             uint4 a, b;
             a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
             a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
@@ -584,6 +585,11 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       // pair p covers chunks chunk_lo + 2p (and + 2p + 1 when it exists)
       auto issue_pair = [&](int p, uint32_t (&r)[32]) {
         const int ch = chunk_lo + 2 * p;
+        if (P.dbg & 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j;
+          return;
+        }
         if (ch + 1 < chunk_hi) tmem_ld_32x32b_x32(t_row + (uint32_t)(ch * 16), r);
         else tmem_ld_x16_lo(t_row + (uint32_t)(ch * 16), r);
       };
@@ -713,6 +719,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
   P.stage_a_bytes = BM * a->BK * 2;
   P.stage_b_bytes = a->BN * a->BK * 2;
+  { const char* e = getenv("DS_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
   P.halo = use_halo(a) ? 1 : 0;
   if (P.halo) {
     P.Wp = a->W + 2;

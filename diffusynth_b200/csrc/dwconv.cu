@@ -171,6 +171,38 @@ stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem as a GEMM: im2col of the 7x7xCin (Cin <= 4) patches into a 16-bit [N, H, W, 224] matrix (k = ky*32 + kx*4 + ci,
+// the 8th pixel slot of every ky row is zero) so that init_conv runs as a 1x1 ds_conv_gemm with K = 224 on the tensor cores.
+// One thread per (pixel, ky): 64 contiguous output bytes.
+// ---------------------------------------------------------------------------------------------
+__global__ void stem_im2col_kernel(const float* __restrict__ x, act_t* __restrict__ col, int Cin, int H, int W, long long total /* N*H*W*7 */) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W);
+    long long r = i / W;
+    const int ky = (int)(r % 7); r /= 7;
+    const int y = (int)(r % H);
+    const long long n = r / H;
+    const int sy = y + ky - 3;
+    uint32_t packed[16];
+#pragma unroll
+    for (int kx = 0; kx < 8; ++kx) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int sx = xx + kx - 3;
+      if (kx < 7 && sy >= 0 && sy < H && sx >= 0 && sx < W) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci < Cin) v[ci] = __ldg(x + ((n * Cin + ci) * H + sy) * W + sx);
+      }
+      packed[2 * kx] = pack16(v[0], v[1]);
+      packed[2 * kx + 1] = pack16(v[2], v[3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(col + ((n * H + y) * W + xx) * 224 + ky * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+  }
+}
+
 }  // namespace ds
 
 using namespace ds;
@@ -214,6 +246,17 @@ int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, cons
                                                                      Cin, Cout, H, W, tiles_w, tps, total);
   if (Cout == 96) { LAUNCH_STEM(48) } else if (Cout == 64) { LAUNCH_STEM(32) } else if (Cout == 32) { LAUNCH_STEM(16) } else { LAUNCH_STEM(64) }
 #undef LAUNCH_STEM
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+/* im2col for the stem (init_conv as a GEMM): d_x fp32 NCHW [N, Cin<=4, H, W] -> d_col act16 [N, H, W, 224]. */
+int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, void* stream) {
+  DS_REQUIRE(d_x && d_col && N > 0 && Cin > 0 && Cin <= 4 && H > 0 && W > 0, "ds_stem_im2col: bad arguments");
+  const long long total = (long long)N * H * W * 7;
+  long long g = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  stem_im2col_kernel<<<(int)(g < cap ? g : cap), 256, 0, (cudaStream_t)stream>>>(d_x, (act_t*)d_col, Cin, H, W, total);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import weights as W
-from .codec import spectrogram_to_waveform
+from .codec import adjust_audio_length, spectrogram_to_waveform, waveform_to_spectrogram
 from .sampler import DiffSynthSampler
 from .unet import ConditionedUnet
 from .vqgan import VQGAN
@@ -73,6 +73,52 @@ class TextToTimbre:
         spec = self.vqgan._decoder(q)                                      # utils.py:224
         wave = spectrogram_to_waveform(spec)                               # utils.py:229-241
         return Timbres(latents, q, spec, wave)
+
+
+    # ---- timbre modification (sound2sound_with_text.py:47-269) -------------------------------------------------------
+    @torch.no_grad()
+    def encode_audio(self, wave: torch.Tensor, width: int = 64) -> torch.Tensor:
+        """receive_upload_origin_audio's tensor path (:75-107): peak-normalise, crop/zero-pad to 256*(4w-1) samples, STFT
+        (1024/256, hann) -> pad_STFT -> encode_stft -> VQGAN encoder.  Returns the UN-quantised latent [B,4,128,w] (:107)."""
+        wave = wave.to(self.device, torch.float32)
+        wave = wave / wave.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12)              # :75
+        wave = adjust_audio_length(wave, 256 * (4 * width - 1))                            # :80-82
+        spec = waveform_to_spectrogram(wave, time_resolution=4 * width)                    # :85-94
+        return self.vqgan._encoder(spec)
+
+    @torch.no_grad()
+    def modify(self, guide_latent: torch.Tensor, cond: torch.Tensor, uncond: Optional[torch.Tensor], steps: int = 20,
+               strength: float = 0.7, cfg_scale: float = 6, sampler: str = "ddim", seed: Optional[int] = None,
+               noise_feed: Optional[torch.Tensor] = None, decode: bool = True) -> Timbres:
+        """sound2sound_sample (:126-269): respace to int(steps/strength) (:185), img_guided_sample(noising_strength=strength,
+        guide_img=latent.repeat(B)) (:194-203), then the same VQ -> decoder -> iSTFT tail as text-to-timbre."""
+        B = cond.shape[0]
+        width = guide_latent.shape[-1]
+        n_steps = int(steps / strength)
+        key = ("modify", B, n_steps)
+        s = self._samplers.get(key)
+        if s is None:
+            s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy=self.noise_strategy,
+                                 mute=True, device=str(self.device), max_batchsize=B)
+            s.respace(list(np.linspace(0, self.timesteps - 1, n_steps, dtype=np.int32)))
+            self._samplers[key] = s
+        s.activate_classifier_free_guidance(cfg_scale, uncond)
+        guide = guide_latent.to(self.device, torch.float32)
+        if guide.shape[0] == 1 and B > 1:
+            guide = guide.repeat(B, 1, 1, 1)
+        init = None
+        s.noise_feed = None
+        if noise_feed is not None:
+            init = noise_feed[0][:B].to(self.device, torch.float32)
+            s.noise_feed = noise_feed[1:]
+        imgs, _ = s.img_guided_sample(self.unet, (B, self.channels, self.height, width), strength, guide, return_tensor=True,
+                                      condition=cond.to(self.device), sampler=sampler, initial_noise=init, seed=seed)
+        latents = imgs[-1]
+        if not decode:
+            return Timbres(latents, None, None, None)
+        q, _, _ = self.vqgan._vq_vae(latents)
+        spec = self.vqgan._decoder(q)
+        return Timbres(latents, q, spec, spectrogram_to_waveform(spec))
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -197,9 +197,17 @@ class ConditionedUnet:
         self.lab_b = sd["label_embedding.embedding.bias"].float().contiguous().to(dev)
         self.tm1_w, self.tm1_b = sd["time_mlp.1.weight"].float().contiguous().to(dev), sd["time_mlp.1.bias"].float().contiguous().to(dev)
         self.tm3_w, self.tm3_b = sd["time_mlp.3.weight"].float().contiguous().to(dev), sd["time_mlp.3.bias"].float().contiguous().to(dev)
-        # stem: [96,4,7,7] -> [(ky,kx,ci)][Cout]
-        self.stem_w = sd["init_conv.weight"].float().permute(2, 3, 1, 0).reshape(-1, dd[0]).contiguous().to(dev)
-        self.stem_b = sd["init_conv.bias"].float().contiguous().to(dev)
+        # stem as a GEMM over im2col patches: [Cout, Cin, 7, 7] -> [Cout, ky*32 + kx*4 + ci] (8th pixel slot and ci >= Cin are zero)
+        w0 = sd["init_conv.weight"].float()
+        wst = torch.zeros(dd[0], 7, 8, 4)
+        wst[:, :, :7, :cfg["in_dim"]] = w0.permute(0, 2, 3, 1)
+        cout_pad = ops.pad16(dd[0])
+        e2 = torch.zeros(1, cout_pad)
+        e2[0, :dd[0]] = sd["init_conv.bias"].float()
+        wp = torch.zeros(1, cout_pad, 224, dtype=ops.ACT)
+        wp[0, :dd[0]] = wst.reshape(dd[0], 224).to(ops.ACT)
+        self.stem = PackedConv(weight=wp.contiguous(), e2=e2, e1=None, taps=[[(0, 0, 0)]], cin=224, cout=dd[0], cout_pad=cout_pad,
+                               ncls=1, kind="s1").to(dev)
         for m in list(self.blocks.values()) + list(self.attns.values()):
             m.to(dev)
         for s in self.samplers.values():
@@ -341,8 +349,9 @@ class _Plan:
         n_stage = len(dd) - 1
         h, w = H, Wd
         x0 = act(N, h, w, dd[0])
-        add("init_conv", lambda: check(lib.ds_stem_conv7(self.x.data_ptr(), x_batch_mod, net.stem_w.data_ptr(), net.stem_b.data_ptr(),
-                                                         x0.data_ptr(), N, cfg["in_dim"], dd[0], H, Wd, stream()), "stem_conv7"))
+        col = act(nb, h, w, 224)
+        add("init_im2col", lambda: check(lib.ds_stem_im2col(self.x.data_ptr(), col.data_ptr(), nb, cfg["in_dim"], H, Wd, stream()), "stem_im2col"))
+        conv("init_conv", net.stem, col, None, h, w, out=x0, src_batch_mod=x_batch_mod)
         self.named["init_conv"] = (x0, dd[0])
         hs = [x0]
         x = x0

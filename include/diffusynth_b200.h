@@ -138,6 +138,8 @@ int ds_dwconv7_stats_slots(int C, int H, int W);
 /* init_conv 7x7 (model/diffusion.py:82,208): fp32 NCHW in, act16 NHWC out. */
 int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out,
                   int N, int Cin, int Cout, int H, int W, void* stream);
+/* init_conv as a tensor-core GEMM: 7x7xCin patches -> act16 [N, H, W, 224] (k = ky*32 + kx*4 + ci), then ds_conv_gemm 1x1. */
+int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, void* stream);
 /* SinusoidalPositionEmbeddings (:42-56) and the small Linear layers (time_mlp, per-block mlp,
    label_embedding, label_key/label_query): out = act_out(bias + W . act_in(in)); act 1 = GELU(erf). */
 int ds_sinusoidal_embedding(const long long* d_t, float* d_out, int N, int dim, void* stream);

@@ -173,3 +173,39 @@ def test_text_to_timbre_pipeline_parity():
     print(f"\npipeline: latent {e_lat:.2e}  spectrogram {e_spec:.2e}  waveform {e_wave:.2e}  (iSTFT alone {e_istft:.2e})")
     assert tuple(out.waveforms.shape) == (B, 65280)
     assert e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL and e_istft < 1e-5
+
+
+def test_timbre_modification_pipeline_parity():
+    """BASELINE config 5 at B=2: waveform -> STFT+ -> encoder -> q_sample(guide, strength) -> partial re-denoise with CFG ->
+    VQ -> decoder -> iSTFT.  strength 0.7, 3 steps -> respaced to int(3/0.7) = 4, start index int(4*0.7) = 2 -> 2 U-Net steps."""
+    from diffusynth_b200 import TextToTimbre, VQGAN
+    usd, vsd = W.unet_random_state_dict(seed=0), W.vqgan_random_state_dict(seed=1)
+    unet = _unet(W.UNET_DEPLOYED, usd)
+    vq = VQGAN(**W.VQGAN_DEPLOYED, device="cuda")
+    vq.load_state_dict(vsd)
+    pipe = TextToTimbre(unet, vq)
+    B, steps, strength = 2, 3, 0.7
+    wave = torch.from_numpy(cases.synthetic_wave(seed=33)).float()[None]
+    guide = pipe.encode_audio(wave.cuda())
+    enc_plan, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
+    with torch.no_grad():
+        spec_ref = torch.from_numpy(O.waveform_to_spectrogram(cases.synthetic_wave(seed=33) / np.abs(cases.synthetic_wave(seed=33)).max())[None])
+        guide_ref = O.vqgan_encode(vsd, enc_plan, spec_ref)
+    e_guide = rel(guide, guide_ref)
+    n_steps = int(steps / strength)
+    draws = W.host_noise(9, 1 + n_steps, B)
+    cond, uncond = W.synthetic_conditions(B, 512)
+    out = pipe.modify(guide_ref.cuda(), cond.cuda(), uncond.cuda(), steps=steps, strength=strength, noise_feed=draws)
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, n_steps, dtype=np.int32)))
+    with torch.no_grad():
+        ref = O.sample_loop(lambda x, t, c: O.unet_forward(usd, x, t, c), sch, (B, 4, 128, 64), cond, uncond, 6, draws,
+                            guide=guide_ref.repeat(B, 1, 1, 1), start_ratio=strength)
+        q_same, _ = O.vq_quantize(out.latents.cpu(), vsd["_vq_vae._embedding.weight"])
+        spec = O.vqgan_decode(vsd, dec_plan, q_same)
+    wave_ref = np.stack([O.spectrogram_to_waveform(s.numpy().astype(np.float64)) for s in spec])
+    e_lat, e_spec, e_wave = rel(out.latents, ref[-1]), rel(out.spectrograms, spec), rel(out.waveforms, torch.from_numpy(wave_ref))
+    print(f"\nmodification: guide latent {e_guide:.2e}  ({len(ref) - 1} U-Net steps) latent {e_lat:.2e}  spectrogram {e_spec:.2e}  waveform {e_wave:.2e}")
+    assert len(ref) == int(n_steps * strength) + 1
+    assert torch.equal(q_same, out.quantized.cpu())
+    assert e_guide < BF16_TOL and e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL

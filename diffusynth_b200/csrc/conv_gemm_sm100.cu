@@ -28,6 +28,7 @@ struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;
+  float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb, inv_Wp;   // reciprocals for fast_divmod
   int dbg;                          // DS_CONV_DBG bitmask (profiling experiments): 1 = no global stores, 2 = no TMEM loads, 4 = no MMA issue
   int sps;                          // K-blocks per pipeline stage (generic mode): keeps >= ~384 MMA cycles behind every barrier round trip
   unsigned stage_a_bytes, stage_b_bytes;
@@ -166,16 +167,23 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
 // ---------------------------------------------------------------------------------------------
 struct TileCoord { int n, g, th, tw, nt, slot; };
 
+// x / d and x % d for 0 <= x < 2^22, 1 <= d: float reciprocal estimate + one correction step (6 instructions instead of the
+// ~25 of an integer division; the tile decode runs once per tile in every role warp).
+__device__ __forceinline__ void fast_divmod(int x, int d, float inv_d, int& q, int& r) {
+  q = __float2int_rz(((float)x + 0.5f) * inv_d);
+  r = x - q * d;
+  if (r < 0) { --q; r += d; }
+  else if (r >= d) { ++q; r -= d; }
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile) {
   TileCoord t;
-  t.nt = tile % P.n_tiles_n;
-  int r = tile / P.n_tiles_n;
-  int m = r % P.tiles_m;
-  r /= P.tiles_m;
-  t.g = r % P.groups;
-  t.n = r / P.groups;
-  t.th = m / P.tiles_w;
-  t.tw = m % P.tiles_w;
+  int r, m;
+  fast_divmod(tile, P.n_tiles_n, P.inv_n_tiles_n, r, t.nt);
+  int r2;
+  fast_divmod(r, P.tiles_m, P.inv_tiles_m, r2, m);
+  fast_divmod(r2, P.groups, P.inv_groups, t.n, t.g);
+  fast_divmod(m, P.tiles_w, P.inv_tiles_w, t.th, t.tw);
   t.slot = (t.g * P.tiles_m + m) * P.n_tiles_n + t.nt;
   return t;
 }
@@ -188,6 +196,13 @@ __device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
                  "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
                  "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
                  "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
                :
                : "memory");
 }
@@ -225,6 +240,31 @@ __device__ __forceinline__ float gelu_epi(float x) {
   p = fmaf(p, t, 0.5f * -0.284496736f);
   p = fmaf(p, t, 0.5f * 0.254829592f);
   return fmaxf(x, 0.0f) - ax * (p * t * e);
+}
+
+// GELU on 16 values, written stage by stage over groups of 8 so that the 8 independent dependency chains interleave
+// (ptxas serialises a per-element formulation when registers are tight: ~80 cycles per element at 2 warps per scheduler).
+__device__ __forceinline__ void gelu16(float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 16; g += 8) {
+    float ax[8], t[8], e[8], p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ax[j] = fabsf(v[g + j]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t[j]) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax[j], 1.0f)));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float w = ax[j] * 0.84932180028801904f; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[j]) : "f"(-w * w)); }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = fmaf(0.5f * 1.061405429f, t[j], 0.5f * -1.453152027f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], t[j], 0.5f * 1.421413741f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], t[j], 0.5f * -0.284496736f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], t[j], 0.5f * 0.254829592f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[g + j] = fmaxf(v[g + j], 0.0f) - ax[j] * (p[j] * t[j] * e[j]);
+  }
 }
 
 #ifdef DS_OPERANDS_BF16
@@ -449,7 +489,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const int chunk_lo = col_half == 0 ? 0 : (chunks + 1) / 2;
     const int chunk_hi = col_half == 0 ? (chunks + 1) / 2 : chunks;
     const int npairs = (chunk_hi - chunk_lo + 1) / 2;
-    const int ph = row / P.Wb, pw = row % P.Wb;
+    int ph, pw;
+    fast_divmod(row, P.Wb, P.inv_Wb, ph, pw);
     int acc = 0;
     uint32_t acc_phase = 0;
     // per-sample bias (to_qkv's label_query/label_key): this warp's column range, fetched one tile ahead into
@@ -469,9 +510,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const TileCoord t = decode_tile(P, tile);
       int h, w;
       if (HALO) {
-        const int q = (t.th * P.tiles_w + t.tw) * BM + row;
-        h = q / P.Wp;
-        w = q - h * P.Wp;
+        fast_divmod((t.th * P.tiles_w + t.tw) * BM + row, P.Wp, P.inv_Wp, h, w);
       } else {
         h = t.th * P.Hb + ph;
         w = t.tw * P.Wb + pw;
@@ -538,10 +577,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             v[4 * q4 + 0] += a4.x; v[4 * q4 + 1] += a4.y; v[4 * q4 + 2] += a4.z; v[4 * q4 + 3] += a4.w;
           }
         }
-        if (P.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = gelu_epi(v[j]);
-        }
+        if (P.act == 1) gelu16(v);
         if (valid && cols_left > 0) {
           if (has_res) {
             const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
@@ -581,49 +617,41 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         if (o32_p) o32_p += 16 * o32_stride;
         cols_left -= 16;
       };
-      const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN);
-      // pair p covers chunks chunk_lo + 2p (and + 2p + 1 when it exists)
-      auto issue_pair = [&](int p, uint32_t (&r)[32]) {
-        const int ch = chunk_lo + 2 * p;
+      const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN + chunk_lo * 16);
+      auto issue_chunk = [&](int c, uint32_t (&r)[16]) {      // c = chunk index inside this warp's column range
         if (P.dbg & 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0x3f800000u + j;
+          for (int j = 0; j < 16; ++j) r[j] = 0x3f800000u + j;
           return;
         }
-        if (ch + 1 < chunk_hi) tmem_ld_32x32b_x32(t_row + (uint32_t)(ch * 16), r);
-        else tmem_ld_x16_lo(t_row + (uint32_t)(ch * 16), r);
+        tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
       };
-      auto fetch_res = [&](int p, uint4 (&rr)[4]) {
-        rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0, 0, 0, 0);
-        if (has_res) {
-          const int ch = chunk_lo + 2 * p;
-          const int left = P.Cout - (t.nt * P.BN + ch * 16);
-          const uint4* rp = reinterpret_cast<const uint4*>(res_p + 32 * p);
-          if (left > 0) { rr[0] = __ldg(rp); rr[1] = __ldg(rp + 1); }
-          if (ch + 1 < chunk_hi && left > 16) { rr[2] = __ldg(rp + 2); rr[3] = __ldg(rp + 3); }
+      auto fetch_res = [&](int c, uint4 (&rr)[2]) {
+        rr[0] = rr[1] = make_uint4(0, 0, 0, 0);
+        if (has_res && cols_left > 0) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res_p + 16 * c);
+          rr[0] = __ldg(rp);
+          rr[1] = __ldg(rp + 1);
         }
-      };
-      auto finish_pair = [&](int p, uint32_t (&r)[32], const uint4 (&rr)[4]) {
-        finish_chunk(&r[0], rr[0], rr[1]);
-        if (chunk_lo + 2 * p + 1 < chunk_hi) finish_chunk(&r[16], rr[2], rr[3]);
       };
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      // software pipeline: while pair p is being finished, the TMEM load of pair p+1 is in flight
-      uint32_t ra_[32], rb_[32];
-      uint4 q[4];
-      if (npairs > 0) issue_pair(0, ra_);
-      for (int p = 0; p < npairs; p += 2) {
-        fetch_res(p, q);
-        tmem_ld_wait32(ra_);
-        if (p + 1 < npairs) issue_pair(p + 1, rb_);
-        finish_pair(p, ra_, q);
-        if (p + 1 < npairs) {
-          fetch_res(p + 1, q);
-          tmem_ld_wait32(rb_);
-          if (p + 2 < npairs) issue_pair(p + 2, ra_);
-          finish_pair(p + 1, rb_, q);
+      // software pipeline at chunk granularity: while chunk c is being finished, the TMEM load of chunk c+1 is in flight
+      uint32_t ra_[16], rb_[16];
+      uint4 q[2];
+      const int nch = chunk_hi - chunk_lo;
+      if (nch > 0) issue_chunk(0, ra_);
+      for (int c = 0; c < nch; c += 2) {
+        fetch_res(c, q);
+        tmem_ld_wait16(ra_);
+        if (c + 1 < nch) issue_chunk(c + 1, rb_);
+        finish_chunk(ra_, q[0], q[1]);
+        if (c + 1 < nch) {
+          fetch_res(c + 1, q);
+          tmem_ld_wait16(rb_);
+          if (c + 2 < nch) issue_chunk(c + 2, ra_);
+          finish_chunk(rb_, q[0], q[1]);
         }
       }
       // release the accumulator stage (one arrive per epilogue warp)
@@ -740,6 +768,8 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   }
   P.tiles_m = P.tiles_h * P.tiles_w;
   P.n_tiles_n = a->Cout_pad / a->BN;
+  P.inv_n_tiles_n = 1.0f / P.n_tiles_n; P.inv_tiles_m = 1.0f / P.tiles_m; P.inv_groups = 1.0f / a->groups;
+  P.inv_tiles_w = 1.0f / P.tiles_w; P.inv_Wb = 1.0f / P.Wb; P.inv_Wp = P.Wp ? 1.0f / P.Wp : 0.f;
   P.BN = a->BN; P.C0 = a->C0; P.C1 = a->C1;
   P.cblocks0 = a->C0 / a->BK;
   P.cblocks = (a->C0 + a->C1) / a->BK;

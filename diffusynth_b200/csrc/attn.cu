@@ -181,15 +181,24 @@ attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __
   }
   __syncthreads();
   act_t* Mn = M + (size_t)n * Cout_pad * hidden;
-  for (int i = tid; i < Cout_pad * AT_D; i += 256) {
-    const int c = i / AT_D, d = i % AT_D;
-    float acc = 0.f;
-    if (c < C) {
-      const float* wr = wout + (size_t)c * hidden + head * AT_D;
-#pragma unroll 8
-      for (int e = 0; e < AT_D; ++e) acc = fmaf(__ldg(wr + e), s_ctx[d][e], acc);
+  // M[c][d] = sum_e Wout[c][head*32 + e] * ctx[d][e], 64 rows of Wout staged in shared memory at a time (the direct
+  // formulation was latency-bound on 32 dependent global loads per output)
+  __shared__ float s_w[64][AT_D + 1];
+  for (int c0 = 0; c0 < Cout_pad; c0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * AT_D; i += 256) {
+      const int cl = i / AT_D, e = i % AT_D;
+      s_w[cl][e] = (c0 + cl < C) ? __ldg(wout + (size_t)(c0 + cl) * hidden + head * AT_D + e) : 0.f;
     }
-    Mn[(size_t)c * hidden + head * AT_D + d] = f2act(acc);
+    __syncthreads();
+    for (int i = tid; i < 64 * AT_D; i += 256) {
+      const int cl = i / AT_D, d = i % AT_D;
+      if (c0 + cl >= Cout_pad) continue;
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < AT_D; ++e) acc = fmaf(s_w[cl][e], s_ctx[d][e], acc);
+      Mn[(size_t)(c0 + cl) * hidden + head * AT_D + d] = f2act(acc);
+    }
   }
 }
 

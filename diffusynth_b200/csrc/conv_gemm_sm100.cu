@@ -488,7 +488,6 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const int chunks = P.BN / 16;          // 16-column chunks
     const int chunk_lo = col_half == 0 ? 0 : (chunks + 1) / 2;
     const int chunk_hi = col_half == 0 ? (chunks + 1) / 2 : chunks;
-    const int npairs = (chunk_hi - chunk_lo + 1) / 2;
     int ph, pw;
     fast_divmod(row, P.Wb, P.inv_Wb, ph, pw);
     int acc = 0;
@@ -626,32 +625,32 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
         tmem_ld_32x32b_x16(t_row + (uint32_t)(c * 16), r);
       };
+      // software pipeline at chunk granularity: while chunk c is being finished, the TMEM load and the residual fetch of
+      // chunk c+1 are in flight (the first residual fetch is issued before waiting for the accumulator)
+      uint32_t ra_[16], rb_[16];
+      uint4 qa[2], qb[2];
+      const int nch = chunk_hi - chunk_lo;
+      const int cols0 = cols_left;
       auto fetch_res = [&](int c, uint4 (&rr)[2]) {
         rr[0] = rr[1] = make_uint4(0, 0, 0, 0);
-        if (has_res && cols_left > 0) {
+        if (has_res && cols0 - 16 * c > 0) {
           const uint4* rp = reinterpret_cast<const uint4*>(res_p + 16 * c);
           rr[0] = __ldg(rp);
           rr[1] = __ldg(rp + 1);
         }
       };
-
+      if (nch > 0) fetch_res(0, qa);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      // software pipeline at chunk granularity: while chunk c is being finished, the TMEM load of chunk c+1 is in flight
-      uint32_t ra_[16], rb_[16];
-      uint4 q[2];
-      const int nch = chunk_hi - chunk_lo;
       if (nch > 0) issue_chunk(0, ra_);
       for (int c = 0; c < nch; c += 2) {
-        fetch_res(c, q);
         tmem_ld_wait16(ra_);
-        if (c + 1 < nch) issue_chunk(c + 1, rb_);
-        finish_chunk(ra_, q[0], q[1]);
+        if (c + 1 < nch) { issue_chunk(c + 1, rb_); fetch_res(c + 1, qb); }
+        finish_chunk(ra_, qa[0], qa[1]);
         if (c + 1 < nch) {
-          fetch_res(c + 1, q);
           tmem_ld_wait16(rb_);
-          if (c + 2 < nch) issue_chunk(c + 2, ra_);
-          finish_chunk(rb_, q[0], q[1]);
+          if (c + 2 < nch) { issue_chunk(c + 2, ra_); fetch_res(c + 2, qa); }
+          finish_chunk(rb_, qb[0], qb[1]);
         }
       }
       // release the accumulator stage (one arrive per epilogue warp)

@@ -11,7 +11,7 @@ import re
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdiffusynth_b200.so")
+LIB_PATH = os.environ.get("DS_LIB_PATH") or os.path.join(HERE, "libdiffusynth_b200.so")   # DS_LIB_PATH: A/B builds (tools_dev)
 HEADER = os.path.join(os.path.dirname(HERE), "include", "diffusynth_b200.h")
 
 DS_MAX_TAPS = 16
@@ -93,7 +93,7 @@ def load(build: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if build:
+    if build and not os.environ.get("DS_LIB_PATH"):
         try:
             from . import _build
             if os.path.exists(_build.NVCC):
@@ -106,6 +106,8 @@ def load(build: bool = True) -> C.CDLL:
                            "there is no CPU fallback")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
+        if os.environ.get("DS_LIB_PATH") and not hasattr(lib, name):
+            continue                # A/B runs against an older build may lack newer entry points
         fn = getattr(lib, name)     # AttributeError here = header/library mismatch: fail loudly
         fn.restype, fn.argtypes = res, args
     _lib = lib

@@ -209,3 +209,49 @@ def test_timbre_modification_pipeline_parity():
     assert len(ref) == int(n_steps * strength) + 1
     assert torch.equal(q_same, out.quantized.cpu())
     assert e_guide < BF16_TOL and e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL
+
+
+@pytest.mark.parametrize("mode", ["inpaint", "guided", "nocfg", "wide"])
+def test_graph_loop_variants_small_unet(mode):
+    """The CUDA-graph loop with the B200 U-Net in its other modes (inpaint blend with a fixed mask, image-guided start,
+    CFG off, latent width != 64) against the oracle loop; small U-Net so the CPU oracle stays fast."""
+    from diffusynth_b200 import DiffSynthSampler
+    cfg, sd, _, _, _ = cases.unet_case("small_w16")
+    net = _unet(cfg, sd)
+    B, steps, Hh = 3, 5, 32
+    Wd = 40 if mode == "wide" else (64 if mode == "guided" else 32)
+    draws = cases.randn((1 + steps + 2, B, 4, Hh, 64), 61)
+    cond, uncond = W.synthetic_conditions(B, 64, seed=300)
+    guide = cases.randn((B, 4, Hh, 64), 62) * 0.5
+    s = DiffSynthSampler(1000, device="cuda", mute=True, max_batchsize=B, height=Hh)
+    sch = O.Schedule(1000)
+    model = lambda x, t, c: O.unet_forward(sd, x, t, c)
+    s.noise_feed = draws[1:]
+    if mode != "nocfg":
+        s.activate_classifier_free_guidance(4, uncond.cuda())
+    cfg_scale, unc = (1.0, None) if mode == "nocfg" else (4, uncond)
+    if mode == "guided":
+        n = int(steps / 0.6)
+        s.respace(list(np.linspace(0, 999, n, dtype=np.int32)))
+        sch.respace(list(np.linspace(0, 999, n, dtype=np.int32)))
+        imgs, _ = s.img_guided_sample(net, (B, 4, Hh, Wd), 0.6, guide.cuda(), return_tensor=True, condition=cond.cuda(),
+                                      initial_noise=draws[0].cuda(), sampler="ddpm")
+        with torch.no_grad():
+            ref = O.sample_loop(model, sch, (B, 4, Hh, Wd), cond, unc, cfg_scale, draws, guide=guide, start_ratio=0.6, sampler="ddpm")
+    else:
+        s.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+        sch.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+        if mode == "inpaint":
+            mask = (cases.randn((B, 1, Hh, Wd), 63) > 0).float()
+            imgs, _ = s.inpaint_sample(net, (B, 4, Hh, Wd), 1.0, guide.cuda(), mask.cuda(), return_tensor=True, condition=cond.cuda(),
+                                       initial_noise=draws[0].cuda())
+            with torch.no_grad():
+                ref = O.sample_loop(model, sch, (B, 4, Hh, Wd), cond, unc, cfg_scale, draws, guide=guide, mask=mask, inpaint=True)
+        else:
+            imgs, _ = s.sample(net, (B, 4, Hh, Wd), return_tensor=True, condition=cond.cuda(), initial_noise=draws[0].cuda())
+            with torch.no_grad():
+                ref = O.sample_loop(model, sch, (B, 4, Hh, Wd), cond, unc, cfg_scale, draws)
+    assert len(imgs) == len(ref)
+    errs = [rel(a, b) for a, b in zip(imgs, ref)]
+    print(f"\n[{mode}] W={Wd} latents rel-L2 per step: {['%.1e' % e for e in errs]}")
+    assert max(errs) < BF16_TOL

@@ -153,52 +153,58 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
   }
 }
 
-// grid = (heads, N), block = 256: merge chunk partials (log-sum-exp style), normalise, then
-// M[n][c][head*32 + d] = sum_e Wout[c][head*32 + e] * ctx[d][e]  -> bf16 [N][Cout_pad][hidden]
+// attn_reduce: grid = (heads, N), block = 256: merge the chunk partials (log-sum-exp style) and normalise
+//   ctx[d][e] = sum_c S_c[d][e] exp(m_c[d] - M[d]) / sum_c Z_c[d] exp(m_c[d] - M[d])        -> fp32 [N][heads][32][32]
 __global__ void __launch_bounds__(256)
-attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad,
-                     int hidden, act_t* __restrict__ M) {
-  __shared__ float s_ctx[AT_D][AT_D + 1];
-  __shared__ float s_M[AT_D], s_Z[AT_D];
+attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ ctx) {
+  __shared__ float s_M[AT_D], s_Zinv[AT_D];
   const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const float* pb = part + ((size_t)n * gridDim.x + head) * chunks * AT_PART;
   if (tid < AT_D) {
     float mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + tid]);
+    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid));
     float z = 0.f;
     for (int c = 0; c < chunks; ++c)
-      z += pb[(size_t)c * AT_PART + AT_D * AT_D + tid] * __expf(pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + tid] - mx);
+      z += __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + tid) * __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid) - mx);
     s_M[tid] = mx;
-    s_Z[tid] = z;
+    s_Zinv[tid] = 1.0f / z;
   }
   __syncthreads();
+  float* co = ctx + ((size_t)n * gridDim.x + head) * AT_D * AT_D;
   for (int i = tid; i < AT_D * AT_D; i += 256) {
     const int d = i / AT_D;
+    const float M = s_M[d];
     float s = 0.f;
+#pragma unroll 4
     for (int c = 0; c < chunks; ++c)
-      s += pb[(size_t)c * AT_PART + i] * __expf(pb[(size_t)c * AT_PART + AT_D * AT_D + AT_D + d] - s_M[d]);
-    s_ctx[d][i % AT_D] = s / s_Z[d];
+      s = fmaf(__ldg(pb + (size_t)c * AT_PART + i), __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d) - M), s);
+    co[i] = s * s_Zinv[d];
+  }
+}
+
+// attn_fold: grid = (ceil(Cout_pad/64), heads, N), block = 256:
+//   M[n][c][head*32 + d] = sum_e Wout[c][head*32 + e] * ctx[n][head][d][e]    -> 16-bit [N][Cout_pad][hidden]
+__global__ void __launch_bounds__(256)
+attn_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad, int hidden,
+                 act_t* __restrict__ M) {
+  __shared__ float s_ctx[AT_D][AT_D + 1];
+  __shared__ float s_w[64][AT_D + 1];
+  const int c0 = blockIdx.x * 64, head = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  const float* ci = ctx + ((size_t)n * gridDim.y + head) * AT_D * AT_D;
+  for (int i = tid; i < AT_D * AT_D; i += 256) s_ctx[i / AT_D][i % AT_D] = __ldg(ci + i);
+  for (int i = tid; i < 64 * AT_D; i += 256) {
+    const int cl = i / AT_D, e = i % AT_D;
+    s_w[cl][e] = (c0 + cl < C) ? __ldg(wout + (size_t)(c0 + cl) * hidden + head * AT_D + e) : 0.f;
   }
   __syncthreads();
   act_t* Mn = M + (size_t)n * Cout_pad * hidden;
-  // M[c][d] = sum_e Wout[c][head*32 + e] * ctx[d][e], 64 rows of Wout staged in shared memory at a time (the direct
-  // formulation was latency-bound on 32 dependent global loads per output)
-  __shared__ float s_w[64][AT_D + 1];
-  for (int c0 = 0; c0 < Cout_pad; c0 += 64) {
-    __syncthreads();
-    for (int i = tid; i < 64 * AT_D; i += 256) {
-      const int cl = i / AT_D, e = i % AT_D;
-      s_w[cl][e] = (c0 + cl < C) ? __ldg(wout + (size_t)(c0 + cl) * hidden + head * AT_D + e) : 0.f;
-    }
-    __syncthreads();
-    for (int i = tid; i < 64 * AT_D; i += 256) {
-      const int cl = i / AT_D, d = i % AT_D;
-      if (c0 + cl >= Cout_pad) continue;
-      float acc = 0.f;
+  for (int i = tid; i < 64 * AT_D; i += 256) {
+    const int cl = i / AT_D, d = i % AT_D;
+    if (c0 + cl >= Cout_pad) continue;
+    float acc = 0.f;
 #pragma unroll
-      for (int e = 0; e < AT_D; ++e) acc = fmaf(s_w[cl][e], s_ctx[d][e], acc);
-      Mn[(size_t)(c0 + cl) * hidden + head * AT_D + d] = f2act(acc);
-    }
+    for (int e = 0; e < AT_D; ++e) acc = fmaf(s_w[cl][e], s_ctx[d][e], acc);
+    Mn[(size_t)(c0 + cl) * hidden + head * AT_D + d] = f2act(acc);
   }
 }
 
@@ -209,7 +215,8 @@ using namespace ds;
 extern "C" {
 
 int ds_attn_chunks(long long npix) { return (int)((npix + AT_PIX - 1) / AT_PIX); }
-long long ds_attn_part_floats(int N, int heads, long long npix) { return (long long)N * heads * ds_attn_chunks(npix) * AT_PART; }
+/* scratch: chunk partials followed by the merged ctx [N][heads][32][32] */
+long long ds_attn_part_floats(int N, int heads, long long npix) { return (long long)N * heads * (ds_attn_chunks(npix) * AT_PART + AT_D * AT_D); }
 
 /* q' (bf16 [N, npix, hidden]) and chunk partials of ctx.  q_mode 0: softmax over head dim * scale; 1: copy. */
 int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, int heads, long long npix, int q_mode, float scale, void* stream) {
@@ -225,8 +232,11 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
 /* Merge partials and fold to_out's weight: d_M bf16 [N][Cout_pad][heads*32]. */
 int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
   DS_REQUIRE(d_part && d_wout && d_M && N > 0 && heads > 0 && C > 0 && Cout_pad >= C, "ds_attn_finalize: bad arguments");
-  attn_finalize_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, ds_attn_chunks(npix), d_wout, C, Cout_pad, heads * AT_D,
-                                                                         (act_t*)d_M);
+  const int chunks = ds_attn_chunks(npix);
+  float* ctx = const_cast<float*>(d_part) + (size_t)N * heads * chunks * AT_PART;
+  DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_finalize: grid too large");
+  attn_reduce_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, chunks, ctx);
+  attn_fold_kernel<<<dim3((Cout_pad + 63) / 64, heads, N), 256, 0, (cudaStream_t)stream>>>(ctx, d_wout, C, Cout_pad, heads * AT_D, (act_t*)d_M);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -14,6 +14,12 @@ ncu)
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 1 --sample-steps 2 > gpurun_out/ncu.log 2>&1; echo "ncu rc=$?" >> gpurun_out/rc.txt
   tail -3 gpurun_out/plain.log; tail -3 gpurun_out/ncu.log ;;
+ncutraffic)
+  export REPS=1
+  timeout 600 python tools_dev/unet_once.py > gpurun_out/plain_traffic.log 2>&1 && \
+  timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none --csv --log-file gpurun_out/traffic.csv \
+      python tools_dev/unet_once.py > gpurun_out/ncu_traffic.log 2>&1; echo "ncutraffic rc=$?" >> gpurun_out/rc.txt
+  tail -2 gpurun_out/ncu_traffic.log ;;
 ncufull)
   export REPS=1
   timeout 600 python tools_dev/unet_once.py > gpurun_out/plain_full.log 2>&1 && \

@@ -187,23 +187,33 @@ attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad, int hidden,
                  act_t* __restrict__ M) {
-  __shared__ float s_ctx[AT_D][AT_D + 1];
-  __shared__ float s_w[64][AT_D + 1];
+  __shared__ __align__(16) float s_w[64][AT_D];
   const int c0 = blockIdx.x * 64, head = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
-  const float* ci = ctx + ((size_t)n * gridDim.y + head) * AT_D * AT_D;
-  for (int i = tid; i < AT_D * AT_D; i += 256) s_ctx[i / AT_D][i % AT_D] = __ldg(ci + i);
+  const int warp = tid >> 5, d = tid & 31;
+  // lane d keeps row d of ctx in registers; the warp walks over Wout rows read as broadcast float4 from shared memory
+  float cr[AT_D];
+  const float4* ci = reinterpret_cast<const float4*>(ctx + ((size_t)n * gridDim.y + head) * AT_D * AT_D + d * AT_D);
+#pragma unroll
+  for (int e4 = 0; e4 < AT_D / 4; ++e4) {
+    const float4 v = __ldg(ci + e4);
+    cr[4 * e4] = v.x; cr[4 * e4 + 1] = v.y; cr[4 * e4 + 2] = v.z; cr[4 * e4 + 3] = v.w;
+  }
   for (int i = tid; i < 64 * AT_D; i += 256) {
     const int cl = i / AT_D, e = i % AT_D;
     s_w[cl][e] = (c0 + cl < C) ? __ldg(wout + (size_t)(c0 + cl) * hidden + head * AT_D + e) : 0.f;
   }
   __syncthreads();
   act_t* Mn = M + (size_t)n * Cout_pad * hidden;
-  for (int i = tid; i < 64 * AT_D; i += 256) {
-    const int cl = i / AT_D, d = i % AT_D;
-    if (c0 + cl >= Cout_pad) continue;
+#pragma unroll 2
+  for (int cl = warp; cl < 64; cl += 8) {
+    if (c0 + cl >= Cout_pad) break;
     float acc = 0.f;
 #pragma unroll
-    for (int e = 0; e < AT_D; ++e) acc = fmaf(s_w[cl][e], s_ctx[d][e], acc);
+    for (int e4 = 0; e4 < AT_D / 4; ++e4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(&s_w[cl][4 * e4]);
+      acc = fmaf(w4.x, cr[4 * e4], acc); acc = fmaf(w4.y, cr[4 * e4 + 1], acc);
+      acc = fmaf(w4.z, cr[4 * e4 + 2], acc); acc = fmaf(w4.w, cr[4 * e4 + 3], acc);
+    }
     Mn[(size_t)(c0 + cl) * hidden + head * AT_D + d] = f2act(acc);
   }
 }

@@ -314,7 +314,9 @@ def run_b200(args):
                     unet_step_roofline=dict(algorithmic_tflop=algo_step_tflop, achieved_tflops=algo_step_tflop / (step_ms / 1e3),
                                             peak_tflops=pk["tf_sustained"], frac=algo_step_tflop / (step_ms / 1e3) / pk["tf_sustained"]),
                     roofline=dict(kernel="conv_gemm_kernel (tcgen05 implicit-GEMM conv; all dense convs of the U-Net)", bound="tensor",
-                                  achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=None,
+                                  achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=conv_traffic(),
+                                  traffic_note="ncu dram__bytes_read+write per conv_gemm launch, averaged over the 98 launches of one U-Net evaluation "
+                                               "(profiles/r01_unet_eval_ncu_summary.md)",
                                   peak_source=pk["source"] + " bf16_tflops_sustained", launches_per_unet_eval=conv_launches,
                                   algorithmic_gflop_per_unet_eval=flops / 1e9, ms_per_unet_eval=conv_ms),
                     kernel_ms_per_unet_eval={k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
@@ -325,6 +327,16 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def conv_traffic():
+    """DRAM bytes per conv_gemm launch from the committed ncu capture (profiles/), or None when the capture is absent."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["avg_dram_bytes_per_conv_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def main():

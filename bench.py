@@ -137,7 +137,7 @@ def run_reference(args):
                 data="synthetic", config=workload_config(args, args.gpus),
                 cpu_baseline=dict(value=v, unit="timbres/s", cores=last["cores"], kind=last["kind"], sample=last["sample"]),
                 e2e=dict(value=v, unit="timbres/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(args, world):
@@ -219,7 +219,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout = the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     from diffusynth_b200 import TextToTimbre, weights as W
     from diffusynth_b200.pipeline import all_gather_waveforms, shard_range
@@ -323,10 +323,29 @@ def run_b200(args):
                     unet_eval_ms_eager=unet_ms)
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Native libraries (NCCL's version banner) write to fd 1; stdout must carry exactly one JSON line, so fd 1 is pointed at
+    stderr for the whole run and the line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
 
 
 def conv_traffic():
@@ -347,6 +366,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sample-steps", type=int, default=20, dest="sample_steps")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

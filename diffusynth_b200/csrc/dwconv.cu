@@ -3,32 +3,39 @@
 // follows (:121), and the 7x7 stem convolution (init_conv, model/diffusion.py:82).
 #include "common.cuh"
 #include "../../include/diffusynth_b200.h"
+#include "tma.cuh"
+#include <cstdlib>
 
 namespace ds {
 
 // ---------------------------------------------------------------------------------------------
-// dwconv7: bf16 NHWC in (one or two channel-concatenated sources), bf16 NHWC out.
-// block = 256 threads = 16 channel pairs x 16 pixel-threads; tile = 8 rows x 16 cols x 32 channels.
+// dwconv7: 16-bit NHWC in (one or two channel-concatenated sources), 16-bit NHWC out.
+// block = 256 threads = 16 channel pairs x 16 pixel-threads; tile = (8*R) rows x 16 cols x 32 channels, R = 1 or 2.
 // (A warp-level tensor-core formulation -- mma.sync m16n8k16 with block-diagonal weight fragments, 1/8 of the lanes
-// useful -- was measured on B200 at 9.6 ms per U-Net evaluation against 6.4 ms for this kernel: legacy HMMA is too slow
+// useful -- was measured on B200 at 9.6 ms per U-Net evaluation against 6.4 ms for the R=1 kernel: legacy HMMA is too slow
 // on sm_100a to pay for the 8x redundancy.  See profiles/r01_notes.md.)
-// The (8+6) x (16+6) halo tile is staged in shared memory as fp32 (row pitch padded to 23 pixels so the two
-// pixel-threads of a warp hit different banks); each thread slides a 7-wide window over 8 outputs with packed FFMA2.
+// The (8R+6) x (16+6) halo tile is staged in shared memory as fp32 (row pitch padded to 23 pixels); each thread slides a
+// 7-wide window over R rows x 8 output columns with packed FFMA2.  With R = 1 the kernel is bound by shared-memory
+// bandwidth (21 LDS.64 per 56 FFMA2); with R = 2 every staged input row feeds two output rows and each weight row is
+// loaded once, which brings the LDS traffic under the FMA-pipe time.
 // ---------------------------------------------------------------------------------------------
-static constexpr int DW_TH = 8, DW_TW = 16, DW_CB = 32;
-static constexpr int DW_HH = DW_TH + 6, DW_HW = DW_TW + 6, DW_PITCH = 23;
+static constexpr int DW_TW = 16, DW_CB = 32;
+static constexpr int DW_HW = DW_TW + 6, DW_PITCH = 23;
 
-__global__ void __launch_bounds__(256)
+template <int R>
+__global__ void __launch_bounds__(256, R == 1 ? 4 : 3)
 dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, int C0, int C1, int src_batch_mod,
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
                act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w, int tiles) {
-  __shared__ __align__(16) float2 s_in[DW_HH * DW_PITCH * (DW_CB / 2)];   // fp32 channel pairs (converted once at staging)
-  __shared__ __align__(16) float2 s_w[49 * (DW_CB / 2)];
+  constexpr int TH = 8 * R, HH = TH + 6;
+  extern __shared__ __align__(16) float2 dw_smem[];
+  float2* s_in = dw_smem;                                   // [HH][DW_PITCH][16] fp32 channel pairs (converted once at staging)
+  float2* s_w = dw_smem + HH * DW_PITCH * (DW_CB / 2);      // [49][16]
   __shared__ float s_red[16];
   const int C = C0 + C1;
   const int tile = blockIdx.x, cblk = blockIdx.y, n = blockIdx.z;
-  const int h0 = (tile / tiles_w) * DW_TH, w0 = (tile % tiles_w) * DW_TW;
+  const int h0 = (tile / tiles_w) * TH, w0 = (tile % tiles_w) * DW_TW;
   const int c0 = cblk * DW_CB;
   const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
   const act_t* src;
@@ -42,7 +49,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
     s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
   }
   // stage the halo tile: 16-byte pieces (8 channels) per thread, converted to fp32 once; 4 pieces per pixel
-  for (int i = threadIdx.x; i < DW_HH * DW_HW * 4; i += 256) {
+  for (int i = threadIdx.x; i < HH * DW_HW * 4; i += 256) {
     const int piece = i & 3, pix = i >> 2;
     const int r = pix / DW_HW, cc = pix - r * DW_HW;
     const int y = h0 + r - 3, x = w0 + cc - 3;
@@ -57,39 +64,52 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   __syncthreads();
 
   const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
-  const int row = pt & 7, col0 = (pt >> 3) * 8;
-  float2 acc[8];       // (channel 2cp, channel 2cp+1) of 8 consecutive output columns: packed FFMA2 lanes
+  const int row0 = (pt & 7) * R, col0 = (pt >> 3) * 8;
+  float2 acc[R][8];    // (channel 2cp, channel 2cp+1) of R rows x 8 consecutive output columns: packed FFMA2 lanes
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = make_float2(0.f, 0.f);
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-  for (int ky = 0; ky < 7; ++ky) {
-    float2 wv[7];
+    for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  float2 wbuf[R][7];   // weight rows ky = r, r-1, .., r-R+1 (slot ky % R)
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) wv[kx] = s_w[(ky * 7 + kx) * (DW_CB / 2) + cp];
-    const float2* rowp = &s_in[((row + ky) * DW_PITCH + col0) * (DW_CB / 2) + cp];
+  for (int r = 0; r < R + 6; ++r) {
+    if (r < 7) {
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wbuf[r % R][kx] = s_w[(r * 7 + kx) * (DW_CB / 2) + cp];
+    }
+    const float2* rowp = &s_in[((row0 + r) * DW_PITCH + col0) * (DW_CB / 2) + cp];
 #pragma unroll
     for (int j = 0; j < 14; ++j) {
       const float2 in = rowp[j * (DW_CB / 2)];
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const int ow = j - kx;
-        if (ow >= 0 && ow < 8) ffma2(acc[ow], in, wv[kx]);
+      for (int i = 0; i < R; ++i) {
+        const int ky = r - i;
+        if (ky >= 0 && ky < 7) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const int ow = j - kx;
+            if (ow >= 0 && ow < 8) ffma2(acc[i][ow], in, wbuf[ky % R][kx]);
+          }
+        }
       }
     }
   }
   const int c = c0 + 2 * cp;
   const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
   const float b0 = __ldg(tb + c), b1 = __ldg(tb + c + 1);
-  const int y = h0 + row;
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int x = w0 + col0 + j;
-    if (y < H && x < W) {
-      const float v0 = acc[j].x + b0, v1 = acc[j].y + b1;
-      s += v0 + v1;
-      q = fmaf(v0, v0, fmaf(v1, v1, q));
-      *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
+  for (int i = 0; i < R; ++i) {
+    const int y = h0 + row0 + i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int x = w0 + col0 + j;
+      if (y < H && x < W) {
+        const float v0 = acc[i][j].x + b0, v1 = acc[i][j].y + b1;
+        s += v0 + v1;
+        q = fmaf(v0, v0, fmaf(v1, v1, q));
+        *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
+      }
     }
   }
   if (stats != nullptr) {
@@ -107,6 +127,142 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// dwconv7, TMA-staged: the same arithmetic as dwconv7_kernel<2> (tile 16 rows x 16 cols x 32 channels, thread = 2 rows x
+// 8 cols x 2 channels, fp32 FFMA2 accumulation) but the 22 x 22 halo tile arrives as ONE cp.async.bulk.tensor box whose
+// out-of-range rows/columns are zero-filled by the TMA unit (= the conv padding), into a 3-deep ring, while the block
+// computes the previous tiles: there is no load->convert->store staging phase and no bounds logic.  The tile stays 16-bit
+// in shared memory (31 KB per stage) and is widened at use (HADD2.F32).  A block is persistent over the (sample, tile)
+// pairs of ONE 32-channel slice, so its 49 x 32 weights are staged once.
+// ---------------------------------------------------------------------------------------------
+static constexpr int DT_HALO = 22, DT_STAGES = 2;
+static constexpr int DT_TILE_BYTES = DT_HALO * DT_HALO * DW_CB * 2;     // 30976, a multiple of 128
+static constexpr int DT_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + 49 * (DW_CB / 2) * 8 + DT_STAGES * 8 + 128;
+
+__global__ void __launch_bounds__(256, 3)
+dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
+                   const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
+                   act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w,
+                   int tiles, int N) {
+  extern __shared__ uint8_t dt_smem_raw[];
+  uint8_t* smem = dt_smem_raw + ((128u - (smem_u32(dt_smem_raw) & 127u)) & 127u);   // offset on the shared array keeps LDS addressing
+  float2* s_w = reinterpret_cast<float2*>(smem + DT_STAGES * DT_TILE_BYTES);             // [49][16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + 49 * (DW_CB / 2));
+  __shared__ float s_red[2][16];   // per-warp (sum, sumsq) of a tile, double-buffered over iterations
+  const int C = C0 + C1;
+  const int cblk = blockIdx.y, c0 = cblk * DW_CB;
+  const CUtensorMap* map = c0 < C0 ? &map0 : &map1;
+  const int cs0 = c0 < C0 ? c0 : c0 - C0;
+  const int total = N * tiles;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(map);
+    for (int s = 0; s < DT_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 49 * (DW_CB / 2); i += 256) {
+    const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
+    s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
+  }
+  __syncthreads();
+
+  auto issue = [&](int item, int stage) {
+    const int n = item / tiles, t = item - n * tiles;
+    const int th = t / tiles_w, tw = t - th * tiles_w;
+    const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
+    mbar_expect_tx(&full[stage], DT_TILE_BYTES);
+    tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
+  };
+  if (threadIdx.x == 0)
+    for (int k = 0; k < DT_STAGES - 1; ++k)
+      if (blockIdx.x + k * gridDim.x < total) issue(blockIdx.x + k * gridDim.x, k);
+
+  const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
+  const int row0 = (pt & 7) * 2, col0 = (pt >> 3) * 8;
+  const int c = c0 + 2 * cp;
+  int it = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int stage = it % DT_STAGES;
+    if (threadIdx.x == 0) {
+      const int nxt = item + (DT_STAGES - 1) * gridDim.x;      // its stage was released by the barrier that ended iteration it-1
+      if (nxt < total) issue(nxt, (it + DT_STAGES - 1) % DT_STAGES);
+    }
+    const int n = item / tiles, t = item - n * tiles;
+    const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
+    const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
+    const float b0 = __ldg(tb + c), b1 = __ldg(tb + c + 1);
+    mbar_wait(&full[stage], (uint32_t)(it / DT_STAGES) & 1u);
+    const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem + stage * DT_TILE_BYTES);   // [22][22][16] channel pairs
+
+    float2 acc[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    float2 wbuf[2][7];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < 7) {
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) wbuf[r % 2][kx] = s_w[(r * 7 + kx) * (DW_CB / 2) + cp];
+      }
+      const uint32_t* rowp = s_in + ((row0 + r) * DT_HALO + col0) * (DW_CB / 2) + cp;
+#pragma unroll
+      for (int j = 0; j < 14; ++j) {
+        const float2 in = cvt16x2(rowp[j * (DW_CB / 2)]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int ky = r - i;
+          if (ky >= 0 && ky < 7) {
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+              const int ow = j - kx;
+              if (ow >= 0 && ow < 8) ffma2(acc[i][ow], in, wbuf[ky % 2][kx]);
+            }
+          }
+        }
+      }
+    }
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int y = h0 + row0 + i;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int x = w0 + col0 + j;
+        if (y < H && x < W) {
+          const float v0 = acc[i][j].x + b0, v1 = acc[i][j].y + b1;
+          s += v0 + v1;
+          q = fmaf(v0, v0, fmaf(v1, v1, q));
+          *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
+        }
+      }
+    }
+    float* red = s_red[it & 1];
+    if (stats != nullptr) {
+      s = warp_sum(s);
+      q = warp_sum(q);
+      const int warp = threadIdx.x >> 5;
+      if ((threadIdx.x & 31) == 0) { red[warp] = s; red[8 + warp] = q; }
+    }
+    __syncthreads();     // every thread is done with this stage before it is refilled; the per-warp partials are visible
+    if (stats != nullptr && threadIdx.x < 32) {     // warp 0 publishes while the others start the next tile (which uses the other s_red)
+      float ts = 0.f, tq = 0.f;
+      if (threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+      const int slots = tiles * gridDim.y;
+      stats_publish(stats_sample(stats, slots, n), slots, cblk * tiles + t, ts, tq, stats_inv_count, eps, threadIdx.x);
+    }
+  }
+}
+
+static inline int dw_rows_per_thread(int H) {
+  static const int forced = [] { const char* e = getenv("DS_DWCONV_R"); return e ? atoi(e) : 0; }();
+  if (forced == 1 || forced == 2) return forced;
+  return H >= 16 ? 2 : 1;
+}
+static inline size_t dw_smem_bytes(int R) { return (size_t)((8 * R + 6) * DW_PITCH + 49) * (DW_CB / 2) * sizeof(float2); }
 
 // ---------------------------------------------------------------------------------------------
 // Stem: 7x7 conv, Cin (<=4) -> Cout (multiple of 32, <= 128), fp32 NCHW in, bf16 NHWC out.
@@ -216,18 +372,65 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
                long long tbias_stride, void* d_out, void* d_stats, float eps, int N, int H, int W, void* stream) {
   DS_REQUIRE(d_src0 && d_weight && d_tbias && d_out && N > 0 && H > 0 && W > 0, "ds_dwconv7: bad arguments");
   DS_REQUIRE(C0 > 0 && C0 % DW_CB == 0 && C1 >= 0 && C1 % DW_CB == 0 && (C1 == 0 || d_src1), "ds_dwconv7: C0=%d C1=%d must be multiples of 32", C0, C1);
-  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
+  const int R = dw_rows_per_thread(H);
+  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + 8 * R - 1) / (8 * R);
   const int tiles = tiles_w * tiles_h;
   DS_REQUIRE(N <= 65535 && (C0 + C1) / DW_CB <= 65535, "ds_dwconv7: grid too large");
-  dwconv7_kernel<<<dim3(tiles, (C0 + C1) / DW_CB, N), 256, 0, (cudaStream_t)stream>>>(
-      (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-      (act_t*)d_out, (float2*)d_stats, 1.0f / ((float)H * (float)W * (float)(C0 + C1)), eps, H, W, tiles_w, tiles);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(1)));
+    DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(2)));
+    attr_set = true;
+  }
+  const dim3 grid(tiles, (C0 + C1) / DW_CB, N);
+  const float inv_count = 1.0f / ((float)H * (float)W * (float)(C0 + C1));
+  static const bool use_tma = [] { const char* e = getenv("DS_DWCONV_TMA"); return !e || atoi(e) != 0; }();
+  if (R == 2 && use_tma) {
+    EncodeTiledFn encode = get_encode_fn();
+    DS_REQUIRE(encode != nullptr, "ds_dwconv7: cuTensorMapEncodeTiled entry point not available");
+    static bool tma_attr_set = false;
+    if (!tma_attr_set) {
+      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
+      tma_attr_set = true;
+    }
+    CUtensorMap maps[2];
+    const int nsamp = src_batch_mod > 0 ? src_batch_mod : N;
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      const int Cs = sidx == 0 ? C0 : C1;
+      const void* base = sidx == 0 ? d_src0 : d_src1;
+      if (Cs == 0) { maps[1] = maps[0]; break; }
+      const cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nsamp};
+      const cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)DW_CB, (cuuint32_t)DT_HALO, (cuuint32_t)DT_HALO, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      const CUresult r = encode(&maps[sidx], kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      DS_REQUIRE(r == CUDA_SUCCESS, "ds_dwconv7: cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d)", (int)r, Cs, W, H);
+    }
+    const int cblks = (C0 + C1) / DW_CB;
+    long long work = (long long)N * tiles;
+    int gx = 3 * num_sms() / cblks;      // never more blocks than resident slots: a straggler wave would cost a whole pass
+    if (gx > work) gx = (int)work;
+    if (gx < 1) gx = 1;
+    dwconv7_tma_kernel<<<dim3(gx, cblks), 256, DT_SMEM_BYTES, (cudaStream_t)stream>>>(
+        maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
+        H, W, tiles_w, tiles, N);
+  } else if (R == 2)
+    dwconv7_kernel<2><<<grid, 256, dw_smem_bytes(2), (cudaStream_t)stream>>>(
+        (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
+        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles);
+  else
+    dwconv7_kernel<1><<<grid, 256, dw_smem_bytes(1), (cudaStream_t)stream>>>(
+        (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
+        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
 
 int ds_dwconv7_stats_slots(int C, int H, int W) {
-  return ((W + DW_TW - 1) / DW_TW) * ((H + DW_TH - 1) / DW_TH) * (C / DW_CB);
+  const int R = dw_rows_per_thread(H);
+  return ((W + DW_TW - 1) / DW_TW) * ((H + 8 * R - 1) / (8 * R)) * (C / DW_CB);
 }
 
 /* Stem 7x7 conv (init_conv).  d_x fp32 NCHW [x_batch_mod or N, Cin, H, W]; d_weight fp32 [49*Cin][Cout]

@@ -28,13 +28,11 @@ struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;
-  float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb, inv_Wp;   // reciprocals for fast_divmod
+  float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb;   // reciprocals for fast_divmod
+  unsigned long long* dbg_buf;      // DS_CONV_DBG & 64: per-CTA wait-cycle counters [grid][8]
   int dbg;                          // DS_CONV_DBG bitmask (profiling experiments): 1 = no global stores, 2 = no TMEM loads, 4 = no MMA issue
   int sps;                          // K-blocks per pipeline stage (generic mode): keeps >= ~384 MMA cycles behind every barrier round trip
   unsigned stage_a_bytes, stage_b_bytes;
-  int halo, Wp, halo_rows;          // halo mode (3x3 stride 1): one (halo_rows x Wp)-pixel activation box per channel block
-  unsigned halo_a_bytes;            // smem stride of one halo box (rounded to 1 KB)
-  unsigned halo_box_bytes;          // bytes one halo TMA box delivers
   int Cout, Cout_pad;
   const float2* stats_in; int stats_in_slots; float out_inv_count, eps;
   const float* e1; const float* e2; int ncls;
@@ -64,6 +62,21 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// One lane of a converged warp (the lowest): the producer and MMA warps run their loops warp-uniformly and predicate only the
+// TMA / MMA / arrive instructions with this, so the loop state stays in uniform registers (a loop under `if (lane == 0)` makes
+// the compiler re-broadcast every operand of every tensor instruction).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// mbar_wait that also accumulates the cycles spent waiting (profiling builds of the role loops: DS_CONV_DBG & 64)
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -226,25 +239,21 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 }
 #endif
 
-// HALO = false: generic mode, one (A tap tile | B) pair per pipeline stage.
-// HALO = true : 3x3 stride-1 convs.  M rows are 128 consecutive positions q = h*Wp + w' of the width-padded image
-//               (Wp = W + 2; w' >= W rows are discarded), so that the input of tap (ky,kx) for row q is the padded-linear
-//               pixel q + ky*Wp + kx: ONE TMA box of halo_rows full padded rows per channel block serves all 9 taps through
-//               row-shifted UMMA descriptors (the swizzle is a function of the absolute shared-memory address, so any
-//               row offset is a valid operand start; tools_dev/umma_shift_test.cu).  Activation traffic drops ~3.4x.
-template <int BK, bool HALO>
+// One pipeline stage = sps x (A tap tile | B tile).  Warp roles: 0 = activation (A) TMA producer, 1 = MMA issuer, 2 = TMEM
+// allocator, then weight (B) TMA producer, 3 = statistics publisher, 4-11 = epilogue.  The two producers split the per-K-block
+// scalar work (barrier probe + coordinates + TMA issue), which otherwise bounds the kernel on one thread; the A producer
+// reads its per-K-block coordinates (tensor map, channel offset, tap shift) from a table built once in shared memory.
+template <int BK>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: generic [stages x (A | B)]  /  halo [2 x A-halo][stages x B]  | barriers | stats partials | sbias | tables e2, e1
+  // carve: [stages x sps x (A | B)] | barriers | stats partials | sbias | tables e2, e1 | K-block table
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const unsigned stage_bytes = HALO ? P.stage_b_bytes : (unsigned)P.sps * (P.stage_a_bytes + P.stage_b_bytes);
-  uint8_t* smem_b0 = HALO ? smem + 2 * (size_t)P.halo_a_bytes : smem;          // start of the per-stage ring
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b0 + (size_t)P.stages * stage_bytes);
+  const unsigned sub_bytes = P.stage_a_bytes + P.stage_b_bytes;
+  const unsigned stage_bytes = (unsigned)P.sps * sub_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* full_a = empty_bar + kMaxStages;        // halo ring (2 stages)
-  uint64_t* empty_a = full_a + 2;
-  uint64_t* tmem_full = empty_a + 2;
+  uint64_t* tmem_full = empty_bar + kMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* stats_full = tmem_empty + 2;
   uint64_t* stats_empty = stats_full + 2;
@@ -253,6 +262,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   float* s_sb = reinterpret_cast<float*>(s_stats + 2 * kEpiWarps);           // [kEpiWarps][128] per-sample bias of the current tile
   float* s_e2 = s_sb + kEpiWarps * 128;
   float* s_e1 = s_e2 + P.ncls * P.Cout_pad;
+  int4* s_kbt = reinterpret_cast<int4*>(s_e1 + P.ncls * P.Cout_pad);         // [groups][num_kb]: {tensor-map byte offset, channel, dx, dy}
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -265,12 +275,10 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < P.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);          // one arrive.expect_tx from each producer
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(&full_a[a], 1);
-      mbar_init(&empty_a[a], 1);
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps);
       mbar_init(&stats_full[a], kEpiWarps);
@@ -283,129 +291,125 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     s_e2[i] = __ldg(P.e2 + i);
     s_e1[i] = P.e1 ? __ldg(P.e1 + i) : 0.f;
   }
+  for (int i = threadIdx.x; i < P.groups * P.num_kb; i += kNumThreads) {
+    const int g = i / P.num_kb, kb = i - g * P.num_kb;
+    const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
+    const ds_conv_tap tp = P.taps[g][tap];
+    const int src = cb < P.cblocks0 ? 0 : 1;
+    s_kbt[i] = make_int4((src * 4 + tp.view) * (int)sizeof(CUtensorMap), (src == 0 ? cb : cb - P.cblocks0) * BK, tp.dx, tp.dy);
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
+  const bool timed = (P.dbg & 64) != 0;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(P, tile);
-        const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
-        const int wz = P.per_sample_w ? t.n : t.g;
-        if (HALO) {
-          const int pr0 = ((t.th * P.tiles_w + t.tw) * BM) / P.Wp;      // first padded row of the halo box
-          for (int cb = 0; cb < P.cblocks; ++cb) {
-            mbar_wait(&empty_a[as], aphase ^ 1u);
-            mbar_expect_tx(&full_a[as], P.halo_box_bytes);
-            const int src = cb < P.cblocks0 ? 0 : 1;
-            const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
-            tma_load_4d(smem + (size_t)as * P.halo_a_bytes, &maps.a[src][0], &full_a[as], c, -1, pr0 - 1, nsrc);
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_expect_tx(&full_bar[stage], P.stage_b_bytes);
-              tma_load_3d(smem_b0 + (size_t)stage * stage_bytes, &maps.b, &full_bar[stage], (tap * P.cblocks + cb) * BK, t.nt * P.BN, wz);
-              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
-            }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
-          }
-        } else {
-          const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
-          const unsigned sub_bytes = P.stage_a_bytes + P.stage_b_bytes;
-          int tap = 0, cb = 0;
-          for (int kb = 0; kb < P.num_kb; kb += P.sps) {
-            const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
-            mbar_wait(&empty_bar[stage], phase ^ 1u);
-            mbar_expect_tx(&full_bar[stage], (unsigned)nsub * sub_bytes);
-            for (int j = 0; j < nsub; ++j) {
-              uint8_t* sa = smem + (size_t)stage * stage_bytes + (size_t)j * sub_bytes;
-              uint8_t* sb = sa + P.stage_a_bytes;
-              const ds_conv_tap tp = P.taps[t.g][tap];
-              const int src = cb < P.cblocks0 ? 0 : 1;
-              const int c = (src == 0 ? cb : cb - P.cblocks0) * BK;
-              tma_load_4d(sa, &maps.a[src][tp.view], &full_bar[stage], c, w0 + tp.dx, h0 + tp.dy, nsrc);
-              tma_load_3d(sb, &maps.b, &full_bar[stage], (kb + j) * BK, t.nt * P.BN, wz);
-              if (++cb == P.cblocks) { cb = 0; ++tap; }
-            }
-            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+    // ================================ activation (A) producer: warp-uniform, one elected lane issues =======================
+    long long w_empty = 0;
+    const long long t_begin = clock64();
+    const uint8_t* map_base = reinterpret_cast<const uint8_t*>(&maps.a[0][0]);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
+      const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
+      const int4* kbt = s_kbt + t.g * P.num_kb;
+      for (int kb = 0; kb < P.num_kb; kb += P.sps) {
+        const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
+        const int4 e0 = kbt[kb];                                     // fetched before the barrier probe
+        mbar_wait_timed(&empty_bar[stage], phase ^ 1u, timed, w_empty);
+        if (elect_one_sync()) {
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], (unsigned)nsub * P.stage_a_bytes);
+          tma_load_4d(sa, reinterpret_cast<const CUtensorMap*>(map_base + e0.x), &full_bar[stage], e0.y, w0 + e0.z, h0 + e0.w, nsrc);
+          for (int j = 1; j < nsub; ++j) {
+            const int4 e = kbt[kb + j];
+            sa += sub_bytes;
+            tma_load_4d(sa, reinterpret_cast<const CUtensorMap*>(map_base + e.x), &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
           }
         }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    if (timed && lane == 0) { P.dbg_buf[blockIdx.x * 16 + 0] = (unsigned long long)w_empty; P.dbg_buf[blockIdx.x * 16 + 1] = (unsigned long long)(clock64() - t_begin); }
+  } else if (warp == 2) {
+    // ================================ weight (B) producer ================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(P, tile);
+      const int wz = P.per_sample_w ? t.n : t.g;
+      const int n0 = t.nt * P.BN;
+      for (int kb = 0; kb < P.num_kb; kb += P.sps) {
+        const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one_sync()) {
+          uint8_t* sb = smem + (size_t)stage * stage_bytes + P.stage_a_bytes;
+          mbar_expect_tx(&full_bar[stage], (unsigned)nsub * P.stage_b_bytes);
+          for (int j = 0; j < nsub; ++j) {
+            tma_load_3d(sb, &maps.b, &full_bar[stage], (kb + j) * BK, n0, wz);
+            sb += sub_bytes;
+          }
+        }
+        __syncwarp();
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
-    if (lane == 0) {
-      // instruction descriptor: D=f32 (bit 4), A/B format (bits 7-9, 10-12), K-major both, N>>3 at 17, M>>4 at 24
-      const uint32_t fmt = kOperandIsFp16 ? 0u : 1u;   // F16F32Format: 0 = f16, 1 = bf16
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    // ================================ MMA issuer (warp-uniform; one elected lane issues) ==================================
+    // instruction descriptor: D=f32 (bit 4), A/B format (bits 7-9, 10-12), K-major both, N>>3 at 17, M>>4 at 24
+    const uint32_t fmt = kOperandIsFp16 ? 0u : 1u;   // F16F32Format: 0 = f16, 1 = bf16
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long w_full = 0, w_tmem = 0, c_fence = 0, c_issue = 0, c_commit = 0;
+    const long long t_begin = clock64();
+    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      mbar_wait_timed(&tmem_empty[acc], acc_phase ^ 1u, timed, w_tmem);
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
+      uint32_t accum = 0;
+      for (int kb = 0; kb < P.num_kb; kb += P.sps) {
+        const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
+        mbar_wait_timed(&full_bar[stage], phase, timed, w_full);
+        long long tq0 = 0, tq1 = 0, tq2 = 0;
+        if (timed) tq0 = clock64();
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
-        if (HALO) {
-          const TileCoord t = decode_tile(P, tile);
-          const int p0 = (t.th * P.tiles_w + t.tw) * BM;
-          const int base_row = p0 - (p0 / P.Wp) * P.Wp;      // row of position q = p0 inside the box for tap (0,0)
-          uint32_t accum = 0;
-          for (int cb = 0; cb < P.cblocks; ++cb) {
-            mbar_wait(&full_a[as], aphase);
-            tcgen05_fence_after();
-            const uint32_t sa0 = smem_u32(smem + (size_t)as * P.halo_a_bytes);
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&full_bar[stage], phase);
-              tcgen05_fence_after();
-              const int off = base_row + (tap / 3) * P.Wp + (tap % 3);
-              const uint64_t adesc = make_kmajor_desc<BK>(sa0 + (uint32_t)off * (BK * 2));
-              const uint64_t bdesc = make_kmajor_desc<BK>(smem_u32(smem_b0 + (size_t)stage * stage_bytes));
+        if (timed) { tq1 = clock64(); c_fence += tq1 - tq0; }
+        if (elect_one_sync()) {
+          uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          for (int j = 0; j < nsub; ++j) {
+            const uint64_t adesc = make_kmajor_desc<BK>(sa);
+            const uint64_t bdesc = make_kmajor_desc<BK>(sa + P.stage_a_bytes);
+            if (!(P.dbg & 4)) {
+              // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-                accum = 1u;
-              }
-              umma_commit(&empty_bar[stage]);
-              if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+              for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || j > 0) ? 1u : accum);
             }
-            umma_commit(&empty_a[as]);        // the halo box is free once the MMAs of its 9 taps retire
-            if (++as == 2) { as = 0; aphase ^= 1u; }
+            sa += sub_bytes;
           }
-        } else {
-          const unsigned sub_bytes = P.stage_a_bytes + P.stage_b_bytes;
-          uint32_t accum = 0;
-          for (int kb = 0; kb < P.num_kb; kb += P.sps) {
-            const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            const uint32_t s0 = smem_u32(smem + (size_t)stage * stage_bytes);
-            for (int j = 0; j < nsub; ++j) {
-              const uint32_t sa = s0 + (uint32_t)j * sub_bytes;
-              const uint64_t adesc = make_kmajor_desc<BK>(sa);
-              const uint64_t bdesc = make_kmajor_desc<BK>(sa + P.stage_a_bytes);
-#pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
-                if (!(P.dbg & 4)) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accum);
-                accum = 1u;
-              }
-            }
-            umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
-            if (++stage == P.stages) { stage = 0; phase ^= 1u; }
-          }
+          if (timed) { tq2 = clock64(); c_issue += tq2 - tq1; }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (timed) c_commit += clock64() - tq2;
         }
-        umma_commit(&tmem_full[acc]);       // accumulator complete
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        accum = 1u;
+        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
+      if (elect_one_sync()) umma_commit(&tmem_full[acc]);       // accumulator complete
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (timed && lane == 0) {
+      P.dbg_buf[blockIdx.x * 16 + 2] = (unsigned long long)w_full; P.dbg_buf[blockIdx.x * 16 + 3] = (unsigned long long)w_tmem;
+      P.dbg_buf[blockIdx.x * 16 + 4] = (unsigned long long)(clock64() - t_begin);
+      P.dbg_buf[blockIdx.x * 16 + 8] = (unsigned long long)c_fence; P.dbg_buf[blockIdx.x * 16 + 9] = (unsigned long long)c_issue;
+      P.dbg_buf[blockIdx.x * 16 + 10] = (unsigned long long)c_commit;
     }
   } else if (warp == 3) {
     // ================================ statistics publisher =========================
@@ -454,15 +458,12 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
     };
     fetch_sbias(blockIdx.x);
+    const bool epi_timed = (P.dbg & 64) != 0;
+    long long epi_wait = 0;
+    const long long epi_begin = clock64();
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(P, tile);
-      int h, w;
-      if (HALO) {
-        fast_divmod((t.th * P.tiles_w + t.tw) * BM + row, P.Wp, P.inv_Wp, h, w);
-      } else {
-        h = t.th * P.Hb + ph;
-        w = t.tw * P.Wb + pw;
-      }
+      const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
       if (P.sbias != nullptr) {
         __syncwarp();
 #pragma unroll
@@ -589,7 +590,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
       };
       if (nch > 0) fetch_res(0, qa);
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_timed(&tmem_full[acc], acc_phase, epi_timed, epi_wait);
       tcgen05_fence_after();
       if (nch > 0) issue_chunk(0, ra_);
       for (int c = 0; c < nch; c += 2) {
@@ -617,6 +618,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         __syncwarp();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (epi_timed && ew == 0 && lane == 0) {
+      P.dbg_buf[blockIdx.x * 16 + 5] = (unsigned long long)epi_wait; P.dbg_buf[blockIdx.x * 16 + 6] = (unsigned long long)(clock64() - epi_begin);
     }
   }
   tcgen05_fence_before();
@@ -654,19 +658,9 @@ static int validate(const ds_conv_gemm_args* a) {
   return DS_OK;
 }
 
-// Halo mode (opt-in, DS_CONV_HALO_MINW=<min width>) applies to plain 3x3 stride-1 'same' convolutions.
-static bool use_halo(const ds_conv_gemm_args* a) {
-  const char* e = getenv("DS_CONV_HALO_MINW");
-  const int minw = e ? atoi(e) : (1 << 30);     // measured ~10% slower than the generic mode on B200 (profiles/r01_notes.md): off by default
-  if (a->ntaps != 9 || a->groups != 1 || a->num_views != 1 || a->H != a->Hv || a->W != a->Wv) return false;
-  if (a->W < minw || a->W + 2 > 256 || a->view_sw != 1 || a->view_sh != a->Wv || a->view_off[0] != 0) return false;
-  for (int t = 0; t < 9; ++t)
-    if (a->taps[0][t].dy != t / 3 - 1 || a->taps[0][t].dx != t % 3 - 1 || a->taps[0][t].view != 0) return false;
-  return true;
-}
-
 static size_t smem_fixed_bytes(const ds_conv_gemm_args* a) {
-  const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float);
+  const size_t kbt_bytes = (size_t)a->groups * a->ntaps * ((a->C0 + a->C1) / a->BK) * sizeof(int4);     // per-K-block TMA coordinates
+  const size_t table_bytes = (size_t)2 * a->ncls * a->Cout_pad * sizeof(float) + kbt_bytes;
   return 1024 + (2 * kMaxStages + 12) * sizeof(uint64_t) + 16 + 2 * kEpiWarps * sizeof(float2) + kEpiWarps * 128 * sizeof(float) + table_bytes + 64;
 }
 static size_t smem_budget(const ds_conv_gemm_args* a) {
@@ -680,28 +674,12 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.stage_a_bytes = BM * a->BK * 2;
   P.stage_b_bytes = a->BN * a->BK * 2;
   { const char* e = getenv("DS_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
-  P.halo = use_halo(a) ? 1 : 0;
-  if (P.halo) {
-    P.Wp = a->W + 2;
-    P.halo_rows = (3 * P.Wp + BM + 1 + P.Wp - 1) / P.Wp;
-    P.halo_box_bytes = (unsigned)((size_t)P.halo_rows * P.Wp * a->BK * 2);
-    P.halo_a_bytes = (P.halo_box_bytes + 1023u) / 1024u * 1024u;
-    const size_t budget = smem_budget(a);
-    if (budget < 2 * (size_t)P.halo_a_bytes + 3 * (size_t)P.stage_b_bytes) P.halo = 0;   // no room for two halo boxes + a weight ring
-  }
-  if (P.halo) {
-    P.Hb = 1; P.Wb = BM;
-    P.tiles_h = 1;
-    P.tiles_w = (a->H * P.Wp + BM - 1) / BM;
-  } else {
-    P.Wp = 0; P.halo_rows = 0; P.halo_a_bytes = 0; P.halo_box_bytes = 0;
-    P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
-    P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
-  }
+  P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
+  P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
   P.tiles_m = P.tiles_h * P.tiles_w;
   P.n_tiles_n = a->Cout_pad / a->BN;
   P.inv_n_tiles_n = 1.0f / P.n_tiles_n; P.inv_tiles_m = 1.0f / P.tiles_m; P.inv_groups = 1.0f / a->groups;
-  P.inv_tiles_w = 1.0f / P.tiles_w; P.inv_Wb = 1.0f / P.Wb; P.inv_Wp = P.Wp ? 1.0f / P.Wp : 0.f;
+  P.inv_tiles_w = 1.0f / P.tiles_w; P.inv_Wb = 1.0f / P.Wb;
   P.BN = a->BN; P.C0 = a->C0; P.C1 = a->C1;
   P.cblocks0 = a->C0 / a->BK;
   P.cblocks = (a->C0 + a->C1) / a->BK;
@@ -744,7 +722,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a->Wv, (cuuint64_t)a->Hv,
                             (cuuint64_t)(a->src_batch_mod > 0 ? a->src_batch_mod : a->N)};
       cuuint64_t strides[3] = {(cuuint64_t)a->view_sw * C * 2, (cuuint64_t)a->view_sh * C * 2, (cuuint64_t)a->view_sn * C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)(P.halo ? P.Wp : a->Wb), (cuuint32_t)(P.halo ? P.halo_rows : a->Hb), 1};
+      cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       void* gaddr = const_cast<char*>(base) + (size_t)a->view_off[v] * C * 2;
       CUresult r = encode(&maps.a[s][v], (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, gaddr, dims, strides, box, estr,
@@ -771,32 +749,47 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   // K-blocks per stage: one barrier round trip per stage costs a few hundred cycles on the single MMA-issuing thread, so every
   // stage should carry >= ~384 cycles of tensor work (BK/16 MMAs of BN/2 cycles each per K-block) while >= 4 stages still fit.
   P.sps = 1;
-  if (!P.halo) {
+  {
     const size_t sub = (size_t)P.stage_a_bytes + P.stage_b_bytes;
     const int cyc = (a->BK / 16) * (a->BN / 2);
     const char* e = getenv("DS_CONV_MAX_SPS");
     const int max_sps = e ? atoi(e) : 4;
     while (P.sps < max_sps && P.sps * cyc < 384 && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * 4 <= budget) ++P.sps;
   }
-  const size_t stage_bytes = P.halo ? (size_t)P.stage_b_bytes : (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
-  int stages = (int)((budget - (P.halo ? 2 * (size_t)P.halo_a_bytes : 0)) / stage_bytes);
+  const size_t stage_bytes = (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
+  int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   { const char* e = getenv("DS_CONV_MAX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }   // experiment knob
   // (the ring spans tiles of the persistent loop: small-K convs prefetch several tiles ahead, so it is never clamped to K)
   DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables leave no room for a 2-stage pipeline (Cout_pad=%d ncls=%d)", a->Cout_pad, a->ncls);
   P.stages = stages;
-  const size_t smem = fixed_bytes + (P.halo ? 2 * (size_t)P.halo_a_bytes : 0) + stages * stage_bytes;
+  const size_t smem = fixed_bytes + stages * stage_bytes;
 
   int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-#define DS_LAUNCH_CONV(BKV, HALOV)                                                                                                   \
-  do {                                                                                                                               \
-    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV, HALOV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    conv_gemm_kernel<BKV, HALOV><<<grid, kNumThreads, smem, stream>>>(maps, P);                                                     \
+  static unsigned long long* dbg_buf = nullptr;
+  P.dbg_buf = nullptr;
+  if (P.dbg & 64) {
+    if (!dbg_buf) DS_CHECK_CUDA(cudaMalloc(&dbg_buf, sizeof(unsigned long long) * 16 * 1024));
+    DS_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(unsigned long long) * 16 * 1024, stream));
+    P.dbg_buf = dbg_buf;
+  }
+#define DS_LAUNCH_CONV(BKV)                                                                                               \
+  do {                                                                                                                    \
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv_gemm_kernel<BKV><<<grid, kNumThreads, smem, stream>>>(maps, P);                                                 \
   } while (0)
-  if (a->BK == 64) { if (P.halo) DS_LAUNCH_CONV(64, true); else DS_LAUNCH_CONV(64, false); }
-  else             { if (P.halo) DS_LAUNCH_CONV(32, true); else DS_LAUNCH_CONV(32, false); }
+  if (a->BK == 64) DS_LAUNCH_CONV(64); else DS_LAUNCH_CONV(32);
 #undef DS_LAUNCH_CONV
   DS_CHECK_CUDA(cudaGetLastError());
+  if (P.dbg & 64) {      // profiling only: where each role of the CTA spent its cycles (mean over CTAs)
+    static unsigned long long host[16 * 1024];
+    DS_CHECK_CUDA(cudaStreamSynchronize(stream));
+    DS_CHECK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
+    double m[16] = {0};
+    for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) m[i] += (double)host[b * 16 + i] / grid;
+    fprintf(stderr, "[conv dbg] tiles/cta %.1f kb/tile %d sps %d stages %d | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tmem_empty %.0f of %.0f | epilogue(w4): wait_tmem_full %.0f of %.0f cycles | mma detail: fence %.0f issue %.0f commit %.0f\n",
+            (double)P.num_tiles / grid, P.num_kb, P.sps, P.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[8], m[9], m[10]);
+  }
   return DS_OK;
 }
 

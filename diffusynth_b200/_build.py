@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC, "-c", src, "-o", obj] + [f for f in FLAGS if f != "--use_fast_math=false"]
+        cmd = [NVCC, "-c", src, "-o", obj] + [f for f in FLAGS if f != "--use_fast_math=false"] + os.environ.get("DS_EXTRA_NVCC_FLAGS", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

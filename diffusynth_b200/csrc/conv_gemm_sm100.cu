@@ -73,9 +73,9 @@ __device__ __forceinline__ bool elect_one_sync() {
 }
 // mbar_wait that also accumulates the cycles spent waiting (profiling builds of the role loops: DS_CONV_DBG & 64)
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if (!timed) { mbar_wait(bar, parity); return; }
+  if (!timed) { mbar_wait_warp(bar, parity); return; }
   const long long t0 = clock64();
-  mbar_wait(bar, parity);
+  mbar_wait_warp(bar, parity);
   acc += clock64() - t0;
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
@@ -345,7 +345,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const int n0 = t.nt * P.BN;
       for (int kb = 0; kb < P.num_kb; kb += P.sps) {
         const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
         if (elect_one_sync()) {
           uint8_t* sb = smem + (size_t)stage * stage_bytes + P.stage_a_bytes;
           mbar_expect_tx(&full_bar[stage], (unsigned)nsub * P.stage_b_bytes);
@@ -420,7 +420,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile);
-        mbar_wait(&stats_full[acc], acc_phase);
+        mbar_wait_warp(&stats_full[acc], acc_phase);
         float s = 0.f, q = 0.f;
         if (lane == 0) {
 #pragma unroll
@@ -450,9 +450,15 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     float* my_sb = s_sb + ew * 128;
     const int sb_cols = (chunk_hi - chunk_lo) * 16;
     float sb_next[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 mr_next = make_float2(0.f, 1.f);      // (mean, rstd) of the next tile's sample, fetched one tile ahead like the bias
     auto fetch_sbias = [&](int tile_idx) {
-      if (P.sbias == nullptr || tile_idx >= P.num_tiles) return;
+      if (tile_idx >= P.num_tiles || (P.sbias == nullptr && P.stats_in == nullptr)) return;
       const TileCoord tt = decode_tile(P, tile_idx);
+      if (P.stats_in != nullptr) {
+        const int nsrc = P.src_batch_mod > 0 ? (tt.n % P.src_batch_mod) : tt.n;
+        mr_next = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc));
+      }
+      if (P.sbias == nullptr) return;
       const float* src = P.sbias + (size_t)tt.n * P.sbias_stride + tt.nt * P.BN + chunk_lo * 16;
 #pragma unroll
       for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
@@ -461,29 +467,26 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const bool epi_timed = (P.dbg & 64) != 0;
     long long epi_wait = 0;
     const long long epi_begin = clock64();
+    long long e_pro = 0, e_chunks = 0, e_tail = 0;
     for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+      long long te0 = 0, te1 = 0, te2 = 0;
+      if (epi_timed) te0 = clock64();
       const TileCoord t = decode_tile(P, tile);
       const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
+      const float mean = mr_next.x, rstd = mr_next.y;
+      const float nmr = -mean * rstd;
+      const bool valid = (h < P.H) && (w < P.W);
+      const int col0 = t.nt * P.BN + chunk_lo * 16;        // first global output channel of this warp's column range
       if (P.sbias != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) my_sb[lane + 32 * i] = sb_next[i];
         __syncwarp();
-        fetch_sbias(tile + gridDim.x);
       }
-      const bool valid = (h < P.H) && (w < P.W);
-      float mean = 0.f, rstd = 1.f;
-      if (P.stats_in != nullptr) {
-        const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
-        const float2 mr = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc));
-        mean = mr.x;
-        rstd = mr.y;
-      }
+      fetch_sbias(tile + gridDim.x);
       int cls = 0;
       if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
-      const float nmr = -mean * rstd;
       const bool use_e1 = P.e1 != nullptr, use_sb = P.sbias != nullptr, do_stats = P.stats_out != nullptr;
-      const int col0 = t.nt * P.BN + chunk_lo * 16;        // first global output channel of this warp's column range
       // running addresses, advanced by one 16-column chunk at a time: 32-bit shared-space addresses for the tables (so the
       // loads are LDS with immediate offsets, not generic LD), element pointers for the tensors
       uint32_t e2_s = smem_u32(s_e2) + (uint32_t)(cls * P.Cout_pad + col0) * 4u;
@@ -590,7 +593,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
       };
       if (nch > 0) fetch_res(0, qa);
+      if (epi_timed) { te1 = clock64(); e_pro += te1 - te0; }
       mbar_wait_timed(&tmem_full[acc], acc_phase, epi_timed, epi_wait);
+      if (epi_timed) te1 = clock64();
       tcgen05_fence_after();
       if (nch > 0) issue_chunk(0, ra_);
       for (int c = 0; c < nch; c += 2) {
@@ -607,6 +612,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (epi_timed) { te2 = clock64(); e_chunks += te2 - te1; }
       if (P.stats_out != nullptr) {
         psum = warp_sum(psum);
         psq = warp_sum(psq);
@@ -617,9 +623,12 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         }
         __syncwarp();
       }
+      if (epi_timed) e_tail += clock64() - te2;
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     if (epi_timed && ew == 0 && lane == 0) {
+      P.dbg_buf[blockIdx.x * 16 + 11] = (unsigned long long)e_pro; P.dbg_buf[blockIdx.x * 16 + 12] = (unsigned long long)e_chunks;
+      P.dbg_buf[blockIdx.x * 16 + 13] = (unsigned long long)e_tail;
       P.dbg_buf[blockIdx.x * 16 + 5] = (unsigned long long)epi_wait; P.dbg_buf[blockIdx.x * 16 + 6] = (unsigned long long)(clock64() - epi_begin);
     }
   }
@@ -754,7 +763,9 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     const int cyc = (a->BK / 16) * (a->BN / 2);
     const char* e = getenv("DS_CONV_MAX_SPS");
     const int max_sps = e ? atoi(e) : 4;
-    while (P.sps < max_sps && P.sps * cyc < 384 && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * 4 <= budget) ++P.sps;
+    const char* e2 = getenv("DS_CONV_MIN_STAGES");
+    const int min_stages = e2 ? atoi(e2) : 3;     // three stages already saturate the pipeline (measured); deeper rings buy nothing
+    while (P.sps < max_sps && P.sps * cyc < 384 && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * min_stages <= budget) ++P.sps;
   }
   const size_t stage_bytes = (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
   int stages = (int)(budget / stage_bytes);
@@ -787,8 +798,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_CHECK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
     double m[16] = {0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) m[i] += (double)host[b * 16 + i] / grid;
-    fprintf(stderr, "[conv dbg] tiles/cta %.1f kb/tile %d sps %d stages %d | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tmem_empty %.0f of %.0f | epilogue(w4): wait_tmem_full %.0f of %.0f cycles | mma detail: fence %.0f issue %.0f commit %.0f\n",
-            (double)P.num_tiles / grid, P.num_kb, P.sps, P.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[8], m[9], m[10]);
+    fprintf(stderr, "[conv dbg] tiles/cta %.1f kb/tile %d sps %d stages %d | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tmem_empty %.0f of %.0f | epilogue(w4): wait_tmem_full %.0f of %.0f cycles | mma detail: fence %.0f issue %.0f commit %.0f | epi detail: prologue %.0f chunks %.0f tail %.0f\n",
+            (double)P.num_tiles / grid, P.num_kb, P.sps, P.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[8], m[9], m[10], m[11], m[12], m[13]);
   }
   return DS_OK;
 }

@@ -29,14 +29,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// DS_WAIT_MODE (experiments): 0 = every calling lane probes; 1 = one elected lane probes, the others park at __syncwarp;
+// 2 = like 1 with a suspend-time hint on the probe.
+#ifndef DS_WAIT_MODE
+#define DS_WAIT_MODE 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+#if DS_WAIT_MODE == 2
+  while (!mbar_try_wait_hint(bar, parity, 2000u)) {
+#else
   while (!mbar_try_wait(bar, parity)) {
+#endif
     if (++spins > (1u << 26)) {
       printf("diffusynth_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_spin(bar, parity); }
+// Wait executed by a converged warp.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#if DS_WAIT_MODE == 0
+  mbar_wait_spin(bar, parity);
+#else
+  uint32_t leader;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+  if (leader) mbar_wait_spin(bar, parity);
+  __syncwarp();
+#endif
 }
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,

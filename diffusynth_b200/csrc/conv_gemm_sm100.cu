@@ -27,7 +27,9 @@ static constexpr int BM = 128;
 struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
-  int num_kb, stages, num_tiles;
+  int num_kb, stages, num_tiles;     // num_tiles = work items: M-tiles (cg = 1) or M-tile pairs (cg = 2)
+  int cg, tiles_md;                  // CTAs per MMA (1 or 2), tiles_m / cg
+  float inv_tiles_md;
   float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb;   // reciprocals for fast_divmod
   unsigned long long* dbg_buf;      // DS_CONV_DBG & 64: per-CTA wait-cycle counters [grid][8]
   int dbg;                          // DS_CONV_DBG bitmask (profiling experiments): 1 = no global stores, 2 = no TMEM loads, 4 = no MMA issue
@@ -77,6 +79,51 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
   const long long t0 = clock64();
   mbar_wait_warp(bar, parity);
   acc += clock64() - t0;
+}
+// ---- 2-CTA (cta_group::2) variants: one MMA instruction drives the tensor cores of both SMs of a cluster pair (M = 256: each CTA
+// holds its own 128 activation rows and HALF of the weight tile), issued by the even ("leader") CTA only.
+static constexpr uint32_t kPeerMask = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// TMA loads of either CTA of the pair that report their bytes to the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // plain arrive on the leader CTA's copy of the barrier
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -138,12 +185,14 @@ __device__ __forceinline__ void fast_divmod(int x, int d, float inv_d, int& q, i
   else if (r >= d) { ++q; r -= d; }
 }
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile) {
+// tile = work index of the CTA (CG = 1) or of the CTA pair (CG = 2: the pair owns M-tiles 2m', 2m'+1 of one (sample, group, n-tile))
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile, int rank) {
   TileCoord t;
   int r, m;
   fast_divmod(tile, P.n_tiles_n, P.inv_n_tiles_n, r, t.nt);
   int r2;
-  fast_divmod(r, P.tiles_m, P.inv_tiles_m, r2, m);
+  fast_divmod(r, P.tiles_md, P.inv_tiles_md, r2, m);
+  m = m * P.cg + rank;
   fast_divmod(r2, P.groups, P.inv_groups, t.n, t.g);
   fast_divmod(m, P.tiles_w, P.inv_tiles_w, t.th, t.tw);
   t.slot = (t.g * P.tiles_m + m) * P.n_tiles_n + t.nt;
@@ -243,7 +292,7 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 // allocator, then weight (B) TMA producer, 3 = statistics publisher, 4-11 = epilogue.  The two producers split the per-K-block
 // scalar work (barrier probe + coordinates + TMA issue), which otherwise bounds the kernel on one thread; the A producer
 // reads its per-K-block coordinates (tensor map, channel offset, tap shift) from a table built once in shared memory.
-template <int BK>
+template <int BK, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -266,6 +315,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;           // 0 = leader of the pair
+  const int w_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_cols = (2 * P.BN <= 32) ? 32u : (2 * P.BN <= 64) ? 64u : (2 * P.BN <= 128) ? 128u : (2 * P.BN <= 256) ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
@@ -280,13 +332,13 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], CG * kEpiWarps);      // CG = 2: the leader's copy collects the epilogue warps of both CTAs
       mbar_init(&stats_full[a], kEpiWarps);
       mbar_init(&stats_empty[a], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tmem_alloc(tmem_base_smem, tmem_cols);
+  if (warp == 2) { if (CG == 2) tmem_alloc_2cta(tmem_base_smem, tmem_cols); else tmem_alloc(tmem_base_smem, tmem_cols); }
   for (int i = threadIdx.x; i < P.ncls * P.Cout_pad; i += kNumThreads) {
     s_e2[i] = __ldg(P.e2 + i);
     s_e1[i] = P.e1 ? __ldg(P.e1 + i) : 0.f;
@@ -300,6 +352,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is signalled across the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
   const bool timed = (P.dbg & 64) != 0;
@@ -311,8 +364,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const uint8_t* map_base = reinterpret_cast<const uint8_t*>(&maps.a[0][0]);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(P, tile);
+    for (int tile = w_first; tile < P.num_tiles; tile += w_step) {
+      const TileCoord t = decode_tile(P, tile, rank);
       const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
       const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
       const int4* kbt = s_kbt + t.g * P.num_kb;
@@ -322,12 +375,13 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         mbar_wait_timed(&empty_bar[stage], phase ^ 1u, timed, w_empty);
         if (elect_one_sync()) {
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], (unsigned)nsub * P.stage_a_bytes);
-          tma_load_4d(sa, reinterpret_cast<const CUtensorMap*>(map_base + e0.x), &full_bar[stage], e0.y, w0 + e0.z, h0 + e0.w, nsrc);
-          for (int j = 1; j < nsub; ++j) {
-            const int4 e = kbt[kb + j];
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], (unsigned)(CG * nsub) * P.stage_a_bytes);      // the pair's activation bytes
+          for (int j = 0; j < nsub; ++j) {
+            const int4 e = j == 0 ? e0 : kbt[kb + j];
+            const CUtensorMap* mp = reinterpret_cast<const CUtensorMap*>(map_base + e.x);
+            if (CG == 2) tma_load_4d_2cta(sa, mp, &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
+            else tma_load_4d(sa, mp, &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
             sa += sub_bytes;
-            tma_load_4d(sa, reinterpret_cast<const CUtensorMap*>(map_base + e.x), &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
           }
         }
         __syncwarp();
@@ -339,18 +393,19 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     // ================================ weight (B) producer ================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(P, tile);
+    for (int tile = w_first; tile < P.num_tiles; tile += w_step) {
+      const TileCoord t = decode_tile(P, tile, rank);
       const int wz = P.per_sample_w ? t.n : t.g;
-      const int n0 = t.nt * P.BN;
+      const int n0 = t.nt * P.BN + rank * (P.BN / CG);       // CG = 2: each CTA stages its half of the weight rows
       for (int kb = 0; kb < P.num_kb; kb += P.sps) {
         const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
         mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
         if (elect_one_sync()) {
           uint8_t* sb = smem + (size_t)stage * stage_bytes + P.stage_a_bytes;
-          mbar_expect_tx(&full_bar[stage], (unsigned)nsub * P.stage_b_bytes);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], (unsigned)(CG * nsub) * P.stage_b_bytes);
           for (int j = 0; j < nsub; ++j) {
-            tma_load_3d(sb, &maps.b, &full_bar[stage], (kb + j) * BK, n0, wz);
+            if (CG == 2) tma_load_3d_2cta(sb, &maps.b, &full_bar[stage], (kb + j) * BK, n0, wz);
+            else tma_load_3d(sb, &maps.b, &full_bar[stage], (kb + j) * BK, n0, wz);
             sb += sub_bytes;
           }
         }
@@ -358,18 +413,18 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer (warp-uniform; one elected lane issues) ==================================
+  } else if (warp == 1 && rank == 0) {
+    // ================================ MMA issuer (warp-uniform; one elected lane issues; leader CTA only) ====================
     // instruction descriptor: D=f32 (bit 4), A/B format (bits 7-9, 10-12), K-major both, N>>3 at 17, M>>4 at 24
     const uint32_t fmt = kOperandIsFp16 ? 0u : 1u;   // F16F32Format: 0 = f16, 1 = bf16
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     long long w_full = 0, w_tmem = 0, c_fence = 0, c_issue = 0, c_commit = 0;
     const long long t_begin = clock64();
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    for (int tile = w_first; tile < P.num_tiles; tile += w_step) {
       mbar_wait_timed(&tmem_empty[acc], acc_phase ^ 1u, timed, w_tmem);
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * P.BN);
@@ -389,19 +444,22 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             if (!(P.dbg & 4)) {
               // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || j > 0) ? 1u : accum);
+              for (int k = 0; k < BK / 16; ++k) {
+                if (CG == 2) umma_f16_2cta(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || j > 0) ? 1u : accum);
+                else umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (k > 0 || j > 0) ? 1u : accum);
+              }
             }
             sa += sub_bytes;
           }
           if (timed) { tq2 = clock64(); c_issue += tq2 - tq1; }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot when these MMAs retire
+          if (CG == 2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);   // frees the smem slot (of both CTAs) when these MMAs retire
           if (timed) c_commit += clock64() - tq2;
         }
         __syncwarp();
         accum = 1u;
         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
       }
-      if (elect_one_sync()) umma_commit(&tmem_full[acc]);       // accumulator complete
+      if (elect_one_sync()) { if (CG == 2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }       // accumulator complete
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -418,8 +476,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     if (P.stats_out != nullptr) {
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(P, tile);
+      for (int tile = w_first; tile < P.num_tiles; tile += w_step) {
+        const TileCoord t = decode_tile(P, tile, rank);
         mbar_wait_warp(&stats_full[acc], acc_phase);
         float s = 0.f, q = 0.f;
         if (lane == 0) {
@@ -453,7 +511,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     float2 mr_next = make_float2(0.f, 1.f);      // (mean, rstd) of the next tile's sample, fetched one tile ahead like the bias
     auto fetch_sbias = [&](int tile_idx) {
       if (tile_idx >= P.num_tiles || (P.sbias == nullptr && P.stats_in == nullptr)) return;
-      const TileCoord tt = decode_tile(P, tile_idx);
+      const TileCoord tt = decode_tile(P, tile_idx, rank);
       if (P.stats_in != nullptr) {
         const int nsrc = P.src_batch_mod > 0 ? (tt.n % P.src_batch_mod) : tt.n;
         mr_next = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc));
@@ -463,15 +521,15 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
       for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
     };
-    fetch_sbias(blockIdx.x);
+    fetch_sbias(w_first);
     const bool epi_timed = (P.dbg & 64) != 0;
     long long epi_wait = 0;
     const long long epi_begin = clock64();
     long long e_pro = 0, e_chunks = 0, e_tail = 0;
-    for (int tile = blockIdx.x; tile < P.num_tiles; tile += gridDim.x) {
+    for (int tile = w_first; tile < P.num_tiles; tile += w_step) {
       long long te0 = 0, te1 = 0, te2 = 0;
       if (epi_timed) te0 = clock64();
-      const TileCoord t = decode_tile(P, tile);
+      const TileCoord t = decode_tile(P, tile, rank);
       const int h = t.th * P.Hb + ph, w = t.tw * P.Wb + pw;
       const float mean = mr_next.x, rstd = mr_next.y;
       const float nmr = -mean * rstd;
@@ -483,7 +541,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         for (int i = 0; i < 4; ++i) my_sb[lane + 32 * i] = sb_next[i];
         __syncwarp();
       }
-      fetch_sbias(tile + gridDim.x);
+      fetch_sbias(tile + w_step);
       int cls = 0;
       if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
       const bool use_e1 = P.e1 != nullptr, use_sb = P.sbias != nullptr, do_stats = P.stats_out != nullptr;
@@ -611,7 +669,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       // release the accumulator stage (one arrive per epilogue warp)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       if (epi_timed) { te2 = clock64(); e_chunks += te2 - te1; }
       if (P.stats_out != nullptr) {
         psum = warp_sum(psum);
@@ -634,9 +692,10 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // neither CTA retires (or frees tensor memory) while its peer may still signal or read it
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -680,12 +739,22 @@ static size_t smem_budget(const ds_conv_gemm_args* a) {
 static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   memset(&P, 0, sizeof(P));
   P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
-  P.stage_a_bytes = BM * a->BK * 2;
-  P.stage_b_bytes = a->BN * a->BK * 2;
   { const char* e = getenv("DS_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
   P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
   P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
   P.tiles_m = P.tiles_h * P.tiles_w;
+  // Two-CTA MMA (cta_group::2): the pair computes two M-tiles of one (sample, group, n-tile) with one instruction stream and
+  // half of the weight tile per CTA.  It needs an even number of M-tiles; convolutions with enough K per tile to be bound by
+  // the MMA issue rate gain from it (ntaps >= 4); DS_CONV_CG=1/2 forces the choice.
+  {
+    const char* e = getenv("DS_CONV_CG");
+    const int want = e ? atoi(e) : (a->ntaps >= 4 ? 2 : 1);
+    P.cg = (want == 2 && P.tiles_m % 2 == 0 && a->BN % 32 == 0) ? 2 : 1;
+  }
+  P.tiles_md = P.tiles_m / P.cg;
+  P.inv_tiles_md = 1.0f / P.tiles_md;
+  P.stage_a_bytes = BM * a->BK * 2;
+  P.stage_b_bytes = (a->BN / P.cg) * a->BK * 2;
   P.n_tiles_n = a->Cout_pad / a->BN;
   P.inv_n_tiles_n = 1.0f / P.n_tiles_n; P.inv_tiles_m = 1.0f / P.tiles_m; P.inv_groups = 1.0f / a->groups;
   P.inv_tiles_w = 1.0f / P.tiles_w; P.inv_Wb = 1.0f / P.Wb;
@@ -695,7 +764,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.ntaps = a->ntaps; P.groups = a->groups; P.per_sample_w = a->per_sample_weights;
   P.src_batch_mod = a->src_batch_mod;
   P.num_kb = P.cblocks * a->ntaps;
-  P.num_tiles = a->N * a->groups * P.tiles_m * P.n_tiles_n;
+  P.num_tiles = a->N * a->groups * P.tiles_md * P.n_tiles_n;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.stats_in = reinterpret_cast<const float2*>(a->d_stats_in);
   P.stats_in_slots = a->stats_in_slots; P.out_inv_count = a->stats_out_inv_count; P.eps = a->eps;
@@ -745,7 +814,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     const int Z = a->per_sample_weights ? a->N : a->groups;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a->Cout_pad, (cuuint64_t)Z};
     cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * 2 * a->Cout_pad};
-    cuuint32_t box[3] = {(cuuint32_t)a->BK, (cuuint32_t)a->BN, 1};
+    cuuint32_t box[3] = {(cuuint32_t)a->BK, (cuuint32_t)(a->BN / P.cg), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&maps.b, (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 3, const_cast<void*>(a->d_weight), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -765,7 +834,9 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     const int max_sps = e ? atoi(e) : 4;
     const char* e2 = getenv("DS_CONV_MIN_STAGES");
     const int min_stages = e2 ? atoi(e2) : 3;     // three stages already saturate the pipeline (measured); deeper rings buy nothing
-    while (P.sps < max_sps && P.sps * cyc < 384 && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * min_stages <= budget) ++P.sps;
+    const char* e3 = getenv("DS_CONV_SPS_CYC");
+    const int cyc_target = e3 ? atoi(e3) : 768;     // measured: two barrier round trips per ~768 MMA cycles keep the single issuing thread off the critical path
+    while (P.sps < max_sps && P.sps * cyc < cyc_target && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * min_stages <= budget) ++P.sps;
   }
   const size_t stage_bytes = (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
   int stages = (int)(budget / stage_bytes);
@@ -777,6 +848,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   const size_t smem = fixed_bytes + stages * stage_bytes;
 
   int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  if (P.cg == 2) { const int pairs = num_sms() / 2; grid = 2 * (P.num_tiles < pairs ? P.num_tiles : pairs); }
   static unsigned long long* dbg_buf = nullptr;
   P.dbg_buf = nullptr;
   if (P.dbg & 64) {
@@ -784,12 +856,20 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(unsigned long long) * 16 * 1024, stream));
     P.dbg_buf = dbg_buf;
   }
-#define DS_LAUNCH_CONV(BKV)                                                                                               \
-  do {                                                                                                                    \
-    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv_gemm_kernel<BKV><<<grid, kNumThreads, smem, stream>>>(maps, P);                                                 \
+#define DS_LAUNCH_CONV(BKV, CGV)                                                                                                \
+  do {                                                                                                                          \
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    cudaLaunchConfig_t cfg;                                                                                                     \
+    memset(&cfg, 0, sizeof(cfg));                                                                                               \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;              \
+    cudaLaunchAttribute attr[1];                                                                                                \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                           \
+    attr[0].val.clusterDim.x = CGV; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                                \
+    cfg.attrs = attr; cfg.numAttrs = (CGV == 2) ? 1 : 0;                                                                        \
+    DS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BKV, CGV>, maps, P));                                               \
   } while (0)
-  if (a->BK == 64) DS_LAUNCH_CONV(64); else DS_LAUNCH_CONV(32);
+  if (a->BK == 64) { if (P.cg == 2) DS_LAUNCH_CONV(64, 2); else DS_LAUNCH_CONV(64, 1); }
+  else             { if (P.cg == 2) DS_LAUNCH_CONV(32, 2); else DS_LAUNCH_CONV(32, 1); }
 #undef DS_LAUNCH_CONV
   DS_CHECK_CUDA(cudaGetLastError());
   if (P.dbg & 64) {      // profiling only: where each role of the CTA spent its cycles (mean over CTAs)
@@ -798,8 +878,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_CHECK_CUDA(cudaMemcpy(host, dbg_buf, sizeof(unsigned long long) * 16 * grid, cudaMemcpyDeviceToHost));
     double m[16] = {0};
     for (int b = 0; b < grid; ++b) for (int i = 0; i < 16; ++i) m[i] += (double)host[b * 16 + i] / grid;
-    fprintf(stderr, "[conv dbg] tiles/cta %.1f kb/tile %d sps %d stages %d | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tmem_empty %.0f of %.0f | epilogue(w4): wait_tmem_full %.0f of %.0f cycles | mma detail: fence %.0f issue %.0f commit %.0f | epi detail: prologue %.0f chunks %.0f tail %.0f\n",
-            (double)P.num_tiles / grid, P.num_kb, P.sps, P.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[8], m[9], m[10], m[11], m[12], m[13]);
+    fprintf(stderr, "[conv dbg] cg %d tiles/cta %.1f kb/tile %d sps %d stages %d | producer: wait_empty %.0f of %.0f | mma: wait_full %.0f wait_tmem_empty %.0f of %.0f | epilogue(w4): wait_tmem_full %.0f of %.0f cycles | mma detail: fence %.0f issue %.0f commit %.0f | epi detail: prologue %.0f chunks %.0f tail %.0f\n",
+            P.cg, (double)P.num_tiles * P.cg / grid, P.num_kb, P.sps, P.stages, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[8], m[9], m[10], m[11], m[12], m[13]);
   }
   return DS_OK;
 }

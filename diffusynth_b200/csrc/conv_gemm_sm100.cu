@@ -232,6 +232,20 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {          // read-only 
   asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane instead of two 16-byte halves
+__device__ __forceinline__ void stg_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ldg_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ int4 lds_i4(uint32_t addr) {
+  int4 v;
+  asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds_f4_volatile(uint32_t addr) { // per-tile buffers rewritten by the same warp
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -368,20 +382,24 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const TileCoord t = decode_tile(P, tile, rank);
       const int nsrc = P.src_batch_mod > 0 ? (t.n % P.src_batch_mod) : t.n;
       const int h0 = t.th * P.Hb, w0 = t.tw * P.Wb;
-      const int4* kbt = s_kbt + t.g * P.num_kb;
+      const uint32_t kbt = smem_u32(s_kbt + t.g * P.num_kb);      // shared-space address: the entries are read with LDS
       for (int kb = 0; kb < P.num_kb; kb += P.sps) {
         const int nsub = (P.num_kb - kb) < P.sps ? (P.num_kb - kb) : P.sps;
-        const int4 e0 = kbt[kb];                                     // fetched before the barrier probe
+        int4 e[4];                                                   // this stage's entries, fetched before the barrier probe
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = lds_i4(kbt + (uint32_t)(kb + (j < nsub ? j : 0)) * 16u);
         mbar_wait_timed(&empty_bar[stage], phase ^ 1u, timed, w_empty);
         if (elect_one_sync()) {
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if (rank == 0) mbar_expect_tx(&full_bar[stage], (unsigned)(CG * nsub) * P.stage_a_bytes);      // the pair's activation bytes
-          for (int j = 0; j < nsub; ++j) {
-            const int4 e = j == 0 ? e0 : kbt[kb + j];
-            const CUtensorMap* mp = reinterpret_cast<const CUtensorMap*>(map_base + e.x);
-            if (CG == 2) tma_load_4d_2cta(sa, mp, &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
-            else tma_load_4d(sa, mp, &full_bar[stage], e.y, w0 + e.z, h0 + e.w, nsrc);
-            sa += sub_bytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nsub) {
+              const CUtensorMap* mp = reinterpret_cast<const CUtensorMap*>(map_base + e[j].x);
+              if (CG == 2) tma_load_4d_2cta(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, nsrc);
+              else tma_load_4d(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, nsrc);
+              sa += sub_bytes;
+            }
           }
         }
         __syncwarp();
@@ -613,8 +631,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
             b.x = pack16_epi(v[8], v[9]);   b.y = pack16_epi(v[10], v[11]);
             b.z = pack16_epi(v[12], v[13]); b.w = pack16_epi(v[14], v[15]);
-            reinterpret_cast<uint4*>(out_p)[0] = a;
-            reinterpret_cast<uint4*>(out_p)[1] = b;
+            stg_256(out_p, a, b);
           }
           if (o32_p != nullptr) {
 #pragma unroll
@@ -645,9 +662,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       auto fetch_res = [&](int c, uint4 (&rr)[2]) {
         rr[0] = rr[1] = make_uint4(0, 0, 0, 0);
         if (has_res && cols0 - 16 * c > 0) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res_p + 16 * c);
-          rr[0] = __ldg(rp);
-          rr[1] = __ldg(rp + 1);
+          ldg_256(res_p + 16 * c, rr[0], rr[1]);
         }
       };
       if (nch > 0) fetch_res(0, qa);
@@ -719,6 +734,12 @@ static int validate(const ds_conv_gemm_args* a) {
   DS_REQUIRE(!(a->d_stats_in && !a->d_e1), "ds_conv_gemm: stats_in needs e1");
   DS_REQUIRE(a->d_out || a->d_out_f32_nchw, "ds_conv_gemm: no output");
   DS_REQUIRE(!a->d_out || a->Cout % 16 == 0, "ds_conv_gemm: bf16 output needs Cout %% 16 == 0 (got %d)", a->Cout);
+  // the epilogue moves 16 channels (32 bytes) per lane with 256-bit accesses
+  DS_REQUIRE(!a->d_out || (reinterpret_cast<uintptr_t>(a->d_out) % 32 == 0 && a->out_sn % 16 == 0 && a->out_sh % 16 == 0 && a->out_sw % 16 == 0),
+             "ds_conv_gemm: 16-bit output must be 32-byte aligned with strides that are multiples of 16 elements");
+  for (int g = 0; g < a->groups; ++g) DS_REQUIRE(!a->d_out || a->out_goff[g] % 16 == 0, "ds_conv_gemm: out_goff[%d] must be a multiple of 16 elements", g);
+  DS_REQUIRE(!a->d_residual || (reinterpret_cast<uintptr_t>(a->d_residual) % 32 == 0 && a->res_sn % 16 == 0 && a->res_sh % 16 == 0 && a->res_sw % 16 == 0),
+             "ds_conv_gemm: residual must be 32-byte aligned with strides that are multiples of 16 elements");
   DS_REQUIRE(!(a->per_sample_weights && a->groups != 1), "ds_conv_gemm: per-sample weights with groups");
   for (int g = 0; g < a->groups; ++g)
     for (int t = 0; t < a->ntaps; ++t)
@@ -831,7 +852,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     const size_t sub = (size_t)P.stage_a_bytes + P.stage_b_bytes;
     const int cyc = (a->BK / 16) * (a->BN / 2);
     const char* e = getenv("DS_CONV_MAX_SPS");
-    const int max_sps = e ? atoi(e) : 4;
+    const int max_sps = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4;      // the producer keeps at most 4 table entries in registers
     const char* e2 = getenv("DS_CONV_MIN_STAGES");
     const int min_stages = e2 ? atoi(e2) : 3;     // three stages already saturate the pipeline (measured); deeper rings buy nothing
     const char* e3 = getenv("DS_CONV_SPS_CYC");

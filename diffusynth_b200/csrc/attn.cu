@@ -39,10 +39,11 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     const bool ok = p0 + pix < npix;
     const uint4* kp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + hidden + half * 16);
     const uint4* vp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + 2 * hidden + half * 16);
+    uint4 k2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, v2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (ok) { ldg_256(kp, k2[0], k2[1]); ldg_256(vp, v2[0], v2[1]); }      // one 32-byte sector per lane and tensor
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (ok) { kv = __ldg(kp + i); vv = __ldg(vp + i); }
+      const uint4 kv = k2[i], vv = v2[i];
       const float2 k0 = cvt16x2(kv.x), k1 = cvt16x2(kv.y), k2 = cvt16x2(kv.z), k3 = cvt16x2(kv.w);
       const float2 v0 = cvt16x2(vv.x), v1 = cvt16x2(vv.y), v2 = cvt16x2(vv.z), v3 = cvt16x2(vv.w);
       const float ninf = -INFINITY;
@@ -58,7 +59,7 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     {
       const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + half * 16);
       uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-      if (ok) { q0 = __ldg(qp); q1 = __ldg(qp + 1); }
+      if (ok) ldg_256(qp, q0, q1);
       if (q_mode == 0) {
         const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         float f[16];
@@ -75,9 +76,7 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
         q1 = make_uint4(pack16(f[8] * inv, f[9] * inv), pack16(f[10] * inv, f[11] * inv), pack16(f[12] * inv, f[13] * inv), pack16(f[14] * inv, f[15] * inv));
       }
       if (ok) {
-        uint4* qo = reinterpret_cast<uint4*>(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16);
-        qo[0] = q0;
-        qo[1] = q1;
+        stg_256(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16, q0, q1);
       }
     }
   }

@@ -353,9 +353,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, act_t* __restric
       packed[2 * kx] = pack16(v[0], v[1]);
       packed[2 * kx + 1] = pack16(v[2], v[3]);
     }
-    uint4* dst = reinterpret_cast<uint4*>(col + ((n * H + y) * W + xx) * 224 + ky * 32);
+    act_t* dst = col + ((n * H + y) * W + xx) * 224 + ky * 32;       // 64 contiguous bytes: two full 32-byte sectors
 #pragma unroll
-    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    for (int q = 0; q < 2; ++q)
+      stg_256(dst + 16 * q, make_uint4(packed[8 * q], packed[8 * q + 1], packed[8 * q + 2], packed[8 * q + 3]),
+              make_uint4(packed[8 * q + 4], packed[8 * q + 5], packed[8 * q + 6], packed[8 * q + 7]));
   }
 }
 

@@ -18,13 +18,37 @@ static constexpr int AT_D = 32;          // dim_head
 static constexpr int AT_PIX = 128;       // pixels per block
 static constexpr int AT_PART = AT_D * AT_D + 2 * AT_D;   // S[32][32], Z[32], m[32]
 
+// ldmatrix (transposing) and the legacy warp-level MMA: the per-chunk context S = P^T V is a 32 x 32 x 128 product -- far too
+// small for a tcgen05 tile, and as FFMA2 from fp32 shared memory it was bound by shared-memory bandwidth (ncu: LSU wavefronts
+// 88 % of peak).  With P and V kept 16-bit in shared memory, eight m16n8k16 MMAs per warp replace 256 FFMA2 per thread.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_half2_bits(uint32_t v) {      // a pair of stored activations as IEEE half2 bits
+#ifdef DS_OPERANDS_BF16
+  const __half2 h = __floats2half2_rn(lo16(v), hi16(v));
+  return *reinterpret_cast<const uint32_t*>(&h);
+#else
+  return v;
+#endif
+}
+
+static constexpr int AT_PITCH = 40;      // halves per shared-memory row (80 bytes): ldmatrix reads of 8 rows are conflict-free
+
 // grid = (chunks, heads, N), block = 256
 __global__ void __launch_bounds__(256)
 attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
                         act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
-  __shared__ __align__(16) float s_kv[2][AT_PIX][AT_D + 4];
-  float (*s_k)[AT_D + 4] = s_kv[0];
-  float (*s_v)[AT_D + 4] = s_kv[1];
+  __shared__ __align__(16) __half s_k[AT_PIX][AT_PITCH];     // k, then p = exp(k - m), as IEEE half
+  __shared__ __align__(16) __half s_v[AT_PIX][AT_PITCH];
   __shared__ float s_red[8][AT_D];
   __shared__ float s_m[AT_D];
   const int chunk = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
@@ -33,33 +57,32 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
   const act_t* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
   const int tid = threadIdx.x;
 
-  // ---- stage k, v (fp32) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
+  // ---- stage k, v (16-bit, as stored) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
   {
     const int pix = tid >> 1, half = tid & 1;   // 16 channels per thread
     const bool ok = p0 + pix < npix;
-    const uint4* kp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + hidden + half * 16);
-    const uint4* vp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + 2 * hidden + half * 16);
-    uint4 k2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, v2[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    if (ok) { ldg_256(kp, k2[0], k2[1]); ldg_256(vp, v2[0], v2[1]); }      // one 32-byte sector per lane and tensor
+    uint4 k2[2], v2[2];
+    const uint32_t ninf2 = 0xFC00FC00u;          // (-inf, -inf) as half2
+    k2[0] = k2[1] = make_uint4(ninf2, ninf2, ninf2, ninf2);
+    v2[0] = v2[1] = make_uint4(0, 0, 0, 0);
+    if (ok) {
+      ldg_256(base + (size_t)pix * ld + hidden + half * 16, k2[0], k2[1]);      // one 32-byte sector per lane and tensor
+      ldg_256(base + (size_t)pix * ld + 2 * hidden + half * 16, v2[0], v2[1]);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const uint4 kv = k2[i], vv = v2[i];
-      const float2 k0 = cvt16x2(kv.x), k1 = cvt16x2(kv.y), k2 = cvt16x2(kv.z), k3 = cvt16x2(kv.w);
-      const float2 v0 = cvt16x2(vv.x), v1 = cvt16x2(vv.y), v2 = cvt16x2(vv.z), v3 = cvt16x2(vv.w);
-      const float ninf = -INFINITY;
-      float4* kd = reinterpret_cast<float4*>(&s_k[pix][half * 16 + i * 8]);     // 128-bit stores: conflict-free at pitch 36
-      float4* vd = reinterpret_cast<float4*>(&s_v[pix][half * 16 + i * 8]);
-      kd[0] = ok ? make_float4(k0.x, k0.y, k1.x, k1.y) : make_float4(ninf, ninf, ninf, ninf);
-      kd[1] = ok ? make_float4(k2.x, k2.y, k3.x, k3.y) : make_float4(ninf, ninf, ninf, ninf);
-      vd[0] = make_float4(v0.x, v0.y, v1.x, v1.y);
-      vd[1] = make_float4(v2.x, v2.y, v3.x, v3.y);
+      for (int i = 0; i < 2; ++i) {
+        k2[i] = make_uint4(to_half2_bits(k2[i].x), to_half2_bits(k2[i].y), to_half2_bits(k2[i].z), to_half2_bits(k2[i].w));
+        v2[i] = make_uint4(to_half2_bits(v2[i].x), to_half2_bits(v2[i].y), to_half2_bits(v2[i].z), to_half2_bits(v2[i].w));
+      }
     }
+    uint4* kd = reinterpret_cast<uint4*>(&s_k[pix][half * 16]);
+    uint4* vd = reinterpret_cast<uint4*>(&s_v[pix][half * 16]);
+    kd[0] = k2[0]; kd[1] = k2[1];
+    vd[0] = v2[0]; vd[1] = v2[1];
     // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
     // The math runs for every thread (rows beyond npix compute on zeros) so the pair shuffles stay convergent.
     {
-      const uint4* qp = reinterpret_cast<const uint4*>(base + (size_t)pix * ld + half * 16);
       uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-      if (ok) ldg_256(qp, q0, q1);
+      if (ok) ldg_256(base + (size_t)pix * ld + half * 16, q0, q1);
       if (q_mode == 0) {
         const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
         float f[16];
@@ -75,9 +98,7 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
         q0 = make_uint4(pack16(f[0] * inv, f[1] * inv), pack16(f[2] * inv, f[3] * inv), pack16(f[4] * inv, f[5] * inv), pack16(f[6] * inv, f[7] * inv));
         q1 = make_uint4(pack16(f[8] * inv, f[9] * inv), pack16(f[10] * inv, f[11] * inv), pack16(f[12] * inv, f[13] * inv), pack16(f[14] * inv, f[15] * inv));
       }
-      if (ok) {
-        stg_256(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16, q0, q1);
-      }
+      if (ok) stg_256(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16, q0, q1);
     }
   }
   __syncthreads();
@@ -85,7 +106,7 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
   const int warp = tid >> 5, lane = tid & 31;
   {
     float mx = -INFINITY;
-    for (int p = warp * 16; p < warp * 16 + 16; ++p) mx = fmaxf(mx, s_k[p][lane]);
+    for (int p = warp * 16; p < warp * 16 + 16; ++p) mx = fmaxf(mx, __half2float(s_k[p][lane]));
     s_red[warp][lane] = mx;
   }
   __syncthreads();
@@ -96,53 +117,37 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
     s_m[tid] = mx;
   }
   __syncthreads();
-  // ---- p = exp(k - m) in place; column sums Z
+  // ---- p = exp(k - m) in place (rounded to half: the same values enter Z and S); column sums Z
   {
     const float m = s_m[lane];
     float z = 0.f;
     for (int p = warp * 16; p < warp * 16 + 16; ++p) {
-      const float e = __expf(s_k[p][lane] - m);
+      const __half e = __float2half_rn(__expf(__half2float(s_k[p][lane]) - m));
       s_k[p][lane] = e;
-      z += e;
+      z += __half2float(e);
     }
     s_red[warp][lane] = z;
   }
   __syncthreads();
-  // ---- S[d][e] = sum_p p[p][d] * v[p][e]: 8x4 register tile per thread (packed FFMA2), 8 pixel groups of 16
-  const int pg = tid >> 5, d0 = ((tid >> 3) & 3) * 8, e0 = (tid & 7) * 4;
-  float2 acc[8][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
-#pragma unroll 4
-  for (int p = pg * 16; p < pg * 16 + 16; ++p) {
-    const float4 ka = *reinterpret_cast<const float4*>(&s_k[p][d0]);
-    const float4 kb4 = *reinterpret_cast<const float4*>(&s_k[p][d0 + 4]);
-    const float4 vv = *reinterpret_cast<const float4*>(&s_v[p][e0]);
-    const float2 v01 = make_float2(vv.x, vv.y), v23 = make_float2(vv.z, vv.w);
-    const float kd[8] = {ka.x, ka.y, ka.z, ka.w, kb4.x, kb4.y, kb4.z, kb4.w};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float2 kb = make_float2(kd[i], kd[i]);
-      ffma2(acc[i][0], kb, v01);
-      ffma2(acc[i][1], kb, v23);
-    }
-  }
-  __syncthreads();                       // everyone is done reading s_k / s_v: reuse them as the cross-group buffer
-  float* s_part = &s_k[0][0];            // [8][32][32] floats = 32 KB <= s_k + s_v (2 x 128*36*4 = 36 KB, contiguous)
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    *reinterpret_cast<float4*>(&s_part[(pg * AT_D + d0 + i) * AT_D + e0]) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
-  __syncthreads();
-  const int d = tid >> 3, e4 = (tid & 7) * 4;
-  float4 s4 = *reinterpret_cast<const float4*>(&s_part[d * AT_D + e4]);
-#pragma unroll
-  for (int g = 1; g < 8; ++g) {
-    const float4 t4 = *reinterpret_cast<const float4*>(&s_part[(g * AT_D + d) * AT_D + e4]);
-    s4.x += t4.x; s4.y += t4.y; s4.z += t4.z; s4.w += t4.w;
-  }
-  const float a0 = s4.x, a1 = s4.y, a2 = s4.z, a3 = s4.w;
+  // ---- S[d][e] = sum over the chunk's 128 pixels of p[pix][d] * v[pix][e]: A = P^T (d x pix), B = V (pix x e), both read
+  //      transposed from their [pixel][channel] rows.  Warp w owns the 16 x 8 output tile (d tile w >> 2, e tile w & 3) for ALL
+  //      pixels (8 MMAs of k = 16), so there is no cross-warp reduction.
   float* po = part + (((size_t)n * gridDim.y + head) * chunks + chunk) * AT_PART;
-  *reinterpret_cast<float4*>(po + d * AT_D + e4) = make_float4(a0, a1, a2, a3);
+  {
+    const int mt = warp >> 2, nt = warp & 3;
+    const int r = lane & 7, mat = lane >> 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < AT_PIX / 16; ++ks) {
+      uint32_t a[4], bfr[2];
+      ldmatrix_x4_trans(a, (uint32_t)__cvta_generic_to_shared(&s_k[ks * 16 + r + ((mat >> 1) & 1) * 8][mt * 16 + (mat & 1) * 8]));
+      ldmatrix_x2_trans(bfr, (uint32_t)__cvta_generic_to_shared(&s_v[ks * 16 + r + (mat & 1) * 8][nt * 8]));
+      mma_m16n8k16_f16(c, a, bfr[0], bfr[1]);
+    }
+    const int d = mt * 16 + (lane >> 2), e = nt * 8 + (lane & 3) * 2;
+    *reinterpret_cast<float2*>(po + d * AT_D + e) = make_float2(c[0], c[1]);
+    *reinterpret_cast<float2*>(po + (d + 8) * AT_D + e) = make_float2(c[2], c[3]);
+  }
   if (tid < AT_D) {
     float z = 0.f;
 #pragma unroll

@@ -85,33 +85,49 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const act_t* __restrict__ in, float
 // (the to_out[1] GroupNorm and the Residual of the attention block, diffusion_components.py:264,22-29)
 // grid = (chunks, N); y/x/out bf16 NHWC with C % 8 == 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x, uint4* __restrict__ out,
-                                         const float2* __restrict__ stats, int slots,
-                                         const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
-                                         long long vec_per_sample) {
+// The host picks gridDim.x * blockDim.x as a multiple of C/8, so a thread always meets the same 8 channels: their folded
+// scale (rstd*gamma) and shift (beta - mean*rstd*gamma) live in registers and the loop is two FMAs per value, four
+// independent 16-byte vectors in flight per thread.
+__global__ void __launch_bounds__(256)
+gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x, uint4* __restrict__ out,
+                         const float2* __restrict__ stats, int slots,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
+                         long long vec_per_sample) {
   const int n = blockIdx.y;
   const float2 mr = __ldg(stats_sample(stats, slots, n));
   const float mean = mr.x, rstd = mr.y;
   const uint4* yb = y + (size_t)n * vec_per_sample;
   const uint4* xb = x ? x + (size_t)n * vec_per_sample : nullptr;
   uint4* ob = out + (size_t)n * vec_per_sample;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < vec_per_sample; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % C8) * 8;
-    const uint4 yv = __ldg(yb + i);
-    uint4 xv = make_uint4(0, 0, 0, 0);
-    if (xb) xv = __ldg(xb + i);
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;          // a multiple of C8
+  const int c0 = (int)(i0 % C8) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = rstd * __ldg(gamma + c0 + j);
+    sh[j] = fmaf(-mean, sc[j], __ldg(beta + c0 + j));
+  }
+  auto apply = [&](const uint4& yv, const uint4& xv) {
     const uint32_t yy[4] = {yv.x, yv.y, yv.z, yv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
     uint32_t oo[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float g0 = __ldg(gamma + c0 + 2 * j), g1 = __ldg(gamma + c0 + 2 * j + 1);
-      const float b0 = __ldg(beta + c0 + 2 * j), b1 = __ldg(beta + c0 + 2 * j + 1);
-      const float a = (lo16(yy[j]) - mean) * rstd * g0 + b0 + lo16(xx[j]);
-      const float b = (hi16(yy[j]) - mean) * rstd * g1 + b1 + hi16(xx[j]);
-      oo[j] = pack16(a, b);
+    for (int j = 0; j < 4; ++j)
+      oo[j] = pack16(fmaf(lo16(yy[j]), sc[2 * j], sh[2 * j]) + lo16(xx[j]), fmaf(hi16(yy[j]), sc[2 * j + 1], sh[2 * j + 1]) + hi16(xx[j]));
+    return make_uint4(oo[0], oo[1], oo[2], oo[3]);
+  };
+  long long i = i0;
+  for (; i + 3 * stride < vec_per_sample; i += 4 * stride) {
+    uint4 yv[4], xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      yv[u] = __ldg(yb + i + u * stride);
+      xv[u] = xb ? __ldg(xb + i + u * stride) : make_uint4(0, 0, 0, 0);
     }
-    ob[i] = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ob[i + u * stride] = apply(yv[u], xv[u]);
   }
+  for (; i < vec_per_sample; i += stride) ob[i] = apply(__ldg(yb + i), xb ? __ldg(xb + i) : make_uint4(0, 0, 0, 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -301,9 +317,16 @@ int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const vo
                          const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream) {
   DS_REQUIRE(d_y && d_out && d_stats && d_gamma && d_beta && N > 0 && C % 8 == 0 && hw > 0 && slots >= 0, "ds_gn_apply_residual: bad arguments");
   const long long vps = hw * C / 8;
-  int gx = (int)((vps + 255) / 256);
+  // threads per sample = gx * 256 must be a multiple of C/8 (see the kernel): gx is a multiple of m = C8 / gcd(C8, 256)
+  const int C8 = C / 8;
+  int g = C8, h256 = 256;
+  while (h256) { const int t = g % h256; g = h256; h256 = t; }      // g = gcd(C8, 256)
+  const int m = C8 / g;
+  int gx = (int)((vps + 4 * 256 - 1) / (4 * 256));
   const int cap = (num_sms() * 8 + N - 1) / N;
-  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  if (gx > cap) gx = cap;
+  gx = (gx + m - 1) / m * m;
+  if (gx < m) gx = m;
   gn_apply_residual_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
                                                                           (const float2*)d_stats, slots, d_gamma,
                                                                           d_beta, C / 8, vps);

@@ -662,6 +662,53 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (epi_timed) te1 = clock64();
       tcgen05_fence_after();
       if (nch > 0) issue_chunk(0, ra_);
+      // Lean path of the store-bound 1x1 convolutions (one border class, no activation / residual, 16-bit output,
+      // full chunks): all table reads of a chunk are issued together and nothing else is live, so they overlap instead of
+      // queueing behind each other through reused registers.
+      const bool lean = P.ncls == 1 && P.act == 0 && P.residual == nullptr && out_p != nullptr && o32_p == nullptr &&
+                        cols_left >= 16 * nch && !(P.dbg & 1);
+      if (lean) {
+        auto lean_chunk = [&](const uint32_t* r) {
+          float4 t2[4], t1[4], tb[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) t2[q4] = lds_f4(e2_s + 16u * q4);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) t1[q4] = use_e1 ? lds_f4(e1_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) tb[q4] = use_sb ? lds_f4_volatile(sb_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float v[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            v[4 * q4 + 0] = fmaf(__uint_as_float(r[4 * q4 + 0]), rstd, fmaf(nmr, t1[q4].x, t2[q4].x) + tb[q4].x);
+            v[4 * q4 + 1] = fmaf(__uint_as_float(r[4 * q4 + 1]), rstd, fmaf(nmr, t1[q4].y, t2[q4].y) + tb[q4].y);
+            v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, fmaf(nmr, t1[q4].z, t2[q4].z) + tb[q4].z);
+            v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, fmaf(nmr, t1[q4].w, t2[q4].w) + tb[q4].w);
+          }
+          if (valid) {
+            if (do_stats) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
+            }
+            uint4 a, b;
+            a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
+            a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
+            b.x = pack16_epi(v[8], v[9]);   b.y = pack16_epi(v[10], v[11]);
+            b.z = pack16_epi(v[12], v[13]); b.w = pack16_epi(v[14], v[15]);
+            stg_256(out_p, a, b);
+          }
+          e2_s += 64u; e1_s += 64u; sb_s += 64u; out_p += 16;
+        };
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait16(ra_);
+          if (c + 1 < nch) issue_chunk(c + 1, rb_);
+          lean_chunk(ra_);
+          if (c + 1 < nch) {
+            tmem_ld_wait16(rb_);
+            if (c + 2 < nch) issue_chunk(c + 2, ra_);
+            lean_chunk(rb_);
+          }
+        }
+      } else {
       for (int c = 0; c < nch; c += 2) {
         tmem_ld_wait16(ra_);
         if (c + 1 < nch) { issue_chunk(c + 1, rb_); fetch_res(c + 1, qb); }
@@ -671,6 +718,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           if (c + 2 < nch) { issue_chunk(c + 2, ra_); fetch_res(c + 2, qa); }
           finish_chunk(rb_, qb[0], qb[1]);
         }
+      }
       }
       // release the accumulator stage (one arrive per epilogue warp)
       tcgen05_fence_before();

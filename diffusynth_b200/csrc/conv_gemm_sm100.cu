@@ -28,7 +28,7 @@ struct __align__(16) ConvGemmDev {
   int N, H, W, Hb, Wb, tiles_h, tiles_w, tiles_m;
   int n_tiles_n, BN, C0, C1, cblocks0, cblocks, ntaps, groups, per_sample_w, src_batch_mod;
   int num_kb, stages, num_tiles;     // num_tiles = work items: M-tiles (cg = 1) or M-tile pairs (cg = 2)
-  int cg, tiles_md;                  // CTAs per MMA (1 or 2), tiles_m / cg
+  int cg, tiles_md, pair_flat;       // CTAs per MMA (1 or 2), tiles_m / cg, pairs over the flattened (sample, M-tile) index
   float inv_tiles_md;
   float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb;   // reciprocals for fast_divmod
   unsigned long long* dbg_buf;      // DS_CONV_DBG & 64: per-CTA wait-cycle counters [grid][8]
@@ -190,10 +190,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmDev& P, int tile,
   TileCoord t;
   int r, m;
   fast_divmod(tile, P.n_tiles_n, P.inv_n_tiles_n, r, t.nt);
-  int r2;
-  fast_divmod(r, P.tiles_md, P.inv_tiles_md, r2, m);
-  m = m * P.cg + rank;
-  fast_divmod(r2, P.groups, P.inv_groups, t.n, t.g);
+  if (P.cg == 2 && P.pair_flat) {
+    // pairs run over the flattened (sample, M-tile) index: also covers an odd number of M-tiles per sample (groups == 1)
+    fast_divmod(2 * r + rank, P.tiles_m, P.inv_tiles_m, t.n, m);
+    t.g = 0;
+  } else {
+    int r2;
+    fast_divmod(r, P.tiles_md, P.inv_tiles_md, r2, m);
+    m = m * P.cg + rank;
+    fast_divmod(r2, P.groups, P.inv_groups, t.n, t.g);
+  }
   fast_divmod(m, P.tiles_w, P.inv_tiles_w, t.th, t.tw);
   t.slot = (t.g * P.tiles_m + m) * P.n_tiles_n + t.nt;
   return t;
@@ -809,9 +815,12 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   {
     const char* e = getenv("DS_CONV_CG");
     const int want = e ? atoi(e) : (a->ntaps >= 4 ? 2 : 1);
-    P.cg = (want == 2 && P.tiles_m % 2 == 0 && a->BN % 32 == 0) ? 2 : 1;
+    const bool even_m = P.tiles_m % 2 == 0;
+    const bool flat_ok = a->groups == 1 && !a->per_sample_weights && ((long long)a->N * P.tiles_m) % 2 == 0;
+    P.cg = (want == 2 && (even_m || flat_ok) && a->BN % 32 == 0) ? 2 : 1;
+    P.pair_flat = (P.cg == 2 && !even_m) ? 1 : 0;
   }
-  P.tiles_md = P.tiles_m / P.cg;
+  P.tiles_md = P.pair_flat ? P.tiles_m : P.tiles_m / P.cg;
   P.inv_tiles_md = 1.0f / P.tiles_md;
   P.stage_a_bytes = BM * a->BK * 2;
   P.stage_b_bytes = (a->BN / P.cg) * a->BK * 2;
@@ -824,7 +833,7 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.ntaps = a->ntaps; P.groups = a->groups; P.per_sample_w = a->per_sample_weights;
   P.src_batch_mod = a->src_batch_mod;
   P.num_kb = P.cblocks * a->ntaps;
-  P.num_tiles = a->N * a->groups * P.tiles_md * P.n_tiles_n;
+  P.num_tiles = (int)((long long)a->N * a->groups * P.tiles_m / P.cg) * P.n_tiles_n;
   P.Cout = a->Cout; P.Cout_pad = a->Cout_pad;
   P.stats_in = reinterpret_cast<const float2*>(a->d_stats_in);
   P.stats_in_slots = a->stats_in_slots; P.out_inv_count = a->stats_out_inv_count; P.eps = a->eps;

@@ -28,6 +28,8 @@ def _run(pc, srcs, N, H, W, reference=False, **kw):
     (96, 192, 3, 32, 16, 2),      # BK=32 (SWIZZLE_64B), 4 m-tiles
     (128, 96, 1, 16, 16, 3),      # 1x1
     (192, 384, 3, 16, 8, 1),      # two n-tiles (BN=192)
+    (192, 384, 3, 16, 8, 4),      # one M-tile per sample: the two-CTA pairs span consecutive samples
+    (128, 96, 3, 16, 24, 3),      # three M-tiles per sample, odd sample count: falls back to one CTA per tile
     (64, 768, 1, 16, 8, 2),       # BN=256, three n-tiles
     (96, 96, 3, 128, 64, 2),      # full-resolution level-0 shape, 64 m-tiles per sample (persistent loop)
     (32, 32, 3, 128, 24, 1),      # width not a multiple of the preferred tile

@@ -393,8 +393,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           for (int j = 0; j < 4; ++j) {
             if (j < nsub) {
               const CUtensorMap* mp = reinterpret_cast<const CUtensorMap*>(map_base + e[j].x);
-              if (CG == 2) tma_load_4d_2cta(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, nsrc);
-              else tma_load_4d(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, nsrc);
+              const int ns = e[j].x < 4 * (int)sizeof(CUtensorMap) ? nsrc : t.n;      // the batch modulus applies to source 0 only
+              if (CG == 2) tma_load_4d_2cta(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, ns);
+              else tma_load_4d(sa, mp, &full_bar[stage], e[j].y, w0 + e[j].z, h0 + e[j].w, ns);
               sa += sub_bytes;
             }
           }
@@ -867,7 +868,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     for (int v = 0; v < 4; ++v) {
       if (C == 0 || v >= a->num_views) { maps.a[s][v] = maps.a[0][0]; continue; }
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a->Wv, (cuuint64_t)a->Hv,
-                            (cuuint64_t)(a->src_batch_mod > 0 ? a->src_batch_mod : a->N)};
+                            (cuuint64_t)((s == 0 && a->src_batch_mod > 0) ? a->src_batch_mod : a->N)};
       cuuint64_t strides[3] = {(cuuint64_t)a->view_sw * C * 2, (cuuint64_t)a->view_sh * C * 2, (cuuint64_t)a->view_sn * C * 2};
       cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
@@ -975,9 +976,10 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, con
       const ds_conv_tap tp = P.taps[g][t];
       const int y = h + tp.dy, x = w + tp.dx;
       if (y < 0 || y >= Hv || x < 0 || x >= Wv) continue;
-      const long long pix = view_off_dev[tp.view] + nsrc * view_sn + y * view_sh + x * view_sw;
+      const long long pix0 = view_off_dev[tp.view] + nsrc * view_sn + y * view_sh + x * view_sw;     // source 0: batch modulus
+      const long long pix1 = view_off_dev[tp.view] + n * view_sn + y * view_sh + x * view_sw;
       for (int c = 0; c < P.C0 + P.C1; ++c) {
-        const float a = c < P.C0 ? act2f(src0[pix * P.C0 + c]) : act2f(src1[pix * P.C1 + (c - P.C0)]);
+        const float a = c < P.C0 ? act2f(src0[pix0 * P.C0 + c]) : act2f(src1[pix1 * P.C1 + (c - P.C0)]);
         acc = fmaf(a, act2f(wrow[(long long)t * (P.C0 + P.C1) + c]), acc);
       }
     }

@@ -37,7 +37,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   const int tile = blockIdx.x, cblk = blockIdx.y, n = blockIdx.z;
   const int h0 = (tile / tiles_w) * TH, w0 = (tile % tiles_w) * DW_TW;
   const int c0 = cblk * DW_CB;
-  const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
+  const int nsrc = (src_batch_mod > 0 && c0 < C0) ? n % src_batch_mod : n;      // the batch modulus applies to source 0 only
   const act_t* src;
   int Cs, cs0;
   if (c0 < C0) { src = src0; Cs = C0; cs0 = c0; } else { src = src1; Cs = C1; cs0 = c0 - C0; }
@@ -170,7 +170,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   auto issue = [&](int item, int stage) {
     const int n = item / tiles, t = item - n * tiles;
     const int th = t / tiles_w, tw = t - th * tiles_w;
-    const int nsrc = src_batch_mod > 0 ? n % src_batch_mod : n;
+    const int nsrc = (src_batch_mod > 0 && c0 < C0) ? n % src_batch_mod : n;
     mbar_expect_tx(&full[stage], DT_TILE_BYTES);
     tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
   };
@@ -396,8 +396,8 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       tma_attr_set = true;
     }
     CUtensorMap maps[2];
-    const int nsamp = src_batch_mod > 0 ? src_batch_mod : N;
     for (int sidx = 0; sidx < 2; ++sidx) {
+      const int nsamp = (sidx == 0 && src_batch_mod > 0) ? src_batch_mod : N;
       const int Cs = sidx == 0 ? C0 : C1;
       const void* base = sidx == 0 ? d_src0 : d_src1;
       if (Cs == 0) { maps[1] = maps[0]; break; }

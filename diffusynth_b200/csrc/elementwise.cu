@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256)
 gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x, uint4* __restrict__ out,
                          const float2* __restrict__ stats, int slots,
                          const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
-                         long long vec_per_sample) {
+                         long long vec_per_sample, int x_batch_mod) {
   const int n = blockIdx.y;
   const float2 mr = __ldg(stats_sample(stats, slots, n));
   const float mean = mr.x, rstd = mr.y;
   const uint4* yb = y + (size_t)n * vec_per_sample;
-  const uint4* xb = x ? x + (size_t)n * vec_per_sample : nullptr;
+  const uint4* xb = x ? x + (size_t)(x_batch_mod > 0 ? n % x_batch_mod : n) * vec_per_sample : nullptr;
   uint4* ob = out + (size_t)n * vec_per_sample;
   const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;          // a multiple of C8
@@ -314,7 +314,7 @@ int ds_nhwc_bf16_to_nchw_f32(const void* d_in, float* d_out, int N, int C, int C
 }
 
 int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots,
-                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream) {
+                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, int x_batch_mod, void* stream) {
   DS_REQUIRE(d_y && d_out && d_stats && d_gamma && d_beta && N > 0 && C % 8 == 0 && hw > 0 && slots >= 0, "ds_gn_apply_residual: bad arguments");
   const long long vps = hw * C / 8;
   // threads per sample = gx * 256 must be a multiple of C/8 (see the kernel): gx is a multiple of m = C8 / gcd(C8, 256)
@@ -329,7 +329,7 @@ int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const vo
   if (gx < m) gx = m;
   gn_apply_residual_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
                                                                           (const float2*)d_stats, slots, d_gamma,
-                                                                          d_beta, C / 8, vps);
+                                                                          d_beta, C / 8, vps, x_batch_mod);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -297,37 +297,39 @@ class _Plan:
         add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1))
         self.named["time_emb"] = (temb, -1)
 
-        def conv(name, pc, s0, s1, h, w, **kw):
-            a, st, keep = conv_args(pc, s0, s1, N, h, w, **kw)
+        def conv(name, pc, s0, s1, h, w, n=None, **kw):
+            a, st, keep = conv_args(pc, s0, s1, N if n is None else n, h, w, **kw)
             self.keep += keep + [a]
             add(name, lambda a=a: run_conv(a))
             return st
 
-        def block(p, s0, s1, h, w):
+        def block(p, s0, s1, h, w, n=N, s0_mod=0):
+            """One ConvNextBlock over n samples; s0_mod > 0: source 0 holds s0_mod samples shared by the guidance halves."""
             b = net.blocks[p]
-            hbuf = scr("dw", N, h, w, b.dim)
+            hbuf = scr("dw", n, h, w, b.dim)
             tb = self.tbias[:, b.t_off:]
-            st_h = ops.dwconv7_stats(N, b.dim, h, w, dev)
-            add(p + "ds_conv", lambda: ops.dwconv7(s0, s1, b.dw, tb, self.t_stride, hbuf, N, h, w, stats=st_h))
-            y = scr("hid", N, h, w, b.conv1.cout)
-            st_y = conv(p + "net.1", b.conv1, hbuf, None, h, w, out=y, stats_in=st_h, act=1, want_stats=True)
+            st_h = ops.dwconv7_stats(n, b.dim, h, w, dev)
+            add(p + "ds_conv", lambda: ops.dwconv7(s0, s1, b.dw, tb, self.t_stride, hbuf, n, h, w, stats=st_h, src_batch_mod=s0_mod))
+            y = scr("hid", n, h, w, b.conv1.cout)
+            st_y = conv(p + "net.1", b.conv1, hbuf, None, h, w, n=n, out=y, stats_in=st_h, act=1, want_stats=True)
             if b.res is not None:
-                r = scr("res", N, h, w, b.dim_out)
-                conv(p + "res_conv", b.res, s0, s1, h, w, out=r)
+                r = scr("res", n, h, w, b.dim_out)
+                conv(p + "res_conv", b.res, s0, s1, h, w, n=n, out=r, src_batch_mod=s0_mod)
             else:
-                assert s1 is None
+                assert s1 is None and s0_mod == 0
                 r = s0
-            o = act(N, h, w, b.dim_out)
-            st_o = conv(p + "net.4", b.conv2, y, None, h, w, out=o, stats_in=st_y, residual=r, want_stats=True)
+            o = act(n, h, w, b.dim_out)
+            st_o = conv(p + "net.4", b.conv2, y, None, h, w, n=n, out=o, stats_in=st_y, residual=r, want_stats=True)
             self.named[p[:-1]] = (o, b.dim_out)
             return o, st_o
 
-        def attn(p, x, st_x, h, w):
+        def attn(p, x, st_x, h, w, x_mod=0):
+            """x_mod > 0: x (and its statistics) hold x_mod samples shared by the guidance halves."""
             a = net.attns[p]
             npix = h * w
             qkv = scr("qkv", N, h, w, 3 * HID)
             sb = self.sbias[:, a.c_off:a.c_off + 3 * HID]
-            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=sb)
+            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=sb, src_batch_mod=x_mod)
             qp = scr("qp", N, h, w, HID)
             part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
             M = torch.empty((N, a.out.cout_pad, HID), dtype=ops.ACT, device=dev)
@@ -339,7 +341,7 @@ class _Plan:
             st_y = conv(p + "to_out", a.out, qp, None, h, w, out=y, want_stats=True, weight_override=M, per_sample_weights=True)
             o = act(N, h, w, a.dim)
             add(p + "gn_res", lambda: check(lib.ds_gn_apply_residual(y.data_ptr(), x.data_ptr(), o.data_ptr(), st_y.buf.data_ptr(), st_y.slots,
-                                                                      a.gamma.data_ptr(), a.beta.data_ptr(), N, a.dim, npix, stream()),
+                                                                      a.gamma.data_ptr(), a.beta.data_ptr(), N, a.dim, npix, x_mod, stream()),
                                             "gn_apply_residual"))
             self.keep += [part, M]
             self.named[p[:-1]] = (o, a.dim)
@@ -348,17 +350,27 @@ class _Plan:
         # ---- network (diffusion.py:187-258) ----
         n_stage = len(dd) - 1
         h, w = H, Wd
-        x0 = act(N, h, w, dd[0])
+        # Classifier-free guidance inside the sampling loop: both halves of the doubled batch share the latent and the timestep
+        # and differ only through the condition, which first enters in downs.0.1 (label_query / label_key).  init_conv and
+        # downs.0.0 are therefore evaluated once for the nb distinct latents and read with a batch modulus afterwards.
+        shared = nb if (x_batch_mod > 0 and uniform_time and nb < N) else 0
+        self.shared = shared
+        n0 = shared if shared else N
+        x0 = act(n0, h, w, dd[0])
         col = act(nb, h, w, 224)
         add("init_im2col", lambda: check(lib.ds_stem_im2col(self.x.data_ptr(), col.data_ptr(), nb, cfg["in_dim"], H, Wd, stream()), "stem_im2col"))
-        conv("init_conv", net.stem, col, None, h, w, out=x0, src_batch_mod=x_batch_mod)
+        conv("init_conv", net.stem, col, None, h, w, n=n0, out=x0, src_batch_mod=0 if shared else x_batch_mod)
         self.named["init_conv"] = (x0, dd[0])
         hs = [x0]
         x = x0
         for i in range(n_stage):
             p = f"downs.{i}."
-            x, st = block(p + "0.", x, None, h, w)
-            x = attn(p + "1.", x, st, h, w); hs.append(x)
+            if i == 0 and shared:
+                x, st = block(p + "0.", x, None, h, w, n=shared)
+                x = attn(p + "1.", x, st, h, w, x_mod=shared); hs.append(x)
+            else:
+                x, st = block(p + "0.", x, None, h, w)
+                x = attn(p + "1.", x, st, h, w); hs.append(x)
             x, st = block(p + "2.", x, None, h, w)
             x = attn(p + "3.", x, st, h, w); hs.append(x)
             pc = net.samplers[p + "4."]
@@ -386,7 +398,7 @@ class _Plan:
             x = attn(p + "4.", x, st, h, w)
             x, st = block(p + "5.", hs.pop(), x, h, w)
             x = attn(p + "6.", x, st, h, w)
-        x, _ = block("final_conv.0.", hs.pop(), x, h, w)
+        x, _ = block("final_conv.0.", hs.pop(), x, h, w, s0_mod=shared)       # the last skip is init_conv's output
         conv("final_conv.1", net.final, x, None, h, w, out_f32=self.eps)
         self.keep.append(scratch)
 
@@ -408,4 +420,7 @@ class _Plan:
             if c < 0:
                 taps[name] = t.clone()
             else:
-                taps[name] = t.float().permute(0, 3, 1, 2).contiguous()
+                v = t.float().permute(0, 3, 1, 2).contiguous()
+                if v.shape[0] < self.N:                      # evaluated once for both guidance halves
+                    v = v.repeat(self.N // v.shape[0], 1, 1, 1)
+                taps[name] = v

@@ -67,7 +67,8 @@ typedef struct ds_conv_gemm_args {
   const void* d_src1;
   int32_t C0, C1;
   int32_t N;                /* samples */
-  int32_t src_batch_mod;    /* if >0, sample n reads source sample n % src_batch_mod */
+  int32_t src_batch_mod;    /* if >0, sample n reads sample n % src_batch_mod of SOURCE 0 (and of d_stats_in); source 1 is indexed by n.
+                               Classifier-free guidance: tensors computed once for both halves of the doubled batch. */
   int32_t Hv, Wv;           /* extent of every view (pixels) */
   int64_t view_sn, view_sh, view_sw;   /* pixel strides of a view per unit of (n, y, x) */
   int64_t view_off[4];      /* pixel offset of each view's origin */
@@ -131,7 +132,8 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
 /* ----------------------------------------------------------------------------------------
  * U-Net pieces that are not GEMMs (model/diffusion_components.py, model/diffusion.py).
  * -------------------------------------------------------------------------------------- */
-/* ConvNextBlock.ds_conv (:118,131) + time-embedding bias (:133-136) + partials of net[0] GroupNorm (:121). */
+/* ConvNextBlock.ds_conv (:118,131) + time-embedding bias (:133-136) + partials of net[0] GroupNorm (:121).
+   src_batch_mod > 0: sample n reads sample n % src_batch_mod of source 0 (source 1 is indexed by n). */
 int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight,
                const float* d_tbias, long long tbias_stride, void* d_out, void* d_stats, float eps, int N, int H, int W, void* stream);
 int ds_dwconv7_stats_slots(int C, int H, int W);
@@ -152,9 +154,9 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
                         int q_mode, float scale, void* stream);
 int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix,
                      int C, int Cout_pad, void* stream);
-/* to_out[1] GroupNorm(1,C) + Residual (:264, :22-29): out = GN(y)*gamma+beta + x. */
+/* to_out[1] GroupNorm(1,C) + Residual (:264, :22-29): out = GN(y)*gamma+beta + x.  x_batch_mod > 0: sample n adds x[n % x_batch_mod]. */
 int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots,
-                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, void* stream);
+                         const float* d_gamma, const float* d_beta, int N, int C, long long hw, int x_batch_mod, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * VQGAN (model/VQGAN.py) and the spectrogram <-> waveform transforms (tools.py + librosa call sites).

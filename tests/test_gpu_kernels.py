@@ -153,8 +153,12 @@ def test_gn_apply_residual():
     out = torch.zeros((N, H, Wd, Cc), dtype=ops.ACT, device="cuda")
     yd, xd = nhwc(y), nhwc(x)
     assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.buf.data_ptr(), st.slots,
-                                      g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, S()) == 0
+                                      g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, 0, S()) == 0
     assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)) < EPS16
+    # residual shared by both halves of a guidance-doubled batch: sample n adds x[n % 1]
+    assert lib().ds_gn_apply_residual(yd.data_ptr(), xd.data_ptr(), out.data_ptr(), st.buf.data_ptr(), st.slots,
+                                      g.cuda().data_ptr(), b.cuda().data_ptr(), N, Cc, H * Wd, 1, S()) == 0
+    assert rel(nchw(out), F.group_norm(yb, 1, g, b, 1e-5) + bf(x)[:1]) < EPS16
 
 
 @pytest.mark.parametrize("act", [1, 2])

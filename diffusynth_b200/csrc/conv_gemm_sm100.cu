@@ -669,13 +669,11 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (epi_timed) te1 = clock64();
       tcgen05_fence_after();
       if (nch > 0) issue_chunk(0, ra_);
-      // Lean path of the store-bound 1x1 convolutions (one border class, no activation / residual, 16-bit output,
-      // full chunks): all table reads of a chunk are issued together and nothing else is live, so they overlap instead of
-      // queueing behind each other through reused registers.
-      const bool lean = P.ncls == 1 && P.act == 0 && P.residual == nullptr && out_p != nullptr && o32_p == nullptr &&
-                        cols_left >= 16 * nch && !(P.dbg & 1);
+      // Main path (16-bit output, full chunks): all table reads of a chunk are issued together, so they overlap instead of
+      // queueing behind each other through reused registers (what bounded the store-bound 1x1 convolutions).
+      const bool lean = out_p != nullptr && o32_p == nullptr && cols_left >= 16 * nch && !(P.dbg & 1);
       if (lean) {
-        auto lean_chunk = [&](const uint32_t* r) {
+        auto lean_chunk = [&](const uint32_t* r, const uint4& ra, const uint4& rb) {
           float4 t2[4], t1[4], tb[4];
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) t2[q4] = lds_f4(e2_s + 16u * q4);
@@ -691,7 +689,13 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, fmaf(nmr, t1[q4].z, t2[q4].z) + tb[q4].z);
             v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, fmaf(nmr, t1[q4].w, t2[q4].w) + tb[q4].w);
           }
+          if (P.act == 1) gelu16(v);
           if (valid) {
+            if (has_res) {
+              const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[2 * j] += lo16(rr[j]); v[2 * j + 1] += hi16(rr[j]); }
+            }
             if (do_stats) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
@@ -707,12 +711,12 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         };
         for (int c = 0; c < nch; c += 2) {
           tmem_ld_wait16(ra_);
-          if (c + 1 < nch) issue_chunk(c + 1, rb_);
-          lean_chunk(ra_);
+          if (c + 1 < nch) { issue_chunk(c + 1, rb_); fetch_res(c + 1, qb); }
+          lean_chunk(ra_, qa[0], qa[1]);
           if (c + 1 < nch) {
             tmem_ld_wait16(rb_);
-            if (c + 2 < nch) issue_chunk(c + 2, ra_);
-            lean_chunk(rb_);
+            if (c + 2 < nch) { issue_chunk(c + 2, ra_); fetch_res(c + 2, qa); }
+            lean_chunk(rb_, qb[0], qb[1]);
           }
         }
       } else {

@@ -43,111 +43,128 @@ __device__ __forceinline__ uint32_t to_half2_bits(uint32_t v) {      // a pair o
 
 static constexpr int AT_PITCH = 40;      // halves per shared-memory row (80 bytes): ldmatrix reads of 8 rows are conflict-free
 
-// grid = (chunks, heads, N), block = 256
+static constexpr int AT_SUB = 4;         // 128-pixel sub-chunks per block: one partial per 512 pixels
+
+// grid = (chunks, heads, N), block = 256.  A block walks over up to AT_SUB sub-chunks of 128 pixels with a running column
+// maximum (online softmax over n): S and Z are rescaled by exp(m_old - m_new) when the maximum moves, so one partial
+// (S[32][32], Z[32], m[32]) leaves the block per 512 pixels.
 __global__ void __launch_bounds__(256)
 attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
                         act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
   __shared__ __align__(16) __half s_k[AT_PIX][AT_PITCH];     // k, then p = exp(k - m), as IEEE half
   __shared__ __align__(16) __half s_v[AT_PIX][AT_PITCH];
   __shared__ float s_red[8][AT_D];
-  __shared__ float s_m[AT_D];
+  __shared__ float s_m[AT_D], s_sc[AT_D];
   const int chunk = blockIdx.x, head = blockIdx.y, n = blockIdx.z;
   const int ld = 3 * hidden;
-  const long long p0 = (long long)chunk * AT_PIX;
-  const act_t* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = warp >> 2, nt = warp & 3;                   // this warp's 16 x 8 tile of S
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  float z_run = 0.f;                                         // running column sum of this warp's pixel rows (column = lane)
+  if (tid < AT_D) s_m[tid] = -INFINITY;
 
-  // ---- stage k, v (16-bit, as stored) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
-  {
-    const int pix = tid >> 1, half = tid & 1;   // 16 channels per thread
-    const bool ok = p0 + pix < npix;
-    uint4 k2[2], v2[2];
-    const uint32_t ninf2 = 0xFC00FC00u;          // (-inf, -inf) as half2
-    k2[0] = k2[1] = make_uint4(ninf2, ninf2, ninf2, ninf2);
-    v2[0] = v2[1] = make_uint4(0, 0, 0, 0);
-    if (ok) {
-      ldg_256(base + (size_t)pix * ld + hidden + half * 16, k2[0], k2[1]);      // one 32-byte sector per lane and tensor
-      ldg_256(base + (size_t)pix * ld + 2 * hidden + half * 16, v2[0], v2[1]);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        k2[i] = make_uint4(to_half2_bits(k2[i].x), to_half2_bits(k2[i].y), to_half2_bits(k2[i].z), to_half2_bits(k2[i].w));
-        v2[i] = make_uint4(to_half2_bits(v2[i].x), to_half2_bits(v2[i].y), to_half2_bits(v2[i].z), to_half2_bits(v2[i].w));
-      }
-    }
-    uint4* kd = reinterpret_cast<uint4*>(&s_k[pix][half * 16]);
-    uint4* vd = reinterpret_cast<uint4*>(&s_v[pix][half * 16]);
-    kd[0] = k2[0]; kd[1] = k2[1];
-    vd[0] = v2[0]; vd[1] = v2[1];
-    // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
-    // The math runs for every thread (rows beyond npix compute on zeros) so the pair shuffles stay convergent.
+  for (int sub = 0; sub < AT_SUB; ++sub) {
+    const long long p0 = ((long long)chunk * AT_SUB + sub) * AT_PIX;
+    if (p0 >= npix) break;
+    const act_t* base = qkv + ((size_t)n * npix + p0) * ld + head * AT_D;
+    if (sub > 0) __syncthreads();                            // the previous sub-chunk's MMAs are done with s_k / s_v
+    // ---- stage k, v (16-bit, as stored) ; rows beyond npix are neutral (k = -inf -> p = 0, v = 0)
     {
-      uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
-      if (ok) ldg_256(base + (size_t)pix * ld + half * 16, q0, q1);
-      if (q_mode == 0) {
-        const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-        float f[16];
-        float mx = -INFINITY;
+      const int pix = tid >> 1, half = tid & 1;   // 16 channels per thread
+      const bool ok = p0 + pix < npix;
+      uint4 k2[2], v2[2];
+      const uint32_t ninf2 = 0xFC00FC00u;          // (-inf, -inf) as half2
+      k2[0] = k2[1] = make_uint4(ninf2, ninf2, ninf2, ninf2);
+      v2[0] = v2[1] = make_uint4(0, 0, 0, 0);
+      if (ok) {
+        ldg_256(base + (size_t)pix * ld + hidden + half * 16, k2[0], k2[1]);      // one 32-byte sector per lane and tensor
+        ldg_256(base + (size_t)pix * ld + 2 * hidden + half * 16, v2[0], v2[1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { f[2 * j] = lo16(qq[j]); f[2 * j + 1] = hi16(qq[j]); mx = fmaxf(mx, fmaxf(f[2 * j], f[2 * j + 1])); }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { f[j] = __expf(f[j] - mx); sum += f[j]; }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        const float inv = scale / sum;
-        q0 = make_uint4(pack16(f[0] * inv, f[1] * inv), pack16(f[2] * inv, f[3] * inv), pack16(f[4] * inv, f[5] * inv), pack16(f[6] * inv, f[7] * inv));
-        q1 = make_uint4(pack16(f[8] * inv, f[9] * inv), pack16(f[10] * inv, f[11] * inv), pack16(f[12] * inv, f[13] * inv), pack16(f[14] * inv, f[15] * inv));
+        for (int i = 0; i < 2; ++i) {
+          k2[i] = make_uint4(to_half2_bits(k2[i].x), to_half2_bits(k2[i].y), to_half2_bits(k2[i].z), to_half2_bits(k2[i].w));
+          v2[i] = make_uint4(to_half2_bits(v2[i].x), to_half2_bits(v2[i].y), to_half2_bits(v2[i].z), to_half2_bits(v2[i].w));
+        }
       }
-      if (ok) stg_256(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16, q0, q1);
-    }
-  }
-  __syncthreads();
-  // ---- column max of k over the chunk
-  const int warp = tid >> 5, lane = tid & 31;
-  {
-    float mx = -INFINITY;
-    for (int p = warp * 16; p < warp * 16 + 16; ++p) mx = fmaxf(mx, __half2float(s_k[p][lane]));
-    s_red[warp][lane] = mx;
-  }
-  __syncthreads();
-  if (tid < AT_D) {
-    float mx = s_red[0][tid];
+      uint4* kd = reinterpret_cast<uint4*>(&s_k[pix][half * 16]);
+      uint4* vd = reinterpret_cast<uint4*>(&s_v[pix][half * 16]);
+      kd[0] = k2[0]; kd[1] = k2[1];
+      vd[0] = v2[0]; vd[1] = v2[1];
+      // ---- q: softmax over the 32 channels of this head (two threads per pixel), scaled; or plain copy.
+      // The math runs for every thread (rows beyond npix compute on zeros) so the pair shuffles stay convergent.
+      {
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = make_uint4(0, 0, 0, 0);
+        if (ok) ldg_256(base + (size_t)pix * ld + half * 16, q0, q1);
+        if (q_mode == 0) {
+          const uint32_t qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+          float f[16];
+          float mx = -INFINITY;
 #pragma unroll
-    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_red[w][tid]);
-    s_m[tid] = mx;
-  }
-  __syncthreads();
-  // ---- p = exp(k - m) in place (rounded to half: the same values enter Z and S); column sums Z
-  {
-    const float m = s_m[lane];
-    float z = 0.f;
-    for (int p = warp * 16; p < warp * 16 + 16; ++p) {
-      const __half e = __float2half_rn(__expf(__half2float(s_k[p][lane]) - m));
-      s_k[p][lane] = e;
-      z += __half2float(e);
+          for (int j = 0; j < 8; ++j) { f[2 * j] = lo16(qq[j]); f[2 * j + 1] = hi16(qq[j]); mx = fmaxf(mx, fmaxf(f[2 * j], f[2 * j + 1])); }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { f[j] = __expf(f[j] - mx); sum += f[j]; }
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          const float inv = scale / sum;
+          q0 = make_uint4(pack16(f[0] * inv, f[1] * inv), pack16(f[2] * inv, f[3] * inv), pack16(f[4] * inv, f[5] * inv), pack16(f[6] * inv, f[7] * inv));
+          q1 = make_uint4(pack16(f[8] * inv, f[9] * inv), pack16(f[10] * inv, f[11] * inv), pack16(f[12] * inv, f[13] * inv), pack16(f[14] * inv, f[15] * inv));
+        }
+        if (ok) stg_256(qout + ((size_t)n * npix + p0 + pix) * hidden + head * AT_D + half * 16, q0, q1);
+      }
     }
-    s_red[warp][lane] = z;
+    __syncthreads();
+    // ---- column max of k over the sub-chunk
+    {
+      float mx = -INFINITY;
+      for (int p = warp * 16; p < warp * 16 + 16; ++p) mx = fmaxf(mx, __half2float(s_k[p][lane]));
+      s_red[warp][lane] = mx;
+    }
+    __syncthreads();
+    if (tid < AT_D) {
+      const float m_old = s_m[tid];
+      float mx = m_old;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_red[w][tid]);
+      s_m[tid] = mx;
+      s_sc[tid] = __expf(m_old - mx);                        // 0 for the first sub-chunk (m_old = -inf)
+    }
+    __syncthreads();
+    // ---- p = exp(k - m) in place (rounded to half: the same values enter Z and S); running column sums Z
+    {
+      const float m = s_m[lane];
+      float z = 0.f;
+      for (int p = warp * 16; p < warp * 16 + 16; ++p) {
+        const __half e = __float2half_rn(__expf(__half2float(s_k[p][lane]) - m));
+        s_k[p][lane] = e;
+        z += __half2float(e);
+      }
+      z_run = fmaf(z_run, s_sc[lane], z);
+    }
+    __syncthreads();
+    // ---- S[d][e] += sum over the sub-chunk's 128 pixels of p[pix][d] * v[pix][e]: A = P^T (d x pix), B = V (pix x e), both
+    //      read transposed from their [pixel][channel] rows.  Warp w owns the 16 x 8 output tile (d tile w >> 2, e tile w & 3)
+    //      for ALL pixels (8 MMAs of k = 16), so there is no cross-warp reduction.
+    {
+      const int r = lane & 7, mat = lane >> 3;
+      const float sc_lo = s_sc[mt * 16 + (lane >> 2)], sc_hi = s_sc[mt * 16 + (lane >> 2) + 8];
+      c[0] *= sc_lo; c[1] *= sc_lo; c[2] *= sc_hi; c[3] *= sc_hi;
+#pragma unroll
+      for (int ks = 0; ks < AT_PIX / 16; ++ks) {
+        uint32_t a[4], bfr[2];
+        ldmatrix_x4_trans(a, (uint32_t)__cvta_generic_to_shared(&s_k[ks * 16 + r + ((mat >> 1) & 1) * 8][mt * 16 + (mat & 1) * 8]));
+        ldmatrix_x2_trans(bfr, (uint32_t)__cvta_generic_to_shared(&s_v[ks * 16 + r + (mat & 1) * 8][nt * 8]));
+        mma_m16n8k16_f16(c, a, bfr[0], bfr[1]);
+      }
+    }
   }
-  __syncthreads();
-  // ---- S[d][e] = sum over the chunk's 128 pixels of p[pix][d] * v[pix][e]: A = P^T (d x pix), B = V (pix x e), both read
-  //      transposed from their [pixel][channel] rows.  Warp w owns the 16 x 8 output tile (d tile w >> 2, e tile w & 3) for ALL
-  //      pixels (8 MMAs of k = 16), so there is no cross-warp reduction.
   float* po = part + (((size_t)n * gridDim.y + head) * chunks + chunk) * AT_PART;
   {
-    const int mt = warp >> 2, nt = warp & 3;
-    const int r = lane & 7, mat = lane >> 3;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < AT_PIX / 16; ++ks) {
-      uint32_t a[4], bfr[2];
-      ldmatrix_x4_trans(a, (uint32_t)__cvta_generic_to_shared(&s_k[ks * 16 + r + ((mat >> 1) & 1) * 8][mt * 16 + (mat & 1) * 8]));
-      ldmatrix_x2_trans(bfr, (uint32_t)__cvta_generic_to_shared(&s_v[ks * 16 + r + (mat & 1) * 8][nt * 8]));
-      mma_m16n8k16_f16(c, a, bfr[0], bfr[1]);
-    }
     const int d = mt * 16 + (lane >> 2), e = nt * 8 + (lane & 3) * 2;
     *reinterpret_cast<float2*>(po + d * AT_D + e) = make_float2(c[0], c[1]);
     *reinterpret_cast<float2*>(po + (d + 8) * AT_D + e) = make_float2(c[2], c[3]);
   }
+  s_red[warp][lane] = z_run;       // (the last read of s_red, the max merge, is behind two barriers)
+  __syncthreads();
   if (tid < AT_D) {
     float z = 0.f;
 #pragma unroll
@@ -228,7 +245,7 @@ using namespace ds;
 
 extern "C" {
 
-int ds_attn_chunks(long long npix) { return (int)((npix + AT_PIX - 1) / AT_PIX); }
+int ds_attn_chunks(long long npix) { return (int)((npix + AT_PIX * AT_SUB - 1) / (AT_PIX * AT_SUB)); }
 /* scratch: chunk partials followed by the merged ctx [N][heads][32][32] */
 long long ds_attn_part_floats(int N, int heads, long long npix) { return (long long)N * heads * (ds_attn_chunks(npix) * AT_PART + AT_D * AT_D); }
 

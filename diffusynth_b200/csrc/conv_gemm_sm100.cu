@@ -303,7 +303,10 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 // allocator, then weight (B) TMA producer, 3 = statistics publisher, 4-11 = epilogue.  The two producers split the per-K-block
 // scalar work (barrier probe + coordinates + TMA issue), which otherwise bounds the kernel on one thread; the A producer
 // reads its per-K-block coordinates (tensor map, channel offset, tap shift) from a table built once in shared memory.
-template <int BK, int CG>
+// EPI specialises the epilogue so that every instantiation carries only the code it runs (the generic kernel is ~9000 SASS
+// instructions and the role warps evict each other from the instruction cache): 0 = everything (fp32 / ragged outputs),
+// 1 = 16-bit output with full chunks, no activation, no residual (the 1x1 convolutions), 2 = + GELU (conv1), 3 = + residual (conv2).
+template <int BK, int CG, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -659,7 +662,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const int cols0 = cols_left;
       auto fetch_res = [&](int c, uint4 (&rr)[2]) {
         rr[0] = rr[1] = make_uint4(0, 0, 0, 0);
-        if (has_res && cols0 - 16 * c > 0) {
+        if ((EPI == 0 || EPI == 3) && has_res && cols0 - 16 * c > 0) {
           ldg_256(res_p + 16 * c, rr[0], rr[1]);
         }
       };
@@ -671,7 +674,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (nch > 0) issue_chunk(0, ra_);
       // Main path (16-bit output, full chunks): all table reads of a chunk are issued together, so they overlap instead of
       // queueing behind each other through reused registers (what bounded the store-bound 1x1 convolutions).
-      const bool lean = out_p != nullptr && o32_p == nullptr && cols_left >= 16 * nch && !(P.dbg & 1);
+      const bool lean = EPI != 0 || (out_p != nullptr && o32_p == nullptr && cols_left >= 16 * nch && !(P.dbg & 1));
       if (lean) {
         auto lean_chunk = [&](const uint32_t* r, const uint4& ra, const uint4& rb) {
           float4 t2[4], t1[4], tb[4];
@@ -689,9 +692,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             v[4 * q4 + 2] = fmaf(__uint_as_float(r[4 * q4 + 2]), rstd, fmaf(nmr, t1[q4].z, t2[q4].z) + tb[q4].z);
             v[4 * q4 + 3] = fmaf(__uint_as_float(r[4 * q4 + 3]), rstd, fmaf(nmr, t1[q4].w, t2[q4].w) + tb[q4].w);
           }
-          if (P.act == 1) gelu16(v);
+          if (EPI == 0 ? P.act == 1 : EPI == 2) gelu16(v);
           if (valid) {
-            if (has_res) {
+            if ((EPI == 0 || EPI == 3) && has_res) {
               const uint32_t rr[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) { v[2 * j] += lo16(rr[j]); v[2 * j + 1] += hi16(rr[j]); }
@@ -719,7 +722,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
             lean_chunk(rb_, qb[0], qb[1]);
           }
         }
-      } else {
+      } else if (EPI == 0) {
       for (int c = 0; c < nch; c += 2) {
         tmem_ld_wait16(ra_);
         if (c + 1 < nch) { issue_chunk(c + 1, rb_); fetch_res(c + 1, qb); }
@@ -930,20 +933,32 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(unsigned long long) * 16 * 1024, stream));
     P.dbg_buf = dbg_buf;
   }
-#define DS_LAUNCH_CONV(BKV, CGV)                                                                                                \
-  do {                                                                                                                          \
-    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV, CGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    cudaLaunchConfig_t cfg;                                                                                                     \
-    memset(&cfg, 0, sizeof(cfg));                                                                                               \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;              \
-    cudaLaunchAttribute attr[1];                                                                                                \
-    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                           \
-    attr[0].val.clusterDim.x = CGV; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                                \
-    cfg.attrs = attr; cfg.numAttrs = (CGV == 2) ? 1 : 0;                                                                        \
-    DS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BKV, CGV>, maps, P));                                               \
+  // epilogue specialisation (see the kernel): the main path needs a 16-bit output whose every chunk is full
+  int epi = 0;
+  if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !getenv("DS_CONV_GENERIC_EPI")) {
+    if (a->act == 0) epi = a->d_residual ? 3 : 1;
+    else if (!a->d_residual) epi = 2;
+  }
+#define DS_LAUNCH_CONV(BKV, CGV, EPIV)                                                                                                \
+  do {                                                                                                                                \
+    DS_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BKV, CGV, EPIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    cudaLaunchConfig_t cfg;                                                                                                           \
+    memset(&cfg, 0, sizeof(cfg));                                                                                                     \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;                    \
+    cudaLaunchAttribute attr[1];                                                                                                      \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                                 \
+    attr[0].val.clusterDim.x = CGV; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                                      \
+    cfg.attrs = attr; cfg.numAttrs = (CGV == 2) ? 1 : 0;                                                                              \
+    DS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BKV, CGV, EPIV>, maps, P));                                               \
   } while (0)
-  if (a->BK == 64) { if (P.cg == 2) DS_LAUNCH_CONV(64, 2); else DS_LAUNCH_CONV(64, 1); }
-  else             { if (P.cg == 2) DS_LAUNCH_CONV(32, 2); else DS_LAUNCH_CONV(32, 1); }
+#define DS_LAUNCH_CONV_E(BKV, CGV)                                                                                  \
+  do {                                                                                                              \
+    if (epi == 1) DS_LAUNCH_CONV(BKV, CGV, 1); else if (epi == 2) DS_LAUNCH_CONV(BKV, CGV, 2);                     \
+    else if (epi == 3) DS_LAUNCH_CONV(BKV, CGV, 3); else DS_LAUNCH_CONV(BKV, CGV, 0);                              \
+  } while (0)
+  if (a->BK == 64) { if (P.cg == 2) DS_LAUNCH_CONV_E(64, 2); else DS_LAUNCH_CONV_E(64, 1); }
+  else             { if (P.cg == 2) DS_LAUNCH_CONV_E(32, 2); else DS_LAUNCH_CONV_E(32, 1); }
+#undef DS_LAUNCH_CONV_E
 #undef DS_LAUNCH_CONV
   DS_CHECK_CUDA(cudaGetLastError());
   if (P.dbg & 64) {      // profiling only: where each role of the CTA spent its cycles (mean over CTAs)

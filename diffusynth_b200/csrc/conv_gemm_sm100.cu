@@ -18,6 +18,13 @@
 
 namespace ds {
 
+// Profiling switches (DS_CONV_DBG bitmask, tools_dev/conv_roles.py) are compiled in only with -DDS_CONV_DEBUG
+// (DS_EXTRA_NVCC_FLAGS=-DDS_CONV_DEBUG python -m diffusynth_b200._build --force): the production kernels carry none of it.
+#ifdef DS_CONV_DEBUG
+#define DS_DBG(P) ((P).dbg)
+#else
+#define DS_DBG(P) 0
+#endif
 static constexpr int kNumThreads = 384;
 static constexpr int kEpiWarp0 = 4;
 static constexpr int kEpiWarps = 8;
@@ -369,7 +376,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is signalled across the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
-  const bool timed = (P.dbg & 64) != 0;
+  const bool timed = (DS_DBG(P) & 64) != 0;
 
   if (warp == 0) {
     // ================================ activation (A) producer: warp-uniform, one elected lane issues =======================
@@ -460,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
           for (int j = 0; j < nsub; ++j) {
             const uint64_t adesc = make_kmajor_desc<BK>(sa);
             const uint64_t bdesc = make_kmajor_desc<BK>(sa + P.stage_a_bytes);
-            if (!(P.dbg & 4)) {
+            if (!(DS_DBG(P) & 4)) {
               // advance 16 elements (32 bytes) along K inside the swizzle span: +2 in the 16-byte address field
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
@@ -541,7 +548,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
     };
     fetch_sbias(w_first);
-    const bool epi_timed = (P.dbg & 64) != 0;
+    const bool epi_timed = (DS_DBG(P) & 64) != 0;
     long long epi_wait = 0;
     const long long epi_begin = clock64();
     long long e_pro = 0, e_chunks = 0, e_tail = 0;
@@ -626,7 +633,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
                 if (j < cols_left) { psum += v[j]; psq = fmaf(v[j], v[j], psq); }
             }
           }
-          if (out_p != nullptr && !(P.dbg & 1)) {           // Cout % 16 == 0 is enforced for 16-bit outputs
+          if (out_p != nullptr && !(DS_DBG(P) & 1)) {           // Cout % 16 == 0 is enforced for 16-bit outputs
             uint4 a, b;
             a.x = pack16_epi(v[0], v[1]);   a.y = pack16_epi(v[2], v[3]);
             a.z = pack16_epi(v[4], v[5]);   a.w = pack16_epi(v[6], v[7]);
@@ -647,7 +654,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       };
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * P.BN + chunk_lo * 16);
       auto issue_chunk = [&](int c, uint32_t (&r)[16]) {      // c = chunk index inside this warp's column range
-        if (P.dbg & 2) {
+        if (DS_DBG(P) & 2) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) r[j] = 0x3f800000u + j;
           return;
@@ -674,7 +681,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (nch > 0) issue_chunk(0, ra_);
       // Main path (16-bit output, full chunks): all table reads of a chunk are issued together, so they overlap instead of
       // queueing behind each other through reused registers (what bounded the store-bound 1x1 convolutions).
-      const bool lean = EPI != 0 || (out_p != nullptr && o32_p == nullptr && cols_left >= 16 * nch && !(P.dbg & 1));
+      const bool lean = EPI != 0 || (out_p != nullptr && o32_p == nullptr && cols_left >= 16 * nch && !(DS_DBG(P) & 1));
       if (lean) {
         auto lean_chunk = [&](const uint32_t* r, const uint4& ra, const uint4& rb) {
           float4 t2[4], t1[4], tb[4];
@@ -772,6 +779,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 static int validate(const ds_conv_gemm_args* a) {
   DS_REQUIRE(a != nullptr, "ds_conv_gemm: null args");
+#ifndef DS_CONV_DEBUG
+  { const char* e = getenv("DS_CONV_DBG"); DS_REQUIRE(!e || atoi(e) == 0, "ds_conv_gemm: DS_CONV_DBG needs a library built with -DDS_CONV_DEBUG"); }
+#endif
   DS_REQUIRE(a->BK == 32 || a->BK == 64, "ds_conv_gemm: BK must be 32 or 64 (got %d)", a->BK);
   DS_REQUIRE(a->C0 > 0 && a->C0 % a->BK == 0 && a->C1 >= 0 && a->C1 % a->BK == 0,
              "ds_conv_gemm: C0=%d C1=%d must be multiples of BK=%d", a->C0, a->C1, a->BK);
@@ -814,6 +824,9 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   memset(&P, 0, sizeof(P));
   P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
   { const char* e = getenv("DS_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
+#ifndef DS_CONV_DEBUG
+  P.dbg = 0;        // (ds_conv_gemm refuses DS_CONV_DBG on a build without -DDS_CONV_DEBUG)
+#endif
   P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
   P.tiles_w = (a->W + a->Wb - 1) / a->Wb;
   P.tiles_m = P.tiles_h * P.tiles_w;

@@ -1,4 +1,5 @@
-"""Per-role wait-cycle breakdown of ds_conv_gemm (DS_CONV_DBG=64 instrumentation) on representative layer shapes."""
+"""Per-role wait-cycle breakdown of ds_conv_gemm (DS_CONV_DBG=64 instrumentation) on representative layer shapes.
+Needs a library built with the instrumentation: DS_EXTRA_NVCC_FLAGS=-DDS_CONV_DEBUG python -m diffusynth_b200._build --force"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

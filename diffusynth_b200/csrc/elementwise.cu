@@ -136,38 +136,47 @@ gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ 
 //   gn_act:      out = act((x - mean_g) * rstd_g * gamma + beta)          act: 0 none, 1 relu, 2 swish
 // x bf16 NHWC with Cp channels stored (C real, Cp - C zero padding), C % G == 0.
 // ---------------------------------------------------------------------------------------------
+// 16-byte (8-channel) accesses: the host picks blockDim.x as a multiple of Cp/8, so a thread always meets the same 8 channels.
 __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
                                    long long hw, int chunks) {
   extern __shared__ float s_acc[];   // [2*G]
-  const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G;
+  const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G, C8 = Cp / 8;
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const long long per = (hw + chunks - 1) / chunks;
   const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
-  const act_t* xb = x + (size_t)n * hw * Cp;
-  // thread handles a fixed channel (so a fixed group) across pixels
-  const int tc = threadIdx.x % Cp;
-  const int tp = threadIdx.x / Cp, pstride = blockDim.x / Cp;
-  float s = 0.f, q = 0.f;
-  if (tc < C && tp < pstride) {
-    for (long long p = p0 + tp; p < p1; p += pstride) {
-      const float v = act2f(xb[p * Cp + tc]);
-      s += v;
-      q = fmaf(v, v, q);
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * hw * Cp);
+  const int tv = threadIdx.x % C8;                       // this thread's 8-channel vector inside a pixel
+  const int tp = threadIdx.x / C8, pstride = blockDim.x / C8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  for (long long p = p0 + tp; p < p1; p += pstride) {
+    const uint4 v = __ldg(xb + p * C8 + tv);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = lo16(w[j]), b = hi16(w[j]);
+      s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
+      s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
     }
-    atomicAdd(&s_acc[2 * (tc / cpg)], s);
-    atomicAdd(&s_acc[2 * (tc / cpg) + 1], q);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = tv * 8 + j;
+    if (c < C) { atomicAdd(&s_acc[2 * (c / cpg)], s[j]); atomicAdd(&s_acc[2 * (c / cpg) + 1], q[j]); }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x)
     part[((size_t)n * G + g) * chunks + chunk] = make_float2(s_acc[2 * g], s_acc[2 * g + 1]);
 }
 
+// grid = (gx, N) with gx * blockDim.x a multiple of Cp/8 (fixed 8 channels per thread: scale/shift in registers)
 __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ out, const float2* __restrict__ part,
                               int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int C, int Cp, int G,
                               long long hw, float eps, int act) {
   extern __shared__ float s_ab[];   // per channel scale, shift  [2*Cp]
-  const int n = blockIdx.y, cpg = C / G;
+  const int n = blockIdx.y, cpg = C / G, C8 = Cp / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int g = warp; g < G; g += nwarps) {
     float2 mr = reduce_stats_warp(part + ((size_t)n * G + g) * chunks, chunks, 1.0f / (float)(cpg * hw), eps, lane);
@@ -179,17 +188,28 @@ __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ o
   }
   for (int c = C + threadIdx.x; c < Cp; c += blockDim.x) { s_ab[2 * c] = 0.f; s_ab[2 * c + 1] = 0.f; }
   __syncthreads();
-  const long long total = hw * Cp;
-  const act_t* xb = x + (size_t)n * total;
-  act_t* ob = out + (size_t)n * total;
-  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2; i < total; i += (long long)gridDim.x * blockDim.x * 2) {
-    const int c = (int)(i % Cp);
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(xb + i);
-    float a = lo16(v) * s_ab[2 * c] + s_ab[2 * c + 1];
-    float b = hi16(v) * s_ab[2 * c + 2] + s_ab[2 * c + 3];
-    if (act == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-    else if (act == 2) { a = a / (1.f + __expf(-a)); b = b / (1.f + __expf(-b)); }
-    *reinterpret_cast<uint32_t*>(ob + i) = pack16(a, b);
+  const long long total = hw * C8;                       // 16-byte vectors per sample
+  const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * hw * Cp);
+  uint4* ob = reinterpret_cast<uint4*>(out + (size_t)n * hw * Cp);
+  const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int c0 = (int)(i0 % C8) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = s_ab[2 * (c0 + j)]; sh[j] = s_ab[2 * (c0 + j) + 1]; }
+  for (long long i = i0; i < total; i += stride) {
+    const uint4 v = __ldg(xb + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = fmaf(lo16(w[j]), sc[2 * j], sh[2 * j]);
+      float b = fmaf(hi16(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
+      if (act == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      else if (act == 2) { a = a / (1.f + __expf(-a)); b = b / (1.f + __expf(-b)); }
+      o[j] = pack16(a, b);
+    }
+    ob[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -336,7 +356,9 @@ int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const vo
 
 int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, long long hw, int chunks, void* stream) {
   DS_REQUIRE(d_x && d_part && N > 0 && C > 0 && Cp >= C && Cp <= 1024 && G > 0 && C % G == 0 && chunks > 0, "ds_group_stats: bad arguments");
-  const int block = (1024 / Cp) * Cp;
+  DS_REQUIRE(Cp % 8 == 0, "ds_group_stats: Cp must be a multiple of 8");
+  const int C8 = Cp / 8;
+  const int block = (512 / C8) * C8;           // a multiple of Cp/8, <= 512
   group_stats_kernel<<<dim3(chunks, N), block, 2 * G * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
                                                                                               C, Cp, G, hw, chunks);
   DS_CHECK_CUDA(cudaGetLastError());
@@ -346,10 +368,17 @@ int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, l
 int ds_gn_act(const void* d_x, void* d_out, const void* d_part, int chunks, const float* d_gamma, const float* d_beta, int N, int C,
               int Cp, int G, long long hw, float eps, int act, void* stream) {
   DS_REQUIRE(d_x && d_out && d_part && d_gamma && d_beta && N > 0 && Cp % 2 == 0 && C % G == 0, "ds_gn_act: bad arguments");
-  const long long total = hw * Cp / 2;
-  int gx = (int)((total + 255) / 256);
+  DS_REQUIRE(Cp % 8 == 0, "ds_gn_act: Cp must be a multiple of 8");
+  const int C8 = Cp / 8;
+  const long long total = hw * C8;
+  int g = C8, h256 = 256;
+  while (h256) { const int t = g % h256; g = h256; h256 = t; }      // gcd(C8, 256)
+  const int m = C8 / g;                                             // gx must be a multiple of m
+  int gx = (int)((total + 2 * 256 - 1) / (2 * 256));
   const int cap = (num_sms() * 8 + N - 1) / N;
-  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  if (gx > cap) gx = cap;
+  gx = (gx + m - 1) / m * m;
+  if (gx < m) gx = m;
   gn_act_kernel<<<dim3(gx, N), 256, (2 * Cp + 4) * sizeof(float), (cudaStream_t)stream>>>(
       (const act_t*)d_x, (act_t*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act);
   DS_CHECK_CUDA(cudaGetLastError());

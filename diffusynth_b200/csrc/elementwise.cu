@@ -139,9 +139,9 @@ gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ 
 // 16-byte (8-channel) accesses: the host picks blockDim.x as a multiple of Cp/8, so a thread always meets the same 8 channels.
 __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
                                    long long hw, int chunks) {
-  extern __shared__ float s_acc[];   // [2*G]
+  extern __shared__ float s_acc[];   // [2*Cp] per-channel (sum, sumsq): far fewer colliding atomics than per-group bins
   const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G, C8 = Cp / 8;
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
   const long long per = (hw + chunks - 1) / chunks;
   const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
@@ -151,8 +151,7 @@ __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restri
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  for (long long p = p0 + tp; p < p1; p += pstride) {
-    const uint4 v = __ldg(xb + p * C8 + tv);
+  auto accumulate = [&](const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -160,15 +159,28 @@ __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restri
       s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
       s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
     }
+  };
+  long long p = p0 + tp;
+  for (; p + 3 * pstride < p1; p += 4 * pstride) {          // four independent loads in flight
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + (p + u * pstride) * C8 + tv);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) accumulate(v[u]);
   }
+  for (; p < p1; p += pstride) accumulate(__ldg(xb + p * C8 + tv));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = tv * 8 + j;
-    if (c < C) { atomicAdd(&s_acc[2 * (c / cpg)], s[j]); atomicAdd(&s_acc[2 * (c / cpg) + 1], q[j]); }
+    atomicAdd(&s_acc[2 * c], s[j]);
+    atomicAdd(&s_acc[2 * c + 1], q[j]);
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x)
-    part[((size_t)n * G + g) * chunks + chunk] = make_float2(s_acc[2 * g], s_acc[2 * g + 1]);
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float gs = 0.f, gq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { gs += s_acc[2 * c]; gq += s_acc[2 * c + 1]; }
+    part[((size_t)n * G + g) * chunks + chunk] = make_float2(gs, gq);
+  }
 }
 
 // grid = (gx, N) with gx * blockDim.x a multiple of Cp/8 (fixed 8 channels per thread: scale/shift in registers)
@@ -197,8 +209,7 @@ __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ o
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sc[j] = s_ab[2 * (c0 + j)]; sh[j] = s_ab[2 * (c0 + j) + 1]; }
-  for (long long i = i0; i < total; i += stride) {
-    const uint4 v = __ldg(xb + i);
+  auto apply = [&](const uint4& v) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
     uint32_t o[4];
 #pragma unroll
@@ -206,11 +217,20 @@ __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ o
       float a = fmaf(lo16(w[j]), sc[2 * j], sh[2 * j]);
       float b = fmaf(hi16(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
       if (act == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-      else if (act == 2) { a = a / (1.f + __expf(-a)); b = b / (1.f + __expf(-b)); }
+      else if (act == 2) { a = __fdividef(a, 1.f + __expf(-a)); b = __fdividef(b, 1.f + __expf(-b)); }
       o[j] = pack16(a, b);
     }
-    ob[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  long long i = i0;
+  for (; i + 3 * stride < total; i += 4 * stride) {        // four independent vectors in flight
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ob[i + u * stride] = apply(v[u]);
   }
+  for (; i < total; i += stride) ob[i] = apply(__ldg(xb + i));
 }
 
 // out = a + b (bf16 NHWC), used for the VQGAN residual adds that are not fused into a conv epilogue
@@ -358,8 +378,8 @@ int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, l
   DS_REQUIRE(d_x && d_part && N > 0 && C > 0 && Cp >= C && Cp <= 1024 && G > 0 && C % G == 0 && chunks > 0, "ds_group_stats: bad arguments");
   DS_REQUIRE(Cp % 8 == 0, "ds_group_stats: Cp must be a multiple of 8");
   const int C8 = Cp / 8;
-  const int block = (512 / C8) * C8;           // a multiple of Cp/8, <= 512
-  group_stats_kernel<<<dim3(chunks, N), block, 2 * G * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
+  const int block = C8 * 8;                    // 8 pixel lanes x Cp/8 channel vectors: few colliding shared atomics at the end
+  group_stats_kernel<<<dim3(chunks, N), block, 2 * Cp * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
                                                                                               C, Cp, G, hw, chunks);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;

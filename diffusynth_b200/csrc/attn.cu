@@ -211,19 +211,22 @@ attn_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout /
   __shared__ __align__(16) float s_w[64][AT_D];
   const int c0 = blockIdx.x * 64, head = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
   const int warp = tid >> 5, d = tid & 31;
-  // lane d keeps row d of ctx in registers; the warp walks over Wout rows read as broadcast float4 from shared memory
-  float cr[AT_D];
-  const float4* ci = reinterpret_cast<const float4*>(ctx + ((size_t)n * gridDim.y + head) * AT_D * AT_D + d * AT_D);
-#pragma unroll
-  for (int e4 = 0; e4 < AT_D / 4; ++e4) {
-    const float4 v = __ldg(ci + e4);
-    cr[4 * e4] = v.x; cr[4 * e4 + 1] = v.y; cr[4 * e4 + 2] = v.z; cr[4 * e4 + 3] = v.w;
+  // lane d keeps row d of ctx in registers (staged through shared memory once per block: every warp needs all 32 rows);
+  // the warp walks over Wout rows read as broadcast float4 from shared memory
+  __shared__ float s_c[AT_D][AT_D + 1];
+  {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ctx + ((size_t)n * gridDim.y + head) * AT_D * AT_D) + tid);   // 256 x 16 B = 4 KB
+    const int r = tid >> 3, e0 = (tid & 7) * 4;
+    s_c[r][e0] = v.x; s_c[r][e0 + 1] = v.y; s_c[r][e0 + 2] = v.z; s_c[r][e0 + 3] = v.w;
   }
   for (int i = tid; i < 64 * AT_D; i += 256) {
     const int cl = i / AT_D, e = i % AT_D;
     s_w[cl][e] = (c0 + cl < C) ? __ldg(wout + (size_t)(c0 + cl) * hidden + head * AT_D + e) : 0.f;
   }
   __syncthreads();
+  float cr[AT_D];
+#pragma unroll
+  for (int e = 0; e < AT_D; ++e) cr[e] = s_c[d][e];
   act_t* Mn = M + (size_t)n * Cout_pad * hidden;
 #pragma unroll 2
   for (int cl = warp; cl < 64; cl += 8) {

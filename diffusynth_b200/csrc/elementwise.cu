@@ -139,10 +139,8 @@ gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ 
 // 16-byte (8-channel) accesses: the host picks blockDim.x as a multiple of Cp/8, so a thread always meets the same 8 channels.
 __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
                                    long long hw, int chunks) {
-  extern __shared__ float s_acc[];   // [2*Cp] per-channel (sum, sumsq): far fewer colliding atomics than per-group bins
+  extern __shared__ float s_acc[];   // [pixel lanes][Cp][2]: per-thread (sum, sumsq) of every channel, summed in fixed order (deterministic)
   const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G, C8 = Cp / 8;
-  for (int i = threadIdx.x; i < 2 * Cp; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   const long long per = (hw + chunks - 1) / chunks;
   const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
   const uint4* xb = reinterpret_cast<const uint4*>(x + (size_t)n * hw * Cp);
@@ -172,13 +170,14 @@ __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restri
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = tv * 8 + j;
-    atomicAdd(&s_acc[2 * c], s[j]);
-    atomicAdd(&s_acc[2 * c + 1], q[j]);
+    s_acc[(tp * Cp + c) * 2] = s[j];
+    s_acc[(tp * Cp + c) * 2 + 1] = q[j];
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float gs = 0.f, gq = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { gs += s_acc[2 * c]; gq += s_acc[2 * c + 1]; }
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+      for (int t = 0; t < pstride; ++t) { gs += s_acc[(t * Cp + c) * 2]; gq += s_acc[(t * Cp + c) * 2 + 1]; }
     part[((size_t)n * G + g) * chunks + chunk] = make_float2(gs, gq);
   }
 }
@@ -379,7 +378,7 @@ int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, l
   DS_REQUIRE(Cp % 8 == 0, "ds_group_stats: Cp must be a multiple of 8");
   const int C8 = Cp / 8;
   const int block = C8 * 8;                    // 8 pixel lanes x Cp/8 channel vectors: few colliding shared atomics at the end
-  group_stats_kernel<<<dim3(chunks, N), block, 2 * Cp * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
+  group_stats_kernel<<<dim3(chunks, N), block, (size_t)8 * Cp * 2 * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
                                                                                               C, Cp, G, hw, chunks);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;

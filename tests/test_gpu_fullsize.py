@@ -1,0 +1,63 @@
+"""Size-independent properties at the benchmark's full size (batch 64, deployed U-Net + VQGAN), where the CPU oracle would take
+minutes: batch independence of the sampler (which also exercises the guidance-shared prefix against an unshared run), VQ
+idempotence, the STFT+ -> iSTFT round trip, and run-to-run determinism."""
+import pytest
+import torch
+
+from diffusynth_b200 import weights as W
+from tests.gpu_util import rel
+
+pytestmark = pytest.mark.gpu
+B = 64
+
+
+@pytest.fixture(scope="module")
+def pipe():
+    from diffusynth_b200 import TextToTimbre
+    return TextToTimbre.random_init(device="cuda", seed=0)
+
+
+def test_batch64_samples_are_independent_of_the_batch(pipe):
+    """Sample k of a 64-prompt job equals the same prompt + noise run in a 2-prompt job (2 DDIM steps, CFG 6): nothing in the
+    CUDA path couples samples, and the prefix shared by the two guidance halves gives the same values as in the small job."""
+    steps = 2
+    draws = W.host_noise(11, 1 + steps, B)
+    cond, uncond = W.synthetic_conditions(B, 512)
+    big = pipe.generate(cond.cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws, decode=False).latents
+    for k0 in (0, 41):
+        sl = slice(k0, k0 + 2)
+        small = pipe.generate(cond[sl].cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws[:, sl].contiguous(), decode=False).latents
+        assert rel(big[sl], small) < 1e-5, (k0, rel(big[sl], small))
+
+
+def test_vq_is_idempotent_at_full_size(pipe):
+    x = torch.randn((B, 4, 128, 64), generator=torch.Generator().manual_seed(3)).cuda() * 2
+    q1, _, _ = pipe.vqgan._vq_vae(x)
+    i1 = pipe.vqgan._vq_vae.last_indices.clone()
+    q2, _, _ = pipe.vqgan._vq_vae(q1)
+    assert torch.equal(i1, pipe.vqgan._vq_vae.last_indices)           # a codebook vector is its own nearest neighbour
+    assert rel(q2, q1) < 1e-6                                          # (x + (q - x) is not bit-stable under re-rounding, q is)
+    assert int(i1.min()) >= 0 and int(i1.max()) < 8192
+
+
+def test_stft_istft_round_trip_at_full_size():
+    """STFT(1024/256, hann) -> (log1p|D|, cos, sin) -> exp/atan2 -> iSTFT returns the waveform (the DC bin is dropped by
+    pad_STFT/depad_STFT, so the input is made zero-mean per frame scale; edges are excluded)."""
+    from diffusynth_b200.codec import spectrogram_to_waveform, waveform_to_spectrogram
+    L = 65280
+    g = torch.Generator().manual_seed(5)
+    t = torch.arange(L, dtype=torch.float32) / 16000.0
+    f = 200.0 + 3000.0 * torch.rand((B, 1), generator=g)
+    wave = (0.6 * torch.sin(2 * torch.pi * f * t) + 0.2 * torch.sin(2 * torch.pi * 2.5 * f * t + 1.0)).cuda()
+    spec = waveform_to_spectrogram(wave, time_resolution=256)
+    back = spectrogram_to_waveform(spec)
+    assert tuple(back.shape) == (B, L)
+    assert rel(back[:, 2048:-2048], wave[:, 2048:-2048]) < 2e-3       # only the (tiny) DC content is lost
+
+
+def test_full_size_generation_is_deterministic(pipe):
+    cond, uncond = W.synthetic_conditions(B, 512)
+    a = pipe.generate(cond.cuda(), uncond.cuda(), steps=2, cfg_scale=6, seed=7)
+    b = pipe.generate(cond.cuda(), uncond.cuda(), steps=2, cfg_scale=6, seed=7)
+    assert torch.equal(a.latents, b.latents) and torch.equal(a.waveforms, b.waveforms)
+    assert tuple(a.waveforms.shape) == (B, 65280) and bool(torch.isfinite(a.waveforms).all())

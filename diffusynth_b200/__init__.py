@@ -23,7 +23,8 @@ def __getattr__(name):
     if name == "TextToTimbre":
         from .pipeline import TextToTimbre
         return TextToTimbre
-    if name in ("spectrogram_to_waveform", "waveform_to_spectrogram", "encodeBatch2GradioOutput_STFT"):
+    if name in ("spectrogram_to_waveform", "waveform_to_spectrogram", "encodeBatch2GradioOutput_STFT", "InputBatch2Encode_STFT",
+                "spectrogram_images", "latent_images", "latent_representation_to_Gradio_image"):
         from . import codec
         return getattr(codec, name)
     raise AttributeError(name)

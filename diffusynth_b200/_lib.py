@@ -29,6 +29,7 @@ class ConvGemmArgs(C.Structure):
         ("Hv", C.c_int32), ("Wv", C.c_int32),
         ("view_sn", C.c_int64), ("view_sh", C.c_int64), ("view_sw", C.c_int64),
         ("view_off", C.c_int64 * 4), ("num_views", C.c_int32),
+        ("view_wv", C.c_int32 * 4), ("view_hv", C.c_int32 * 4),
         ("H", C.c_int32), ("W", C.c_int32), ("Hb", C.c_int32), ("Wb", C.c_int32),
         ("d_weight", C.c_void_p),
         ("Cout_pad", C.c_int32), ("Cout", C.c_int32), ("BN", C.c_int32), ("BK", C.c_int32),
@@ -77,6 +78,8 @@ _SIGNATURES = {
     "ds_istft_length": (_L, [_I]),
     "ds_stft_decode_istft": (_I, [_P, _P, _P, _I, _I, _P]),
     "ds_stft_encode": (_I, [_P, _L, _P, _I, _I, _P]),
+    "ds_spec_images": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "ds_latent_image": (_I, [_P, _P, _P, _I, _I, _I, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

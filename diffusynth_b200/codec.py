@@ -48,14 +48,80 @@ def waveform_to_spectrogram(wave: torch.Tensor, time_resolution: int = 256) -> t
 
 
 @torch.no_grad()
+def spectrogram_images(spec: torch.Tensor):
+    """[B,3,512,T] fp32 spectral representation -> (dB-magnitude image, phase image), uint8 [B,513,T,3] each: what
+    ``spectrogram_to_Gradio_image(np.abs(D))`` / ``phase_to_Gradio_image(np.angle(D))`` (utils.py:8-91) give for
+    ``D = depad_STFT(decode_stft(spec[b]))`` (utils.py:229-238), for the whole batch in two kernels."""
+    spec = spec.float().contiguous()
+    assert spec.dim() == 4 and spec.shape[1] == 3 and spec.shape[2] == 512, "expected [B,3,512,T]"
+    B, T = spec.shape[0], spec.shape[3]
+    mag = torch.empty((B, 513, T, 3), dtype=torch.uint8, device=spec.device)
+    ph = torch.empty_like(mag)
+    scratch = torch.empty((B,), dtype=torch.int64, device=spec.device)
+    check(_lib.load().ds_spec_images(spec.data_ptr(), mag.data_ptr(), ph.data_ptr(), scratch.data_ptr(), B, T, ops._stream()),
+          "ds_spec_images")
+    return mag, ph
+
+
+@torch.no_grad()
+def latent_images(latents: torch.Tensor) -> torch.Tensor:
+    """[B,4,H,W] fp32 -> uint8 [B,8H,8W,4] (latent_representation_to_Gradio_image, utils.py:94-128, batched;
+    the input is left untouched -- the reference normalises its numpy argument in place)."""
+    lat = latents.float().contiguous()
+    assert lat.dim() == 4 and lat.shape[1] == 4, "expected [B,4,H,W]"
+    B, _, H, W = lat.shape
+    img = torch.empty((B, 8 * H, 8 * W, 4), dtype=torch.uint8, device=lat.device)
+    scratch = torch.empty((B, 4, 2), dtype=torch.float32, device=lat.device)
+    check(_lib.load().ds_latent_image(lat.data_ptr(), img.data_ptr(), scratch.data_ptr(), B, H, W, ops._stream()), "ds_latent_image")
+    return img
+
+
+def latent_representation_to_Gradio_image(latent_representation) -> np.ndarray:
+    """Drop-in for utils.py:94-128: one latent [4,H,W] (tensor or numpy) -> uint8 [8H,8W,4] numpy."""
+    if isinstance(latent_representation, np.ndarray):
+        latent_representation = torch.from_numpy(latent_representation)
+    dev = latent_representation.device if latent_representation.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    return latent_images(latent_representation.to(dev)[None])[0].cpu().numpy()
+
+
+def _decode_lists(spec: torch.Tensor):
+    mag, ph = spectrogram_images(spec)
+    wave = spectrogram_to_waveform(spec)
+    mag, ph, wave = mag.cpu().numpy(), ph.cpu().numpy(), wave.cpu().numpy()
+    return [m for m in mag], [p for p in ph], [w for w in wave]
+
+
+@torch.no_grad()
 def encodeBatch2GradioOutput_STFT(decoder, latent_vector_batch, resolution=(512, 256), original_STFT_batch=None):
-    """Tensor->waveform part of utils.py:194-267.  Returns the reference's 6-tuple; the two image lists
-    (dB spectrogram / phase uint8 renderings, utils.py:237-238) are not produced here and come
-    back empty, the signals are float32 numpy arrays like the reference's float64 ones."""
-    if original_STFT_batch is not None:
-        raise NotImplementedError("original_STFT_batch amplitude swap")
+    """utils.py:194-267 without the per-sample CPU loop.  Returns the reference's 6 lists
+    (dB-spectrogram images, phase images, signals, and the same three with channel 0 of the reconstruction replaced by
+    ``original_STFT_batch``'s when that is given, else empty).  Images are uint8 [513,T,3] numpy arrays; signals are
+    float32 numpy arrays (the reference's are float64)."""
     if isinstance(latent_vector_batch, np.ndarray):
         latent_vector_batch = torch.from_numpy(latent_vector_batch).to(next(decoder.parameters()).device)
     rec = decoder(latent_vector_batch)
-    wave = spectrogram_to_waveform(rec).cpu().numpy()
-    return [], [], [w for w in wave], [], [], []
+    imgs, phases, signals = _decode_lists(rec)
+    if original_STFT_batch is None:
+        return imgs, phases, signals, [], [], []
+    if isinstance(original_STFT_batch, np.ndarray):
+        original_STFT_batch = torch.from_numpy(original_STFT_batch)
+    swapped = rec.float().clone()
+    swapped[:, 0] = original_STFT_batch[:, 0].to(rec.device, torch.float32)          # utils.py:251
+    return (imgs, phases, signals) + _decode_lists(swapped)
+
+
+@torch.no_grad()
+def InputBatch2Encode_STFT(encoder, STFT_batch, resolution=(512, 256), quantizer=None, squared=True):
+    """utils.py:131-191: encode a batch of spectral representations (and quantise), and render the INPUT batch back to
+    images / signals.  Only the VQ path exists (the reference's ``quantizer=None`` branch expects a VAE encoder returning
+    (mu, logvar, z), which the deployed VQGAN encoder is not)."""
+    if quantizer is None:
+        raise NotImplementedError("InputBatch2Encode_STFT without a quantizer (VAE encoder variant)")
+    device = next(encoder.parameters()).device
+    if isinstance(STFT_batch, np.ndarray):
+        STFT_batch = torch.from_numpy(STFT_batch)
+    spec = STFT_batch.to(device, torch.float32)
+    latents = encoder(spec)
+    quantized, _loss, (_, _, _) = quantizer(latents)
+    imgs, phases, signals = _decode_lists(spec)
+    return imgs, phases, signals, latents, quantized

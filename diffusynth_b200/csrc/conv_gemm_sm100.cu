@@ -844,7 +844,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     const char* base = reinterpret_cast<const char*>(s == 0 ? a->d_src0 : a->d_src1);
     for (int v = 0; v < 4; ++v) {
       if (C == 0 || v >= a->num_views) { maps.a[s][v] = maps.a[0][0]; continue; }
-      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a->Wv, (cuuint64_t)a->Hv,
+      const int Wv = a->view_wv[v] > 0 ? a->view_wv[v] : a->Wv, Hv = a->view_hv[v] > 0 ? a->view_hv[v] : a->Hv;
+      cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv,
                             (cuuint64_t)((s == 0 && a->src_batch_mod > 0) ? a->src_batch_mod : a->N)};
       cuuint64_t strides[3] = {(cuuint64_t)a->view_sw * C * 2, (cuuint64_t)a->view_sh * C * 2, (cuuint64_t)a->view_sn * C * 2};
       cuuint32_t box[4] = {(cuuint32_t)a->BK, (cuuint32_t)a->Wb, (cuuint32_t)a->Hb, 1};
@@ -853,7 +854,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
       CUresult r = encode(&maps.a[s][v], (kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4, gaddr, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(A src %d view %d) failed with %d (C=%d Wv=%d Hv=%d)", s, v, (int)r, C, a->Wv, a->Hv);
+      DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(A src %d view %d) failed with %d (C=%d Wv=%d Hv=%d)", s, v, (int)r, C, Wv, Hv);
     }
   }
   {
@@ -947,8 +948,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
 // CUDA-core cross-check of the same contract (tests only): one thread per (pixel, out channel).
 // ---------------------------------------------------------------------------------------------
 __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, const act_t* src1,
-                                     const act_t* weight, int Hv, int Wv, long long view_sn, long long view_sh,
-                                     long long view_sw, const long long* view_off_dev) {
+                                     const act_t* weight, long long view_sn, long long view_sh,
+                                     long long view_sw, const long long* view_off_dev /* [4] offsets, [4] widths, [4] heights */) {
   const long long total = (long long)P.N * P.groups * P.H * P.W * P.Cout;
   const long long K = (long long)P.ntaps * (P.C0 + P.C1);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -964,7 +965,7 @@ __global__ void conv_gemm_ref_kernel(const ConvGemmDev P, const act_t* src0, con
     for (int t = 0; t < P.ntaps; ++t) {
       const ds_conv_tap tp = P.taps[g][t];
       const int y = h + tp.dy, x = w + tp.dx;
-      if (y < 0 || y >= Hv || x < 0 || x >= Wv) continue;
+      if (y < 0 || y >= view_off_dev[8 + tp.view] || x < 0 || x >= view_off_dev[4 + tp.view]) continue;
       const long long pix0 = view_off_dev[tp.view] + nsrc * view_sn + y * view_sh + x * view_sw;     // source 0: batch modulus
       const long long pix1 = view_off_dev[tp.view] + n * view_sn + y * view_sh + x * view_sw;
       for (int c = 0; c < P.C0 + P.C1; ++c) {
@@ -992,11 +993,17 @@ static int conv_gemm_reference_launch(const ds_conv_gemm_args* a, cudaStream_t s
   ConvGemmDev P;
   fill_dev(a, P);
   long long* voff = nullptr;
-  DS_CHECK_CUDA(cudaMallocAsync(&voff, 4 * sizeof(long long), stream));
-  DS_CHECK_CUDA(cudaMemcpyAsync(voff, a->view_off, 4 * sizeof(long long), cudaMemcpyHostToDevice, stream));
+  long long vtab[12];      // (pageable host source: the copy is staged before cudaMemcpyAsync returns)
+  for (int v = 0; v < 4; ++v) {
+    vtab[v] = a->view_off[v];
+    vtab[4 + v] = a->view_wv[v] > 0 ? a->view_wv[v] : a->Wv;
+    vtab[8 + v] = a->view_hv[v] > 0 ? a->view_hv[v] : a->Hv;
+  }
+  DS_CHECK_CUDA(cudaMallocAsync(&voff, sizeof(vtab), stream));
+  DS_CHECK_CUDA(cudaMemcpyAsync(voff, vtab, sizeof(vtab), cudaMemcpyHostToDevice, stream));
   conv_gemm_ref_kernel<<<num_sms() * 8, 256, 0, stream>>>(P, reinterpret_cast<const act_t*>(a->d_src0),
                                                           reinterpret_cast<const act_t*>(a->d_src1),
-                                                          reinterpret_cast<const act_t*>(a->d_weight), a->Hv, a->Wv,
+                                                          reinterpret_cast<const act_t*>(a->d_weight),
                                                           a->view_sn, a->view_sh, a->view_sw, voff);
   DS_CHECK_CUDA(cudaGetLastError());
   DS_CHECK_CUDA(cudaFreeAsync(voff, stream));

@@ -137,9 +137,24 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
 // pairs of ONE 32-channel slice, so its 49 x 32 weights are staged once.
 // ---------------------------------------------------------------------------------------------
 static constexpr int DT_HALO = 22, DT_STAGES = 2;
+static constexpr bool DW_HACC_DEFAULT = false;
 static constexpr int DT_TILE_BYTES = DT_HALO * DT_HALO * DW_CB * 2;     // 30976, a multiple of 128
 static constexpr int DT_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + 49 * (DW_CB / 2) * 8 + DT_STAGES * 8 + 128;
 
+// HACC (fp16 operands only): the taps of TWO input rows (<= 14 products per output) are accumulated with packed HFMA2 directly on
+// the staged 16-bit pairs and folded into the fp32 accumulators with FHADD (add.f32.f16) after every second input row: the FMA
+// pipe sees 1 HFMA2 (rt 2) per two MACs instead of 1 FFMA2 (rt 4) and the 16->32-bit widening of every staged value disappears.
+// Rounding: each fp16 partial sum carries <= 14 roundings of 2^-11 relative to its running value, the 49-tap total stays fp32.
+__device__ __forceinline__ void hfma2_acc(uint32_t& acc, uint32_t a, uint32_t b) {
+  asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void fold16(float2& acc, uint32_t& h) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}"
+      : "+f"(acc.x), "+f"(acc.y) : "r"(h));
+  h = 0u;
+}
+
+template <bool HACC>
 __global__ void __launch_bounds__(256, 3)
 dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
                    const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
@@ -161,9 +176,12 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     for (int s = 0; s < DT_STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  uint32_t* s_wh = reinterpret_cast<uint32_t*>(s_w);      // HACC: the same table as 16-bit pairs
   for (int i = threadIdx.x; i < 49 * (DW_CB / 2); i += 256) {
     const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
-    s_w[i] = make_float2(__ldg(weight + (size_t)tap * C + c0 + 2 * cp), __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1));
+    const float w0 = __ldg(weight + (size_t)tap * C + c0 + 2 * cp), w1 = __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1);
+    if (HACC) s_wh[i] = pack16(w0, w1);
+    else s_w[i] = make_float2(w0, w1);
   }
   __syncthreads();
 
@@ -200,6 +218,42 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    if (HACC) {
+      uint32_t acc16[2][8], wh[2][7];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc16[i][j] = 0u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r < 7) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) wh[r % 2][kx] = s_wh[(r * 7 + kx) * (DW_CB / 2) + cp];
+        }
+        const uint32_t* rowp = s_in + ((row0 + r) * DT_HALO + col0) * (DW_CB / 2) + cp;
+#pragma unroll
+        for (int j = 0; j < 14; ++j) {
+          const uint32_t in = rowp[j * (DW_CB / 2)];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int ky = r - i;
+            if (ky >= 0 && ky < 7) {
+#pragma unroll
+              for (int kx = 0; kx < 7; ++kx) {
+                const int ow = j - kx;
+                if (ow >= 0 && ow < 8) hfma2_acc(acc16[i][ow], in, wh[ky % 2][kx]);
+              }
+            }
+          }
+        }
+        if (r & 1) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fold16(acc[i][j], acc16[i][j]);
+        }
+      }
+    } else {
     float2 wbuf[2][7];
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -223,6 +277,7 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
           }
         }
       }
+    }
     }
     float s = 0.f, q = 0.f;
 #pragma unroll
@@ -392,7 +447,8 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
     DS_REQUIRE(encode != nullptr, "ds_dwconv7: cuTensorMapEncodeTiled entry point not available");
     static bool tma_attr_set = false;
     if (!tma_attr_set) {
-      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
+      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
+      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
       tma_attr_set = true;
     }
     CUtensorMap maps[2];
@@ -415,7 +471,10 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
     int gx = 3 * num_sms() / cblks;      // never more blocks than resident slots: a straggler wave would cost a whole pass
     if (gx > work) gx = (int)work;
     if (gx < 1) gx = 1;
-    dwconv7_tma_kernel<<<dim3(gx, cblks), 256, DT_SMEM_BYTES, (cudaStream_t)stream>>>(
+    // DS_DWCONV_HACC=1: packed fp16 accumulation over pairs of input rows (see hfma2_acc); fp16 operand builds only
+    static const bool hacc = [] { const char* e = getenv("DS_DWCONV_HACC"); return kOperandIsFp16 && (e ? atoi(e) != 0 : DW_HACC_DEFAULT); }();
+    auto kern = hacc ? dwconv7_tma_kernel<true> : dwconv7_tma_kernel<false>;
+    kern<<<dim3(gx, cblks), 256, DT_SMEM_BYTES, (cudaStream_t)stream>>>(
         maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
         H, W, tiles_w, tiles, N);
   } else if (R == 2)

@@ -211,6 +211,9 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
         a.view_sn, a.view_sh, a.view_sw = Hin * Win, 2 * Win, 2
         for v in range(4):
             a.view_off[v] = (v // 2) * Win + (v % 2)
+            # odd input sizes: the even-parity view holds one more column / row than the odd one (the conv's last tap
+            # still reads input column 2*Wg = Win-1)
+            a.view_hv[v], a.view_wv[v] = (Hin - v // 2 + 1) // 2, (Win - v % 2 + 1) // 2
         a.num_views = 4
         Ho, Wo = Hg, Wg
     else:
@@ -247,9 +250,14 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
         Co = out.shape[-1]
         a.d_out = _ptr(out)
         if pc.kind == "up":
-            a.out_sn, a.out_sh, a.out_sw = Ho * Wo * Co, 2 * Wo * Co, 2 * Co
+            # the output may be a larger zero-initialised map [N, Hp, Wp, Co] (pad_to_match, diffusion_components.py:210-232:
+            # the upsampled map sits at (delta // 2) from the top/left, the remainder stays zero)
+            Hp, Wp = out.shape[1], out.shape[2]
+            assert Hp >= Ho and Wp >= Wo, (Hp, Wp, Ho, Wo)
+            org = ((Hp - Ho) // 2) * Wp + (Wp - Wo) // 2
+            a.out_sn, a.out_sh, a.out_sw = Hp * Wp * Co, 2 * Wp * Co, 2 * Co
             for g in range(4):
-                a.out_goff[g] = ((g // 2) * Wo + (g % 2)) * Co
+                a.out_goff[g] = (org + (g // 2) * Wp + (g % 2)) * Co
         else:
             a.out_sn, a.out_sh, a.out_sw = Ho * Wo * Co, Wo * Co, Co
     a.d_out_f32_nchw = _ptr(out_f32)

@@ -121,6 +121,37 @@ class TextToTimbre:
         return Timbres(latents, q, spec, spectrogram_to_waveform(spec))
 
 
+    # ---- per-note synthesis for arrangements (track_maker.py:228-283) ---------------------------------------------------
+    @torch.no_grad()
+    def synthesize_note(self, instrument_latent: torch.Tensor, condition: torch.Tensor, duration_sec: float, sample_steps: int = 20,
+                        noising_strength: float = 1.0, attack: float = 0.5, before_release: float = 0.5, sampler: str = "ddim",
+                        time_resolution: int = 256, vae_scale: int = 4, noise_feed: Optional[torch.Tensor] = None) -> Timbres:
+        """One note of an instrument at an arbitrary duration: the ``diffSynthSampler`` closure of track_maker.DiffSynth.
+        ``instrument_latent`` [1,4,128,64] is the instrument's latent (re-laid to the note's width by the repeat strategy),
+        ``condition`` [1,512] the empty-prompt embedding the reference passes (:231-233; no classifier-free guidance here);
+        attack and tail are frozen by a mask that shrinks over the steps (``use_dynamic_mask``, mask_flexivity 1.0).
+        The width ``int(256 * ((duration + 1) / 4) / 4)`` is arbitrary, odd levels included (pad_to_match)."""
+        width = int(time_resolution * ((duration_sec + 1) / 4) / vae_scale)                                   # :245
+        s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy="repeat", mute=True,
+                             device=str(self.device), max_batchsize=1)                                         # :248
+        s.respace(list(np.linspace(0, self.timesteps - 1, sample_steps, dtype=np.int32)))                      # :249
+        mask = torch.zeros((1, 1, self.height, width), dtype=torch.float32, device=self.device)                # :252-254
+        mask[:, :, :, :int(time_resolution * (attack / 4) / vae_scale)] = 1.0
+        mask[:, :, :, -int(time_resolution * ((before_release + 1) / 4) / vae_scale):] = 1.0
+        init = None
+        if noise_feed is not None:
+            init = noise_feed[0][:1].to(self.device, torch.float32)
+            s.noise_feed = noise_feed[1:]
+        imgs, _ = s.inpaint_sample(self.unet, (1, self.channels, self.height, width), noising_strength,
+                                   instrument_latent.to(self.device, torch.float32), mask, return_tensor=True,
+                                   condition=condition.to(self.device), sampler=sampler, initial_noise=init,
+                                   use_dynamic_mask=True, end_noise_level_ratio=0.0, mask_flexivity=1.0)       # :257-269
+        latents = imgs[-1]
+        q, _, _ = self.vqgan._vq_vae(latents)                                                                  # :275
+        spec = self.vqgan._decoder(q)
+        return Timbres(latents, q, spec, spectrogram_to_waveform(spec))                                        # :277-283
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous split of ``total`` prompts: rank r owns [lo, hi); per = ceil(total/world)."""
     per = -(-total // world)

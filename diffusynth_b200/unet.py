@@ -231,8 +231,8 @@ class ConditionedUnet:
         N, Cin, H, Wd = x.shape
         assert Cin == self.cfg["in_dim"]
         n_stage = len(self.cfg["down_dims"]) - 1
-        if H % (1 << n_stage) or Wd % (1 << n_stage):
-            raise NotImplementedError(f"H={H}, W={Wd} must be divisible by {1 << n_stage} (pad_to_match path not implemented)")
+        if (H >> n_stage) < 1 or (Wd >> n_stage) < 1:
+            raise RuntimeError(f"H={H}, W={Wd}: the map vanishes after {n_stage} stride-2 stages")      # torch: "Output size is too small"
         pl = self.plan(N, H, Wd)
         pl.x.copy_(x.to(self.device, torch.float32))
         pl.t.copy_(time.to(self.device, torch.long))
@@ -362,6 +362,7 @@ class _Plan:
         conv("init_conv", net.stem, col, None, h, w, n=n0, out=x0, src_batch_mod=0 if shared else x_batch_mod)
         self.named["init_conv"] = (x0, dd[0])
         hs = [x0]
+        sizes: List[Tuple[int, int]] = []
         x = x0
         for i in range(n_stage):
             p = f"downs.{i}."
@@ -377,6 +378,7 @@ class _Plan:
             d = act(N, h // 2, w // 2, pc.cout)
             conv(p + "4", pc, x, None, h, w, out=d)
             self.named[p + "4"] = (d, pc.cout)
+            sizes.append((h, w))
             x = d; h //= 2; w //= 2; hs.append(x)
         for j in range(cfg["mid_depth"] - 1):
             x, _ = block(f"mid_left.{j}.", x, None, h, w); hs.append(x)
@@ -390,10 +392,14 @@ class _Plan:
             x, st = block(p + "0.", hs.pop(), x, h, w)
             x = attn(p + "1.", x, st, h, w)
             pc = net.samplers[p + "2."]
-            u = act(N, 2 * h, 2 * w, pc.cout)
+            hp, wp = sizes.pop()                  # the skip's size: 2h / 2w, or one more where the level was odd (pad_to_match)
+            if (hp, wp) == (2 * h, 2 * w):
+                u = act(N, hp, wp, pc.cout)
+            else:
+                u = torch.zeros((N, hp, wp, pc.cout), dtype=ops.ACT, device=dev)      # the conv never writes the padding
             conv(p + "2", pc, x, None, h, w, out=u)
             self.named[p + "2"] = (u, pc.cout)
-            x = u; h *= 2; w *= 2
+            x = u; h, w = hp, wp
             x, st = block(p + "3.", hs.pop(), x, h, w)
             x = attn(p + "4.", x, st, h, w)
             x, st = block(p + "5.", hs.pop(), x, h, w)

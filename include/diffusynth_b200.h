@@ -73,6 +73,8 @@ typedef struct ds_conv_gemm_args {
   int64_t view_sn, view_sh, view_sw;   /* pixel strides of a view per unit of (n, y, x) */
   int64_t view_off[4];      /* pixel offset of each view's origin */
   int32_t num_views;
+  int32_t view_wv[4], view_hv[4];      /* per-view extents where they differ (odd input sizes of the stride-2 conv: the even-parity
+                                          view holds one more column/row than the odd one); 0 = Wv / Hv */
   /* GEMM pixel grid (per sample) and tile shape */
   int32_t H, W;             /* output-tile grid extent */
   int32_t Hb, Wb;           /* Hb*Wb == 128 */
@@ -178,6 +180,18 @@ long long ds_istft_length(int T);
 int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, int B, int T, void* stream);
 /* librosa.stft(n_fft 1024, hop 256) + pad_STFT + encode_stft (sound2sound_with_text.py:85-94; tools.py:170-182,320-331). */
 int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int Tpad, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Image products of the decode glue (webUI/natural_language_guided_4/utils.py), batched:
+ *   spectrogram_to_Gradio_image (:8-50, with tools.np_power_to_db tools.py:41-50) and phase_to_Gradio_image (:53-91)
+ *   of |D| / angle(D) for D = depad_STFT(decode_stft(spec)) (:229-238): uint8 [B, 513, T, 3], flipped vertically;
+ *   latent_representation_to_Gradio_image (:94-128): per-channel min-max to 0..255, 8x enlarged, flipped: uint8 [B, 8H, 8W, 4].
+ * dB scale and angle are evaluated in float64 like the reference (numpy on complex128).
+ * -------------------------------------------------------------------------------------- */
+int ds_spec_images(const float* d_spec, void* d_mag_img, void* d_phase_img, void* d_absmax /* scratch: 8 bytes per sample */,
+                   int B, int T, void* stream);
+int ds_latent_image(const float* d_lat, void* d_img, void* d_minmax /* scratch: 32 bytes per sample */, int B, int H, int W,
+                    void* stream);
 
 #ifdef __cplusplus
 }

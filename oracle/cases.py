@@ -22,8 +22,12 @@ def unet_case(name: str):
         cfg, B, Wd = W.UNET_DEPLOYED, 2, 64
     elif name == "deployed_w24":
         cfg, B, Wd = W.UNET_DEPLOYED, 1, 24
+    elif name == "deployed_w28":        # 28 -> 14 -> 7 -> 3: the 7-wide level is odd (pad_to_match pads the upsampled 6 to 7)
+        cfg, B, Wd = W.UNET_DEPLOYED, 1, 28
     elif name == "small_w16":
         cfg, B, Wd = SMALL_UNET, 2, 16
+    elif name == "small_w10":           # 10 -> 5 -> 2
+        cfg, B, Wd = SMALL_UNET, 2, 10
     else:
         raise KeyError(name)
     sd = W.unet_random_state_dict(cfg, seed=0)
@@ -51,3 +55,16 @@ def synthetic_wave(n=65280, seed=31, sr=16000):
     y = sum(np.sin(2 * np.pi * 220.0 * k * t + g.uniform(0, 6.28)) / k for k in range(1, 9))
     y = y * np.exp(-t * 1.2) + 0.01 * g.standard_normal(n)
     return (y / np.abs(y).max()).astype(np.float64)
+
+
+def spec_representation(B=2, T=12, seed=51):
+    """A spectral representation [B, 3, 512, T] like the decoder's output: channel 0 = softplus-like (> 0),
+    channels 1/2 = tanh-like (not unit-norm)."""
+    e = randn((B, 3, 512, T), seed)
+    e[:, 0] = torch.nn.functional.softplus(1.5 * e[:, 0] - 1.0)
+    e[:, 1:] = torch.tanh(e[:, 1:])
+    return e
+
+
+def small_latents(B=2, H=16, Wd=8, seed=52):
+    return randn((B, 4, H, Wd), seed) * 2.0

@@ -128,10 +128,42 @@ def ddim_update(x: Tensor, eps_u: Optional[Tensor], eps_c: Tensor, cfg_scale: fl
     return f(co["sqrt_ap"]) * x0 + f(co["dir_coef"]) * eps + f(co["sigma"]) * step_noise
 
 
+def dynamic_masks(n_masks: int, shape, concat_points: Sequence[int], mask_flexivity: float = 0.8,
+                  train_width: int = 64) -> List[Tensor]:
+    """get_dynamic_masks, model/DiffSynthSampler.py:365-422: freeze masks (1 = keep the guide) that shrink over the
+    first ``int(n_masks * mask_flexivity)`` blends towards the release area only; returned in pop() order."""
+    rel = int(train_width / 4)
+    assert shape[3] == concat_points[-1] + rel, "shape[3] != (concat_points[-1] + release_length)"
+    seg = [concat_points[i + 1] - concat_points[i] for i in range(len(concat_points) - 1)]
+    n_guided = int(n_masks * mask_flexivity)
+    masks = []
+    for i in range(n_guided):
+        m = torch.zeros((shape[0], 1, shape[2], shape[3]))
+        m[..., shape[3] - rel:] = 1.0
+        for k, length in enumerate(seg):
+            keep = int((n_guided - 1 - i) / (n_guided - 1) * length)
+            if k == 0:
+                m[..., :keep] = 1.0
+            elif k == len(seg) - 1:
+                if keep != 0:
+                    m[..., shape[3] - keep - rel:] = 1.0
+            else:
+                s0 = concat_points[k] + int((length - keep) / 2)
+                m[..., s0:s0 + keep] = 1.0
+        masks.append(m)
+    for _ in range(n_masks - n_guided):
+        m = torch.zeros((shape[0], 1, shape[2], shape[3]))
+        m[..., shape[3] - rel:] = 1.0
+        masks.append(m)
+    masks.reverse()
+    return masks
+
+
 def sample_loop(model, sch: Schedule, shape, cond: Tensor, uncond: Optional[Tensor], cfg_scale: float,
                 noise_draws: Tensor, sampler: str = "ddim", guide: Optional[Tensor] = None,
                 start_ratio: float = 1.0, end_ratio: float = 0.0, mask: Optional[Tensor] = None,
-                inpaint: bool = False, train_width: int = 64, trace: Optional[list] = None) -> List[Tensor]:
+                inpaint: bool = False, train_width: int = 64, trace: Optional[list] = None,
+                dynamic_mask_flexivity: Optional[float] = None) -> List[Tensor]:
     """p_sample_loop with host-fed noise.  model/DiffSynthSampler.py:425-517 (+ :297-363).
 
     ``noise_draws`` [1+steps, B, C, H, train_width]: draw 0 is the initial noise, draw k the
@@ -150,8 +182,11 @@ def sample_loop(model, sch: Schedule, shape, cond: Tensor, uncond: Optional[Tens
     if guide is None:
         img = init
     else:
-        guide, _ = noise_layout_repeat(guide, B, W, train_width)
+        guide, concat_points = noise_layout_repeat(guide, B, W, train_width)
         img = q_sample(sch, guide, start - 1, init) if start > 0 else guide
+    # :483-487: one mask per blend, popped from the end; the caller's mask is ignored when the dynamic ones are used
+    masks = dynamic_masks(start - end, shape, concat_points, dynamic_mask_flexivity, train_width) \
+        if dynamic_mask_flexivity is not None else [mask] * (start - end)
     imgs = [img]
     k = 1
     for i in reversed(range(end, start)):
@@ -170,6 +205,7 @@ def sample_loop(model, sch: Schedule, shape, cond: Tensor, uncond: Optional[Tens
         img = new
         if inpaint:
             if i > 0:
+                mask = masks.pop()
                 img = mask * q_sample(sch, guide, i - 1, init) + (1 - mask) * img
             else:
                 img = mask * guide + (1 - mask) * img
@@ -469,3 +505,67 @@ def spectrogram_to_waveform(spec3: np.ndarray) -> np.ndarray:
 def waveform_to_spectrogram(y: np.ndarray, time_resolution: int = 256) -> np.ndarray:
     """stft -> pad_STFT -> encode_stft.  sound2sound_with_text.py:85-94."""
     return encode_stft(pad_stft(stft(y), time_resolution)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# 5. Image products of the decode glue   (webUI/natural_language_guided_4/utils.py:8-128)
+# --------------------------------------------------------------------------------------
+
+def _np_log10(x: np.ndarray) -> np.ndarray:
+    """tools.py:11-15."""
+    return np.log(x + 1e-16) / np.log(10)
+
+
+def np_power_to_db(S: np.ndarray, amin: float = 1e-16, top_db: float = 80.0) -> np.ndarray:
+    """tools.py:41-50."""
+    ref = S.max()
+    log_spec = 10.0 * _np_log10(np.maximum(amin, S))
+    log_spec -= 10.0 * _np_log10(np.maximum(amin, ref))
+    return np.maximum(log_spec, log_spec.max() - top_db)
+
+
+def _to_u8(x: np.ndarray) -> np.ndarray:
+    """``.astype(np.uint8)`` of a float array as numpy does it on x86-64 (truncate, keep the low byte)."""
+    with np.errstate(invalid="ignore"):
+        return x.astype(np.uint8)
+
+
+def spectrogram_image(spc: np.ndarray) -> np.ndarray:
+    """spectrogram_to_Gradio_image, utils.py:8-50: |D| [F, T] -> uint8 [F, T, 3]."""
+    nf, T = spc.shape[-2], spc.shape[-1]
+    flipped = np.flipud(np_power_to_db(np.abs(np.reshape(spc, (nf, T)))))
+    img = np.ones((nf, T, 3)) * -80.0
+    img[:, :, 0] = flipped
+    img[:, :, 1] = flipped
+    img[:, :, 2] = -60.0
+    return _to_u8(255.0 * ((img + 80.0) / 80.0))
+
+
+def phase_image(phase: np.ndarray) -> np.ndarray:
+    """phase_to_Gradio_image, utils.py:53-91: angle(D) [F, T] -> uint8 [F, T, 3]."""
+    nf, T = phase.shape[-2], phase.shape[-1]
+    flipped = (np.flipud(np.reshape(phase, (nf, T))) + 1.0) / 2.0
+    img = np.zeros((nf, T, 3))
+    img[:, :, 0] = flipped
+    img[:, :, 1] = flipped
+    img[:, :, 2] = 0.2
+    return _to_u8(255.0 * img)
+
+
+def latent_image(latent: np.ndarray) -> np.ndarray:
+    """latent_representation_to_Gradio_image, utils.py:94-128: [4, H, W] float32 -> uint8 [8H, 8W, 4]
+    (works on a copy; the reference normalises its argument in place)."""
+    image = np.array(latent, dtype=np.float32, copy=True)
+    for c in range(4):
+        ch = image[c]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            image[c] = (ch - ch.min()) / (ch.max() - ch.min()) * 255
+    big = np.repeat(np.repeat(np.transpose(image, (1, 2, 0)), 8, axis=0), 8, axis=1)
+    return _to_u8(np.flipud(big))
+
+
+def decode_products(spec3: np.ndarray):
+    """The loop body of encodeBatch2GradioOutput_STFT / InputBatch2Encode_STFT for one sample [3, 512, T]
+    (utils.py:229-241): -> (spectrogram image, phase image, waveform)."""
+    D = depad_stft(decode_stft(spec3))
+    return spectrogram_image(np.abs(D)), phase_image(np.angle(D)), istft(D)

@@ -22,10 +22,57 @@ def stats(t):
 
 
 @torch.no_grad()
+def extra(ref):
+    """tests/golden/extra.npz: odd-width U-Net cases (pad_to_match) and the image products / 6-list result of the decode
+    glue (utils.py:8-128,194-267), minted from the unmodified reference.  `python -m oracle.make_golden --extra` writes
+    only this file."""
+    g = {}
+    for name in ("deployed_w28", "small_w10"):
+        cfg, sd, x, t, cond = cases.unet_case(name)
+        net = ref.ConditionedUnet(**cfg).eval()
+        net.load_state_dict(sd, strict=True)
+        g[f"{name}_eps"] = net(x, t, cond).numpy()
+    # inpainting with the shrinking dynamic masks (DiffSynthSampler.py:365-422,483-487) on the toy model: W = 150 has a
+    # repeated middle segment, height 16 keeps the fixture small
+    B, Wd, Hh = 2, 150, 16
+    draws = cases.randn((10, B, 4, Hh, 64), 71)
+    cond, uncond = W.synthetic_conditions(B, 16, seed=78)
+    guide = cases.randn((B, 4, Hh, 64), 72) * 0.5
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B, height=Hh), draws)
+    S.activate_classifier_free_guidance(3, uncond)
+    S.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+    imgs, _ = S.inpaint_sample(cases.toy_model, (B, 4, Hh, Wd), 1.0, guide, None, return_tensor=True, condition=cond,
+                               initial_noise=draws[0], use_dynamic_mask=True, mask_flexivity=0.8)
+    g["loop_dynmask_last"], g["loop_dynmask_mid"] = imgs[-1].numpy(), imgs[4].numpy()
+    _, pts = S.get_deterministic_noise_tensor_repeat(B, Wd, reference_noise=guide)
+    for k, m in enumerate(S.get_dynamic_masks(8, (B, 4, Hh, Wd), pts, 0.8)):
+        g[f"dynmask_{k}"] = m[0, 0, 0].numpy().astype(np.uint8)
+    glue = ref_loader.load_glue()
+    spec = cases.spec_representation()
+    other = cases.spec_representation(seed=53)
+
+    class FakeDecoder:            # the glue only calls decoder(latents) (utils.py:221-224)
+        def __call__(self, z):
+            return spec.clone()
+
+    out = glue.encodeBatch2GradioOutput_STFT(FakeDecoder(), torch.zeros(2, 4, 128, 3), resolution=(512, 12),
+                                             original_STFT_batch=other.numpy())
+    for k, lst in zip(("mag_img", "phase_img", "signal", "mag_img_amp", "phase_img_amp", "signal_amp"), out):
+        g[f"glue_{k}"] = np.stack(lst)
+    lat = cases.small_latents().numpy()
+    g["latent_img"] = np.stack([glue.latent_representation_to_Gradio_image(lat[b].copy()) for b in range(lat.shape[0])])
+    np.savez_compressed(os.path.join(OUT, "extra.npz"), **g)
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    extra(ref)
+    if "--extra" in sys.argv:
+        print("extra.npz", os.path.getsize(os.path.join(OUT, "extra.npz")))
+        return
 
     # ---- sampler ---------------------------------------------------------------------------
     g = {}

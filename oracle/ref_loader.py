@@ -55,3 +55,18 @@ def feed_noise(sampler, draws):
 
     sampler.get_deterministic_noise_tensor_repeat = patched
     return sampler
+
+
+def load_glue():
+    """webUI/natural_language_guided_4/utils.py, imported UNMODIFIED from its file (the webUI package itself needs gradio).
+    ``librosa`` is absent from this image: the stand-in module gets ``istft`` = the oracle's restatement of
+    librosa.istft, so the reference's decode loop (utils.py:194-267) runs end to end."""
+    load()
+    import importlib.util
+    from oracle import ds_oracle as O
+    sys.modules["librosa"].istft = lambda D, hop_length=256, win_length=1024: O.istft(D, hop_length, win_length)
+    path = os.path.join(REFERENCE_ROOT, "webUI", "natural_language_guided_4", "utils.py")
+    spec = importlib.util.spec_from_file_location("_ds_ref_glue", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -125,6 +125,35 @@ def test_downsample_and_upsample():
     assert rel(nchw(outu), F.conv_transpose2d(bf(x), bf(wt), bt, stride=2, padding=1)) < TOL
 
 
+@pytest.mark.parametrize("H,W", [(16, 7), (9, 5), (32, 13)])
+def test_downsample_odd_sizes_and_padded_upsample(H, W):
+    """Odd input sizes of the 4x4 stride-2 conv (per-view extents), and the ConvTranspose written into a larger
+    zero map at pad_to_match's offset (diffusion_components.py:210-232)."""
+    from diffusynth_b200 import ops
+    N = 2
+    x = cases.randn((N, 96, H, W), 26)
+    w, b = cases.randn((96, 96, 4, 4), 17) * 0.03, cases.randn((96,), 18)
+    pc = ops.pack_conv_down(w, b)
+    ref = F.conv2d(bf(x), bf(w), b, stride=2, padding=1)
+    out = torch.zeros((N, H // 2, W // 2, 96), dtype=ops.ACT, device="cuda")
+    _run(pc, [nhwc(x)], N, H, W, out=out)
+    assert tuple(ref.shape[2:]) == (H // 2, W // 2) and rel(nchw(out), ref) < TOL
+    out2 = torch.zeros_like(out)
+    _run(pc, [nhwc(x)], N, H, W, reference=True, out=out2)
+    assert rel(nchw(out2), ref) < TOL
+    # up: the half-size map back to (2*(H//2), 2*(W//2)), placed in an H x W map
+    y = cases.randn((N, 96, H // 2, W // 2), 27)
+    wt, bt = cases.randn((96, 64, 4, 4), 19) * 0.05, cases.randn((64,), 20)
+    pcu = ops.pack_conv_up(wt, bt)
+    outu = torch.zeros((N, H, W, 64), dtype=ops.ACT, device="cuda")
+    _run(pcu, [nhwc(y)], N, H // 2, W // 2, out=outu)
+    up = F.conv_transpose2d(bf(y), bf(wt), bt, stride=2, padding=1)
+    dh, dw = H - up.shape[2], W - up.shape[3]
+    refu = F.pad(up, (dw // 2, dw - dw // 2, dh // 2, dh - dh // 2))
+    assert rel(nchw(outu), refu) < TOL
+    assert float(nchw(outu)[:, :, :, W - (dw - dw // 2):].abs().max() if dw else 0.0) == 0.0
+
+
 def test_final_conv_fp32_nchw_and_batch_mod():
     from diffusynth_b200 import ops
     N, H, W = 4, 16, 8

@@ -213,3 +213,64 @@ def test_istft_and_stft_kernels():
     # encode -> decode round trip at full size
     back = codec.spectrogram_to_waveform(enc.cuda()).cpu()
     assert float((back[:, 2048:-2048] - (w - w.mean(dim=1, keepdim=True))[:, 2048:-2048]).abs().max()) < 5e-3
+
+
+def _circ(a, b):
+    """Distance between uint8 images modulo 256 (the phase image wraps where numpy's cast does)."""
+    d = (a.astype(np.int16) - b.astype(np.int16)) % 256
+    return np.minimum(d, 256 - d)
+
+
+def test_decode_glue_images_and_lists(golden):
+    """ds_spec_images / ds_latent_image and the 6-list decode glue vs the reference's own output (tests/golden/extra.npz)
+    and the oracle.  The latent image is bit-exact (fp32 sub/div/mul); the spectrogram / phase images pass through
+    expm1f / float64 log / atan2, so a pixel may sit one level off where the value lands within float round-off of an
+    integer: at most 1 level, on fewer than 0.5 % of the pixels."""
+    from diffusynth_b200 import codec
+    g = golden["extra"]
+    spec, other = cases.spec_representation(), cases.spec_representation(seed=53)
+
+    class FakeDecoder:
+        def __call__(self, z):
+            return spec.cuda()
+
+    out = codec.encodeBatch2GradioOutput_STFT(FakeDecoder(), torch.zeros(2, 4, 128, 3), resolution=(512, 12), original_STFT_batch=other.numpy())
+    assert [len(o) for o in out] == [2] * 6
+    for key, lst in zip(("mag_img", "phase_img", "mag_img_amp", "phase_img_amp"), (out[0], out[1], out[3], out[4])):
+        got, ref = np.stack(lst), g[f"glue_{key}"]
+        assert got.dtype == np.uint8 and got.shape == ref.shape == (2, 513, 12, 3)
+        d = _circ(got, ref)
+        assert d.max() <= 1 and (d != 0).mean() < 5e-3, (key, d.max(), (d != 0).mean())
+    for key, lst in zip(("signal", "signal_amp"), (out[2], out[5])):
+        assert rel(torch.from_numpy(np.stack(lst)), torch.from_numpy(g[f"glue_{key}"])) < 1e-5
+    assert codec.encodeBatch2GradioOutput_STFT(FakeDecoder(), torch.zeros(2, 4, 128, 3))[3:] == ([], [], [])
+    lat = cases.small_latents()
+    img = codec.latent_images(lat.cuda()).cpu().numpy()
+    assert np.array_equal(img, g["latent_img"])
+    assert np.array_equal(codec.latent_representation_to_Gradio_image(lat[1]), g["latent_img"][1])
+    # full size (batch 8 of [3,512,256]) against the oracle on one sample; a constant channel gives NaN -> 0 like numpy
+    big = cases.spec_representation(B=8, T=256, seed=54)
+    mag, ph = codec.spectrogram_images(big.cuda())
+    m_ref, p_ref, _ = O.decode_products(big[5].numpy())
+    for got, ref in ((mag[5].cpu().numpy(), m_ref), (ph[5].cpu().numpy(), p_ref)):
+        d = _circ(got, ref)
+        assert d.max() <= 1 and (d != 0).mean() < 5e-3
+    flat = torch.zeros((1, 4, 16, 8)); flat[0, 1] = cases.randn((16, 8), 55)
+    assert np.array_equal(codec.latent_images(flat.cuda())[0].cpu().numpy(), O.latent_image(flat[0].numpy()))
+
+
+def test_input_batch_encode_glue():
+    """InputBatch2Encode_STFT (utils.py:131-191): latents / quantised latents from the VQGAN encoder + quantiser, and the
+    renderings of the INPUT representation."""
+    from diffusynth_b200 import VQGAN, codec
+    vq = VQGAN(**W.VQGAN_DEPLOYED, device="cuda")
+    vq.load_state_dict(W.vqgan_random_state_dict(seed=1))
+    spec = torch.from_numpy(O.waveform_to_spectrogram(cases.synthetic_wave())[None])
+    imgs, phases, signals, lat, q = codec.InputBatch2Encode_STFT(vq._encoder, spec, quantizer=vq._vq_vae)
+    assert tuple(lat.shape) == tuple(q.shape) == (1, 4, 128, 64) and len(imgs) == len(phases) == len(signals) == 1
+    m_ref, p_ref, s_ref = O.decode_products(spec[0].numpy())
+    d = _circ(imgs[0], m_ref)
+    assert d.max() <= 1 and (d != 0).mean() < 5e-3
+    assert rel(torch.from_numpy(signals[0]), torch.from_numpy(s_ref)) < 1e-5
+    with pytest.raises(NotImplementedError):
+        codec.InputBatch2Encode_STFT(vq._encoder, spec)

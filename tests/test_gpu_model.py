@@ -21,6 +21,19 @@ def _unet(cfg, sd):
     return net
 
 
+@pytest.mark.parametrize("name", ["small_w10", "deployed_w28"])
+def test_unet_odd_width_parity(name, golden):
+    """Widths whose stride-2 levels are odd (track_maker's per-note widths, track_maker.py:245): pad_to_match."""
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    net = _unet(cfg, sd)
+    eps = net.forward(x.cuda(), t.cuda(), cond.cuda()).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, cond)
+    print(f"\n[{name}] eps rel-L2 {rel(eps, ref):.3e}")
+    assert rel(eps, ref) < BF16_TOL
+    assert rel(eps, torch.from_numpy(golden["extra"][f"{name}_eps"])) < BF16_TOL       # the reference's own output
+
+
 @pytest.mark.parametrize("name", ["small_w16", "deployed_w64", "deployed_w24"])
 def test_unet_forward_parity(name, golden):
     cfg, sd, x, t, cond = cases.unet_case(name)
@@ -255,3 +268,53 @@ def test_graph_loop_variants_small_unet(mode):
     errs = [rel(a, b) for a, b in zip(imgs, ref)]
     print(f"\n[{mode}] W={Wd} latents rel-L2 per step: {['%.1e' % e for e in errs]}")
     assert max(errs) < BF16_TOL
+
+
+def test_dynamic_mask_inpaint_generic_model_matches_reference_golden(golden):
+    """inpaint_sample(use_dynamic_mask=True) with an arbitrary model vs the reference's own output (fp32 kernels)."""
+    from diffusynth_b200 import DiffSynthSampler
+    g = golden["extra"]
+    B, Wd, Hh = 2, 150, 16
+    draws = cases.randn((10, B, 4, Hh, 64), 71)
+    cond, uncond = W.synthetic_conditions(B, 16, seed=78)
+    guide = cases.randn((B, 4, Hh, 64), 72) * 0.5
+    s = DiffSynthSampler(1000, device="cuda", mute=True, max_batchsize=B, height=Hh)
+    s.noise_feed = draws[1:]
+    s.activate_classifier_free_guidance(3, uncond.cuda())
+    s.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+    imgs, _ = s.inpaint_sample(lambda x, t, c: cases.toy_model(x, t, c), (B, 4, Hh, Wd), 1.0, guide.cuda(), None, return_tensor=True,
+                               condition=cond.cuda(), initial_noise=draws[0].cuda(), use_dynamic_mask=True, mask_flexivity=0.8)
+    assert rel(imgs[-1], torch.from_numpy(g["loop_dynmask_last"])) < 1e-5 and rel(imgs[4], torch.from_numpy(g["loop_dynmask_mid"])) < 1e-5
+    _, pts = s.get_deterministic_noise_tensor_repeat(B, Wd, reference_noise=guide.cuda())
+    for k, m in enumerate(s.get_dynamic_masks(8, (B, 4, Hh, Wd), pts, 0.8)):
+        assert np.array_equal(m[0, 0, 0].cpu().numpy().astype(np.uint8), g[f"dynmask_{k}"])
+
+
+def test_note_synthesis_odd_width_parity():
+    """track_maker's per-note synthesis (track_maker.py:228-283) through TextToTimbre.synthesize_note: duration 0.9 s -> width 30
+    (levels 30/15/7/3, two of them odd), no guidance, dynamic-mask inpainting from the instrument's latent, then VQ -> decoder ->
+    iSTFT, against the oracle loop on the same host noise."""
+    from diffusynth_b200 import TextToTimbre
+    pipe = TextToTimbre.random_init(device="cuda", seed=0)
+    usd, vsd = W.unet_random_state_dict(seed=0), W.vqgan_random_state_dict(seed=1)
+    _, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
+    steps, dur = 4, 0.9
+    Wd = int(256 * ((dur + 1) / 4) / 4)
+    assert Wd == 30
+    draws = W.host_noise(21, 1 + steps, 1)
+    cond, _ = W.synthetic_conditions(1, 512)
+    inst = cases.vq_latents(B=1, seed=22)
+    out = pipe.synthesize_note(inst.cuda(), cond.cuda(), dur, sample_steps=steps, noise_feed=draws)
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    with torch.no_grad():
+        ref = O.sample_loop(lambda x, t, c: O.unet_forward(usd, x, t, c), sch, (1, 4, 128, Wd), cond, None, 1.0, draws, guide=inst,
+                            inpaint=True, dynamic_mask_flexivity=1.0)
+        q_same, _ = O.vq_quantize(out.latents.cpu(), vsd["_vq_vae._embedding.weight"])
+        spec = O.vqgan_decode(vsd, dec_plan, q_same)
+    wave_ref = O.spectrogram_to_waveform(spec[0].numpy().astype(np.float64))
+    e_lat, e_spec, e_wave = rel(out.latents, ref[-1]), rel(out.spectrograms, spec), rel(out.waveforms[0], torch.from_numpy(wave_ref))
+    print(f"\nnote (W={Wd}): latent {e_lat:.2e}  spectrogram {e_spec:.2e}  waveform {e_wave:.2e}")
+    assert tuple(out.spectrograms.shape) == (1, 3, 512, 4 * Wd) and tuple(out.waveforms.shape) == (1, 256 * (4 * Wd - 1))
+    assert torch.equal(q_same, out.quantized.cpu())
+    assert e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL

@@ -136,3 +136,54 @@ def test_istft_stft_against_torch():
     # STFT+ -> iSTFT round trip reproduces the note (interior; the zeroed DC bin and the edge frames differ)
     back = O.spectrogram_to_waveform(O.waveform_to_spectrogram(w).astype(np.float64))
     assert np.abs(back[2048:-2048] - (w - w.mean())[2048:-2048]).max() < 5e-3
+
+
+# ---- image products of the decode glue (utils.py:8-128, 194-267) and odd-width U-Net (pad_to_match) --------------------
+def test_decode_glue_products_match_reference(golden):
+    """Oracle restatement vs the 6 lists the unmodified reference glue returned (oracle/make_golden.py --extra):
+    uint8 images bit-exact, signals to float64 round-off."""
+    g = golden["extra"]
+    spec = cases.spec_representation().numpy()
+    other = cases.spec_representation(seed=53).numpy()
+    for b in range(spec.shape[0]):
+        mag, ph, sig = O.decode_products(spec[b])
+        assert np.array_equal(mag, g["glue_mag_img"][b]) and np.array_equal(ph, g["glue_phase_img"][b])
+        assert rel(sig, g["glue_signal"][b]) < 1e-12
+        swapped = spec[b].copy()
+        swapped[0] = other[b, 0]
+        mag, ph, sig = O.decode_products(swapped)
+        assert np.array_equal(mag, g["glue_mag_img_amp"][b]) and np.array_equal(ph, g["glue_phase_img_amp"][b])
+        assert rel(sig, g["glue_signal_amp"][b]) < 1e-12
+    lat = cases.small_latents().numpy()
+    for b in range(lat.shape[0]):
+        assert np.array_equal(O.latent_image(lat[b]), g["latent_img"][b])
+
+
+@pytest.mark.parametrize("name", ["small_w10", "deployed_w28"])
+def test_unet_odd_width_matches_reference(golden, name):
+    """Widths whose stride-2 levels are odd: the upsampled map is zero-padded to the skip's size (diffusion_components.py:210-232)."""
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    with torch.no_grad():
+        eps = O.unet_forward(sd, x, t, cond)
+    assert rel(eps.numpy(), golden["extra"][f"{name}_eps"]) < 2e-6
+
+
+def _dynmask_loop():
+    B, Wd, Hh = 2, 150, 16
+    draws = cases.randn((10, B, 4, Hh, 64), 71)
+    cond, uncond = W.synthetic_conditions(B, 16, seed=78)
+    guide = cases.randn((B, 4, Hh, 64), 72) * 0.5
+    s = O.Schedule(1000)
+    s.respace(list(np.linspace(0, 999, 8, dtype=np.int32)))
+    return O.sample_loop(cases.toy_model, s, (B, 4, Hh, Wd), cond, uncond, 3, draws, guide=guide, inpaint=True,
+                         dynamic_mask_flexivity=0.8)
+
+
+def test_inpaint_with_dynamic_masks(golden):
+    """use_dynamic_mask=True (DiffSynthSampler.py:365-422,483-487), the mode track_maker's per-note synthesis uses."""
+    g = golden["extra"]
+    _, pts = O.noise_layout_repeat(cases.randn((2, 4, 16, 64), 72), 2, 150)
+    for k, m in enumerate(O.dynamic_masks(8, (2, 4, 16, 150), pts, 0.8)):
+        assert np.array_equal(m[0, 0, 0].numpy().astype(np.uint8), g[f"dynmask_{k}"])
+    imgs = _dynmask_loop()
+    assert rel(imgs[-1].numpy(), g["loop_dynmask_last"]) < 2e-6 and rel(imgs[4].numpy(), g["loop_dynmask_mid"]) < 2e-6

@@ -24,7 +24,7 @@ def __getattr__(name):
         from .pipeline import TextToTimbre
         return TextToTimbre
     if name in ("spectrogram_to_waveform", "waveform_to_spectrogram", "encodeBatch2GradioOutput_STFT", "InputBatch2Encode_STFT",
-                "spectrogram_images", "latent_images", "latent_representation_to_Gradio_image"):
+                "spectrogram_images", "latent_images", "latent_representation_to_Gradio_image", "griffinlim"):
         from . import codec
         return getattr(codec, name)
     raise AttributeError(name)

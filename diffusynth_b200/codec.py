@@ -48,6 +48,38 @@ def waveform_to_spectrogram(wave: torch.Tensor, time_resolution: int = 256) -> t
 
 
 @torch.no_grad()
+def griffinlim(magnitude: torch.Tensor, n_iter: int = 32, momentum: float = 0.99, init_phase: Optional[torch.Tensor] = None,
+               generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Magnitude-only reconstruction: ``librosa.griffinlim(abs_spec, n_iter=n_iter, hop_length=256, win_length=1024)`` as the
+    reference's helpers call it (tools.py:63-76 ``save_results``, :194-217 ``nnData2Audio``, :220-223 ``amp_to_audio``;
+    librosa defaults: momentum 0.99, random initial phases, centre zero padding), batched on the GPU from the fused STFT kernels.
+    ``magnitude`` [B,512,T] holds bins 1..512 of the [513,T] matrix the reference builds (its DC row is zero, :205-210).
+    ``init_phase`` [B,512,T] in radians replaces the random start (librosa draws it from an unseeded numpy generator)."""
+    mag = magnitude.float().contiguous()
+    assert mag.dim() == 3 and mag.shape[1] == 512, "expected [B,512,T]"
+    B, _, T = mag.shape
+    dev = mag.device
+    if init_phase is None:
+        init_phase = 2 * np.pi * torch.rand((B, 512, T), device=dev, generator=generator)
+    ph = init_phase.to(dev, torch.float32)
+    spec = torch.stack([torch.log1p(mag), torch.cos(ph), torch.sin(ph)], dim=1).contiguous()
+    rebuilt = torch.empty_like(spec)
+    tprev = torch.empty((B, 512, T, 2), dtype=torch.float32, device=dev)
+    frames = torch.empty((B, T, 1024), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    L = lib.ds_istft_length(T)
+    wave = torch.empty((B, L), dtype=torch.float32, device=dev)
+    st = ops._stream()
+    for it in range(n_iter):
+        check(lib.ds_stft_decode_istft(spec.data_ptr(), frames.data_ptr(), wave.data_ptr(), B, T, st), "ds_stft_decode_istft")
+        check(lib.ds_stft_encode(wave.data_ptr(), L, rebuilt.data_ptr(), B, T, st), "ds_stft_encode")
+        check(lib.ds_griffinlim_update(rebuilt.data_ptr(), tprev.data_ptr(), spec.data_ptr(), float(momentum), 1 if it == 0 else 0, B, T, st),
+              "ds_griffinlim_update")
+    check(lib.ds_stft_decode_istft(spec.data_ptr(), frames.data_ptr(), wave.data_ptr(), B, T, st), "ds_stft_decode_istft")
+    return wave
+
+
+@torch.no_grad()
 def spectrogram_images(spec: torch.Tensor):
     """[B,3,512,T] fp32 spectral representation -> (dB-magnitude image, phase image), uint8 [B,513,T,3] each: what
     ``spectrogram_to_Gradio_image(np.abs(D))`` / ``phase_to_Gradio_image(np.angle(D))`` (utils.py:8-91) give for

@@ -138,6 +138,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
 // ---------------------------------------------------------------------------------------------
 static constexpr int DT_HALO = 22, DT_STAGES = 2;
 static constexpr bool DW_HACC_DEFAULT = false;
+static constexpr bool DW_MMA_DEFAULT = false;
 static constexpr int DT_TILE_BYTES = DT_HALO * DT_HALO * DW_CB * 2;     // 30976, a multiple of 128
 static constexpr int DT_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + 49 * (DW_CB / 2) * 8 + DT_STAGES * 8 + 128;
 
@@ -312,6 +313,223 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// dwconv7 on the warp-level tensor cores (mma.sync.m16n8k16, fp32 accumulate), Toeplitz formulation.
+// A depthwise convolution has no channel contraction, so the block-diagonal GEMM (M = pixels, K = taps x channels) wastes 7/8
+// of every MMA (measured: slower than FFMA2, see above).  Here the contraction runs over the INPUT COLUMN instead: for one
+// channel and one kernel row dy,   out[y, x] += sum_k In[y + dy, k] * T_dy[k, x],   T_dy[k, x] = w[dy][k - x] (0 <= k - x <= 6),
+// i.e. a [16 rows x 16 input columns] x [16 x 8] product per 16 x 8 outputs: 7 of the 16 k of every row of T are non-zero for
+// every output column (44 % of the MMA is useful work), 14 MMAs per channel and 16 x 16 output tile instead of 784 FFMA2 lanes.
+// The operands of such an MMA are x-contiguous for a fixed channel, the tensors are channels-last: each TMA-staged halo tile
+// [22 y][22 x][32 c] is first transposed into per-channel planes [c][22 y][24 x] with ldmatrix.trans (an 8 pixels x 8 channels
+// block per matrix), the fp32 results go back through per-channel planes [c][16 y][16 x] and a second ldmatrix.trans that
+// yields channel pairs per pixel for the channels-last stores.  A warp owns 4 of the block's 32 channels and keeps their
+// 7 x 2 Toeplitz B fragments in registers for the whole (persistent) kernel.  Plane pitches (1072 / 528 bytes) make every
+// ldmatrix and every 32-bit plane store conflict-free.  The output planes alias the raw stage that was just transposed.
+// ---------------------------------------------------------------------------------------------
+static constexpr int DM_PLANE = 22 * 48 + 16;      // bytes per input plane: 22 rows of 24 halves, padded
+static constexpr int DM_OPLANE = 16 * 32 + 16;     // bytes per output plane: 16 rows of 16 halves, padded
+static constexpr int DM_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + DW_CB * DM_PLANE + DW_CB * DM_OPLANE + 64 + DT_STAGES * 8 + 128;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef DS_OPERANDS_BF16
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+#else
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+#endif
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack16_sat(float lo, float hi) {
+#ifdef DS_OPERANDS_BF16
+  return pack16(lo, hi);
+#else
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
+}
+// address of 16-byte chunk `chunk` of 64-byte row `row` of a TMA SWIZZLE_64B box at `base`: address bits [4:5] ^= bits [7:8]
+__device__ __forceinline__ uint32_t swz64(uint32_t base, int row, int chunk) {
+  const uint32_t a = base + (uint32_t)(row * 64 + chunk * 16);
+  return a ^ (((a >> 7) & 3u) << 4);
+}
+
+__global__ void __launch_bounds__(256, 2)
+dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
+                   const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
+                   act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w,
+                   int tiles, int N) {
+  extern __shared__ uint8_t dm_smem_raw[];
+  uint8_t* smem = dm_smem_raw + ((128u - (smem_u32(dm_smem_raw) & 127u)) & 127u);
+  const uint32_t s_raw = smem_u32(smem);                                      // [stage][22 y][22 x][32 c] halves, 64B-swizzled by the TMA unit
+  const uint32_t s_plane = s_raw + DT_STAGES * DT_TILE_BYTES;                 // [32 c][DM_PLANE]
+  const uint32_t s_oplane = s_plane + DW_CB * DM_PLANE;                       // [32 c][DM_OPLANE]
+  const uint32_t s_zero = s_oplane + DW_CB * DM_OPLANE;                       // 64 zero bytes
+  uint8_t* tail = smem + DT_STAGES * DT_TILE_BYTES + DW_CB * DM_PLANE + DW_CB * DM_OPLANE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail + 64);
+  __shared__ float s_red[2][16];
+  const int C = C0 + C1;
+  const int cblk = blockIdx.y, c0 = cblk * DW_CB;
+  const CUtensorMap* map = c0 < C0 ? &map0 : &map1;
+  const int cs0 = c0 < C0 ? c0 : c0 - C0;
+  const int total = N * tiles;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(map);
+    for (int s = 0; s < DT_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(tail)[threadIdx.x] = 0u;
+
+  // Toeplitz B fragments of this warp's 4 channels.  b0 holds T[k = 2q (+1)][n = g], b1 holds T[k = 2q + 8 (+1)][n = g] with
+  // T[k][n] = w[dy][k - n] for 0 <= k - n <= 6: b0 is non-zero only for g <= 2q + 1 and b1 only for g >= 2q + 2, so one register
+  // per (channel, kernel row) and two lane masks carry both.
+  const uint32_t m0 = g <= 2 * q + 1 ? 0xffffffffu : 0u, m1 = ~m0;
+  uint32_t bfr[4][7];
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci) {
+    const int c = c0 + 4 * warp + ci;
+#pragma unroll
+    for (int dy = 0; dy < 7; ++dy) {
+      const int d0 = 2 * q - g + (m0 ? 0 : 8), d1 = d0 + 1;
+      const float w0 = (d0 >= 0 && d0 < 7) ? __ldg(weight + (size_t)(dy * 7 + d0) * C + c) : 0.f;
+      const float w1 = (d1 >= 0 && d1 < 7) ? __ldg(weight + (size_t)(dy * 7 + d1) * C + c) : 0.f;
+      bfr[ci][dy] = pack16(w0, w1);
+    }
+  }
+  __syncthreads();
+
+  auto issue = [&](int item, int stage) {
+    const int n = item / tiles, t = item - n * tiles;
+    const int th = t / tiles_w, tw = t - th * tiles_w;
+    const int nsrc = (src_batch_mod > 0 && c0 < C0) ? n % src_batch_mod : n;
+    mbar_expect_tx(&full[stage], DT_TILE_BYTES);
+    tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
+  };
+  if (threadIdx.x == 0) {
+    if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
+    if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+  }
+
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;
+  const int t_i = lane & 7, t_j = lane >> 3;                 // transposes: lane supplies row t_i of matrix t_j
+  int it = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const int n = item / tiles, t = item - n * tiles;
+    const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
+    const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
+    mbar_wait(&full[stage], (uint32_t)(it >> 1) & 1u);
+    const uint32_t raw = s_raw + stage * DT_TILE_BYTES;
+
+    // ---- channels-last halo tile -> per-channel planes.  Warp w takes rows w, w + 8, w + 16; per row three 8-pixel groups; one
+    // ldmatrix.x4.trans per group: matrix j = channel chunk j, its 8 rows = the 8 pixels; afterwards lane (g, q) holds pixels
+    // (2q, 2q + 1) of channel 8j + g.
+    for (int y = warp; y < DT_HALO; y += 8) {
+      const uint32_t dst = s_plane + (uint32_t)(g * DM_PLANE + y * 48 + q * 4);
+#pragma unroll
+      for (int xg = 0; xg < 3; ++xg) {
+        const int x = 8 * xg + t_i;
+        const uint32_t addr = (xg < 2 || x < DT_HALO) ? swz64(raw, y * DT_HALO + x, t_j) : s_zero;
+        uint32_t r[4];
+        ldsm_x4_t(r, addr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts32(dst + (uint32_t)(8 * j * DM_PLANE + xg * 16), r[j]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();          // planes complete; this raw stage is free again; everyone is done with the previous output planes
+    if (threadIdx.x == 0 && item + 2 * (int)gridDim.x < total) issue(item + 2 * gridDim.x, stage);
+
+    // ---- 4 channels per warp, two at a time: 7 kernel rows x 2 column halves of m16n8k16 each
+    const bool full_tile = h0 + 16 <= H && w0 + DW_TW <= W;
+    float s = 0.f, sq = 0.f;
+#pragma unroll
+    for (int cp = 0; cp < 2; ++cp) {
+      float d[2][2][4];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const float bias = __ldg(tb + c0 + 4 * warp + 2 * cp + cc);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) d[cc][h][k] = bias;
+      }
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ci = 2 * cp + cc;
+          const uint32_t pl = s_plane + (uint32_t)((4 * warp + ci) * DM_PLANE + (a_row + dy) * 48 + a_chunk * 16);
+          uint32_t a[4], e[4];
+          ldsm_x4(a, pl);            // rows 0-7 / 8-15 of input columns 0-7 and 8-15
+          ldsm_x4(e, pl + 16);       // the same rows of input columns 8-15 and 16-23
+          const uint32_t b0 = bfr[ci][dy] & m0, b1 = bfr[ci][dy] & m1;
+          mma16816(d[cc][0], a, b0, b1);      // output columns 0-7
+          mma16816(d[cc][1], e, b0, b1);      // output columns 8-15
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint32_t op = s_oplane + (uint32_t)((4 * warp + 2 * cp + cc) * DM_OPLANE + g * 32 + q * 4);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float v0 = d[cc][h][2 * rr], v1 = d[cc][h][2 * rr + 1];
+            if (full_tile) {
+              s += v0 + v1;
+              sq = fmaf(v0, v0, fmaf(v1, v1, sq));
+            } else if (h0 + g + 8 * rr < H) {
+              const int x = w0 + 8 * h + 2 * q;
+              if (x < W) { s += v0; sq = fmaf(v0, v0, sq); }
+              if (x + 1 < W) { s += v1; sq = fmaf(v1, v1, sq); }
+            }
+            sts32(op + (uint32_t)(rr * 8 * 32 + h * 16), pack16_sat(v0, v1));
+          }
+      }
+    }
+    float* red = s_red[it & 1];
+    if (stats != nullptr) {
+      s = warp_sum(s);
+      sq = warp_sum(sq);
+      if (lane == 0) { red[warp] = s; red[8 + warp] = sq; }
+    }
+    __syncthreads();          // output planes complete (and the per-warp partials visible); the input planes are free again
+
+    // ---- planes -> channels-last: matrix j = channels 8j..8j+7 of one (row, 8-pixel group); .trans gives channel pairs per pixel
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int y = 2 * warp + (u >> 1), xc = u & 1;
+      uint32_t r[4];
+      ldsm_x4_t(r, s_oplane + (uint32_t)(lane * DM_OPLANE + y * 32 + xc * 16));      // lane = 8j + i: channel row i of matrix j
+      const int yy = h0 + y, xx = w0 + 8 * xc + g;
+      if (yy < H && xx < W) {
+        uint32_t* o = reinterpret_cast<uint32_t*>(out + (((size_t)n * H + yy) * W + xx) * C + c0) + q;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[4 * j] = r[j];
+      }
+    }
+    if (stats != nullptr && threadIdx.x < 32) {
+      float ts = 0.f, tq = 0.f;
+      if (threadIdx.x == 0)
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+      const int slots = tiles * gridDim.y;
+      stats_publish(stats_sample(stats, slots, n), slots, cblk * tiles + t, ts, tq, stats_inv_count, eps, threadIdx.x);
+    }
+  }
+}
+
 static inline int dw_rows_per_thread(int H) {
   static const int forced = [] { const char* e = getenv("DS_DWCONV_R"); return e ? atoi(e) : 0; }();
   if (forced == 1 || forced == 2) return forced;
@@ -451,6 +669,8 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
       tma_attr_set = true;
     }
+    // DS_DWCONV_MMA=0/1: Toeplitz formulation on mma.sync (dwconv7_mma_kernel; its halo tile is staged with the 64-byte swizzle)
+    static const bool use_mma = [] { const char* e = getenv("DS_DWCONV_MMA"); return e ? atoi(e) != 0 : DW_MMA_DEFAULT; }();
     CUtensorMap maps[2];
     for (int sidx = 0; sidx < 2; ++sidx) {
       const int nsamp = (sidx == 0 && src_batch_mod > 0) ? src_batch_mod : N;
@@ -462,7 +682,8 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       const cuuint32_t box[4] = {(cuuint32_t)DW_CB, (cuuint32_t)DT_HALO, (cuuint32_t)DT_HALO, 1};
       const cuuint32_t estr[4] = {1, 1, 1, 1};
       const CUresult r = encode(&maps[sidx], kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                                4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                use_mma ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       DS_REQUIRE(r == CUDA_SUCCESS, "ds_dwconv7: cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d)", (int)r, Cs, W, H);
     }
@@ -471,6 +692,21 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
     int gx = 3 * num_sms() / cblks;      // never more blocks than resident slots: a straggler wave would cost a whole pass
     if (gx > work) gx = (int)work;
     if (gx < 1) gx = 1;
+    if (use_mma) {
+      static bool mma_attr_set = false;
+      if (!mma_attr_set) {
+        DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
+        mma_attr_set = true;
+      }
+      int gm = 2 * num_sms() / cblks;
+      if (gm > work) gm = (int)work;
+      if (gm < 1) gm = 1;
+      dwconv7_mma_kernel<<<dim3(gm, cblks), 256, DM_SMEM_BYTES, (cudaStream_t)stream>>>(
+          maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
+          H, W, tiles_w, tiles, N);
+      DS_CHECK_CUDA(cudaGetLastError());
+      return DS_OK;
+    }
     // DS_DWCONV_HACC=1: packed fp16 accumulation over pairs of input rows (see hfma2_acc); fp16 operand builds only
     static const bool hacc = [] { const char* e = getenv("DS_DWCONV_HACC"); return kOperandIsFp16 && (e ? atoi(e) != 0 : DW_HACC_DEFAULT); }();
     auto kern = hacc ? dwconv7_tma_kernel<true> : dwconv7_tma_kernel<false>;

@@ -153,6 +153,27 @@ stft_encode_kernel(const float* __restrict__ wave, long long L, float* __restric
   }
 }
 
+// ---- Griffin-Lim phase update (librosa.griffinlim's loop body, called from tools.py:63-76,194-223 with hop 256 / win 1024) ----
+// rebuilt = STFT(iSTFT(S * angles)) arrives as a spectral representation (log1p|.|, cos, sin); with momentum m
+//   a = rebuilt - m/(1+m) * tprev;   angles = a / (|a| + tiny);   tprev <- rebuilt
+// and the new (cos, sin) go into channels 1, 2 of the working representation whose channel 0 holds log1p(S).
+__global__ void griffinlim_update_kernel(const float* __restrict__ rebuilt, float2* __restrict__ tprev, float* __restrict__ spec,
+                                         float coef, int first, long long plane /* 512*T */, long long total /* B*plane */) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / plane, k = i - b * plane;
+    const float* rb = rebuilt + b * 3 * plane + k;
+    const float mag = expm1f(__ldg(rb));
+    const float2 r = make_float2(mag * __ldg(rb + plane), mag * __ldg(rb + 2 * plane));
+    float2 a = r;
+    if (!first) { const float2 p = tprev[i]; a.x -= coef * p.x; a.y -= coef * p.y; }
+    tprev[i] = r;
+    const float d = sqrtf(a.x * a.x + a.y * a.y) + 1.17549435e-38f;
+    float* sp = spec + b * 3 * plane + k;
+    sp[plane] = a.x / d;
+    sp[2 * plane] = a.y / d;
+  }
+}
+
 __global__ void twiddle_init_kernel(float2* tw512, float2* tw1024) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 256) { double s, c; sincospi((double)i / 256.0, &s, &c); tw512[i] = make_float2((float)c, (float)s); }
@@ -214,6 +235,20 @@ int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int T
   const size_t smem = 2 * FR * NH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(stft_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   stft_encode_kernel<<<dim3((Tpad + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_wave, L, d_spec, T, Tpad, tw512, tw1024);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+/* One Griffin-Lim phase update on spectral representations [B,3,512,T] (see griffinlim_update_kernel):
+   d_rebuilt = ds_stft_encode(ds_stft_decode_istft(d_spec)); d_tprev fp32 [B,512,T,2] carries the previous rebuilt STFT. */
+int ds_griffinlim_update(const float* d_rebuilt, float* d_tprev, float* d_spec, float momentum, int first, int B, int T, void* stream) {
+  DS_REQUIRE(d_rebuilt && d_tprev && d_spec && B > 0 && T > 0 && momentum >= 0.f, "ds_griffinlim_update: bad arguments");
+  const long long plane = (long long)NH * T, total = plane * B;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  griffinlim_update_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_rebuilt, reinterpret_cast<float2*>(d_tprev), d_spec,
+                                                                                momentum / (1.0f + momentum), first, plane, total);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -180,6 +180,11 @@ long long ds_istft_length(int T);
 int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, int B, int T, void* stream);
 /* librosa.stft(n_fft 1024, hop 256) + pad_STFT + encode_stft (sound2sound_with_text.py:85-94; tools.py:170-182,320-331). */
 int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int Tpad, void* stream);
+/* Griffin-Lim phase update (the loop body of librosa.griffinlim as called by tools.py:63-76,194-223: hop 256, win 1024,
+   momentum 0.99): d_rebuilt = ds_stft_encode(ds_stft_decode_istft(d_spec)) as [B,3,512,T]; d_tprev fp32 [B,512,T,2] holds the
+   previous rebuilt STFT (ignored and initialised when first != 0); channels 1, 2 (cos, sin) of d_spec are overwritten. */
+int ds_griffinlim_update(const float* d_rebuilt, float* d_tprev, float* d_spec, float momentum, int first, int B, int T,
+                         void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * Image products of the decode glue (webUI/natural_language_guided_4/utils.py), batched:

@@ -569,3 +569,27 @@ def decode_products(spec3: np.ndarray):
     (utils.py:229-241): -> (spectrogram image, phase image, waveform)."""
     D = depad_stft(decode_stft(spec3))
     return spectrogram_image(np.abs(D)), phase_image(np.angle(D)), istft(D)
+
+
+# --------------------------------------------------------------------------------------
+# 6. Griffin-Lim   (librosa.griffinlim as called at tools.py:75,214,222: n_iter 32/50, hop 256, win 1024)
+# --------------------------------------------------------------------------------------
+
+def griffinlim(S: np.ndarray, init_phase: np.ndarray, n_iter: int = 32, momentum: float = 0.99) -> np.ndarray:
+    """Third-party arithmetic (librosa, unpinned, absent here: parity unpinned).  Restatement of the published
+    fast Griffin-Lim loop (Perraudin et al. 2013) as librosa >= 0.7 implements it: angles_0 = exp(i * init_phase)
+    (librosa draws init_phase = 2*pi*U[0,1) from an unseeded generator); each iteration
+    rebuilt = stft(istft(S * angles)); angles = rebuilt - momentum/(1+momentum) * tprev (from the second iteration on);
+    angles /= |angles| + tiny(float32); tprev = rebuilt; result = istft(S * angles).  S is the [513, T] magnitude."""
+    angles = np.exp(1j * init_phase) * S
+    tprev = None
+    eps = np.finfo(np.float32).tiny
+    for _ in range(n_iter):
+        rebuilt = stft(istft(angles), pad_mode="constant")
+        angles = rebuilt.copy()
+        if tprev is not None:
+            angles = angles - (momentum / (1 + momentum)) * tprev
+        angles = angles / (np.abs(angles) + eps)
+        angles = angles * S
+        tprev = rebuilt
+    return istft(angles)

@@ -294,9 +294,11 @@ def test_note_synthesis_odd_width_parity():
     """track_maker's per-note synthesis (track_maker.py:228-283) through TextToTimbre.synthesize_note: duration 0.9 s -> width 30
     (levels 30/15/7/3, two of them odd), no guidance, dynamic-mask inpainting from the instrument's latent, then VQ -> decoder ->
     iSTFT, against the oracle loop on the same host noise."""
-    from diffusynth_b200 import TextToTimbre
-    pipe = TextToTimbre.random_init(device="cuda", seed=0)
+    from diffusynth_b200 import TextToTimbre, VQGAN
     usd, vsd = W.unet_random_state_dict(seed=0), W.vqgan_random_state_dict(seed=1)
+    vq = VQGAN(**W.VQGAN_DEPLOYED, device="cuda")
+    vq.load_state_dict(vsd)
+    pipe = TextToTimbre(_unet(W.UNET_DEPLOYED, usd), vq)
     _, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
     steps, dur = 4, 0.9
     Wd = int(256 * ((dur + 1) / 4) / 4)

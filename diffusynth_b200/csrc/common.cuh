@@ -157,6 +157,38 @@ __device__ __forceinline__ void stats_publish(float2* sb, int slots, int slot, f
   }
 }
 
+// Run form: one block contributes the (s, q) of `k` consecutive slots [slot, slot + k) of one sample with a single fence + atomic:
+// the sum goes to the first slot, the others are cleared, the arrival counter advances by k.  The fence + atomic round trip of a
+// per-tile publish (2-3 us behind the block's own output stores) otherwise sits on the critical path of every tile.
+__device__ __forceinline__ void stats_publish_run(float2* sb, int slots, int slot, int k, float s, float q, float inv_count, float eps, int lane) {
+  for (int i = lane; i < k; i += 32) sb[2 + slot + i] = i == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+  __syncwarp();
+  unsigned old = 0;
+  if (lane == 0) {
+    __threadfence();
+    old = atomicAdd(reinterpret_cast<unsigned*>(&sb[1]), (unsigned)k);
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  if (old + (unsigned)k == (unsigned)slots) {
+    __threadfence();
+    double ds = 0.0, dq = 0.0;
+    for (int i = lane; i < slots; i += 32) {
+      const float2 v = __ldcg(sb + 2 + i);
+      ds += (double)v.x;
+      dq += (double)v.y;
+    }
+    ds = warp_sum(ds);
+    dq = warp_sum(dq);
+    if (lane == 0) {
+      const double mean = ds * (double)inv_count;
+      double var = dq * (double)inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      sb[0] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+      *reinterpret_cast<unsigned*>(&sb[1]) = 0u;
+    }
+  }
+}
+
 // Branch-free GELU(erf): erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), straight-line code so the
 // 16 independent elements of an epilogue chunk interleave.
 __device__ __forceinline__ float gelu_erf_fast(float x) {

@@ -138,7 +138,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
 // ---------------------------------------------------------------------------------------------
 static constexpr int DT_HALO = 22, DT_STAGES = 2;
 static constexpr bool DW_HACC_DEFAULT = false;
-static constexpr bool DW_MMA_DEFAULT = false;
+static constexpr bool DW_MMA_DEFAULT = true;
 static constexpr int DT_TILE_BYTES = DT_HALO * DT_HALO * DW_CB * 2;     // 30976, a multiple of 128
 static constexpr int DT_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + 49 * (DW_CB / 2) * 8 + DT_STAGES * 8 + 128;
 
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256, 2)
 dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
                    const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
                    act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w,
-                   int tiles, int N) {
+                   int tiles, int N, int dbg) {
   extern __shared__ uint8_t dm_smem_raw[];
   uint8_t* smem = dm_smem_raw + ((128u - (smem_u32(dm_smem_raw) & 127u)) & 127u);
   const uint32_t s_raw = smem_u32(smem);                                      // [stage][22 y][22 x][32 c] halves, 64B-swizzled by the TMA unit
@@ -416,15 +416,21 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     mbar_expect_tx(&full[stage], DT_TILE_BYTES);
     tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
   };
+  // each block walks a contiguous run of (sample, tile) items: neighbouring halos stay in L2 and the statistics of a sample
+  // are published once per run instead of once per tile
+  const int per_block = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int item0 = blockIdx.x * per_block, item1 = min(item0 + per_block, total);
   if (threadIdx.x == 0) {
-    if ((int)blockIdx.x < total) issue(blockIdx.x, 0);
-    if ((int)(blockIdx.x + gridDim.x) < total) issue(blockIdx.x + gridDim.x, 1);
+    if (item0 < item1) issue(item0, 0);
+    if (item0 + 1 < item1) issue(item0 + 1, 1);
   }
+  float run_s = 0.f, run_q = 0.f;      // warp 0: statistics of the current run of tiles of one sample
+  int run_first = -1;
 
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;
   const int t_i = lane & 7, t_j = lane >> 3;                 // transposes: lane supplies row t_i of matrix t_j
   int it = 0;
-  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+  for (int item = item0; item < item1; ++item, ++it) {
     const int stage = it & 1;
     const int n = item / tiles, t = item - n * tiles;
     const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
@@ -435,7 +441,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     // ---- channels-last halo tile -> per-channel planes.  Warp w takes rows w, w + 8, w + 16; per row three 8-pixel groups; one
     // ldmatrix.x4.trans per group: matrix j = channel chunk j, its 8 rows = the 8 pixels; afterwards lane (g, q) holds pixels
     // (2q, 2q + 1) of channel 8j + g.
-    for (int y = warp; y < DT_HALO; y += 8) {
+    for (int y = warp; y < ((dbg & 8) ? 0 : DT_HALO); y += 8) {
       const uint32_t dst = s_plane + (uint32_t)(g * DM_PLANE + y * 48 + q * 4);
 #pragma unroll
       for (int xg = 0; xg < 3; ++xg) {
@@ -449,7 +455,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();          // planes complete; this raw stage is free again; everyone is done with the previous output planes
-    if (threadIdx.x == 0 && item + 2 * (int)gridDim.x < total) issue(item + 2 * gridDim.x, stage);
+    if (threadIdx.x == 0 && item + 2 < item1) issue(item + 2, stage);
 
     // ---- 4 channels per warp, two at a time: 7 kernel rows x 2 column halves of m16n8k16 each
     const bool full_tile = h0 + 16 <= H && w0 + DW_TW <= W;
@@ -467,6 +473,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       }
 #pragma unroll
       for (int dy = 0; dy < 7; ++dy) {
+        if (dbg & 1) break;
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const int ci = 2 * cp + cc;
@@ -514,18 +521,22 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       uint32_t r[4];
       ldsm_x4_t(r, s_oplane + (uint32_t)(lane * DM_OPLANE + y * 32 + xc * 16));      // lane = 8j + i: channel row i of matrix j
       const int yy = h0 + y, xx = w0 + 8 * xc + g;
-      if (yy < H && xx < W) {
+      if (yy < H && xx < W && !(dbg & 2)) {
         uint32_t* o = reinterpret_cast<uint32_t*>(out + (((size_t)n * H + yy) * W + xx) * C + c0) + q;
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[4 * j] = r[j];
       }
     }
-    if (stats != nullptr && threadIdx.x < 32) {
-      float ts = 0.f, tq = 0.f;
+    if (stats != nullptr && threadIdx.x < 32 && !(dbg & 4)) {
       if (threadIdx.x == 0)
-        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
-      const int slots = tiles * gridDim.y;
-      stats_publish(stats_sample(stats, slots, n), slots, cblk * tiles + t, ts, tq, stats_inv_count, eps, threadIdx.x);
+        for (int i = 0; i < 8; ++i) { run_s += red[i]; run_q += red[8 + i]; }
+      if (run_first < 0) run_first = t;
+      if (t == tiles - 1 || item + 1 == item1) {      // last tile of this sample in the run
+        const int slots = tiles * gridDim.y;
+        stats_publish_run(stats_sample(stats, slots, n), slots, cblk * tiles + run_first, t - run_first + 1, run_s, run_q, stats_inv_count, eps,
+                          threadIdx.x);
+        run_s = 0.f; run_q = 0.f; run_first = -1;
+      }
     }
   }
 }
@@ -703,7 +714,7 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       if (gm < 1) gm = 1;
       dwconv7_mma_kernel<<<dim3(gm, cblks), 256, DM_SMEM_BYTES, (cudaStream_t)stream>>>(
           maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
-          H, W, tiles_w, tiles, N);
+          H, W, tiles_w, tiles, N, [] { const char* e = getenv("DS_DW_DBG"); return e ? atoi(e) : 0; }());
       DS_CHECK_CUDA(cudaGetLastError());
       return DS_OK;
     }

@@ -157,12 +157,12 @@ __device__ __forceinline__ void stats_publish(float2* sb, int slots, int slot, f
   }
 }
 
-// Run form: one block contributes the (s, q) of `k` consecutive slots [slot, slot + k) of one sample with a single fence + atomic:
-// the sum goes to the first slot, the others are cleared, the arrival counter advances by k.  The fence + atomic round trip of a
-// per-tile publish (2-3 us behind the block's own output stores) otherwise sits on the critical path of every tile.
-__device__ __forceinline__ void stats_publish_run(float2* sb, int slots, int slot, int k, float s, float q, float inv_count, float eps, int lane) {
-  for (int i = lane; i < k; i += 32) sb[2 + slot + i] = i == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
-  __syncwarp();
+// Run form: a block that produced `k` slots of one sample (each written with a plain store by lane 0 of the calling warp)
+// announces them with ONE fence + atomic; the slots, and therefore the slot-ordered double-precision reduction of the last
+// arriver, are exactly those of the per-tile protocol (results do not depend on how tiles are grouped into runs).  The fence +
+// atomic round trip of a per-tile publish (2-3 us behind the block's own output stores) otherwise sits on the critical path
+// of every tile.
+__device__ __forceinline__ void stats_arrive_run(float2* sb, int slots, int k, float inv_count, float eps, int lane) {
   unsigned old = 0;
   if (lane == 0) {
     __threadfence();

@@ -424,8 +424,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     if (item0 < item1) issue(item0, 0);
     if (item0 + 1 < item1) issue(item0 + 1, 1);
   }
-  float run_s = 0.f, run_q = 0.f;      // warp 0: statistics of the current run of tiles of one sample
-  int run_first = -1;
+  int run_len = 0;      // warp 0: tiles of the current sample whose statistics slots are written but not yet announced
 
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;
   const int t_i = lane & 7, t_j = lane >> 3;                 // transposes: lane supplies row t_i of matrix t_j
@@ -528,14 +527,17 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       }
     }
     if (stats != nullptr && threadIdx.x < 32 && !(dbg & 4)) {
-      if (threadIdx.x == 0)
-        for (int i = 0; i < 8; ++i) { run_s += red[i]; run_q += red[8 + i]; }
-      if (run_first < 0) run_first = t;
+      const int slots = tiles * gridDim.y;
+      float2* sb = stats_sample(stats, slots, n);
+      if (threadIdx.x == 0) {
+        float ts = 0.f, tq = 0.f;
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+        sb[2 + cblk * tiles + t] = make_float2(ts, tq);       // this tile's slot: a plain store, announced with the run
+      }
+      ++run_len;
       if (t == tiles - 1 || item + 1 == item1) {      // last tile of this sample in the run
-        const int slots = tiles * gridDim.y;
-        stats_publish_run(stats_sample(stats, slots, n), slots, cblk * tiles + run_first, t - run_first + 1, run_s, run_q, stats_inv_count, eps,
-                          threadIdx.x);
-        run_s = 0.f; run_q = 0.f; run_first = -1;
+        stats_arrive_run(sb, slots, run_len, stats_inv_count, eps, threadIdx.x);
+        run_len = 0;
       }
     }
   }

@@ -193,19 +193,23 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     mbar_expect_tx(&full[stage], DT_TILE_BYTES);
     tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
   };
+  // contiguous run of (sample, tile) items per block; statistics slots are announced once per run (see stats_arrive_run)
+  const int per_block = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int item0 = blockIdx.x * per_block, item1 = min(item0 + per_block, total);
   if (threadIdx.x == 0)
     for (int k = 0; k < DT_STAGES - 1; ++k)
-      if (blockIdx.x + k * gridDim.x < total) issue(blockIdx.x + k * gridDim.x, k);
+      if (item0 + k < item1) issue(item0 + k, k);
+  int run_len = 0;
 
   const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
   const int row0 = (pt & 7) * 2, col0 = (pt >> 3) * 8;
   const int c = c0 + 2 * cp;
   int it = 0;
-  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+  for (int item = item0; item < item1; ++item, ++it) {
     const int stage = it % DT_STAGES;
     if (threadIdx.x == 0) {
-      const int nxt = item + (DT_STAGES - 1) * gridDim.x;      // its stage was released by the barrier that ended iteration it-1
-      if (nxt < total) issue(nxt, (it + DT_STAGES - 1) % DT_STAGES);
+      const int nxt = item + (DT_STAGES - 1);      // its stage was released by the barrier that ended iteration it-1
+      if (nxt < item1) issue(nxt, (it + DT_STAGES - 1) % DT_STAGES);
     }
     const int n = item / tiles, t = item - n * tiles;
     const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
@@ -303,12 +307,19 @@ dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       if ((threadIdx.x & 31) == 0) { red[warp] = s; red[8 + warp] = q; }
     }
     __syncthreads();     // every thread is done with this stage before it is refilled; the per-warp partials are visible
-    if (stats != nullptr && threadIdx.x < 32) {     // warp 0 publishes while the others start the next tile (which uses the other s_red)
-      float ts = 0.f, tq = 0.f;
-      if (threadIdx.x == 0)
-        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+    if (stats != nullptr && threadIdx.x < 32) {     // warp 0 writes the tile's slot while the others start the next tile (which uses the other s_red)
       const int slots = tiles * gridDim.y;
-      stats_publish(stats_sample(stats, slots, n), slots, cblk * tiles + t, ts, tq, stats_inv_count, eps, threadIdx.x);
+      float2* sb = stats_sample(stats, slots, n);
+      if (threadIdx.x == 0) {
+        float ts = 0.f, tq = 0.f;
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
+        sb[2 + cblk * tiles + t] = make_float2(ts, tq);
+      }
+      ++run_len;
+      if (t == tiles - 1 || item + 1 == item1) {
+        stats_arrive_run(sb, slots, run_len, stats_inv_count, eps, threadIdx.x);
+        run_len = 0;
+      }
     }
   }
 }

@@ -346,6 +346,9 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
 __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -438,6 +441,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   int run_len = 0;      // warp 0: tiles of the current sample whose statistics slots are written but not yet announced
 
   const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_chunk = lane >> 4;
+  const uint32_t pl2 = s_plane + (uint32_t)(a_row * 48 + 32);      // ldmatrix.x2: lanes 0-15 address rows 0-15 of columns 16-23
   const int t_i = lane & 7, t_j = lane >> 3;                 // transposes: lane supplies row t_i of matrix t_j
   int it = 0;
   for (int item = item0; item < item1; ++item, ++it) {
@@ -488,9 +492,10 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         for (int cc = 0; cc < 2; ++cc) {
           const int ci = 2 * cp + cc;
           const uint32_t pl = s_plane + (uint32_t)((4 * warp + ci) * DM_PLANE + (a_row + dy) * 48 + a_chunk * 16);
-          uint32_t a[4], e[4];
+          uint32_t a[4], e2[2];
           ldsm_x4(a, pl);            // rows 0-7 / 8-15 of input columns 0-7 and 8-15
-          ldsm_x4(e, pl + 16);       // the same rows of input columns 8-15 and 16-23
+          ldsm_x2(e2, pl2 + (uint32_t)((4 * warp + ci) * DM_PLANE + dy * 48));      // the same rows of input columns 16-23
+          const uint32_t e[4] = {a[2], a[3], e2[0], e2[1]};      // (shared memory is the busiest unit: 6 matrices per kernel row, not 8)
           const uint32_t b0 = bfr[ci][dy] & m0, b1 = bfr[ci][dy] & m1;
           mma16816(d[cc][0], a, b0, b1);      // output columns 0-7
           mma16816(d[cc][1], e, b0, b1);      // output columns 8-15

@@ -4,8 +4,9 @@
 //   librosa.stft(y, n_fft=1024, hop_length=256, win_length=1024) + pad_STFT + encode_stft
 //                                    webUI/natural_language_guided_4/sound2sound_with_text.py:85-94; tools.py:170-182,320-331
 // n_fft = 1024 (fixed by the 512 (+DC) frequency rows of the spectral representation), hop = 256,
-// periodic Hann window.  Real transforms run as 512-point complex FFTs (even/odd packing) with
-// radix-2 Stockham passes in shared memory; everything is fp32 (the reference runs float64 on the CPU).
+// periodic Hann window.  Real transforms run as 512-point complex FFTs (even/odd packing), one frame per warp: radix-2
+// butterflies in registers and across lanes with warp shuffles, one staging pass through shared memory for the natural-order
+// result; everything is fp32 (the reference runs float64 on the CPU).
 #include "common.cuh"
 #include "../../include/diffusynth_b200.h"
 
@@ -16,39 +17,60 @@ static constexpr int FR = 8;   // frames per block
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// In-place-by-ping-pong 512-point complex DFT of FR frames held in smem: out[n] = sum_k in[k] e^{sign*2*pi*i*k*n/512}.
-// buf[2][FR][NH]; returns which buffer holds the result.  blockDim.x == 256.
+// 512-point complex DFT of one frame per WARP, in registers with warp-shuffle butterflies:
+//   out[n] = sum_k in[k] e^{SIGN*2*pi*i*k*n/512}.
+// Lane l holds the 16 points i = l + 32 r (r = register index).  Radix-2 decimation in frequency: the four stages that pair
+// points 256 / 128 / 64 / 32 apart are register-to-register, the five that pair points 16 .. 1 apart exchange registers between
+// lanes with __shfl_xor_sync; no shared memory and no block barrier inside the transform.  On return x[r] holds
+// out[bitrev9(l + 32 r)] = out[(bitrev5(l) << 4) | bitrev4(r)].
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
 template <int SIGN>
-__device__ __forceinline__ int fft512_block(float2 (*buf)[FR][NH], const float2* __restrict__ tw /* e^{+2 pi i j/512}, j<256 */) {
-  int cur = 0;
-  // Stockham autosort, decimation in frequency: Ns = 1, 2, 4, ..., 256
-#pragma unroll 1
-  for (int Ns = 1; Ns < NH; Ns <<= 1) {
-    for (int i = threadIdx.x; i < FR * (NH / 2); i += blockDim.x) {
-      const int f = i / (NH / 2), j = i % (NH / 2);
-      const int k = j % Ns;                       // position inside the current sub-transform
-      const float2 a = buf[cur][f][j];
-      float2 b = buf[cur][f][j + NH / 2];
-      float2 w = tw[k * (NH / 2 / Ns)];           // e^{+2 pi i k / (2 Ns)}
+__device__ __forceinline__ void fft512_warp(float2 (&x)[16], const float2* __restrict__ tw /* e^{+2 pi i j/512}, j<256 */, int lane) {
+#pragma unroll
+  for (int rb = 3; rb >= 0; --rb) {          // point-index bit b = rb + 5 lives in the register index
+    const int half = 1 << rb;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r & half) continue;
+      float2 w = __ldg(tw + ((lane + 32 * (r & (half - 1))) << (3 - rb)));      // W_512^((i mod 2^b) * 2^(8-b))
       if (SIGN < 0) w.y = -w.y;
-      b = cmul(b, w);
-      const int o = (j / Ns) * 2 * Ns + k;
-      buf[cur ^ 1][f][o] = make_float2(a.x + b.x, a.y + b.y);
-      buf[cur ^ 1][f][o + Ns] = make_float2(a.x - b.x, a.y - b.y);
+      const float2 u = x[r], v = x[r + half];
+      x[r] = cadd(u, v);
+      x[r + half] = cmul(csub(u, v), w);
     }
-    __syncthreads();
-    cur ^= 1;
   }
-  return cur;
+#pragma unroll
+  for (int b = 4; b >= 0; --b) {             // point-index bit b is lane bit b
+    const int m = 1 << b;
+    const bool upper = (lane & m) != 0;
+    float2 w = __ldg(tw + ((lane & (m - 1)) << (8 - b)));
+    if (SIGN < 0) w.y = -w.y;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float2 o = make_float2(__shfl_xor_sync(0xffffffffu, x[r].x, m), __shfl_xor_sync(0xffffffffu, x[r].y, m));
+      x[r] = upper ? cmul(csub(o, x[r]), w) : cadd(x[r], o);
+    }
+  }
+}
+// The transform's results are staged once in shared memory in natural order, one padding entry per 16 (the lanes of a warp
+// write bins 16 apart): xs[frame][pidx(bin)].
+static constexpr int XS_PITCH = NH + NH / 16;
+__device__ __forceinline__ int pidx(int k) { return k + (k >> 4); }
+__device__ __forceinline__ void store_bitrev(float2* __restrict__ xs, const float2 (&x)[16], int lane) {
+  const int hi = (int)(__brev((unsigned)lane) >> 27) << 4;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) xs[pidx(hi | (int)(__brev((unsigned)r) >> 28))] = x[r];
 }
 
-// ---- inverse: spec [B,3,512,T] fp32 -> windowed frames [B][T][1024] fp32 -------------------------
+// ---- inverse: spec [B,3,512,T] fp32 -> windowed frames [B][T][1024] fp32; one frame per warp, FR = 8 frames per block ----
 __global__ void __launch_bounds__(256)
 istft_frames_kernel(const float* __restrict__ spec, float* __restrict__ frames, int T, const float2* __restrict__ tw512,
                     const float2* __restrict__ tw1024 /* e^{+2 pi i k/1024}, k<512 */) {
   extern __shared__ __align__(16) uint8_t is_smem[];
-  float2 (*buf)[FR][NH] = reinterpret_cast<float2 (*)[FR][NH]>(is_smem);          // [2][FR][NH]
-  float2 (*X)[NH + 1] = reinterpret_cast<float2 (*)[NH + 1]>(is_smem + 2 * FR * NH * sizeof(float2));   // [FR][513]
+  float2 (*X)[NH + 1] = reinterpret_cast<float2 (*)[NH + 1]>(is_smem);                                        // [FR][513]
+  float2 (*xs)[XS_PITCH] = reinterpret_cast<float2 (*)[XS_PITCH]>(is_smem + FR * (NH + 1) * sizeof(float2));   // [FR][544]
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
   const float* sp = spec + (size_t)b * 3 * NH * T;
   // decode: bin f (1..512) <- row f-1 of the representation; bin 0 (DC) = 0
@@ -68,22 +90,26 @@ istft_frames_kernel(const float* __restrict__ spec, float* __restrict__ frames, 
   }
   if (threadIdx.x < FR) X[threadIdx.x][0] = make_float2(0.f, 0.f);
   __syncthreads();
+  const int fr = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Z[k] = (X[k] + conj(X[512-k])) + i * w^k * (X[k] - conj(X[512-k])),  w = e^{2 pi i/1024}; c2r ignores Im of DC/Nyquist
-  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
-    const int fr = i / NH, k = i % NH;
+  float2 x[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int k = lane + 32 * r;
     float2 a = X[fr][k], c = X[fr][NH - k];
     if (k == 0) { a.y = 0.f; c.y = 0.f; }
     const float2 e = make_float2(a.x + c.x, a.y - c.y);
     const float2 o = cmul(make_float2(a.x - c.x, a.y + c.y), __ldg(tw1024 + k));
-    buf[0][fr][k] = make_float2(e.x - o.y, e.y + o.x);
+    x[r] = make_float2(e.x - o.y, e.y + o.x);
   }
-  __syncthreads();
-  const int cur = fft512_block<+1>(buf, tw512);
+  fft512_warp<+1>(x, tw512, lane);
+  store_bitrev(xs[fr], x, lane);
+  __syncwarp();
   // x[2n] = Re z[n] / 1024, x[2n+1] = Im z[n] / 1024; times the periodic Hann window
-  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
-    const int fr = i / NH, n = i % NH, t = t0 + fr;
-    if (t >= T) continue;
-    const float2 z = buf[cur][fr][n];
+  const int t = t0 + fr;
+  if (t >= T) return;
+  for (int n = lane; n < NH; n += 32) {
+    const float2 z = xs[fr][pidx(n)];
     const float w0 = 0.5f - 0.5f * cospif((float)(2 * n) / 512.0f), w1 = 0.5f - 0.5f * cospif((float)(2 * n + 1) / 512.0f);
     reinterpret_cast<float2*>(frames + ((size_t)b * T + t) * NFFT)[n] = make_float2(z.x * (1.0f / NFFT) * w0, z.y * (1.0f / NFFT) * w1);
   }
@@ -112,23 +138,29 @@ __global__ void __launch_bounds__(256)
 stft_encode_kernel(const float* __restrict__ wave, long long L, float* __restrict__ spec, int T, int Tpad, const float2* __restrict__ tw512,
                    const float2* __restrict__ tw1024) {
   extern __shared__ __align__(16) uint8_t st_smem[];
-  float2 (*buf)[FR][NH] = reinterpret_cast<float2 (*)[FR][NH]>(st_smem);
+  float2 (*xs)[XS_PITCH] = reinterpret_cast<float2 (*)[XS_PITCH]>(st_smem);      // [FR][544]
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
   const float* wv = wave + (size_t)b * L;
-  // z[n] = x[2n] + i x[2n+1] of the windowed frame
-  for (int i = threadIdx.x; i < FR * NH; i += blockDim.x) {
-    const int fr = i / NH, n = i % NH, t = t0 + fr;
-    const long long s0 = (long long)t * HOP - NFFT / 2 + 2 * n;
-    float a = 0.f, c = 0.f;
-    if (t < T) {
-      if (s0 >= 0 && s0 < L) a = __ldg(wv + s0);
-      if (s0 + 1 >= 0 && s0 + 1 < L) c = __ldg(wv + s0 + 1);
+  {
+    // one frame per warp: z[n] = x[2n] + i x[2n+1] of the windowed frame, straight into the transform's registers
+    const int fr = threadIdx.x >> 5, lane = threadIdx.x & 31, t = t0 + fr;
+    float2 x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int n = lane + 32 * r;
+      const long long s0 = (long long)t * HOP - NFFT / 2 + 2 * n;
+      float a = 0.f, c = 0.f;
+      if (t < T) {
+        if (s0 >= 0 && s0 < L) a = __ldg(wv + s0);
+        if (s0 + 1 >= 0 && s0 + 1 < L) c = __ldg(wv + s0 + 1);
+      }
+      const float w0 = 0.5f - 0.5f * cospif((float)(2 * n) / 512.0f), w1 = 0.5f - 0.5f * cospif((float)(2 * n + 1) / 512.0f);
+      x[r] = make_float2(a * w0, c * w1);
     }
-    const float w0 = 0.5f - 0.5f * cospif((float)(2 * n) / 512.0f), w1 = 0.5f - 0.5f * cospif((float)(2 * n + 1) / 512.0f);
-    buf[0][fr][n] = make_float2(a * w0, c * w1);
+    fft512_warp<-1>(x, tw512, lane);
+    store_bitrev(xs[fr], x, lane);
   }
   __syncthreads();
-  const int cur = fft512_block<-1>(buf, tw512);
   // X[k] = (Z[k] + conj Z[512-k])/2 - i/2 * e^{-2 pi i k/1024} (Z[k] - conj Z[512-k]),  k = 1..512 (row k-1); DC row dropped (pad_STFT)
   float* sp = spec + (size_t)b * 3 * NH * Tpad;
   for (int i = threadIdx.x; i < NH * FR; i += blockDim.x) {
@@ -136,7 +168,7 @@ stft_encode_kernel(const float* __restrict__ wave, long long L, float* __restric
     if (t >= Tpad) continue;
     float lm = 0.f, co = 1.f, si = 0.f;      // padded frames: |D| = 0 -> log1p 0 = 0, angle(0) = 0 -> cos 1, sin 0
     if (t < T) {
-      const float2 zk = buf[cur][fr][k & (NH - 1)], zc = buf[cur][fr][(NH - k) & (NH - 1)];
+      const float2 zk = xs[fr][pidx(k & (NH - 1))], zc = xs[fr][pidx((NH - k) & (NH - 1))];
       const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y - zc.y));
       const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y + zc.y));
       float2 w = k < NH ? __ldg(tw1024 + k) : make_float2(-1.f, 0.f);
@@ -214,7 +246,7 @@ int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, in
   float2 *tw512, *tw1024;
   int rc = get_twiddles((cudaStream_t)stream, &tw512, &tw1024);
   if (rc) return rc;
-  const size_t smem = 2 * FR * NH * sizeof(float2) + FR * (NH + 1) * sizeof(float2);
+  const size_t smem = FR * (NH + 1) * sizeof(float2) + FR * XS_PITCH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   istft_frames_kernel<<<dim3((T + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_spec, d_frames, T, tw512, tw1024);
   DS_CHECK_CUDA(cudaGetLastError());
@@ -232,7 +264,7 @@ int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int T
   float2 *tw512, *tw1024;
   int rc = get_twiddles((cudaStream_t)stream, &tw512, &tw1024);
   if (rc) return rc;
-  const size_t smem = 2 * FR * NH * sizeof(float2);
+  const size_t smem = FR * XS_PITCH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(stft_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   stft_encode_kernel<<<dim3((Tpad + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_wave, L, d_spec, T, Tpad, tw512, tw1024);
   DS_CHECK_CUDA(cudaGetLastError());

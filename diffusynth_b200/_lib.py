@@ -67,6 +67,7 @@ _SIGNATURES = {
     "ds_attn_part_floats": (_L, [_I, _I, _L]),
     "ds_attn_ctx_partial": (_I, [_P, _P, _P, _I, _I, _L, _I, _F, _P]),
     "ds_attn_finalize": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _P]),
+    "ds_attn_finalize_cat": (_I, [_P, _P, _P, _L, _P, _P, _I, _I, _L, _I, _I, _P]),
     "ds_gn_apply_residual": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _L, _I, _P]),
     "ds_vq_quantize": (_I, [_P, _P, _I, _P, _P, _I, _L, _P]),
     "ds_group_stats": (_I, [_P, _P, _I, _I, _I, _I, _L, _I, _P]),

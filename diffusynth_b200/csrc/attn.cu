@@ -176,19 +176,28 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
 
 // attn_reduce: grid = (heads, N), block = 256: merge the chunk partials (log-sum-exp style) and normalise
 //   ctx[d][e] = sum_c S_c[d][e] exp(m_c[d] - M[d]) / sum_c Z_c[d] exp(m_c[d] - M[d])        -> fp32 [N][heads][32][32]
+// label_k / label_v (nullable, [N][label_stride], element head*32 + d): the extra key / value token of LinearCrossAttention
+// ("linear_cat", diffusion_components.py:187-195: k = cat([k, label_k]), v = cat([v, label_v]) along the sequence) joins the merge
+// like one more chunk with a single position: max candidate label_k[d], Z += exp(label_k[d] - M), S[d][e] += exp(.) * label_v[e].
 __global__ void __launch_bounds__(256)
-attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ ctx) {
-  __shared__ float s_M[AT_D], s_Zinv[AT_D];
+attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ ctx, const float* __restrict__ label_k,
+                   const float* __restrict__ label_v, long long label_stride) {
+  __shared__ float s_M[AT_D], s_Zinv[AT_D], s_lw[AT_D];
   const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const float* pb = part + ((size_t)n * gridDim.x + head) * chunks * AT_PART;
   if (tid < AT_D) {
     float mx = -INFINITY;
     for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid));
+    const float lk = label_k ? __ldg(label_k + (size_t)n * label_stride + head * AT_D + tid) : -INFINITY;
+    mx = fmaxf(mx, lk);
     float z = 0.f;
     for (int c = 0; c < chunks; ++c)
       z += __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + tid) * __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid) - mx);
+    const float lw = label_k ? __expf(lk - mx) : 0.f;
+    z += lw;
     s_M[tid] = mx;
     s_Zinv[tid] = 1.0f / z;
+    s_lw[tid] = lw;
   }
   __syncthreads();
   float* co = ctx + ((size_t)n * gridDim.x + head) * AT_D * AT_D;
@@ -199,6 +208,7 @@ attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict
 #pragma unroll 4
     for (int c = 0; c < chunks; ++c)
       s = fmaf(__ldg(pb + (size_t)c * AT_PART + i), __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d) - M), s);
+    if (label_v) s = fmaf(s_lw[d], __ldg(label_v + (size_t)n * label_stride + head * AT_D + (i - d * AT_D)), s);
     co[i] = s * s_Zinv[d];
   }
 }
@@ -264,15 +274,27 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
 }
 
 /* Merge partials and fold to_out's weight: d_M bf16 [N][Cout_pad][heads*32]. */
-int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
+static int attn_finalize_impl(const float* d_part, const float* d_label_k, const float* d_label_v, long long label_stride, const float* d_wout,
+                              void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
   DS_REQUIRE(d_part && d_wout && d_M && N > 0 && heads > 0 && C > 0 && Cout_pad >= C, "ds_attn_finalize: bad arguments");
+  DS_REQUIRE((d_label_k == nullptr) == (d_label_v == nullptr) && (!d_label_k || label_stride >= heads * AT_D), "ds_attn_finalize_cat: label_k/label_v");
   const int chunks = ds_attn_chunks(npix);
   float* ctx = const_cast<float*>(d_part) + (size_t)N * heads * chunks * AT_PART;
   DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_finalize: grid too large");
-  attn_reduce_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, chunks, ctx);
+  attn_reduce_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, chunks, ctx, d_label_k, d_label_v, label_stride);
   attn_fold_kernel<<<dim3((Cout_pad + 63) / 64, heads, N), 256, 0, (cudaStream_t)stream>>>(ctx, d_wout, C, Cout_pad, heads * AT_D, (act_t*)d_M);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
+}
+int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
+  return attn_finalize_impl(d_part, nullptr, nullptr, 0, d_wout, d_M, N, heads, npix, C, Cout_pad, stream);
+}
+/* The same with the condition's extra key / value token of LinearCrossAttention ("linear_cat"): d_label_k, d_label_v fp32
+   [N][label_stride] (element head*32 + d) = label_key(emb), label_value(emb). */
+int ds_attn_finalize_cat(const float* d_part, const float* d_label_k, const float* d_label_v, long long label_stride, const float* d_wout,
+                         void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream) {
+  DS_REQUIRE(d_label_k && d_label_v, "ds_attn_finalize_cat: label_k and label_v are required");
+  return attn_finalize_impl(d_part, d_label_k, d_label_v, label_stride, d_wout, d_M, N, heads, npix, C, Cout_pad, stream);
 }
 
 }  // extern "C"

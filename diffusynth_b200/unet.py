@@ -77,9 +77,9 @@ class ConditionedUnet:
             raise NotImplementedError()                       # diffusion.py:96
         if condition_type not in ("instrument_family", "natural_language_prompt"):
             raise NotImplementedError()                       # diffusion_components.py:165
-        if not use_convnext or attn_type != "linear_add" or condition_type != "natural_language_prompt" or not with_time_emb:
-            raise NotImplementedError("diffusynth_b200 implements the deployed variant: ConvNeXt blocks, "
-                                      "attn_type='linear_add', condition_type='natural_language_prompt' (app.py:40)")
+        if not use_convnext or condition_type != "natural_language_prompt" or not with_time_emb:
+            raise NotImplementedError("diffusynth_b200 implements ConvNeXt blocks with attn_type 'linear_add' (deployed, app.py:40) or "
+                                      "'linear_cat', condition_type='natural_language_prompt', with_time_emb=True")
         if up_dims is None:
             up_dims = [128, 128, 64, 32]
         if down_dims is None:
@@ -184,12 +184,14 @@ class ConditionedUnet:
             off += b.dim
         self.t_total = off
         self.t_w, self.t_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
-        # fused condition projection: per attention site [label_query | label_key | zeros(v)]
+        # fused condition projection: per attention site [label_query | label_key | zeros(v)] (added to q, k in the to_qkv epilogue),
+        # or for "linear_cat" [label_key | label_value | zeros] (the extra key / value token, consumed by ds_attn_finalize_cat)
         rows, biases, off = [], [], 0
+        first, second = ("label_query", "label_key") if cfg["attn_type"] == "linear_add" else ("label_key", "label_value")
         for a in self.attns.values():
             a.c_off = off
-            rows += [sd[a.p + "fn.fn.label_query.weight"].float(), sd[a.p + "fn.fn.label_key.weight"].float(), torch.zeros(HID, L)]
-            biases += [sd[a.p + "fn.fn.label_query.bias"].float(), sd[a.p + "fn.fn.label_key.bias"].float(), torch.zeros(HID)]
+            rows += [sd[a.p + f"fn.fn.{first}.weight"].float(), sd[a.p + f"fn.fn.{second}.weight"].float(), torch.zeros(HID, L)]
+            biases += [sd[a.p + f"fn.fn.{first}.bias"].float(), sd[a.p + f"fn.fn.{second}.bias"].float(), torch.zeros(HID)]
             off += 3 * HID
         self.c_total = off
         self.c_w, self.c_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
@@ -329,14 +331,21 @@ class _Plan:
             npix = h * w
             qkv = scr("qkv", N, h, w, 3 * HID)
             sb = self.sbias[:, a.c_off:a.c_off + 3 * HID]
-            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=sb, src_batch_mod=x_mod)
+            cat = cfg["attn_type"] == "linear_cat"
+            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=None if cat else sb, src_batch_mod=x_mod)
             qp = scr("qp", N, h, w, HID)
             part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
             M = torch.empty((N, a.out.cout_pad, HID), dtype=ops.ACT, device=dev)
             add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
                                                                   float(DHEAD ** -0.5), stream()), "attn_ctx_partial"))
-            add(p + "fin", lambda: check(lib.ds_attn_finalize(part.data_ptr(), a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim,
-                                                               a.out.cout_pad, stream()), "attn_finalize"))
+            if cat:
+                lk, lv = sb[:, :HID], sb[:, HID:2 * HID]
+                add(p + "fin", lambda: check(lib.ds_attn_finalize_cat(part.data_ptr(), lk.data_ptr(), lv.data_ptr(), self.sbias.stride(0),
+                                                                       a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim, a.out.cout_pad,
+                                                                       stream()), "attn_finalize_cat"))
+            else:
+                add(p + "fin", lambda: check(lib.ds_attn_finalize(part.data_ptr(), a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim,
+                                                                   a.out.cout_pad, stream()), "attn_finalize"))
             y = scr("atty", N, h, w, a.dim)
             st_y = conv(p + "to_out", a.out, qp, None, h, w, out=y, want_stats=True, weight_override=M, per_sample_weights=True)
             o = act(N, h, w, a.dim)

@@ -62,14 +62,17 @@ def _convnext(spec: Spec, p: str, dim: int, dim_out: int, mult: int, time_dim) -
         spec += [(p + "res_conv.weight", (dim_out, dim, 1, 1)), (p + "res_conv.bias", (dim_out,))]
 
 
-def _attn(spec: Spec, p: str, dim: int, label_dim: int) -> None:
+def _attn(spec: Spec, p: str, dim: int, label_dim: int, attn_type: str = "linear_add") -> None:
+    """LinearCrossAttentionAdd (label_key, label_query; diffusion_components.py:252-269) or LinearCrossAttention
+    ("linear_cat": label_key, label_value; :171-185), wrapped in Residual(PreNorm(.))."""
     hid = ATTN_HEADS * ATTN_DIM_HEAD
+    second = "label_query" if attn_type == "linear_add" else "label_value"
     spec += [
         (p + "fn.fn.to_qkv.weight", (hid * 3, dim, 1, 1)),
         (p + "fn.fn.to_out.0.weight", (dim, hid, 1, 1)), (p + "fn.fn.to_out.0.bias", (dim,)),
         (p + "fn.fn.to_out.1.weight", (dim,)), (p + "fn.fn.to_out.1.bias", (dim,)),
         (p + "fn.fn.label_key.weight", (hid, label_dim)), (p + "fn.fn.label_key.bias", (hid,)),
-        (p + "fn.fn.label_query.weight", (hid, label_dim)), (p + "fn.fn.label_query.bias", (hid,)),
+        (p + f"fn.fn.{second}.weight", (hid, label_dim)), (p + f"fn.fn.{second}.bias", (hid,)),
         (p + "fn.norm.weight", (dim,)), (p + "fn.norm.bias", (dim,)),
     ]
 
@@ -79,7 +82,8 @@ def unet_param_spec(cfg: dict) -> Spec:
     cfg = unet_config(**cfg)
     dd, ud = cfg["down_dims"], cfg["up_dims"]
     L, td, mult = cfg["label_emb_dim"], cfg["time_dim"], cfg["convnext_mult"]
-    assert cfg["attn_type"] == "linear_add" and cfg["condition_type"] == "natural_language_prompt"
+    assert cfg["attn_type"] in ("linear_add", "linear_cat") and cfg["condition_type"] == "natural_language_prompt"
+    at = cfg["attn_type"]
     spec: Spec = [("label_embedding.embedding.weight", (L, L)), ("label_embedding.embedding.bias", (L,)),
                   ("init_conv.weight", (dd[0], cfg["in_dim"], 7, 7)), ("init_conv.bias", (dd[0],)),
                   ("time_mlp.1.weight", (td, dd[0])), ("time_mlp.1.bias", (td,)),
@@ -88,9 +92,9 @@ def unet_param_spec(cfg: dict) -> Spec:
     for i, (cin, cout) in enumerate(zip(dd[:-1], dd[1:])):
         p = f"downs.{i}."
         _convnext(spec, p + "0.", cin, cout, mult, td)
-        _attn(spec, p + "1.", cout, L)
+        _attn(spec, p + "1.", cout, L, at)
         _convnext(spec, p + "2.", cout, cout, mult, td)
-        _attn(spec, p + "3.", cout, L)
+        _attn(spec, p + "3.", cout, L, at)
         spec += [(p + "4.weight", (cout, cout, 4, 4)), (p + "4.bias", (cout,))]
         skips.append(cout)
     mid = dd[-1]
@@ -101,19 +105,19 @@ def unet_param_spec(cfg: dict) -> Spec:
         s = sk.pop()
         p = f"ups.{i}."
         _convnext(ups_spec, p + "0.", cin + s, cin, mult, td)
-        _attn(ups_spec, p + "1.", cin, L)
+        _attn(ups_spec, p + "1.", cin, L, at)
         ups_spec += [(p + "2.weight", (cin, cin, 4, 4)), (p + "2.bias", (cin,))]
         _convnext(ups_spec, p + "3.", cin + s, cout, mult, td)
-        _attn(ups_spec, p + "4.", cout, L)
+        _attn(ups_spec, p + "4.", cout, L, at)
         _convnext(ups_spec, p + "5.", cout + s, cout, mult, td)
-        _attn(ups_spec, p + "6.", cout, L)
+        _attn(ups_spec, p + "6.", cout, L, at)
     spec += ups_spec
     for j in range(cfg["mid_depth"] - 1):
         _convnext(spec, f"mid_left.{j}.", mid, mid, mult, td)
     for j in range(cfg["mid_depth"] - 1):
         _convnext(spec, f"mid_right.{j}.", mid * 2, mid, mult, td)
     _convnext(spec, "mid_mid.0.", mid, mid, mult, td)
-    _attn(spec, "mid_mid.1.", mid, L)
+    _attn(spec, "mid_mid.1.", mid, L, at)
     _convnext(spec, "mid_mid.2.", mid, mid, mult, td)
     _convnext(spec, "final_conv.0.", dd[0] + ud[-1], ud[-1], mult, None)
     spec += [("final_conv.1.weight", (cfg["out_dim"], ud[-1], 3, 3)), ("final_conv.1.bias", (cfg["out_dim"],))]

@@ -156,6 +156,10 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
                         int q_mode, float scale, void* stream);
 int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix,
                      int C, int Cout_pad, void* stream);
+/* LinearCrossAttention ("linear_cat", diffusion_components.py:171-207): the condition contributes one extra key / value token,
+   k = cat([k, label_key(emb)]), v = cat([v, label_value(emb)]) (:187-195); d_label_k / d_label_v fp32 [N][label_stride]. */
+int ds_attn_finalize_cat(const float* d_part, const float* d_label_k, const float* d_label_v, long long label_stride,
+                         const float* d_wout, void* d_M, int N, int heads, long long npix, int C, int Cout_pad, void* stream);
 /* to_out[1] GroupNorm(1,C) + Residual (:264, :22-29): out = GN(y)*gamma+beta + x.  x_batch_mod > 0: sample n adds x[n % x_batch_mod]. */
 int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const void* d_stats, int slots,
                          const float* d_gamma, const float* d_beta, int N, int C, long long hw, int x_batch_mod, void* stream);

@@ -11,6 +11,9 @@ SMALL_UNET = dict(in_dim=4, down_dims=[32, 32, 64], up_dims=[64, 64, 32], mid_de
                   attn_type="linear_add", condition_type="natural_language_prompt", label_emb_dim=64)
 
 
+SMALL_UNET_CAT = dict(SMALL_UNET, attn_type="linear_cat")
+
+
 def randn(shape, seed):
     g = torch.Generator(device="cpu"); g.manual_seed(seed)
     return torch.randn(shape, generator=g)
@@ -28,6 +31,8 @@ def unet_case(name: str):
         cfg, B, Wd = SMALL_UNET, 2, 16
     elif name == "small_w10":           # 10 -> 5 -> 2
         cfg, B, Wd = SMALL_UNET, 2, 10
+    elif name == "small_cat_w16":       # attn_type="linear_cat" (LinearCrossAttention: the condition is an extra key / value token)
+        cfg, B, Wd = SMALL_UNET_CAT, 2, 16
     else:
         raise KeyError(name)
     sd = W.unet_random_state_dict(cfg, seed=0)

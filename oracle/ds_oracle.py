@@ -264,6 +264,34 @@ def linear_attention_add(sd: SD, p: str, x: Tensor, cemb: Optional[Tensor], head
     return _gn(out, sd, p + "fn.fn.to_out.1.") + x
 
 
+def linear_attention_cat(sd: SD, p: str, x: Tensor, cemb: Optional[Tensor], heads: int = 4, dh: int = 32) -> Tensor:
+    """Residual(PreNorm(LinearCrossAttention)), attn_type="linear_cat".  diffusion_components.py:22-29,142-152,171-207:
+    the condition contributes one extra key / value token instead of being added to q and k."""
+    B, C, H, W = x.shape
+    n = H * W
+    xn = _gn(x, sd, p + "fn.norm.")
+    qkv = F.conv2d(xn, sd[p + "fn.fn.to_qkv.weight"]).reshape(B, 3, heads, dh, n)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    if cemb is not None:
+        lk = F.linear(cemb, sd[p + "fn.fn.label_key.weight"], sd[p + "fn.fn.label_key.bias"]).view(B, heads, dh, 1)
+        lv = F.linear(cemb, sd[p + "fn.fn.label_value.weight"], sd[p + "fn.fn.label_value.bias"]).view(B, heads, dh, 1)
+        k, v = torch.cat([k, lk], dim=-1), torch.cat([v, lv], dim=-1)
+    q = q.softmax(dim=-2)
+    k = k.softmax(dim=-1)
+    q = q * dh ** -0.5
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(B, heads * dh, H, W)
+    out = F.conv2d(out, sd[p + "fn.fn.to_out.0.weight"], sd[p + "fn.fn.to_out.0.bias"])
+    return _gn(out, sd, p + "fn.fn.to_out.1.") + x
+
+
+def _attention(sd: SD, p: str, x: Tensor, cemb: Optional[Tensor]) -> Tensor:
+    """The variant is read off the state_dict: label_value exists only in LinearCrossAttention ("linear_cat")."""
+    if (p + "fn.fn.label_value.weight") in sd:
+        return linear_attention_cat(sd, p, x, cemb)
+    return linear_attention_add(sd, p, x, cemb)
+
+
 def pad_and_concat(enc: Tensor, dec: Tensor) -> Tensor:
     """diffusion_components.py:210-249: zero-pad ``dec`` to ``enc``'s H,W, cat (enc first)."""
     dh, dw = enc.shape[2] - dec.shape[2], enc.shape[3] - dec.shape[3]
@@ -273,7 +301,7 @@ def pad_and_concat(enc: Tensor, dec: Tensor) -> Tensor:
 
 
 def unet_forward(sd: SD, x: Tensor, t: Tensor, cond: Optional[Tensor], taps: Optional[dict] = None) -> Tensor:
-    """ConditionedUnet.forward, ConvNeXt + linear_add variant.  model/diffusion.py:187-258.
+    """ConditionedUnet.forward, ConvNeXt blocks with linear_add or linear_cat attention.  model/diffusion.py:187-258.
     The architecture is read off the state_dict keys.  ``taps`` (optional dict) receives
     named intermediates for per-layer parity tests."""
     n_stage = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("downs."))
@@ -295,26 +323,26 @@ def unet_forward(sd: SD, x: Tensor, t: Tensor, cond: Optional[Tensor], taps: Opt
     for i in range(n_stage):
         p = f"downs.{i}."
         x = tap(p + "0", convnext_block(sd, p + "0.", x, temb))
-        x = tap(p + "1", linear_attention_add(sd, p + "1.", x, cemb)); hs.append(x)
+        x = tap(p + "1", _attention(sd, p + "1.", x, cemb)); hs.append(x)
         x = tap(p + "2", convnext_block(sd, p + "2.", x, temb))
-        x = tap(p + "3", linear_attention_add(sd, p + "3.", x, cemb)); hs.append(x)
+        x = tap(p + "3", _attention(sd, p + "3.", x, cemb)); hs.append(x)
         x = tap(p + "4", F.conv2d(x, sd[p + "4.weight"], sd[p + "4.bias"], stride=2, padding=1)); hs.append(x)
     for j in range(n_midl):
         x = tap(f"mid_left.{j}", convnext_block(sd, f"mid_left.{j}.", x, temb)); hs.append(x)
     x = tap("mid_mid.0", convnext_block(sd, "mid_mid.0.", x, temb))
-    x = tap("mid_mid.1", linear_attention_add(sd, "mid_mid.1.", x, cemb))
+    x = tap("mid_mid.1", _attention(sd, "mid_mid.1.", x, cemb))
     x = tap("mid_mid.2", convnext_block(sd, "mid_mid.2.", x, temb))
     for j in range(n_midl):
         x = tap(f"mid_right.{j}", convnext_block(sd, f"mid_right.{j}.", pad_and_concat(hs.pop(), x), temb))
     for i in range(n_stage):
         p = f"ups.{i}."
         x = tap(p + "0", convnext_block(sd, p + "0.", pad_and_concat(hs.pop(), x), temb))
-        x = tap(p + "1", linear_attention_add(sd, p + "1.", x, cemb))
+        x = tap(p + "1", _attention(sd, p + "1.", x, cemb))
         x = tap(p + "2", F.conv_transpose2d(x, sd[p + "2.weight"], sd[p + "2.bias"], stride=2, padding=1))
         x = tap(p + "3", convnext_block(sd, p + "3.", pad_and_concat(hs.pop(), x), temb))
-        x = tap(p + "4", linear_attention_add(sd, p + "4.", x, cemb))
+        x = tap(p + "4", _attention(sd, p + "4.", x, cemb))
         x = tap(p + "5", convnext_block(sd, p + "5.", pad_and_concat(hs.pop(), x), temb))
-        x = tap(p + "6", linear_attention_add(sd, p + "6.", x, cemb))
+        x = tap(p + "6", _attention(sd, p + "6.", x, cemb))
     x = tap("final_conv.0", convnext_block(sd, "final_conv.0.", pad_and_concat(hs.pop(), x), None))
     return F.conv2d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"], padding=1)
 

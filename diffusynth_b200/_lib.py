@@ -73,6 +73,7 @@ _SIGNATURES = {
     "ds_group_stats": (_I, [_P, _P, _I, _I, _I, _I, _L, _I, _P]),
     "ds_gn_act": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _L, _F, _I, _P]),
     "ds_add_bf16": (_I, [_P, _P, _P, _L, _P]),
+    "ds_add_channel_bias": (_I, [_P, _P, _L, _I, _I, _L, _P]),
     "ds_decoder_head": (_I, [_P, _P, _P, _I, _L, _P]),
     "ds_nchw_f32_to_nhwc_bf16": (_I, [_P, _P, _I, _I, _I, _L, _P]),
     "ds_nhwc_bf16_to_nchw_f32": (_I, [_P, _P, _I, _I, _I, _L, _P]),

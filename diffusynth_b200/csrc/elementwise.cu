@@ -232,6 +232,20 @@ __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ o
   for (; i < total; i += stride) ob[i] = apply(__ldg(xb + i));
 }
 
+// x[n][p][c] += bias[n * bias_stride + c] in place (16-bit NHWC): the time embedding ResnetBlock adds between its two blocks
+// (diffusion_components.py:97-100).  bias_stride 0 = one row for all samples.
+__global__ void add_channel_bias_kernel(act_t* __restrict__ x, const float* __restrict__ bias, long long bias_stride, int C, long long per_sample /* hw*C/2 */,
+                                        long long total) {
+  uint32_t* xv = reinterpret_cast<uint32_t*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / per_sample;
+    const int c = (int)((i % (C / 2)) * 2);
+    const float* b = bias + n * bias_stride + c;
+    const uint32_t v = xv[i];
+    xv[i] = pack16(lo16(v) + __ldg(b), hi16(v) + __ldg(b + 1));
+  }
+}
+
 // out = a + b (bf16 NHWC), used for the VQGAN residual adds that are not fused into a conv epilogue
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
@@ -256,7 +270,7 @@ __global__ void decoder_head_kernel(const float* __restrict__ a, const float* __
 
 // ---------------------------------------------------------------------------------------------
 // Tiny linears (time MLP, per-block time projections, condition projections):
-//   out[n][o] = bias[o] + sum_k act(in[n][k]) * W[o][k]        act_in: 0 none, 1 GELU(erf)
+//   out[n][o] = bias[o] + sum_k act(in[n][k]) * W[o][k]        act_in: 0 none, 1 GELU(erf), 2 SiLU
 // One warp per output feature, looping over samples (the weight row stays in registers/L1).
 // SinusoidalPositionEmbeddings (diffusion_components.py:42-56) is a separate small kernel.
 // ---------------------------------------------------------------------------------------------
@@ -273,6 +287,7 @@ __global__ void linear_kernel(const float* __restrict__ in, long long in_stride,
     for (int k = lane; k < K; k += 32) {
       float v = xr[k];
       if (act_in == 1) v = gelu_erf(v);
+      else if (act_in == 2) v = v / (1.0f + expf(-v));      // SiLU (ResnetBlock.mlp, diffusion_components.py:85-89)
       acc = fmaf(v, __ldg(wr + k), acc);
     }
     acc = warp_sum(acc);
@@ -332,6 +347,14 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
   DS_REQUIRE(d_guide && d_noise && d_mask && d_coef && d_img && B > 0 && C > 0 && hw > 0, "ds_mask_blend: bad arguments");
   const long long total = (long long)B * C * hw;
   mask_blend_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_guide, d_noise, d_mask, d_coef, d_img, C, hw, total);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_add_channel_bias(void* d_x, const float* d_bias, long long bias_stride, int N, int C, long long hw, void* stream) {
+  DS_REQUIRE(d_x && d_bias && N > 0 && C > 0 && C % 2 == 0 && hw > 0 && bias_stride >= 0, "ds_add_channel_bias: bad arguments");
+  const long long per = hw * C / 2, total = per * N;
+  add_channel_bias_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((act_t*)d_x, d_bias, bias_stride, C, per, total);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

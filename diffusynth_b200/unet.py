@@ -36,12 +36,40 @@ class _Block:
         self.conv2 = pack_conv_s1(sd[p + "net.4.weight"], sd[p + "net.4.bias"], sd[p + "net.3.weight"].float(), sd[p + "net.3.bias"].float())
         self.res = pack_conv_s1(sd[p + "res_conv.weight"], sd[p + "res_conv.bias"]) if (p + "res_conv.weight") in sd else None
         self.t_off = 0   # column offset of this block's time projection in the fused [N, sum(dim)] buffer
+        self.t_dim = dim
 
     def to(self, dev):
         self.dw = self.dw.to(dev)
         for c in (self.conv1, self.conv2, self.res):
             if c is not None:
                 c.to(dev)
+        return self
+
+
+class _ResBlock:
+    """Packed constants of one ResnetBlock (use_convnext=False; diffusion_components.py:59-104): two (conv3x3 -> GroupNorm(groups) ->
+    SiLU) blocks with the time embedding added in between, plus the 1x1 residual projection (an identity matrix where the reference
+    uses nn.Identity, so the residual add and the statistics of the block's output stay in the conv epilogue)."""
+
+    def __init__(self, sd, p, dim, dim_out, has_time):
+        self.p, self.dim, self.dim_out = p, dim, dim_out
+        self.has_time = has_time
+        self.t_dim = dim_out                          # width of this block's slice of the fused time projection
+        self.dw_bias = torch.zeros(dim_out)            # (nothing to add to mlp.1.bias)
+        self.conv1 = pack_conv_s1(sd[p + "block1.proj.weight"], sd[p + "block1.proj.bias"].float())
+        self.conv2 = pack_conv_s1(sd[p + "block2.proj.weight"], sd[p + "block2.proj.bias"].float())
+        self.g1, self.b1 = sd[p + "block1.norm.weight"].float().contiguous(), sd[p + "block1.norm.bias"].float().contiguous()
+        self.g2, self.b2 = sd[p + "block2.norm.weight"].float().contiguous(), sd[p + "block2.norm.bias"].float().contiguous()
+        if (p + "res_conv.weight") in sd:
+            self.res = pack_conv_s1(sd[p + "res_conv.weight"], sd[p + "res_conv.bias"].float())
+        else:
+            self.res = pack_conv_s1(torch.eye(dim).reshape(dim, dim, 1, 1), torch.zeros(dim))
+        self.t_off = 0
+
+    def to(self, dev):
+        for c in (self.conv1, self.conv2, self.res):
+            c.to(dev)
+        self.g1, self.b1, self.g2, self.b2 = self.g1.to(dev), self.b1.to(dev), self.g2.to(dev), self.b2.to(dev)
         return self
 
 
@@ -77,9 +105,9 @@ class ConditionedUnet:
             raise NotImplementedError()                       # diffusion.py:96
         if condition_type not in ("instrument_family", "natural_language_prompt"):
             raise NotImplementedError()                       # diffusion_components.py:165
-        if not use_convnext or condition_type != "natural_language_prompt" or not with_time_emb:
-            raise NotImplementedError("diffusynth_b200 implements ConvNeXt blocks with attn_type 'linear_add' (deployed, app.py:40) or "
-                                      "'linear_cat', condition_type='natural_language_prompt', with_time_emb=True")
+        if condition_type != "natural_language_prompt" or not with_time_emb:
+            raise NotImplementedError("diffusynth_b200 implements condition_type='natural_language_prompt' with with_time_emb=True "
+                                      "(ConvNeXt or ResNet blocks, attn_type 'linear_add' = deployed, app.py:40, or 'linear_cat')")
         if up_dims is None:
             up_dims = [128, 128, 64, 32]
         if down_dims is None:
@@ -89,7 +117,7 @@ class ConditionedUnet:
         assert up_dims[0] == down_dims[-1], "up_dims[0] != down_dims[-1]"
         self.cfg = W.unet_config(in_dim=in_dim, out_dim=out_dim, down_dims=list(down_dims), up_dims=list(up_dims), mid_depth=mid_depth,
                                  time_dim=time_dim, convnext_mult=convnext_mult, attn_type=attn_type, condition_type=condition_type,
-                                 label_emb_dim=label_emb_dim)
+                                 label_emb_dim=label_emb_dim, use_convnext=bool(use_convnext), resnet_block_groups=int(resnet_block_groups))
         for d in set(self.cfg["down_dims"] + self.cfg["up_dims"]):
             if d % 32:
                 raise NotImplementedError(f"channel widths must be multiples of 32 (got {d})")
@@ -144,7 +172,7 @@ class ConditionedUnet:
         self.samplers: Dict[str, PackedConv] = {}
 
         def blk(p, dim, dim_out, has_time=True):
-            self.blocks[p] = _Block(sd, p, dim, dim_out, has_time)
+            self.blocks[p] = (_Block if cfg["use_convnext"] else _ResBlock)(sd, p, dim, dim_out, has_time)
 
         def att(p, dim):
             self.attns[p] = _Attn(sd, p, dim)
@@ -179,9 +207,9 @@ class ConditionedUnet:
                 rows.append(sd[b.p + "mlp.1.weight"].float())
                 biases.append(sd[b.p + "mlp.1.bias"].float() + b.dw_bias)
             else:
-                rows.append(torch.zeros(b.dim, td))
+                rows.append(torch.zeros(b.t_dim, td))
                 biases.append(b.dw_bias.clone())
-            off += b.dim
+            off += b.t_dim
         self.t_total = off
         self.t_w, self.t_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
         # fused condition projection: per attention site [label_query | label_key | zeros(v)] (added to q, k in the to_qkv epilogue),
@@ -296,7 +324,7 @@ class _Plan:
         add("time_sin", lambda: check(lib.ds_sinusoidal_embedding(self.t.data_ptr(), sin.data_ptr(), NT, dd[0], stream()), "sinusoidal"))
         add("time_mlp1", lambda: ops.linear(sin, net.tm1_w, net.tm1_b, t1, act_out=1))
         add("time_mlp3", lambda: ops.linear(t1, net.tm3_w, net.tm3_b, temb))
-        add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1))
+        add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1 if cfg["use_convnext"] else 2))
         self.named["time_emb"] = (temb, -1)
 
         def conv(name, pc, s0, s1, h, w, n=None, **kw):
@@ -324,6 +352,40 @@ class _Plan:
             st_o = conv(p + "net.4", b.conv2, y, None, h, w, n=n, out=o, stats_in=st_y, residual=r, want_stats=True)
             self.named[p[:-1]] = (o, b.dim_out)
             return o, st_o
+
+        GN_CHUNKS = 32
+
+        def gn_silu(name, x, c, h, w, n, gamma, beta, role):
+            """GroupNorm(groups, eps 1e-5) + SiLU as statistics + apply passes (the VQGAN GroupNorm kernels)."""
+            G = cfg["resnet_block_groups"]
+            part = torch.empty((n, G, GN_CHUNKS, 2), **f32)
+            out = scr(role, n, h, w, c)
+            add(name + ".stats", lambda: check(lib.ds_group_stats(x.data_ptr(), part.data_ptr(), n, c, c, G, h * w, GN_CHUNKS, stream()), "group_stats"))
+            add(name + ".apply", lambda: check(lib.ds_gn_act(x.data_ptr(), out.data_ptr(), part.data_ptr(), GN_CHUNKS, gamma.data_ptr(),
+                                                            beta.data_ptr(), n, c, c, G, h * w, 1e-5, 2, stream()), "gn_act"))
+            self.keep.append(part)
+            return out
+
+        def res_block(p, s0, s1, h, w, n=N, s0_mod=0):
+            """One ResnetBlock over n samples (diffusion_components.py:79-104)."""
+            b = net.blocks[p]
+            y1 = scr("rb_y1", n, h, w, b.dim_out)
+            conv(p + "block1.proj", b.conv1, s0, s1, h, w, n=n, out=y1, src_batch_mod=s0_mod)
+            h1 = gn_silu(p + "block1.norm", y1, b.dim_out, h, w, n, b.g1, b.b1, "rb_h1")
+            if b.has_time:
+                tb = self.tbias[:, b.t_off:]
+                add(p + "temb", lambda: check(lib.ds_add_channel_bias(h1.data_ptr(), tb.data_ptr(), self.t_stride, n, b.dim_out, h * w, stream()),
+                                              "add_channel_bias"))
+            y2 = scr("rb_y2", n, h, w, b.dim_out)
+            conv(p + "block2.proj", b.conv2, h1, None, h, w, n=n, out=y2)
+            h2 = gn_silu(p + "block2.norm", y2, b.dim_out, h, w, n, b.g2, b.b2, "rb_h2")
+            o = act(n, h, w, b.dim_out)
+            st_o = conv(p + "res_conv", b.res, s0, s1, h, w, n=n, out=o, residual=h2, want_stats=True, src_batch_mod=s0_mod)
+            self.named[p[:-1]] = (o, b.dim_out)
+            return o, st_o
+
+        if not cfg["use_convnext"]:
+            block = res_block
 
         def attn(p, x, st_x, h, w, x_mod=0):
             """x_mod > 0: x (and its statistics) hold x_mod samples shared by the guidance halves."""

@@ -45,6 +45,8 @@ def unet_config(**overrides) -> dict:
         cfg["out_dim"] = cfg["in_dim"]
     if cfg.get("time_dim") is None:
         cfg["time_dim"] = int(cfg["down_dims"][0] * 4)
+    cfg.setdefault("use_convnext", True)
+    cfg.setdefault("resnet_block_groups", 8)
     return cfg
 
 
@@ -58,6 +60,17 @@ def _convnext(spec: Spec, p: str, dim: int, dim_out: int, mult: int, time_dim) -
         (p + "net.3.weight", (dim_out * mult,)), (p + "net.3.bias", (dim_out * mult,)),
         (p + "net.4.weight", (dim_out, dim_out * mult, 3, 3)), (p + "net.4.bias", (dim_out,)),
     ]
+    if dim != dim_out:
+        spec += [(p + "res_conv.weight", (dim_out, dim, 1, 1)), (p + "res_conv.bias", (dim_out,))]
+
+
+def _resnet(spec: Spec, p: str, dim: int, dim_out: int, time_dim) -> None:
+    """ResnetBlock (use_convnext=False), registration order of diffusion_components.py:82-93."""
+    if time_dim is not None:
+        spec += [(p + "mlp.1.weight", (dim_out, time_dim)), (p + "mlp.1.bias", (dim_out,))]
+    for b, cin in (("block1.", dim), ("block2.", dim_out)):
+        spec += [(p + b + "proj.weight", (dim_out, cin, 3, 3)), (p + b + "proj.bias", (dim_out,)),
+                 (p + b + "norm.weight", (dim_out,)), (p + b + "norm.bias", (dim_out,))]
     if dim != dim_out:
         spec += [(p + "res_conv.weight", (dim_out, dim, 1, 1)), (p + "res_conv.bias", (dim_out,))]
 
@@ -84,6 +97,13 @@ def unet_param_spec(cfg: dict) -> Spec:
     L, td, mult = cfg["label_emb_dim"], cfg["time_dim"], cfg["convnext_mult"]
     assert cfg["attn_type"] in ("linear_add", "linear_cat") and cfg["condition_type"] == "natural_language_prompt"
     at = cfg["attn_type"]
+
+    def _blk(spec, p, dim, dim_out, mult, time_dim):      # block_klass (diffusion.py:83-87)
+        if cfg["use_convnext"]:
+            _convnext(spec, p, dim, dim_out, mult, time_dim)
+        else:
+            _resnet(spec, p, dim, dim_out, time_dim)
+
     spec: Spec = [("label_embedding.embedding.weight", (L, L)), ("label_embedding.embedding.bias", (L,)),
                   ("init_conv.weight", (dd[0], cfg["in_dim"], 7, 7)), ("init_conv.bias", (dd[0],)),
                   ("time_mlp.1.weight", (td, dd[0])), ("time_mlp.1.bias", (td,)),
@@ -91,9 +111,9 @@ def unet_param_spec(cfg: dict) -> Spec:
     skips = []
     for i, (cin, cout) in enumerate(zip(dd[:-1], dd[1:])):
         p = f"downs.{i}."
-        _convnext(spec, p + "0.", cin, cout, mult, td)
+        _blk(spec, p + "0.", cin, cout, mult, td)
         _attn(spec, p + "1.", cout, L, at)
-        _convnext(spec, p + "2.", cout, cout, mult, td)
+        _blk(spec, p + "2.", cout, cout, mult, td)
         _attn(spec, p + "3.", cout, L, at)
         spec += [(p + "4.weight", (cout, cout, 4, 4)), (p + "4.bias", (cout,))]
         skips.append(cout)
@@ -104,22 +124,22 @@ def unet_param_spec(cfg: dict) -> Spec:
     for i, (cin, cout) in enumerate(zip(ud[:-1], ud[1:])):
         s = sk.pop()
         p = f"ups.{i}."
-        _convnext(ups_spec, p + "0.", cin + s, cin, mult, td)
+        _blk(ups_spec, p + "0.", cin + s, cin, mult, td)
         _attn(ups_spec, p + "1.", cin, L, at)
         ups_spec += [(p + "2.weight", (cin, cin, 4, 4)), (p + "2.bias", (cin,))]
-        _convnext(ups_spec, p + "3.", cin + s, cout, mult, td)
+        _blk(ups_spec, p + "3.", cin + s, cout, mult, td)
         _attn(ups_spec, p + "4.", cout, L, at)
-        _convnext(ups_spec, p + "5.", cout + s, cout, mult, td)
+        _blk(ups_spec, p + "5.", cout + s, cout, mult, td)
         _attn(ups_spec, p + "6.", cout, L, at)
     spec += ups_spec
     for j in range(cfg["mid_depth"] - 1):
-        _convnext(spec, f"mid_left.{j}.", mid, mid, mult, td)
+        _blk(spec, f"mid_left.{j}.", mid, mid, mult, td)
     for j in range(cfg["mid_depth"] - 1):
-        _convnext(spec, f"mid_right.{j}.", mid * 2, mid, mult, td)
-    _convnext(spec, "mid_mid.0.", mid, mid, mult, td)
+        _blk(spec, f"mid_right.{j}.", mid * 2, mid, mult, td)
+    _blk(spec, "mid_mid.0.", mid, mid, mult, td)
     _attn(spec, "mid_mid.1.", mid, L, at)
-    _convnext(spec, "mid_mid.2.", mid, mid, mult, td)
-    _convnext(spec, "final_conv.0.", dd[0] + ud[-1], ud[-1], mult, None)
+    _blk(spec, "mid_mid.2.", mid, mid, mult, td)
+    _blk(spec, "final_conv.0.", dd[0] + ud[-1], ud[-1], mult, None)
     spec += [("final_conv.1.weight", (cfg["out_dim"], ud[-1], 3, 3)), ("final_conv.1.bias", (cfg["out_dim"],))]
     return spec
 

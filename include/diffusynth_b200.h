@@ -175,6 +175,9 @@ int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, l
 int ds_gn_act(const void* d_x, void* d_out, const void* d_part, int chunks, const float* d_gamma, const float* d_beta,
               int N, int C, int Cp, int G, long long hw, float eps, int act, void* stream);
 int ds_add_bf16(const void* d_a, const void* d_b, void* d_out, long long n, void* stream);
+/* x[n][pixel][c] += bias[n*bias_stride + c] in place, act16 NHWC [N, hw, C] (bias_stride 0: one row): the time embedding that
+   ResnetBlock adds between its two conv + GroupNorm + SiLU blocks (model/diffusion_components.py:79-104, use_convnext=False). */
+int ds_add_channel_bias(void* d_x, const float* d_bias, long long bias_stride, int N, int C, long long hw, void* stream);
 /* Decoder heads (:394-398): softplus / tanh / tanh of (a + b), fp32 NCHW [N,3,H,W]; b (nin_shortcut branch) nullable. */
 int ds_decoder_head(const float* d_a, const float* d_b, float* d_out, int N, long long hw, void* stream);
 int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int Cp, long long hw, void* stream);

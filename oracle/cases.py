@@ -12,6 +12,7 @@ SMALL_UNET = dict(in_dim=4, down_dims=[32, 32, 64], up_dims=[64, 64, 32], mid_de
 
 
 SMALL_UNET_CAT = dict(SMALL_UNET, attn_type="linear_cat")
+SMALL_UNET_RESNET = dict(SMALL_UNET, use_convnext=False, resnet_block_groups=8)
 
 
 def randn(shape, seed):
@@ -31,6 +32,8 @@ def unet_case(name: str):
         cfg, B, Wd = SMALL_UNET, 2, 16
     elif name == "small_w10":           # 10 -> 5 -> 2
         cfg, B, Wd = SMALL_UNET, 2, 10
+    elif name == "small_resnet_w16":    # use_convnext=False: ResnetBlock (conv3x3 -> GroupNorm(8) -> SiLU) x 2
+        cfg, B, Wd = SMALL_UNET_RESNET, 2, 16
     elif name == "small_cat_w16":       # attn_type="linear_cat" (LinearCrossAttention: the condition is an extra key / value token)
         cfg, B, Wd = SMALL_UNET_CAT, 2, 16
     else:

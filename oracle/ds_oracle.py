@@ -246,6 +246,28 @@ def convnext_block(sd: SD, p: str, x: Tensor, temb: Optional[Tensor]) -> Tensor:
     return h + x
 
 
+def resnet_block(sd: SD, p: str, x: Tensor, temb: Optional[Tensor], groups: int = 8) -> Tensor:
+    """ResnetBlock.forward (use_convnext=False).  diffusion_components.py:59-104: Block = conv3x3 -> GroupNorm(groups) -> SiLU;
+    the time embedding (SiLU -> Linear) is added between the two blocks."""
+    def blk(h, q):
+        h = F.conv2d(h, sd[q + "proj.weight"], sd[q + "proj.bias"], padding=1)
+        return F.silu(F.group_norm(h, groups, sd[q + "norm.weight"], sd[q + "norm.bias"], eps=1e-5))
+    h = blk(x, p + "block1.")
+    if temb is not None and (p + "mlp.1.weight") in sd:
+        h = F.linear(F.silu(temb), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None] + h
+    h = blk(h, p + "block2.")
+    if (p + "res_conv.weight") in sd:
+        return h + F.conv2d(x, sd[p + "res_conv.weight"], sd[p + "res_conv.bias"])
+    return h + x
+
+
+def _block(sd: SD, p: str, x: Tensor, temb: Optional[Tensor]) -> Tensor:
+    """block_klass (diffusion.py:83-87), read off the state_dict."""
+    if (p + "block1.proj.weight") in sd:
+        return resnet_block(sd, p, x, temb)
+    return convnext_block(sd, p, x, temb)
+
+
 def linear_attention_add(sd: SD, p: str, x: Tensor, cemb: Optional[Tensor], heads: int = 4, dh: int = 32) -> Tensor:
     """Residual(PreNorm(LinearCrossAttentionAdd)).  diffusion_components.py:22-29,142-152,252-293."""
     B, C, H, W = x.shape
@@ -301,7 +323,7 @@ def pad_and_concat(enc: Tensor, dec: Tensor) -> Tensor:
 
 
 def unet_forward(sd: SD, x: Tensor, t: Tensor, cond: Optional[Tensor], taps: Optional[dict] = None) -> Tensor:
-    """ConditionedUnet.forward, ConvNeXt blocks with linear_add or linear_cat attention.  model/diffusion.py:187-258.
+    """ConditionedUnet.forward, ConvNeXt or ResNet blocks with linear_add or linear_cat attention.  model/diffusion.py:187-258.
     The architecture is read off the state_dict keys.  ``taps`` (optional dict) receives
     named intermediates for per-layer parity tests."""
     n_stage = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("downs."))
@@ -322,28 +344,28 @@ def unet_forward(sd: SD, x: Tensor, t: Tensor, cond: Optional[Tensor], taps: Opt
     temb = tap("time_emb", time_embedding(sd, t, dim0))
     for i in range(n_stage):
         p = f"downs.{i}."
-        x = tap(p + "0", convnext_block(sd, p + "0.", x, temb))
+        x = tap(p + "0", _block(sd, p + "0.", x, temb))
         x = tap(p + "1", _attention(sd, p + "1.", x, cemb)); hs.append(x)
-        x = tap(p + "2", convnext_block(sd, p + "2.", x, temb))
+        x = tap(p + "2", _block(sd, p + "2.", x, temb))
         x = tap(p + "3", _attention(sd, p + "3.", x, cemb)); hs.append(x)
         x = tap(p + "4", F.conv2d(x, sd[p + "4.weight"], sd[p + "4.bias"], stride=2, padding=1)); hs.append(x)
     for j in range(n_midl):
-        x = tap(f"mid_left.{j}", convnext_block(sd, f"mid_left.{j}.", x, temb)); hs.append(x)
-    x = tap("mid_mid.0", convnext_block(sd, "mid_mid.0.", x, temb))
+        x = tap(f"mid_left.{j}", _block(sd, f"mid_left.{j}.", x, temb)); hs.append(x)
+    x = tap("mid_mid.0", _block(sd, "mid_mid.0.", x, temb))
     x = tap("mid_mid.1", _attention(sd, "mid_mid.1.", x, cemb))
-    x = tap("mid_mid.2", convnext_block(sd, "mid_mid.2.", x, temb))
+    x = tap("mid_mid.2", _block(sd, "mid_mid.2.", x, temb))
     for j in range(n_midl):
-        x = tap(f"mid_right.{j}", convnext_block(sd, f"mid_right.{j}.", pad_and_concat(hs.pop(), x), temb))
+        x = tap(f"mid_right.{j}", _block(sd, f"mid_right.{j}.", pad_and_concat(hs.pop(), x), temb))
     for i in range(n_stage):
         p = f"ups.{i}."
-        x = tap(p + "0", convnext_block(sd, p + "0.", pad_and_concat(hs.pop(), x), temb))
+        x = tap(p + "0", _block(sd, p + "0.", pad_and_concat(hs.pop(), x), temb))
         x = tap(p + "1", _attention(sd, p + "1.", x, cemb))
         x = tap(p + "2", F.conv_transpose2d(x, sd[p + "2.weight"], sd[p + "2.bias"], stride=2, padding=1))
-        x = tap(p + "3", convnext_block(sd, p + "3.", pad_and_concat(hs.pop(), x), temb))
+        x = tap(p + "3", _block(sd, p + "3.", pad_and_concat(hs.pop(), x), temb))
         x = tap(p + "4", _attention(sd, p + "4.", x, cemb))
-        x = tap(p + "5", convnext_block(sd, p + "5.", pad_and_concat(hs.pop(), x), temb))
+        x = tap(p + "5", _block(sd, p + "5.", pad_and_concat(hs.pop(), x), temb))
         x = tap(p + "6", _attention(sd, p + "6.", x, cemb))
-    x = tap("final_conv.0", convnext_block(sd, "final_conv.0.", pad_and_concat(hs.pop(), x), None))
+    x = tap("final_conv.0", _block(sd, "final_conv.0.", pad_and_concat(hs.pop(), x), None))
     return F.conv2d(x, sd["final_conv.1.weight"], sd["final_conv.1.bias"], padding=1)
 
 

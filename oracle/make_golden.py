@@ -27,7 +27,7 @@ def extra(ref):
     glue (utils.py:8-128,194-267), minted from the unmodified reference.  `python -m oracle.make_golden --extra` writes
     only this file."""
     g = {}
-    for name in ("deployed_w28", "small_w10", "small_cat_w16"):
+    for name in ("deployed_w28", "small_w10", "small_cat_w16", "small_resnet_w16"):
         cfg, sd, x, t, cond = cases.unet_case(name)
         net = ref.ConditionedUnet(**cfg).eval()
         net.load_state_dict(sd, strict=True)

@@ -21,10 +21,11 @@ def _unet(cfg, sd):
     return net
 
 
-@pytest.mark.parametrize("name", ["small_w10", "deployed_w28", "small_cat_w16"])
+@pytest.mark.parametrize("name", ["small_w10", "deployed_w28", "small_cat_w16", "small_resnet_w16"])
 def test_unet_odd_width_parity(name, golden):
     """Widths whose stride-2 levels are odd (track_maker's per-note widths, track_maker.py:245): pad_to_match; and the
-    attn_type="linear_cat" variant (the condition as an extra key / value token, ds_attn_finalize_cat)."""
+    attn_type="linear_cat" variant (the condition as an extra key / value token, ds_attn_finalize_cat) and the ResnetBlock variant
+    (use_convnext=False: conv3x3 -> GroupNorm(8) -> SiLU blocks)."""
     cfg, sd, x, t, cond = cases.unet_case(name)
     net = _unet(cfg, sd)
     eps = net.forward(x.cuda(), t.cuda(), cond.cuda()).cpu()

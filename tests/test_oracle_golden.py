@@ -159,10 +159,10 @@ def test_decode_glue_products_match_reference(golden):
         assert np.array_equal(O.latent_image(lat[b]), g["latent_img"][b])
 
 
-@pytest.mark.parametrize("name", ["small_w10", "deployed_w28", "small_cat_w16"])
+@pytest.mark.parametrize("name", ["small_w10", "deployed_w28", "small_cat_w16", "small_resnet_w16"])
 def test_unet_odd_width_matches_reference(golden, name):
     """Widths whose stride-2 levels are odd: the upsampled map is zero-padded to the skip's size (diffusion_components.py:210-232);
-    and the attn_type="linear_cat" variant (LinearCrossAttention, :171-207)."""
+    and the attn_type="linear_cat" (LinearCrossAttention, :171-207) and use_convnext=False (ResnetBlock, :59-104) variants."""
     cfg, sd, x, t, cond = cases.unet_case(name)
     with torch.no_grad():
         eps = O.unet_forward(sd, x, t, cond)

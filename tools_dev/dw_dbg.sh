@@ -1,1 +1,1 @@
-timeout 300 python -m pytest tests/test_gpu_model.py tests/test_gpu_kernels.py -q -m gpu --tb=short -s -k "unet_odd or unet_forward or attention or rejects" 2>&1 | grep -E "passed|failed|Error|assert|eps rel" | tail -14
+timeout 300 python -m pytest tests/test_gpu_model.py -q -m gpu --tb=short -s -k "unet_odd or rejects" 2>&1 | grep -E "passed|failed|Error|error|assert|eps rel" | tail -14

@@ -381,7 +381,15 @@ __global__ void __launch_bounds__(256, 2)
 dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
                    const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
                    act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w,
-                   int tiles, int N, int dbg) {
+                   int tiles, int N, int dbg_arg) {
+  // phase switches for timing experiments (1 skip the MMAs, 2 the output stores, 4 the statistics, 8 the transposes): compiled in
+  // only with -DDS_CONV_DEBUG (DS_DW_DBG=<mask>), a constant 0 otherwise
+#ifdef DS_CONV_DEBUG
+  const int dbg = dbg_arg;
+#else
+  constexpr int dbg = 0;
+  (void)dbg_arg;
+#endif
   extern __shared__ uint8_t dm_smem_raw[];
   uint8_t* smem = dm_smem_raw + ((128u - (smem_u32(dm_smem_raw) & 127u)) & 127u);
   const uint32_t s_raw = smem_u32(smem);                                      // [stage][22 y][22 x][32 c] halves, 64B-swizzled by the TMA unit

@@ -730,6 +730,7 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
     if (gx > work) gx = (int)work;
     if (gx < 1) gx = 1;
     if (use_mma) {
+      static const int dw_dbg = [] { const char* e = getenv("DS_DW_DBG"); return e ? atoi(e) : 0; }();
       static bool mma_attr_set = false;
       if (!mma_attr_set) {
         DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
@@ -740,7 +741,7 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       if (gm < 1) gm = 1;
       dwconv7_mma_kernel<<<dim3(gm, cblks), 256, DM_SMEM_BYTES, (cudaStream_t)stream>>>(
           maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
-          H, W, tiles_w, tiles, N, [] { const char* e = getenv("DS_DW_DBG"); return e ? atoi(e) : 0; }());
+          H, W, tiles_w, tiles, N, dw_dbg);
       DS_CHECK_CUDA(cudaGetLastError());
       return DS_OK;
     }

@@ -102,3 +102,40 @@ def test_tile_and_blocking_choices():
     for hw in [(128, 64), (64, 32), (32, 16), (16, 8), (512, 256), (128, 144), (128, 24)]:
         hb, wb = ops.choose_tile(*hw)
         assert hb * wb == 128
+
+
+@pytest.mark.parametrize("H,W", [(16, 7), (9, 5), (32, 13), (8, 8)])
+def test_conv_args_odd_sizes_and_padded_upsample(H, W):
+    """Host side of pad_to_match (diffusion_components.py:210-232) without a GPU: the stride-2 conv's four parity views get their
+    own extents when the input size is odd, and the ConvTranspose's output addressing (per-phase offsets + strides) lands the
+    upsampled map at (delta // 2) inside a larger zero map -- checked by replaying the addressing on the CPU."""
+    N, C = 2, 32
+    x = torch.zeros((N, H, W, C), dtype=ops.ACT)
+    pc = ops.pack_conv_down(torch.zeros(C, C, 4, 4), torch.zeros(C))
+    out = torch.zeros((N, H // 2, W // 2, C), dtype=ops.ACT)
+    a, _, _ = ops.conv_args(pc, x, None, N, H, W, out=out)
+    assert (a.H, a.W) == (H // 2, W // 2) and a.num_views == 4
+    for v in range(4):
+        py, px = v // 2, v % 2
+        assert (a.view_hv[v], a.view_wv[v]) == (len(range(py, H, 2)), len(range(px, W, 2)))
+        assert a.view_off[v] == py * W + px
+    # the last tap column of the last output pixel exists exactly when the even-parity view is one wider
+    assert (2 * (W // 2 - 1) + 2 < W) == (a.view_wv[0] > W // 2)
+    # up: (H//2, W//2) -> (2*(H//2), 2*(W//2)) written into an (H, W) map
+    pcu = ops.pack_conv_up(torch.zeros(C, C, 4, 4), torch.zeros(C))
+    y = torch.zeros((N, H // 2, W // 2, C), dtype=ops.ACT)
+    big = torch.zeros((N, H, W, C), dtype=ops.ACT)
+    au, _, _ = ops.conv_args(pcu, y, None, N, H // 2, W // 2, out=big)
+    hit = torch.zeros(N * H * W * C, dtype=torch.int32)
+    for g in range(4):
+        for n in range(N):
+            for h in range(H // 2):
+                for w in range(W // 2):
+                    off = au.out_goff[g] + n * au.out_sn + h * au.out_sh + w * au.out_sw
+                    hit[off:off + C] += 1
+    hit = hit.view(N, H, W, C)
+    Ho, Wo = 2 * (H // 2), 2 * (W // 2)
+    top, left = (H - Ho) // 2, (W - Wo) // 2
+    expect = torch.zeros(N, H, W, C, dtype=torch.int32)
+    expect[:, top:top + Ho, left:left + Wo] = 1
+    assert torch.equal(hit, expect)          # every upsampled pixel written exactly once, the padding never

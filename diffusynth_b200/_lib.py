@@ -55,8 +55,8 @@ _SIGNATURES = {
     "ds_conv_gemm_reference": (_I, [C.POINTER(ConvGemmArgs), _P]),
     "ds_conv_gemm_stats_slots": (_I, [C.POINTER(ConvGemmArgs)]),
     "ds_ddim_step": (_I, [_P, _P, _P, _P, _P, _P, _L, _P]),
-    "ds_q_sample": (_I, [_P, _P, _P, _P, _L, _P]),
-    "ds_mask_blend": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _P]),
+    "ds_q_sample": (_I, [_P, _P, _P, _P, _L, _L, _P]),
+    "ds_mask_blend": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _L, _P]),
     "ds_dwconv7": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _F, _I, _I, _I, _P]),
     "ds_dwconv7_stats_slots": (_I, [_I, _I, _I]),
     "ds_stem_conv7": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),

@@ -31,13 +31,17 @@ const char* get_error();
     }                                         \
   } while (0)
 
+// SM count of the CURRENT device (cached per device: one process may drive several GPUs).
 inline int num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;      // (benign race: every thread computes the same value)
   }
   return n;
 }

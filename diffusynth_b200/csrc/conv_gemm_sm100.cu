@@ -734,10 +734,31 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
+// Tuning / profiling knobs.  Production builds have none: every launch parameter is a function of the call's shapes.  Builds
+// with -DDS_CONV_DEBUG (tools_dev experiments) read the DS_CONV_* environment variables ONCE, at the first launch.
+struct Knobs { int dbg, cg, max_sps, min_stages, sps_cyc, max_stages, generic_epi; };
+static const Knobs& knobs() {
+  static const Knobs k = [] {
+    Knobs v{0, 0, 4, 3, 768, 0, 0};
+    const char* e = getenv("DS_CONV_DBG");
+    v.dbg = e ? atoi(e) : 0;
+#ifdef DS_CONV_DEBUG
+    if ((e = getenv("DS_CONV_CG"))) v.cg = atoi(e);
+    if ((e = getenv("DS_CONV_MAX_SPS")) && atoi(e) >= 1 && atoi(e) <= 4) v.max_sps = atoi(e);
+    if ((e = getenv("DS_CONV_MIN_STAGES"))) v.min_stages = atoi(e);
+    if ((e = getenv("DS_CONV_SPS_CYC"))) v.sps_cyc = atoi(e);
+    if ((e = getenv("DS_CONV_MAX_STAGES"))) v.max_stages = atoi(e);
+    if (getenv("DS_CONV_GENERIC_EPI")) v.generic_epi = 1;
+#endif
+    return v;
+  }();
+  return k;
+}
+
 static int validate(const ds_conv_gemm_args* a) {
   DS_REQUIRE(a != nullptr, "ds_conv_gemm: null args");
 #ifndef DS_CONV_DEBUG
-  { const char* e = getenv("DS_CONV_DBG"); DS_REQUIRE(!e || atoi(e) == 0, "ds_conv_gemm: DS_CONV_DBG needs a library built with -DDS_CONV_DEBUG"); }
+  DS_REQUIRE(knobs().dbg == 0, "ds_conv_gemm: DS_CONV_DBG needs a library built with -DDS_CONV_DEBUG");
 #endif
   DS_REQUIRE(a->BK == 32 || a->BK == 64, "ds_conv_gemm: BK must be 32 or 64 (got %d)", a->BK);
   DS_REQUIRE(a->C0 > 0 && a->C0 % a->BK == 0 && a->C1 >= 0 && a->C1 % a->BK == 0,
@@ -780,8 +801,9 @@ static size_t smem_budget(const ds_conv_gemm_args* a) {
 static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   memset(&P, 0, sizeof(P));
   P.N = a->N; P.H = a->H; P.W = a->W; P.Hb = a->Hb; P.Wb = a->Wb;
-  { const char* e = getenv("DS_CONV_DBG"); P.dbg = e ? atoi(e) : 0; }
-#ifndef DS_CONV_DEBUG
+#ifdef DS_CONV_DEBUG
+  P.dbg = knobs().dbg;
+#else
   P.dbg = 0;        // (ds_conv_gemm refuses DS_CONV_DBG on a build without -DDS_CONV_DEBUG)
 #endif
   P.tiles_h = (a->H + a->Hb - 1) / a->Hb;
@@ -789,10 +811,9 @@ static void fill_dev(const ds_conv_gemm_args* a, ConvGemmDev& P) {
   P.tiles_m = P.tiles_h * P.tiles_w;
   // Two-CTA MMA (cta_group::2): the pair computes two M-tiles of one (sample, group, n-tile) with one instruction stream and
   // half of the weight tile per CTA.  It needs an even number of M-tiles; convolutions with enough K per tile to be bound by
-  // the MMA issue rate gain from it (ntaps >= 4); DS_CONV_CG=1/2 forces the choice.
+  // the MMA issue rate gain from it (ntaps >= 4); DS_CONV_CG=1/2 forces the choice in -DDS_CONV_DEBUG builds.
   {
-    const char* e = getenv("DS_CONV_CG");
-    const int want = e ? atoi(e) : (a->ntaps >= 4 ? 2 : 1);
+    const int want = knobs().cg ? knobs().cg : (a->ntaps >= 4 ? 2 : 1);
     const bool even_m = P.tiles_m % 2 == 0;
     const bool flat_ok = a->groups == 1 && !a->per_sample_weights && ((long long)a->N * P.tiles_m) % 2 == 0;
     P.cg = (want == 2 && (even_m || flat_ok) && a->BN % 32 == 0) ? 2 : 1;
@@ -834,7 +855,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_fn();
   DS_REQUIRE(encode != nullptr, "ds_conv_gemm: cuTensorMapEncodeTiled entry point not available");
 
-  static TmaMaps maps;   // zero-initialised; unused slots are copies of a valid map (prefetch-safe)
+  TmaMaps maps;          // per call (host threads may launch concurrently); unused slots are copies of a valid map (prefetch-safe)
   ConvGemmDev P;
   fill_dev(a, P);
   const CUtensorMapSwizzle swz = a->BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -878,18 +899,15 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   {
     const size_t sub = (size_t)P.stage_a_bytes + P.stage_b_bytes;
     const int cyc = (a->BK / 16) * (a->BN / 2);
-    const char* e = getenv("DS_CONV_MAX_SPS");
-    const int max_sps = (e && atoi(e) >= 1 && atoi(e) <= 4) ? atoi(e) : 4;      // the producer keeps at most 4 table entries in registers
-    const char* e2 = getenv("DS_CONV_MIN_STAGES");
-    const int min_stages = e2 ? atoi(e2) : 3;     // three stages already saturate the pipeline (measured); deeper rings buy nothing
-    const char* e3 = getenv("DS_CONV_SPS_CYC");
-    const int cyc_target = e3 ? atoi(e3) : 768;     // measured: two barrier round trips per ~768 MMA cycles keep the single issuing thread off the critical path
+    const int max_sps = knobs().max_sps;          // 4: the producer keeps at most 4 table entries in registers
+    const int min_stages = knobs().min_stages;    // 3: three stages already saturate the pipeline (measured); deeper rings buy nothing
+    const int cyc_target = knobs().sps_cyc;       // 768: measured, two barrier round trips per ~768 MMA cycles keep the single issuing thread off the critical path
     while (P.sps < max_sps && P.sps * cyc < cyc_target && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * min_stages <= budget) ++P.sps;
   }
   const size_t stage_bytes = (size_t)P.sps * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
   int stages = (int)(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  { const char* e = getenv("DS_CONV_MAX_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e); }   // experiment knob
+  if (knobs().max_stages >= 2 && knobs().max_stages < stages) stages = knobs().max_stages;      // (-DDS_CONV_DEBUG experiment knob)
   // (the ring spans tiles of the persistent loop: small-K convs prefetch several tiles ahead, so it is never clamped to K)
   DS_REQUIRE(stages >= 2, "ds_conv_gemm: epilogue tables leave no room for a 2-stage pipeline (Cout_pad=%d ncls=%d)", a->Cout_pad, a->ncls);
   P.stages = stages;
@@ -906,7 +924,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   }
   // epilogue specialisation (see the kernel): the main path needs a 16-bit output whose every chunk is full
   int epi = 0;
-  if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !getenv("DS_CONV_GENERIC_EPI")) {
+  if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !knobs().generic_epi) {
     if (a->act == 0) epi = a->d_residual ? 3 : 1;
     else if (!a->d_residual) epi = 2;
   }

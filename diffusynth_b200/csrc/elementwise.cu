@@ -37,11 +37,13 @@ __global__ void ddim_step_kernel(const float4* __restrict__ eps_u, const float4*
   }
 }
 
-// q_sample: a*x0 + b*noise (model/DiffSynthSampler.py:290-294); coef = {a, b}
+// q_sample: a*x0 + b*noise (model/DiffSynthSampler.py:290-294); coef = {a, b}, or one {a, b} pair per sample when
+// per_sample4 > 0 (= float4 vectors per sample: the reference gathers the coefficients per batch element, :17-22,290-293)
 __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, const float* __restrict__ coef,
-                                float4* __restrict__ out, long long n4) {
-  const float a = coef[0], b = coef[1];
+                                float4* __restrict__ out, long long n4, long long per_sample4) {
+  float a = coef[0], b = coef[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    if (per_sample4 > 0) { const long long n = i / per_sample4; a = __ldg(coef + 2 * n); b = __ldg(coef + 2 * n + 1); }
     float4 p = __ldg(x0 + i), q = __ldg(noise + i);
     out[i] = make_float4(__fadd_rn(__fmul_rn(a, p.x), __fmul_rn(b, q.x)), __fadd_rn(__fmul_rn(a, p.y), __fmul_rn(b, q.y)),
                          __fadd_rn(__fmul_rn(a, p.z), __fmul_rn(b, q.z)), __fadd_rn(__fmul_rn(a, p.w), __fmul_rn(b, q.w)));
@@ -49,13 +51,14 @@ __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __r
 }
 
 // inpaint blend: img = m*(a*guide + b*noise) + (1-m)*img   (model/DiffSynthSampler.py:502-510);
-// mask is [B,1,H,W] broadcast over C channels; coef = {a, b} (a=1,b=0 reproduces the i==0 branch).
+// mask is [B,1,H,W] broadcast over the C channels (mask_c == 1) or [B,C,H,W] (mask_c == C: the reference's inpaint caller repeats
+// its mask over the channels, inpaint_with_text.py:229-231); coef = {a, b} (a=1,b=0 reproduces the i==0 branch).
 __global__ void mask_blend_kernel(const float* __restrict__ guide, const float* __restrict__ noise, const float* __restrict__ mask,
-                                  const float* __restrict__ coef, float* __restrict__ img, int C, long long hw, long long total) {
+                                  const float* __restrict__ coef, float* __restrict__ img, int C, int mask_c, long long hw, long long total) {
   const float a = coef[0], b = coef[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / (C * hw), p = i % hw;
-    const float m = __ldg(mask + n * hw + p);
+    const float m = __ldg(mask_c == 1 ? mask + n * hw + p : mask + i);
     const float g = b == 0.f ? __fmul_rn(a, guide[i]) : __fadd_rn(__fmul_rn(a, guide[i]), __fmul_rn(b, noise[i]));
     img[i] = __fadd_rn(__fmul_rn(m, g), __fmul_rn(__fsub_rn(1.0f, m), img[i]));
   }
@@ -334,19 +337,22 @@ int ds_ddim_step(const float* d_eps_u, const float* d_eps_c, const float* d_x, c
   return DS_OK;
 }
 
-int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, float* d_out, long long n, void* stream) {
+int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, float* d_out, long long n, long long per_sample,
+                void* stream) {
   DS_REQUIRE(d_x0 && d_noise && d_coef && d_out && n > 0 && n % 4 == 0, "ds_q_sample: bad arguments");
+  DS_REQUIRE(per_sample >= 0 && per_sample % 4 == 0 && (per_sample == 0 || n % per_sample == 0), "ds_q_sample: per_sample=%lld must divide n=%lld and be a multiple of 4", per_sample, n);
   q_sample_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_x0, (const float4*)d_noise, d_coef,
-                                                                          (float4*)d_out, n / 4);
+                                                                          (float4*)d_out, n / 4, per_sample / 4);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
 
-int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mask, const float* d_coef, float* d_img, int B, int C,
-                  long long hw, void* stream) {
+int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mask, int mask_channels, const float* d_coef, float* d_img,
+                  int B, int C, long long hw, void* stream) {
   DS_REQUIRE(d_guide && d_noise && d_mask && d_coef && d_img && B > 0 && C > 0 && hw > 0, "ds_mask_blend: bad arguments");
+  DS_REQUIRE(mask_channels == 1 || mask_channels == C, "ds_mask_blend: mask_channels=%d must be 1 or C=%d", mask_channels, C);
   const long long total = (long long)B * C * hw;
-  mask_blend_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_guide, d_noise, d_mask, d_coef, d_img, C, hw, total);
+  mask_blend_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_guide, d_noise, d_mask, d_coef, d_img, C, mask_channels, hw, total);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -8,6 +8,7 @@
 // butterflies in registers and across lanes with warp shuffles, one staging pass through shared memory for the natural-order
 // result; everything is fp32 (the reference runs float64 on the CPU).
 #include "common.cuh"
+#include <mutex>
 #include "../../include/diffusynth_b200.h"
 
 namespace ds {
@@ -212,20 +213,32 @@ __global__ void twiddle_init_kernel(float2* tw512, float2* tw1024) {
   if (i < 512) { double s, c; sincospi((double)i / 512.0, &s, &c); tw1024[i] = make_float2((float)c, (float)s); }
 }
 
-struct Twiddles { float2* tw512 = nullptr; float2* tw1024 = nullptr; int dev = -1; };
-static Twiddles g_tw[16];
+struct Twiddles { float2* tw512 = nullptr; float2* tw1024 = nullptr; bool ready = false; };
+static Twiddles g_tw[64];
+static std::mutex g_tw_mutex;
 
+// Per-device twiddle tables, built once under a mutex on a private blocking stream and synchronised before the first use, so
+// the first caller's stream (or a second host thread on another stream) can never read a half-built table.  The build
+// allocates, so it must not run during a stream capture: a capturing first call is refused (callers warm up once).
 static int get_twiddles(cudaStream_t stream, float2** a, float2** b) {
   int dev = 0;
   DS_CHECK_CUDA(cudaGetDevice(&dev));
-  DS_REQUIRE(dev >= 0 && dev < 16, "istft: device index %d out of range", dev);
+  DS_REQUIRE(dev >= 0 && dev < 64, "istft: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_tw_mutex);
   Twiddles& t = g_tw[dev];
-  if (t.tw512 == nullptr) {
-    // one-time table build on the legacy stream (must not happen inside a graph capture: callers warm up first)
+  if (!t.ready) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    DS_CHECK_CUDA(cudaStreamIsCapturing(stream, &cs));
+    DS_REQUIRE(cs == cudaStreamCaptureStatusNone, "istft: the first STFT/iSTFT call on a device builds its twiddle tables and cannot be captured in a graph; run it once eagerly");
     DS_CHECK_CUDA(cudaMalloc(&t.tw512, 256 * sizeof(float2)));
     DS_CHECK_CUDA(cudaMalloc(&t.tw1024, 512 * sizeof(float2)));
-    twiddle_init_kernel<<<2, 256, 0, stream>>>(t.tw512, t.tw1024);
+    cudaStream_t s0;
+    DS_CHECK_CUDA(cudaStreamCreate(&s0));
+    twiddle_init_kernel<<<2, 256, 0, s0>>>(t.tw512, t.tw1024);
     DS_CHECK_CUDA(cudaGetLastError());
+    DS_CHECK_CUDA(cudaStreamSynchronize(s0));
+    DS_CHECK_CUDA(cudaStreamDestroy(s0));
+    t.ready = true;
   }
   *a = t.tw512;
   *b = t.tw1024;

@@ -286,13 +286,27 @@ def ddim_step(eps_u, eps_c, x, z, coef, out):
           "ds_ddim_step")
 
 
-def q_sample(x0, noise, coef, out):
-    check(_lib.load().ds_q_sample(_ptr(x0), _ptr(noise), _ptr(coef), _ptr(out), x0.numel(), _stream()), "ds_q_sample")
+def q_sample(x0, noise, coef, out, per_sample: int = 0):
+    """coef [2] (one (a, b) pair) or [B, 2] with per_sample = elements per sample."""
+    check(_lib.load().ds_q_sample(_ptr(x0), _ptr(noise), _ptr(coef), _ptr(out), x0.numel(), per_sample, _stream()), "ds_q_sample")
+
+
+def normalize_mask(mask: torch.Tensor, shape, device) -> torch.Tensor:
+    """The reference multiplies ``mask * img`` (DiffSynthSampler.py:506,510), i.e. any mask broadcastable to [B,C,H,W]
+    works there; its callers pass [B,1,H,W] (track_maker.py:252) and [B,C,H,W] (inpaint_with_text.py:229-231).
+    Returns a contiguous fp32 [B,1,H,W] or [B,C,H,W] tensor."""
+    B, Cc, H, W = shape
+    m = mask.to(device, torch.float32)
+    while m.dim() < 4:
+        m = m.unsqueeze(0)
+    mc = 1 if m.shape[1] == 1 else Cc
+    return m.expand(B, mc, H, W).contiguous()
 
 
 def mask_blend(guide, noise, mask, coef, img):
     B, Cc, H, W = img.shape
-    check(_lib.load().ds_mask_blend(_ptr(guide), _ptr(noise), _ptr(mask), _ptr(coef), _ptr(img), B, Cc, H * W, _stream()),
+    assert mask.shape[0] == B and mask.shape[1] in (1, Cc) and tuple(mask.shape[2:]) == (H, W) and mask.is_contiguous(), tuple(mask.shape)
+    check(_lib.load().ds_mask_blend(_ptr(guide), _ptr(noise), _ptr(mask), mask.shape[1], _ptr(coef), _ptr(img), B, Cc, H * W, _stream()),
           "ds_mask_blend")
 
 

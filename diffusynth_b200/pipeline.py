@@ -83,7 +83,9 @@ class TextToTimbre:
         wave = wave.to(self.device, torch.float32)
         wave = wave / wave.abs().amax(dim=-1, keepdim=True).clamp_min(1e-12)              # :75
         wave = adjust_audio_length(wave, 256 * (4 * width - 1))                            # :80-82
-        spec = waveform_to_spectrogram(wave, time_resolution=4 * width)                    # :85-94
+        # pad_STFT(D) is called with its default time_resolution = 256 frames and never crops (tools.py:170-182): clips of
+        # <= 3 s (width <= 64) always encode to a 64-column latent, longer ones to ``width`` columns
+        spec = waveform_to_spectrogram(wave, time_resolution=max(256, 4 * width))          # :85-94
         return self.vqgan._encoder(spec)
 
     @torch.no_grad()
@@ -132,9 +134,17 @@ class TextToTimbre:
         attack and tail are frozen by a mask that shrinks over the steps (``use_dynamic_mask``, mask_flexivity 1.0).
         The width ``int(256 * ((duration + 1) / 4) / 4)`` is arbitrary, odd levels included (pad_to_match)."""
         width = int(time_resolution * ((duration_sec + 1) / 4) / vae_scale)                                   # :245
-        s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy="repeat", mute=True,
-                             device=str(self.device), max_batchsize=1)                                         # :248
-        s.respace(list(np.linspace(0, self.timesteps - 1, sample_steps, dtype=np.int32)))                      # :249
+        # the reference builds a fresh sampler per note (:248-249); here it is cached per step count so that the captured graph
+        # of a (width, steps) pair is reused by every later note of that duration instead of being re-captured
+        key = ("note", sample_steps)
+        s = self._samplers.get(key)
+        if s is None:
+            s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy="repeat", mute=True,
+                                 device=str(self.device), max_batchsize=1)                                     # :248
+            s.respace(list(np.linspace(0, self.timesteps - 1, sample_steps, dtype=np.int32)))                  # :249
+            self._samplers[key] = s
+        s.activate_classifier_free_guidance(1.0, None)
+        s.noise_feed = None
         mask = torch.zeros((1, 1, self.height, width), dtype=torch.float32, device=self.device)                # :252-254
         mask[:, :, :, :int(time_resolution * (attack / 4) / vae_scale)] = 1.0
         mask[:, :, :, -int(time_resolution * ((before_release + 1) / 4) / vae_scale):] = 1.0

@@ -69,7 +69,9 @@ class DiffSynthSampler:
         self.noise_strategy = noise_strategy
         self.noise_feed: Optional[torch.Tensor] = None     # [K, >=B, C, H, train_width]; consumed in draw order
         self._feed_pos = 0
-        self.faithful_rng = False    # draw (and discard) the per-step noise even when eta == 0, like the reference :340
+        # The reference draws the per-step noise even when eta == 0 (:340), which advances the global RNG; True reproduces that RNG
+        # state after sample() at the cost of n_iter discarded randn launches (TextToTimbre turns it off for throughput runs).
+        self.faithful_rng = True
         self._graphs: Dict[tuple, "_GraphLoop"] = {}
         self.last_graph_launches = 0
 
@@ -185,16 +187,19 @@ class DiffSynthSampler:
         if noise is None:
             noise, _ = self.get_deterministic_noise_tensor(x_start.shape[0], x_start.shape[3])
         assert noise.shape == x_start.shape
-        tv = t.reshape(-1)
-        t0 = int(tv[0])
-        if not bool((tv == t0).all()):
-            raise NotImplementedError("q_sample with per-sample timesteps")
-        coef = torch.tensor([np.float32(self.sqrt_alphas_cumprod[t0]), np.float32(self.sqrt_one_minus_alphas_cumprod[t0])],
-                            dtype=torch.float32, device=self.device)
+        tv = [int(v) for v in torch.as_tensor(t).reshape(-1).tolist()]
         x0 = x_start.to(self.device, torch.float32).contiguous()
         nz = noise.to(self.device, torch.float32).contiguous()
         out = torch.empty_like(x0)
-        ops.q_sample(x0, nz, coef, out)
+        if all(v == tv[0] for v in tv):
+            coef = torch.tensor([np.float32(self.sqrt_alphas_cumprod[tv[0]]), np.float32(self.sqrt_one_minus_alphas_cumprod[tv[0]])],
+                                dtype=torch.float32, device=self.device)
+            ops.q_sample(x0, nz, coef, out)
+        else:       # per-sample timesteps: one coefficient pair per batch element, gathered like _extract_into_tensor (:6-22)
+            assert len(tv) == x0.shape[0], "t must hold one timestep per sample"
+            coef = torch.tensor([[np.float32(self.sqrt_alphas_cumprod[v]), np.float32(self.sqrt_one_minus_alphas_cumprod[v])] for v in tv],
+                                dtype=torch.float32, device=self.device)
+            ops.q_sample(x0, nz, coef, out, per_sample=x0[0].numel())
         return out
 
     @torch.no_grad()
@@ -288,6 +293,8 @@ class DiffSynthSampler:
         if use_dynamic_mask:
             masks = self.get_dynamic_masks(n_iter, shape, concat_points, mask_flexivity)
         else:
+            if inpaint and mask is not None:
+                mask = ops.normalize_mask(mask, shape, self.device)       # [B,1,H,W] or [B,C,H,W], as the reference's callers pass
             masks = [mask for _ in range(n_iter)]
         steps = list(reversed(range(end, start)))
 
@@ -313,7 +320,7 @@ class DiffSynthSampler:
                                         dtype=torch.float32, device=self.device)
                 else:
                     coef = torch.tensor([1.0, 0.0], dtype=torch.float32, device=self.device)
-                ops.mask_blend(guide_img, initial_noise, current_mask.to(self.device, torch.float32).contiguous(), coef, img)
+                ops.mask_blend(guide_img, initial_noise, ops.normalize_mask(current_mask, img.shape, self.device), coef, img)
             imgs.append(img)
         return imgs
 
@@ -321,9 +328,13 @@ class DiffSynthSampler:
         B, Cc, H, Wd = shape
         cfg_on = self.CFG != 1.0
         n_iter = len(steps)
-        key = (id(model), shape, n_iter, eta > 0, cfg_on, inpaint)
+        # the captured graph points at the model's packed weights: a repack (load_state_dict / .to) bumps weights_version and
+        # retires every loop built on the old tensors; the loop also holds the model, so its id() cannot be recycled
+        key = (id(model), model.weights_version, shape, n_iter, eta > 0, cfg_on, inpaint)
         loop = self._graphs.get(key)
         if loop is None:
+            for k in [k for k, v in self._graphs.items() if v.model is model and k[1] != model.weights_version]:
+                del self._graphs[k]
             loop = _GraphLoop(self, model, shape, n_iter, eta > 0, cfg_on, inpaint)
             self._graphs[key] = loop
         # per-call inputs (device buffers the graph reads)
@@ -352,7 +363,7 @@ class DiffSynthSampler:
                     ab.append([np.float32(self.sqrt_alphas_cumprod[i - 1]), np.float32(self.sqrt_one_minus_alphas_cumprod[i - 1])])
                 else:
                     ab.append([1.0, 0.0])
-                loop.masks[k].copy_(cur.to(self.device, torch.float32))
+                loop.masks[k].copy_(ops.normalize_mask(cur, shape, self.device).expand(B, Cc, H, Wd))
             loop.blend_coef.copy_(torch.tensor(ab, dtype=torch.float32))
             loop.guide.copy_(guide_img)
             loop.init_noise.copy_(initial_noise)
@@ -406,12 +417,13 @@ class _GraphLoop:
         B, Cc, H, Wd = shape
         f32 = dict(dtype=torch.float32, device=dev)
         self.n_iter, self.cfg_on = n_iter, cfg_on
+        self.model = model
         self.imgs = torch.zeros((n_iter + 1, B, Cc, H, Wd), **f32)
         self.coef = torch.zeros((n_iter, 8), **f32)
         self.ttab = torch.zeros((n_iter,), dtype=torch.long, device=dev)
         self.noise = torch.zeros((n_iter, B, Cc, H, Wd), **f32) if stochastic else None
         if inpaint:
-            self.masks = torch.zeros((n_iter, B, 1, H, Wd), **f32)
+            self.masks = torch.zeros((n_iter, B, Cc, H, Wd), **f32)      # per channel: the reference broadcasts any mask shape
             self.blend_coef = torch.zeros((n_iter, 2), **f32)
             self.guide = torch.zeros((B, Cc, H, Wd), **f32)
             self.init_noise = torch.zeros((B, Cc, H, Wd), **f32)

@@ -124,6 +124,7 @@ class ConditionedUnet:
         self.device = torch.device(device if device is not None else "cuda")
         self._sd: Optional[OrderedDict] = None
         self._plans: Dict[Tuple, "_Plan"] = {}
+        self.weights_version = 0      # bumped by every repack; graph caches key on it (sampler._run_graph_loop)
         self.training = False
 
     # ---- nn.Module-like surface ------------------------------------------------------------
@@ -166,6 +167,7 @@ class ConditionedUnet:
     def _pack(self):
         sd, cfg, dev = self._sd, self.cfg, self.device
         dd, ud, td, L = cfg["down_dims"], cfg["up_dims"], cfg["time_dim"], cfg["label_emb_dim"]
+        self.weights_version += 1
         self._probe = torch.zeros(1, device=dev)
         self.blocks: "OrderedDict[str, _Block]" = OrderedDict()
         self.attns: "OrderedDict[str, _Attn]" = OrderedDict()

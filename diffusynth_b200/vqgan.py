@@ -36,6 +36,9 @@ class VectorQuantizerEMA:
         self.codebook: Optional[torch.Tensor] = None
         self.training = False
         self.last_indices: Optional[torch.Tensor] = None
+        # loss / perplexity of the eval branch (:130,:136-142) are computed like the reference does unless this is switched
+        # off; every caller on the sampling path discards them (text2sound.py:128), so TextToTimbre asks for None instead
+        self.compute_aux = True
 
     def load_codebook(self, weight: torch.Tensor):
         assert tuple(weight.shape) == (self._num_embeddings, self._embedding_dim)
@@ -52,9 +55,10 @@ class VectorQuantizerEMA:
         assert Cc == self._embedding_dim
         out = torch.empty_like(x)
         idx = torch.empty((B * H * Wd,), dtype=torch.long, device=self.device)
-        check(_lib.load().ds_vq_quantize(x.data_ptr(), self.codebook.data_ptr(), self._num_embeddings, out.data_ptr(), idx.data_ptr(),
-                                         B, H * Wd, ops._stream()), "ds_vq_quantize")
+        self.quantize_into(x, out, idx)
         self.last_indices = idx
+        if not self.compute_aux:
+            return out, None, (None, None, idx if return_indices else None)
         q = self.codebook[idx].view(B, H, Wd, Cc).permute(0, 3, 1, 2)
         loss = self._commitment_cost * torch.mean((q - x) ** 2)
         probs = torch.bincount(idx, minlength=self._num_embeddings).float() / idx.numel()
@@ -64,6 +68,12 @@ class VectorQuantizerEMA:
         return out, loss, (perplexity, None, None)
 
     __call__ = forward
+
+    def quantize_into(self, x: torch.Tensor, out: torch.Tensor, idx: torch.Tensor) -> None:
+        """The quantiser kernel alone on caller-owned buffers (capturable in a CUDA graph): x, out fp32 [B,4,H,W], idx int64 [B*H*W]."""
+        B, Cc, H, Wd = x.shape
+        check(_lib.load().ds_vq_quantize(x.data_ptr(), self.codebook.data_ptr(), self._num_embeddings, out.data_ptr(), idx.data_ptr(),
+                                         B, H * Wd, ops._stream()), "ds_vq_quantize")
 
     def eval(self):
         return self

@@ -125,10 +125,13 @@ int ds_conv_gemm_reference(const ds_conv_gemm_args* args, void* stream);
    d_eps_u NULL <=> CFG == 1.0 (:311-312).  d_z NULL only when sigma == 0.  n = element count (%4). */
 int ds_ddim_step(const float* d_eps_u, const float* d_eps_c, const float* d_x, const float* d_z,
                  const float* d_coef, float* d_out, long long n, void* stream);
-/* q_sample (:271-294): out = coef[0]*x0 + coef[1]*noise. */
-int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, float* d_out, long long n, void* stream);
-/* inpaint blend (:499-510): img = m*(coef[0]*guide + coef[1]*noise) + (1-m)*img, mask [B,1,H,W]. */
-int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mask, const float* d_coef,
+/* q_sample (:271-294): out = coef[0]*x0 + coef[1]*noise; per_sample > 0: d_coef holds one {a, b} pair per sample of
+   per_sample elements (per-sample timesteps, :17-22), 0: one pair for the whole tensor. */
+int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, float* d_out, long long n, long long per_sample,
+                void* stream);
+/* inpaint blend (:499-510): img = m*(coef[0]*guide + coef[1]*noise) + (1-m)*img; mask [B,mask_channels,H,W] with
+   mask_channels 1 (broadcast over C) or C (the reference's inpaint caller repeats it, inpaint_with_text.py:229-231). */
+int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mask, int mask_channels, const float* d_coef,
                   float* d_img, int B, int C, long long hw, void* stream);
 
 /* ----------------------------------------------------------------------------------------

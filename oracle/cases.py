@@ -76,3 +76,29 @@ def spec_representation(B=2, T=12, seed=51):
 
 def small_latents(B=2, H=16, Wd=8, seed=52):
     return randn((B, 4, H, Wd), seed) * 2.0
+
+
+HEADLINE_SEEDS = dict(ddim20=101, ddpm20=102, modify20=103)
+
+
+def headline_inputs(name: str):
+    """Seeded inputs of the headline-configuration runs (shared with tests/test_gpu_headline.py and test_oracle_golden.py):
+    deployed U-Net, B = 2, CFG 6, 20 steps; "modify20" = BASELINE config 5 (strength 0.7 -> 28 respaced steps, 19 U-Net steps)."""
+    B = 2
+    cond, uncond = W.synthetic_conditions(B, 512)
+    if name == "modify20":
+        n_steps = int(20 / 0.7)
+        draws = W.host_noise(HEADLINE_SEEDS[name], 1 + int(n_steps * 0.7), B)
+        guide = vq_latents(B=1, seed=23).repeat(B, 1, 1, 1)
+        return dict(B=B, cond=cond, uncond=uncond, draws=draws, n_steps=n_steps, strength=0.7, guide=guide, sampler="ddim")
+    draws = W.host_noise(HEADLINE_SEEDS[name], 21, B)
+    return dict(B=B, cond=cond, uncond=uncond, draws=draws, n_steps=20, strength=1.0, guide=None,
+                sampler="ddpm" if name == "ddpm20" else "ddim")
+
+
+def headline_digest(imgs):
+    """What the fixture keeps of a list of per-step latents: every 64th value of every step, per-step (mean, rms, absmax),
+    and the final latent in full."""
+    sub = np.stack([im.flatten()[::64].numpy() for im in imgs])
+    st = np.stack([np.array([im.double().mean().item(), im.double().pow(2).mean().sqrt().item(), im.abs().max().item()]) for im in imgs])
+    return sub.astype(np.float32), st, imgs[-1].numpy()

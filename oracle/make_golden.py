@@ -65,10 +65,39 @@ def extra(ref):
 
 
 @torch.no_grad()
+def headline(ref):
+    """tests/golden/headline.npz: the benchmark's own sampling configuration (deployed U-Net, 20 respaced steps, CFG 6, DDIM and
+    DDPM) and BASELINE config 5 (timbre modification, 20 / 0.7 -> 28 respaced, 19 U-Net steps) run through the UNMODIFIED reference
+    (DiffSynthSampler.py:520-536, :562-583) at B = 2 with host-fed noise.  `python -m oracle.make_golden --headline`."""
+    g = {}
+    usd = W.unet_random_state_dict(seed=0)
+    net = ref.ConditionedUnet(**W.UNET_DEPLOYED).eval()
+    net.load_state_dict(usd, strict=True)
+    for name in ("ddim20", "ddpm20", "modify20"):
+        I = cases.headline_inputs(name)
+        S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=I["B"]), I["draws"])
+        S.activate_classifier_free_guidance(6, I["uncond"])
+        S.respace(list(np.linspace(0, 999, I["n_steps"], dtype=np.int32)))
+        shape = (I["B"], 4, 128, 64)
+        if name == "modify20":
+            imgs, _ = S.img_guided_sample(net, shape, I["strength"], I["guide"], return_tensor=True, condition=I["cond"],
+                                          sampler=I["sampler"], initial_noise=I["draws"][0])
+        else:
+            imgs, _ = S.sample(net, shape, return_tensor=True, condition=I["cond"], sampler=I["sampler"], initial_noise=I["draws"][0])
+        g[f"{name}_sub"], g[f"{name}_stats"], g[f"{name}_final"] = cases.headline_digest(imgs)
+        print(name, len(imgs), "latents; rms per step", np.round(g[f"{name}_stats"][:, 1], 3))
+    np.savez_compressed(os.path.join(OUT, "headline.npz"), **g)
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--headline" in sys.argv:
+        headline(ref)
+        print("headline.npz", os.path.getsize(os.path.join(OUT, "headline.npz")))
+        return
     extra(ref)
     if "--extra" in sys.argv:
         print("extra.npz", os.path.getsize(os.path.join(OUT, "extra.npz")))

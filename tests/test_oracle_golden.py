@@ -203,3 +203,24 @@ def test_griffinlim_oracle_converges():
     assert e[2] < e[1] < e[0] and e[2] < 0.25 * e[0]
     back = O.griffinlim(S, np.angle(D), n_iter=3)
     assert rel(back[1024:-1024], y[1024:-1024]) < 1e-9
+
+
+def test_headline_modify20_oracle_matches_reference(golden):
+    """The oracle at the benchmark's own scale -- deployed U-Net, CFG 6, BASELINE config 5 (20 / 0.7 -> 28 respaced steps,
+    19 guided U-Net steps) -- against the unmodified reference's run (tests/golden/headline.npz, oracle/make_golden.py --headline).
+    (The 20-step DDIM / DDPM oracle runs are checked against the same fixture inside tests/test_gpu_headline.py, where they are
+    computed anyway; one of the three here keeps the CPU suite short.)"""
+    I = cases.headline_inputs("modify20")
+    usd = W.unet_random_state_dict(seed=0)
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, I["n_steps"], dtype=np.int32)))
+    torch.set_num_threads(max(1, min(16, __import__("os").cpu_count() or 1)))
+    with torch.no_grad():
+        imgs = O.sample_loop(lambda x, t, c: O.unet_forward(usd, x, t, c), sch, (I["B"], 4, 128, 64), I["cond"], I["uncond"], 6, I["draws"],
+                             sampler=I["sampler"], guide=I["guide"], start_ratio=I["strength"])
+    g = golden["headline"]
+    sub, st, final = cases.headline_digest(imgs)
+    assert sub.shape == g["modify20_sub"].shape == (20, 1024)
+    assert np.linalg.norm(final - g["modify20_final"]) / np.linalg.norm(g["modify20_final"]) < 1e-4
+    for k in range(sub.shape[0]):
+        assert np.linalg.norm(sub[k] - g["modify20_sub"][k]) / np.linalg.norm(g["modify20_sub"][k]) < 1e-4, k

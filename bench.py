@@ -32,6 +32,7 @@ BATCH = 64
 WIDTH = 64
 CFG_SCALE = 6
 METRIC = "timbres_per_sec"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # nominal CUDA-core fp32 FMA peak of a B200 at its 1965 MHz maximum clock (74.4)
 
 
 def peaks():
@@ -83,17 +84,23 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle port) on the host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_arm(sample_steps: int, unet_evals: int = 2, threads: int | None = None):
+def _cpu_models():
     from diffusynth_b200 import weights as W
-    from oracle import ds_oracle as O
-    threads = threads or os.cpu_count() or 1
-    torch.set_num_threads(threads)
     usd, vsd = W.unet_random_state_dict(seed=0, perturb_norm=False), W.vqgan_random_state_dict(seed=1, perturb_norm=False)
     _, dec_plan = W.vqgan_layer_plan(W.VQGAN_DEPLOYED)
+    return usd, vsd, dec_plan
+
+
+def cpu_timbre(models, sample_steps: int, noise_seed: int = 0):
+    """ONE full batch-1 timbre on the host: `sample_steps` CFG-doubled U-Net steps -> quantiser -> decoder -> iSTFT (BASELINE.json
+    configs[0] / BASELINE.md section 3), fp32 torch oracle port of the reference.  Returns (timings, latent, waveform)."""
+    from diffusynth_b200 import weights as W
+    from oracle import ds_oracle as O
+    usd, vsd, dec_plan = models
     cond, uncond = W.synthetic_conditions(1, 512)
     sch = O.Schedule(1000)
-    sch.respace(list(np.linspace(0, 999, unet_evals, dtype=np.int32)))
-    draws = W.host_noise(0, 1 + unet_evals, 1)
+    sch.respace(list(np.linspace(0, 999, sample_steps, dtype=np.int32)))
+    draws = W.host_noise(noise_seed, 1 + sample_steps, 1)
     with torch.no_grad():
         t0 = time.perf_counter()
         lat = O.sample_loop(lambda x, t, c: O.unet_forward(usd, x, t, c), sch, (1, 4, 128, WIDTH), cond, uncond, CFG_SCALE, draws)[-1]
@@ -107,35 +114,63 @@ def cpu_arm(sample_steps: int, unet_evals: int = 2, threads: int | None = None):
         t2 = time.perf_counter()
         spec = O.vqgan_decode(vsd, dec_plan, q)
         t3 = time.perf_counter()
-        O.spectrogram_to_waveform(spec[0].numpy().astype(np.float64))
+        wave = O.spectrogram_to_waveform(spec[0].numpy().astype(np.float64))
         t4 = time.perf_counter()
-    step_s = (t1 - t0) / unet_evals
-    tail_s = t4 - t1
-    per_timbre = step_s * sample_steps + tail_s
-    return dict(value=1.0 / per_timbre, unit="timbres/s", cores=threads, kind="port",
-                sample=f"batch 1: {unet_evals} CFG-doubled U-Net steps ({step_s:.3f} s each) + VQ {t2 - t1:.3f} s + decoder {t3 - t2:.3f} s + iSTFT {t4 - t3:.3f} s, "
-                       f"extrapolated to {sample_steps} steps; fp32 torch oracle port of the reference",
-                s_per_unet_step=step_s, s_tail=tail_s, s_per_timbre=per_timbre)
+    return dict(total=t4 - t0, sampler=t1 - t0, vq=t2 - t1, decoder=t3 - t2, istft=t4 - t3), lat, wave
+
+
+def cpu_arm(sample_steps: int, threads: int | None = None, repeats: int = 3, also_steps=(10,), keep_outputs: bool = False):
+    """batch 1, fp32, all host cores, 1 warm-up, median of `repeats` FULL runs (no extrapolation) at the
+    benchmark's step count, plus the same at the reference's CPU default of 10 steps."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    models = _cpu_models()
+    cpu_timbre(models, 2)                                   # warm-up (thread pool, allocator, oneDNN primitive caches)
+    res = {}
+    outs = None
+    for st in tuple(also_steps) + (sample_steps,):
+        runs = []
+        for _ in range(repeats):
+            tm, lat, wave = cpu_timbre(models, st)
+            runs.append(tm)
+            if st == sample_steps:
+                outs = (lat, wave)
+        runs.sort(key=lambda r: r["total"])
+        res[st] = runs[len(runs) // 2]
+    m = res[sample_steps]
+    sample = (f"batch 1, median of {repeats} full runs after 1 warm-up: {sample_steps} CFG-doubled U-Net steps {m['sampler']:.2f} s "
+              f"({m['sampler'] / sample_steps:.3f} s/step) + VQ {m['vq']:.3f} s + decoder {m['decoder']:.3f} s + iSTFT {m['istft']:.3f} s = {m['total']:.2f} s/timbre; "
+              + "; ".join(f"{st} steps: {res[st]['total']:.2f} s/timbre" for st in also_steps)
+              + "; fp32 torch oracle port of the reference (the reference tree does not exist on the GPU box)")
+    out = dict(value=1.0 / m["total"], unit="timbres/s", cores=threads, kind="port", sample=sample,
+               s_per_timbre={str(st): res[st]["total"] for st in res}, s_per_unet_step=m["sampler"] / sample_steps,
+               split_s={k: m[k] for k in ("sampler", "vq", "decoder", "istft")})
+    if keep_outputs:
+        out["_outputs"] = outs
+    return out
 
 
 def run_reference(args):
+    """Reference arm: every step is ONE full batch-1 timbre of the workload (all `sample_steps` U-Net steps + tail) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for _ in range(args.warmup):
-        cpu_arm(args.sample_steps, unet_evals=1)
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    models = _cpu_models()
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_timbre(models, 2)
     t0 = time.perf_counter()
-    last = None
-    for _ in range(args.steps):
-        last = cpu_arm(args.sample_steps, unet_evals=2)
-        vals.append(last["value"])
+    runs = [cpu_timbre(models, args.sample_steps)[0] for _ in range(args.steps)]
     wall = time.perf_counter() - t0
-    v = float(np.mean(vals))
+    v = args.steps / wall
+    m = sorted(runs, key=lambda r: r["total"])[len(runs) // 2]
+    sample = (f"each step = one full batch-1 timbre ({args.sample_steps} CFG-doubled U-Net steps + VQ + decoder + iSTFT), no extrapolation; median split: "
+              f"sampler {m['sampler']:.2f} s, VQ {m['vq']:.3f} s, decoder {m['decoder']:.3f} s, iSTFT {m['istft']:.3f} s; fp32 torch oracle port of the reference")
     line = dict(metric=METRIC, value=v, unit="timbres/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000.0 * wall / max(1, args.steps), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=workload_config(args, args.gpus),
-                cpu_baseline=dict(value=v, unit="timbres/s", cores=last["cores"], kind=last["kind"], sample=last["sample"]),
+                cpu_baseline=dict(value=v, unit="timbres/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=v, unit="timbres/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(json.dumps(line))
 
@@ -151,64 +186,51 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def conv_flops(a) -> float:
-    """Algorithmic FLOPs (2/MAC, real channels, no padding) of one ds_conv_gemm argument block."""
-    k = a.ntaps * (a.C0 + a.C1)
-    return 2.0 * a.N * a.groups * a.H * a.W * a.Cout * k
-
-
-def profile_unet_eval(plan):
-    """One eager (un-graphed) U-Net evaluation with CUDA events around every launch -> ms per kernel family and the
-    algorithmic FLOPs of the tcgen05 conv launches."""
-    from diffusynth_b200._lib import ConvGemmArgs
-    evs = []
-    torch.cuda.synchronize()
-    for name, fn in plan.ops:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        evs.append((name, e0, e1))
-    torch.cuda.synchronize()
-    fam = {}
-    for name, e0, e1 in evs:
-        if False:
-            pass
-        elif name.endswith(("net.1", "net.4", "final_conv.1")):
-            key = "conv_gemm(3x3)"
-        elif name.endswith(("res_conv", "to_qkv", "to_out")):
-            key = "conv_gemm(1x1)"
-        elif name.endswith(("ds_conv",)):
-            key = "dwconv7"
-        elif name.endswith(("ctx", "fin")):
-            key = "attn_core"
-        elif name.endswith("gn_res"):
-            key = "gn_apply_residual"
-        elif name == "init_conv":
-            key = "conv_gemm(1x1)"
-        elif name == "init_im2col":
-            key = "stem_im2col"
-        elif name.startswith("time_"):
-            key = "time_mlp"
-        else:
-            key = "conv_gemm(4x4s2/T)"
-        fam[key] = fam.get(key, 0.0) + e0.elapsed_time(e1)
-    flops = sum(conv_flops(k) for k in plan.keep if isinstance(k, ConvGemmArgs))
-    launches = sum(1 for k in plan.keep if isinstance(k, ConvGemmArgs))
-    if os.environ.get("DS_DUMP_OPS"):
-        convs = [k for k in plan.keep if isinstance(k, ConvGemmArgs)]
-        ci, rows = 0, []
+def timed_ops(op_list, reps: int = 2):
+    """Eager (un-graphed) pass over a plan's ops with CUDA events around every launch (on torch's current stream, which is
+    the stream the launches go to); best of `reps` per op.  -> {op name: ms}."""
+    best = {}
+    for _ in range(reps):
+        evs = []
+        torch.cuda.synchronize()
+        for name, fn in op_list:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((name, e0, e1))
+        torch.cuda.synchronize()
         for name, e0, e1 in evs:
             ms = e0.elapsed_time(e1)
-            row = dict(op=name, ms=round(ms, 4))
-            is_conv = name == "init_conv" or name.endswith(("net.1", "net.4", "final_conv.1", "res_conv", "to_qkv", "to_out")) or name.split(".")[-1] in ("2", "4") and name.count(".") == 2
-            if is_conv and ci < len(convs):
-                a = convs[ci]; ci += 1
-                row.update(tflops=round(conv_flops(a) / (ms / 1e3) / 1e12, 1), H=a.H, W=a.W, Cin=a.C0 + a.C1, Cout=a.Cout, taps=a.ntaps, BN=a.BN, BK=a.BK)
-            rows.append(row)
-        with open(os.environ["DS_DUMP_OPS"], "w") as f:
-            json.dump(rows, f, indent=0)
-    return fam, flops, launches
+            best[name] = min(best.get(name, 1e30), ms)
+    return best
+
+
+def family_rooflines(ms_by_op, meta, pk, per=1.0):
+    """Group ops into kernel families; per family: launches, ms, algorithmic FLOPs / bytes, the roofline time
+    max(flops / tensor peak, bytes / HBM peak), which roof binds, and frac = roofline time / measured time."""
+    fams = {}
+    for name, ms in ms_by_op.items():
+        m = meta.get(name, dict(family="misc", flops=0.0, bytes=0.0))
+        f = fams.setdefault(m["family"], dict(launches=0, ms=0.0, gflop=0.0, mbytes=0.0, gflop32=0.0))
+        f["launches"] += 1
+        f["ms"] += ms
+        f["gflop"] += m["flops"] / 1e9
+        f["mbytes"] += m["bytes"] / 1e6
+        f["gflop32"] += m.get("fp32_flops", 0.0) / 1e9
+    out = {}
+    for k, f in sorted(fams.items(), key=lambda kv: -kv[1]["ms"]):
+        t_tensor = f["gflop"] / (pk["tf_sustained"] * 1e3)         # ms
+        t_hbm = f["mbytes"] / (pk["hbm"] * 1e3) * 1e3 / 1e3           # MB / (GB/s) = ms
+        t_fp32 = f["gflop32"] / (FP32_PEAK_TFLOPS * 1e3)              # CUDA-core fp32 work (the quantiser's distance search)
+        t_roof = max(t_tensor, t_hbm, t_fp32)
+        out[k] = dict(launches=f["launches"], ms=round(f["ms"] / per, 4), algorithmic_gflop=round((f["gflop"] + f["gflop32"]) / per, 2),
+                      algorithmic_mbytes=round(f["mbytes"] / per, 1),
+                      bound="fp32-alu" if t_fp32 >= max(t_tensor, t_hbm) else "tensor" if t_tensor >= t_hbm else "hbm",
+                      achieved_tflops=round(f["gflop"] / f["ms"], 1) if f["ms"] > 0 else None,
+                      achieved_gbs=round(f["mbytes"] / f["ms"], 1) if f["ms"] > 0 else None,
+                      frac=round(t_roof / f["ms"], 4) if f["ms"] > 0 and t_roof > 0 else None)
+    return out
 
 
 def run_b200(args):
@@ -232,9 +254,11 @@ def run_b200(args):
     uncond_dev = uncond.to(dev)
     cond_dev = cond_host.to(dev)
     wave_host = torch.empty((BATCH, 256 * (4 * WIDTH - 1)), dtype=torch.float32).pin_memory()
+    finite = []
 
     def step_device():
         out = pipe.generate(cond_dev, uncond_dev, steps=args.sample_steps, cfg_scale=CFG_SCALE, width=WIDTH, seed=None)
+        finite.append(torch.isfinite(out.waveforms).all())            # device-side flag, read after the timed region
         if world > 1:
             return all_gather_waveforms(out.waveforms, total, world)
         return out.waveforms
@@ -268,29 +292,37 @@ def run_b200(args):
         return float(ms.item())
 
     torch.manual_seed(1234 + rank)
-    for _ in range(max(3, args.warmup)):
+    warm = max(3, args.warmup)
+    for _ in range(warm):
         step_device()
+    finite.clear()
     with ClockSampler(local) as clk:
         ms_dev = timed(step_device, args.steps)
     clocks = clk.summary()
+    all_finite = all(bool(f) for f in finite)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    all_finite = all_finite and bool(np.isfinite(wave_host.numpy()).all())
 
     value = total * args.steps / (ms_dev / 1e3)
     e2e_value = total * args.steps / (ms_e2e / 1e3)
-    line = None
     if rank == 0:
         pk = peaks()
         sampler = pipe._samplers[(BATCH, args.sample_steps)]
         loop = next(iter(sampler._graphs.values()))
         plan = loop.plan
-        fam, flops, conv_launches = profile_unet_eval(plan)
-        fam2, _, _ = profile_unet_eval(plan)
-        fam = {k: min(v, fam2[k]) for k, v in fam.items()}
-        conv_ms = sum(v for k, v in fam.items() if k.startswith("conv_gemm"))
-        unet_ms = sum(fam.values())
-        achieved = flops / (conv_ms / 1e3) / 1e12
+        # ---- per-kernel rooflines of one U-Net evaluation (CFG-doubled batch) and of the tail, measured here with CUDA events ----
+        unet_ms = timed_ops(plan.ops)
+        unet_fams = family_rooflines(unet_ms, plan.meta, pk)
+        conv_keys = [k for k in unet_fams if k.startswith("conv")]
+        conv_ms = sum(unet_fams[k]["ms"] for k in conv_keys)
+        conv_gflop = sum(unet_fams[k]["algorithmic_gflop"] for k in conv_keys)
+        conv_launches = sum(unet_fams[k]["launches"] for k in conv_keys)
+        achieved = conv_gflop / conv_ms
+        tail = pipe.tail_for(BATCH, WIDTH)
+        tail_ms = timed_ops(tail.ops)
+        tail_fams = family_rooflines(tail_ms, tail.meta, pk)
         # time of the sampling graph alone (U-Net step ms)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -299,30 +331,49 @@ def run_b200(args):
             loop.launch()
         e1.record()
         torch.cuda.synchronize()
-        step_ms = e0.elapsed_time(e1) / 3 / loop.n_iter
+        graph_ms = e0.elapsed_time(e1) / 3
+        tail_graph_ms = max(0.0, ms_dev / args.steps - graph_ms) if world == 1 else None
+        step_ms = (graph_ms - (sum(tail_ms.values()) if loop.has_tail else 0.0)) / loop.n_iter
         algo_step_tflop = 2 * BATCH * 136.70e9 / 1e12
-        dec_plan = next(iter(pipe.vqgan._decoder._stack._plans.values()))
-        launches = loop.launches + len(plan.cond_ops) + 1 + len(dec_plan.ops) + 2
-        cpu = cpu_arm(args.sample_steps, unet_evals=2) if world == 1 else None
-        line = dict(metric=METRIC, value=value, unit="timbres/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+        launches = pipe.last_launches
+        # ---- CPU baseline doubling as the validation reference: the same prompt + host noise on the GPU ----
+        cpu, validation = None, dict(finite=all_finite)
+        if world == 1:
+            cpu = cpu_arm(args.sample_steps, keep_outputs=True)
+            lat_cpu, wave_cpu = cpu.pop("_outputs")
+            draws = W.host_noise(0, 1 + args.sample_steps, 1)
+            out = pipe.generate(cond_all[:1].to(dev), uncond_dev, steps=args.sample_steps, cfg_scale=CFG_SCALE, width=WIDTH, noise_feed=draws)
+            rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+            validation.update(latent_rel_l2=rel(out.latents, lat_cpu), waveform_rel_l2=rel(out.waveforms[0], torch.from_numpy(wave_cpu)),
+                              against=f"CPU oracle port, same prompt and host noise, batch 1, {args.sample_steps} steps, CFG {CFG_SCALE}",
+                              tolerance=dict(latent=1e-2, waveform=2e-2))
+            validation["passed"] = bool(all_finite and validation["latent_rel_l2"] < 1e-2 and validation["waveform_rel_l2"] < 2e-2)
+        else:
+            validation["passed"] = bool(all_finite)
+        line = dict(metric=METRIC, value=value, unit="timbres/s", n_gpus=world, steps=args.steps, warmup=warm,
                     ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp16", data="synthetic",
                     config=workload_config(args, world), clocks=clocks,
                     e2e=dict(value=e2e_value, unit="timbres/s", h2d_bytes_per_step=int(cond_host.numel() * 4),
                              d2h_bytes_per_step=int(wave_host.numel() * 4), ms_per_step=ms_e2e / args.steps),
                     gpu_launches=int(launches * args.steps),
+                    validated=validation["passed"], validation=validation,
                     unet_step_ms=step_ms,
                     unet_step_roofline=dict(algorithmic_tflop=algo_step_tflop, achieved_tflops=algo_step_tflop / (step_ms / 1e3),
                                             peak_tflops=pk["tf_sustained"], frac=algo_step_tflop / (step_ms / 1e3) / pk["tf_sustained"]),
                     roofline=dict(kernel="conv_gemm_kernel (tcgen05 implicit-GEMM conv; all dense convs of the U-Net)", bound="tensor",
                                   achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"], traffic=conv_traffic(),
-                                  traffic_note="ncu dram__bytes_read+write per conv_gemm launch, averaged over the 98 launches of one U-Net evaluation "
-                                               "(profiles/r01_unet_eval_ncu_summary.md)",
+                                  traffic_note="ncu dram__bytes_read+write per conv_gemm launch, averaged over the conv launches of one U-Net evaluation "
+                                               "(committed capture under profiles/; not re-measured inside this run)",
                                   peak_source=pk["source"] + " bf16_tflops_sustained", launches_per_unet_eval=conv_launches,
-                                  algorithmic_gflop_per_unet_eval=flops / 1e9, ms_per_unet_eval=conv_ms),
-                    kernel_ms_per_unet_eval={k: round(v, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
-                    unet_eval_ms_eager=unet_ms)
+                                  algorithmic_gflop_per_unet_eval=conv_gflop, ms_per_unet_eval=conv_ms),
+                    roofline_per_kernel=dict(
+                        note="CUDA-event time of every launch of one eager U-Net evaluation (128 guidance-doubled samples) and one eager tail pass "
+                             "(64 timbres); frac = max(algorithmic FLOPs / sustained bf16 peak, algorithmic bytes / HBM copy peak) / measured time",
+                        peaks=dict(tensor_tflops=pk["tf_sustained"], hbm_gbs=pk["hbm"], source=pk["source"]),
+                        unet_eval=unet_fams, tail=tail_fams),
+                    unet_eval_ms_eager=sum(unet_ms.values()), tail_ms_eager=sum(tail_ms.values()), sampling_graph_ms=graph_ms)
         if cpu is not None:
-            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "s_per_timbre", "s_per_unet_step", "split_s")}
         emit(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -350,12 +401,14 @@ def emit(text):
 
 def conv_traffic():
     """DRAM bytes per conv_gemm launch from the committed ncu capture (profiles/), or None when the capture is absent."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_traffic.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["avg_dram_bytes_per_conv_launch"])
-    except (OSError, KeyError, ValueError):
-        return None
+    for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)
+        try:
+            with open(path) as f:
+                return float(json.load(f)["avg_dram_bytes_per_conv_launch"])
+        except (OSError, KeyError, ValueError):
+            continue
+    return None
 
 
 def main():

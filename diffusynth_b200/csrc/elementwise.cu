@@ -73,6 +73,21 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, act_t
     out[i] = f2act(c < C ? in[(n * C + c) * hw + p] : 0.f);
   }
 }
+// Fast form (Cp % 8 == 0): one thread per pixel; the C plane reads are coalesced across the warp (consecutive pixels of one
+// plane) and each thread writes its pixel's Cp channels as 16-byte vectors, so a warp writes one contiguous 32*Cp*2-byte span.
+__global__ void __launch_bounds__(256)
+nchw_f32_to_nhwc_vec_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp8, long long hw, long long total_pix) {
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total_pix; pix += (long long)gridDim.x * blockDim.x) {
+    const long long n = pix / hw, p = pix % hw;
+    const float* src = in + n * C * hw + p;
+    for (int v = 0; v < Cp8; ++v) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int c = 8 * v + j; f[j] = c < C ? __ldg(src + (long long)c * hw) : 0.f; }
+      out[pix * Cp8 + v] = make_uint4(pack16(f[0], f[1]), pack16(f[2], f[3]), pack16(f[4], f[5]), pack16(f[6], f[7]));
+    }
+  }
+}
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const act_t* __restrict__ in, float* __restrict__ out, int C, int Cp,
                                              long long hw, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -367,8 +382,11 @@ int ds_add_channel_bias(void* d_x, const float* d_bias, long long bias_stride, i
 
 int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int Cp, long long hw, void* stream) {
   DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nchw_f32_to_nhwc_bf16: bad arguments");
-  nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)N * hw * Cp, 256), 256, 0, (cudaStream_t)stream>>>(
-      d_in, (act_t*)d_out, C, Cp, hw, (long long)N * hw);
+  if (Cp % 8 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0)
+    nchw_f32_to_nhwc_vec_kernel<<<grid_for((long long)N * hw, 256), 256, 0, (cudaStream_t)stream>>>(d_in, (uint4*)d_out, C, Cp / 8, hw, (long long)N * hw);
+  else
+    nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)N * hw * Cp, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_in, (act_t*)d_out, C, Cp, hw, (long long)N * hw);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -272,6 +272,26 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
     return a, st, keep
 
 
+def conv_cost(a: ConvGemmArgs, pc: PackedConv) -> Tuple[str, float, float]:
+    """(kernel family, algorithmic FLOPs, algorithmic HBM bytes) of one ds_conv_gemm call: 2 FLOP per MAC over the real channels,
+    every operand moved once (activations in, weights, residual, output)."""
+    cin = a.C0 + a.C1
+    flops = 2.0 * a.N * a.groups * a.H * a.W * a.Cout * a.ntaps * cin
+    n_in = a.src_batch_mod if a.src_batch_mod > 0 else a.N
+    hin, win = (2 * a.H, 2 * a.W) if pc.kind == "down" else (a.H, a.W)
+    by = n_in * hin * win * a.C0 * 2.0 + a.N * hin * win * a.C1 * 2.0
+    by += (a.N if a.per_sample_weights else a.groups) * a.Cout_pad * a.ntaps * cin * 2.0
+    out_px = a.N * a.groups * a.H * a.W
+    if a.d_out:
+        by += out_px * a.Cout * 2.0
+    if a.d_out_f32_nchw:
+        by += out_px * a.Cout * 4.0
+    if a.d_residual:
+        by += out_px * a.Cout * 2.0
+    fam = "conv3x3" if (pc.kind == "s1" and a.ntaps == 9) else "conv1x1" if pc.kind == "s1" else "conv4x4s2" if pc.kind == "down" else "convT4x4s2"
+    return fam, flops, by
+
+
 def run_conv(a: ConvGemmArgs, reference: bool = False) -> None:
     lib = _lib.load()
     fn = lib.ds_conv_gemm_reference if reference else lib.ds_conv_gemm

@@ -9,7 +9,8 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import weights as W
+from . import _lib, ops, weights as W
+from ._lib import check
 from .codec import adjust_audio_length, spectrogram_to_waveform, waveform_to_spectrogram
 from .sampler import DiffSynthSampler
 from .unet import ConditionedUnet
@@ -24,6 +25,39 @@ class Timbres:
     waveforms: torch.Tensor      # [B, 256*(4W-1)]
 
 
+class _Tail:
+    """quantiser -> decoder -> STFT+ decode + iSTFT (text2sound.py:128-134, utils.py:224-241) as a fixed launch sequence on
+    static buffers, so that it is captured in the same CUDA graph as the sampling loop: ``src`` is the loop's final-latent
+    buffer; the quantiser writes straight into the decoder plan's input, the iSTFT reads the decoder plan's output."""
+
+    def __init__(self, vqgan: VQGAN, src: torch.Tensor):
+        B, Cc, H, Wd = src.shape
+        dev = src.device
+        lib = _lib.load()
+        self.src = src
+        self.dec = vqgan._decoder._stack.plan(B, H, Wd)
+        self.q = self.dec.inp                                   # [B,4,H,W] fp32: decoder input = quantiser output
+        self.idx = torch.empty((B * H * Wd,), dtype=torch.long, device=dev)
+        self.spec = self.dec.out_f32                            # [B,3,4H,4W]
+        T = self.spec.shape[3]
+        self.frames = torch.empty((B, T, 1024), dtype=torch.float32, device=dev)
+        self.wave = torch.empty((B, lib.ds_istft_length(T)), dtype=torch.float32, device=dev)
+        vq = vqgan._vq_vae
+        K = vq._num_embeddings
+        self.ops = [("vq", lambda: vq.quantize_into(self.src, self.q, self.idx))] + list(self.dec.ops) + [
+            ("istft", lambda: check(lib.ds_stft_decode_istft(self.spec.data_ptr(), self.frames.data_ptr(), self.wave.data_ptr(), B, T,
+                                                             ops._stream()), "ds_stft_decode_istft"))]
+        self.meta = dict(self.dec.meta)
+        # the quantiser is fp32-ALU work: 4 FMAs per (position, code) for the dot product + the compare (VQGAN.py:107-112)
+        self.meta["vq"] = dict(family="vq_quantize", flops=0.0, bytes=B * H * Wd * (2 * Cc * 4.0 + 8.0), fp32_flops=B * H * Wd * K * 2.0 * Cc)
+        self.meta["istft"] = dict(family="istft(decode+frames+ola)", flops=0.0, bytes=B * (3 * 512 * T * 4.0 + self.wave.shape[1] * 4.0))
+        self.num_launches = len(self.ops) + 1 + sum(1 for n, _ in self.ops if n.endswith(".fin"))      # iSTFT = 2 kernels, finalize = 2
+
+    def run(self):
+        for _, fn in self.ops:
+            fn()
+
+
 class TextToTimbre:
     def __init__(self, unet: ConditionedUnet, vqgan: VQGAN, timesteps: int = 1000, height: int = 128, channels: int = 4,
                  noise_strategy: str = "repeat", device=None):
@@ -31,6 +65,23 @@ class TextToTimbre:
         self.timesteps, self.height, self.channels, self.noise_strategy = timesteps, height, channels, noise_strategy
         self.device = torch.device(device if device is not None else unet.device)
         self._samplers = {}
+        self._tail_factory = lambda src: _Tail(self.vqgan, src)      # one object: its id() is part of the samplers' graph keys
+        self.last_launches = 0
+        self._last_tail: Optional[_Tail] = None
+
+    def tail_for(self, batch: int, width: int) -> _Tail:
+        """The tail captured with the most recent graph of this batch / width (bench.py times its launches one by one)."""
+        t = self._last_tail
+        assert t is not None and t.src.shape[0] == batch and t.src.shape[3] == width, "no generate() call with this shape yet"
+        return t
+
+    def _decode(self, s: DiffSynthSampler, latents: torch.Tensor) -> Timbres:
+        """Results of the tail that ran inside the sampler's graph (copied out of its static buffers)."""
+        t = s.last_tail
+        self._last_tail = t
+        self.last_launches = s.last_graph_launches
+        self.vqgan._vq_vae.last_indices = t.idx.clone()
+        return Timbres(latents, t.q.clone(), t.spec.clone(), t.wave.clone())
 
     @classmethod
     def random_init(cls, device="cuda", seed: int = 0, perturb_norm: bool = False) -> "TextToTimbre":
@@ -64,15 +115,14 @@ class TextToTimbre:
         if noise_feed is not None:
             init = noise_feed[0][:B].to(self.device, torch.float32)
             s.noise_feed = noise_feed[1:]
+        s.graph_tail, s.final_only = (self._tail_factory if decode else None), True
         imgs, _ = s.sample(self.unet, (B, self.channels, self.height, width), return_tensor=True, condition=cond.to(self.device),
                            sampler=sampler, initial_noise=init, seed=seed)
         latents = imgs[-1]
         if not decode:
+            self.last_launches = s.last_graph_launches
             return Timbres(latents, None, None, None)
-        q, _, _ = self.vqgan._vq_vae(latents)                              # text2sound.py:128
-        spec = self.vqgan._decoder(q)                                      # utils.py:224
-        wave = spectrogram_to_waveform(spec)                               # utils.py:229-241
-        return Timbres(latents, q, spec, wave)
+        return self._decode(s, latents)       # quantiser (text2sound.py:128), decoder (utils.py:224), iSTFT (utils.py:229-241): same graph
 
 
     # ---- timbre modification (sound2sound_with_text.py:47-269) -------------------------------------------------------
@@ -113,14 +163,14 @@ class TextToTimbre:
         if noise_feed is not None:
             init = noise_feed[0][:B].to(self.device, torch.float32)
             s.noise_feed = noise_feed[1:]
+        s.graph_tail, s.final_only = (self._tail_factory if decode else None), True
         imgs, _ = s.img_guided_sample(self.unet, (B, self.channels, self.height, width), strength, guide, return_tensor=True,
                                       condition=cond.to(self.device), sampler=sampler, initial_noise=init, seed=seed)
         latents = imgs[-1]
         if not decode:
+            self.last_launches = s.last_graph_launches
             return Timbres(latents, None, None, None)
-        q, _, _ = self.vqgan._vq_vae(latents)
-        spec = self.vqgan._decoder(q)
-        return Timbres(latents, q, spec, spectrogram_to_waveform(spec))
+        return self._decode(s, latents)
 
 
     # ---- per-note synthesis for arrangements (track_maker.py:228-283) ---------------------------------------------------
@@ -145,6 +195,7 @@ class TextToTimbre:
             self._samplers[key] = s
         s.activate_classifier_free_guidance(1.0, None)
         s.noise_feed = None
+        s.graph_tail, s.final_only = self._tail_factory, True
         mask = torch.zeros((1, 1, self.height, width), dtype=torch.float32, device=self.device)                # :252-254
         mask[:, :, :, :int(time_resolution * (attack / 4) / vae_scale)] = 1.0
         mask[:, :, :, -int(time_resolution * ((before_release + 1) / 4) / vae_scale):] = 1.0
@@ -156,10 +207,7 @@ class TextToTimbre:
                                    instrument_latent.to(self.device, torch.float32), mask, return_tensor=True,
                                    condition=condition.to(self.device), sampler=sampler, initial_noise=init,
                                    use_dynamic_mask=True, end_noise_level_ratio=0.0, mask_flexivity=1.0)       # :257-269
-        latents = imgs[-1]
-        q, _, _ = self.vqgan._vq_vae(latents)                                                                  # :275
-        spec = self.vqgan._decoder(q)
-        return Timbres(latents, q, spec, spectrogram_to_waveform(spec))                                        # :277-283
+        return self._decode(s, imgs[-1])       # quantiser :275, decoder + iSTFT :277-283, inside the note's graph
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

@@ -74,6 +74,12 @@ class DiffSynthSampler:
         self.faithful_rng = True
         self._graphs: Dict[tuple, "_GraphLoop"] = {}
         self.last_graph_launches = 0
+        # Optional continuation captured in the SAME CUDA graph as the step loop (TextToTimbre: quantiser -> decoder -> iSTFT):
+        # a callable ``factory(final_latent_buffer) -> object with .run() and .num_launches``; ``last_tail`` is the tail whose
+        # static output buffers the last graph launch filled.  ``final_only`` skips the copy of the per-step latents.
+        self.graph_tail = None
+        self.last_tail = None
+        self.final_only = False
 
     # ---- schedule (host, float64) -----------------------------------------------------------
     def define_beta_schedule(self):
@@ -330,12 +336,12 @@ class DiffSynthSampler:
         n_iter = len(steps)
         # the captured graph points at the model's packed weights: a repack (load_state_dict / .to) bumps weights_version and
         # retires every loop built on the old tensors; the loop also holds the model, so its id() cannot be recycled
-        key = (id(model), model.weights_version, shape, n_iter, eta > 0, cfg_on, inpaint)
+        key = (id(model), model.weights_version, shape, n_iter, eta > 0, cfg_on, inpaint, id(self.graph_tail) if self.graph_tail else 0)
         loop = self._graphs.get(key)
         if loop is None:
             for k in [k for k, v in self._graphs.items() if v.model is model and k[1] != model.weights_version]:
                 del self._graphs[k]
-            loop = _GraphLoop(self, model, shape, n_iter, eta > 0, cfg_on, inpaint)
+            loop = _GraphLoop(self, model, shape, n_iter, eta > 0, cfg_on, inpaint, self.graph_tail)
             self._graphs[key] = loop
         # per-call inputs (device buffers the graph reads)
         loop.imgs[0].copy_(img)
@@ -369,7 +375,11 @@ class DiffSynthSampler:
             loop.init_noise.copy_(initial_noise)
         loop.plan.run_cond()        # condition projections are step-invariant: once per call, outside the graph
         loop.launch()
-        self.last_graph_launches = loop.launches
+        self.last_graph_launches = loop.launches + len(loop.plan.cond_ops)
+        self.last_tail = loop.tail
+        if self.final_only:         # (pipeline use: only imgs[0] and imgs[-1] are read)
+            first, last = loop.imgs[0].clone(), loop.imgs[n_iter].clone()
+            return [first] + [None] * (n_iter - 1) + [last]
         out = loop.imgs.clone()
         return [out[k] for k in range(n_iter + 1)]
 
@@ -412,7 +422,8 @@ class _GraphLoop:
     Step-dependent scalars (timestep, update coefficients, masks, noise) live in device tables the graph reads, so the
     same graph serves any schedule / seed / prompt of the same shape and step count."""
 
-    def __init__(self, sampler: DiffSynthSampler, model: ConditionedUnet, shape, n_iter: int, stochastic: bool, cfg_on: bool, inpaint: bool):
+    def __init__(self, sampler: DiffSynthSampler, model: ConditionedUnet, shape, n_iter: int, stochastic: bool, cfg_on: bool, inpaint: bool,
+                 tail_factory=None):
         dev = sampler.device
         B, Cc, H, Wd = shape
         f32 = dict(dtype=torch.float32, device=dev)
@@ -429,17 +440,23 @@ class _GraphLoop:
             self.init_noise = torch.zeros((B, Cc, H, Wd), **f32)
         N = 2 * B if cfg_on else B
         self.plan = model.plan(N, H, Wd, x_batch_mod=B if cfg_on else 0, uniform_time=True)
-        self.launches = n_iter * (self.plan.num_launches() + 1 + (1 if inpaint else 0))
+        self.tail = tail_factory(self.imgs[n_iter]) if tail_factory is not None else None
+        self.has_tail = self.tail is not None
+        self.launches = n_iter * (self.plan.num_launches() + 1 + (1 if inpaint else 0)) + (self.tail.num_launches if self.tail else 0)
         self.inpaint = inpaint
         self.B = B
         # warm-up run outside capture (lazy one-time initialisations, kernel attribute sets), then capture
         self._body(first_only=True)
+        if self.tail is not None:
+            self.tail.run()
         torch.cuda.synchronize()
         self.graph = None
         if os.environ.get("DS_NO_GRAPH", "0") != "1":      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._body()
+                if self.tail is not None:
+                    self.tail.run()
 
     def _body(self, first_only: bool = False):
         pl, B = self.plan, self.B
@@ -458,3 +475,5 @@ class _GraphLoop:
             self.graph.replay()
         else:
             self._body()
+            if self.tail is not None:
+                self.tail.run()

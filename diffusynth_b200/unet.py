@@ -310,8 +310,11 @@ class _Plan:
                 scratch[k] = act(n, h, w, c)
             return scratch[k]
 
-        def add(name, fn):
+        self.meta: Dict[str, dict] = {}       # per op: kernel family + algorithmic FLOPs / HBM bytes (bench.py's per-kernel rooflines)
+
+        def add(name, fn, family="misc", flops=0.0, bytes=0.0):
             self.ops.append((name, fn))
+            self.meta[name] = dict(family=family, flops=float(flops), bytes=float(bytes))
 
         # ---- condition path (step-invariant: run once per sample() call) ----
         cemb = torch.empty((N, cfg["label_emb_dim"]), **f32)
@@ -332,7 +335,8 @@ class _Plan:
         def conv(name, pc, s0, s1, h, w, n=None, **kw):
             a, st, keep = conv_args(pc, s0, s1, N if n is None else n, h, w, **kw)
             self.keep += keep + [a]
-            add(name, lambda a=a: run_conv(a))
+            fam, fl, by = ops.conv_cost(a, pc)
+            add(name, lambda a=a: run_conv(a), fam, fl, by)
             return st
 
         def block(p, s0, s1, h, w, n=N, s0_mod=0):
@@ -341,7 +345,8 @@ class _Plan:
             hbuf = scr("dw", n, h, w, b.dim)
             tb = self.tbias[:, b.t_off:]
             st_h = ops.dwconv7_stats(n, b.dim, h, w, dev)
-            add(p + "ds_conv", lambda: ops.dwconv7(s0, s1, b.dw, tb, self.t_stride, hbuf, n, h, w, stats=st_h, src_batch_mod=s0_mod))
+            add(p + "ds_conv", lambda: ops.dwconv7(s0, s1, b.dw, tb, self.t_stride, hbuf, n, h, w, stats=st_h, src_batch_mod=s0_mod),
+                "dwconv7", 2.0 * 49 * n * h * w * b.dim, 2.0 * n * h * w * b.dim * 2)
             y = scr("hid", n, h, w, b.conv1.cout)
             st_y = conv(p + "net.1", b.conv1, hbuf, None, h, w, n=n, out=y, stats_in=st_h, act=1, want_stats=True)
             if b.res is not None:
@@ -401,21 +406,22 @@ class _Plan:
             part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
             M = torch.empty((N, a.out.cout_pad, HID), dtype=ops.ACT, device=dev)
             add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
-                                                                  float(DHEAD ** -0.5), stream()), "attn_ctx_partial"))
+                                                                  float(DHEAD ** -0.5), stream()), "attn_ctx_partial"),
+                "attn_ctx", 2.0 * N * HEADS * DHEAD * DHEAD * npix, N * npix * (3 * HID + HID) * 2.0)
             if cat:
                 lk, lv = sb[:, :HID], sb[:, HID:2 * HID]
                 add(p + "fin", lambda: check(lib.ds_attn_finalize_cat(part.data_ptr(), lk.data_ptr(), lv.data_ptr(), self.sbias.stride(0),
                                                                        a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim, a.out.cout_pad,
-                                                                       stream()), "attn_finalize_cat"))
+                                                                       stream()), "attn_finalize_cat"), "attn_finalize", 0.0, part.numel() * 4.0)
             else:
                 add(p + "fin", lambda: check(lib.ds_attn_finalize(part.data_ptr(), a.wout.data_ptr(), M.data_ptr(), N, HEADS, npix, a.dim,
-                                                                   a.out.cout_pad, stream()), "attn_finalize"))
+                                                                   a.out.cout_pad, stream()), "attn_finalize"), "attn_finalize", 0.0, part.numel() * 4.0)
             y = scr("atty", N, h, w, a.dim)
             st_y = conv(p + "to_out", a.out, qp, None, h, w, out=y, want_stats=True, weight_override=M, per_sample_weights=True)
             o = act(N, h, w, a.dim)
             add(p + "gn_res", lambda: check(lib.ds_gn_apply_residual(y.data_ptr(), x.data_ptr(), o.data_ptr(), st_y.buf.data_ptr(), st_y.slots,
                                                                       a.gamma.data_ptr(), a.beta.data_ptr(), N, a.dim, npix, x_mod, stream()),
-                                            "gn_apply_residual"))
+                                            "gn_apply_residual"), "gn_apply_residual", 0.0, 3.0 * N * npix * a.dim * 2)
             self.keep += [part, M]
             self.named[p[:-1]] = (o, a.dim)
             return o
@@ -431,7 +437,8 @@ class _Plan:
         n0 = shared if shared else N
         x0 = act(n0, h, w, dd[0])
         col = act(nb, h, w, 224)
-        add("init_im2col", lambda: check(lib.ds_stem_im2col(self.x.data_ptr(), col.data_ptr(), nb, cfg["in_dim"], H, Wd, stream()), "stem_im2col"))
+        add("init_im2col", lambda: check(lib.ds_stem_im2col(self.x.data_ptr(), col.data_ptr(), nb, cfg["in_dim"], H, Wd, stream()), "stem_im2col"),
+            "stem_im2col", 0.0, nb * H * Wd * (cfg["in_dim"] * 4.0 + 224 * 2.0))
         conv("init_conv", net.stem, col, None, h, w, n=n0, out=x0, src_batch_mod=0 if shared else x_batch_mod)
         self.named["init_conv"] = (x0, dd[0])
         hs = [x0]

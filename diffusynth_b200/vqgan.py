@@ -144,28 +144,35 @@ class _StackPlan:
         def act(h, w, c):      # zero-initialised: padded channels must stay zero
             return torch.zeros((B, h, w, _cp(c)), dtype=ops.ACT, device=dev)
 
-        def add(name, fn):
+        self.meta: Dict[str, dict] = {}       # per op: kernel family + algorithmic FLOPs / HBM bytes (bench.py's per-kernel rooflines)
+
+        def add(name, fn, family="misc", flops=0.0, bytes=0.0):
             self.ops.append((name, fn))
+            self.meta[name] = dict(family=family, flops=float(flops), bytes=float(bytes))
 
         def conv(name, pc, src, h, w, **kw):
             a, stt, keep = conv_args(pc, src, None, B, h, w, **kw)
             self.keep += keep + [a]
-            add(name, lambda a=a: run_conv(a))
+            fam, fl, by = ops.conv_cost(a, pc)
+            add(name, lambda a=a: run_conv(a), "vqgan_" + fam, fl, by)
             return stt
 
         def gn_act(name, x, c, h, w, gamma, beta, actv):
             part = torch.empty((B, st.G, GN_CHUNKS, 2), **f32)
             out = act(h, w, c)
             cp = x.shape[-1]
-            add(name + ".stats", lambda: check(lib.ds_group_stats(x.data_ptr(), part.data_ptr(), B, c, cp, st.G, h * w, GN_CHUNKS, stream()), "group_stats"))
+            add(name + ".stats", lambda: check(lib.ds_group_stats(x.data_ptr(), part.data_ptr(), B, c, cp, st.G, h * w, GN_CHUNKS, stream()), "group_stats"),
+                "group_stats", 0.0, B * h * w * cp * 2.0)
             add(name + ".apply", lambda: check(lib.ds_gn_act(x.data_ptr(), out.data_ptr(), part.data_ptr(), GN_CHUNKS, gamma.data_ptr(),
-                                                            beta.data_ptr(), B, c, cp, st.G, h * w, 1e-6, actv, stream()), "gn_act"))
+                                                            beta.data_ptr(), B, c, cp, st.G, h * w, 1e-6, actv, stream()), "gn_act"),
+                "gn_act", 0.0, 2.0 * B * h * w * cp * 2.0)
             self.keep.append(part)
             return out
 
         h, w = H, Wd
         x = act(h, w, first_c)
-        add("to_nhwc", lambda x=x: check(lib.ds_nchw_f32_to_nhwc_bf16(self.inp.data_ptr(), x.data_ptr(), B, first_c, x.shape[-1], H * Wd, stream()), "to_nhwc"))
+        add("to_nhwc", lambda x=x: check(lib.ds_nchw_f32_to_nhwc_bf16(self.inp.data_ptr(), x.data_ptr(), B, first_c, x.shape[-1], H * Wd, stream()), "to_nhwc"),
+            "nchw_to_nhwc", 0.0, B * H * Wd * (first_c * 4.0 + x.shape[-1] * 2.0))
         self.out_f32: Optional[torch.Tensor] = None
         pending_norm = None
         last_idx = st.plan_spec[-1][0]
@@ -198,7 +205,8 @@ class _StackPlan:
                     conv(name, L["conv"], t, h, w, out_f32=a32)
                     conv(name + ".short", L["short"], x, h, w, out_f32=b32)
                     self.out_f32 = torch.empty((B, cout, h, w), **f32)
-                    add("heads", lambda: check(lib.ds_decoder_head(a32.data_ptr(), b32.data_ptr(), self.out_f32.data_ptr(), B, h * w, stream()), "decoder_head"))
+                    add("heads", lambda: check(lib.ds_decoder_head(a32.data_ptr(), b32.data_ptr(), self.out_f32.data_ptr(), B, h * w, stream()), "decoder_head"),
+                        "decoder_head", 0.0, 3.0 * B * cout * h * w * 4.0)
                     x = None
             elif kind == "attn":
                 npix = h * w
@@ -208,9 +216,11 @@ class _StackPlan:
                 part = torch.empty((lib.ds_attn_part_floats(B, 1, npix),), **f32)
                 M = torch.empty((B, L["out"].cout_pad, DH), dtype=ops.ACT, device=dev)
                 add(name + ".ctx", lambda qkv=qkv, qp=qp, part=part, npix=npix: check(
-                    lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), B, 1, npix, 1, 1.0, stream()), "attn_ctx_partial"))
+                    lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), B, 1, npix, 1, 1.0, stream()), "attn_ctx_partial"),
+                    "attn_ctx", 2.0 * B * DH * DH * npix, B * npix * (3 * DH + DH) * 2.0)
                 add(name + ".fin", lambda part=part, M=M, L=L, npix=npix, cin=cin: check(
-                    lib.ds_attn_finalize(part.data_ptr(), L["wout"].data_ptr(), M.data_ptr(), B, 1, npix, cin, L["out"].cout_pad, stream()), "attn_finalize"))
+                    lib.ds_attn_finalize(part.data_ptr(), L["wout"].data_ptr(), M.data_ptr(), B, 1, npix, cin, L["out"].cout_pad, stream()), "attn_finalize"),
+                    "attn_finalize", 0.0, part.numel() * 4.0)
                 r = None
                 if "short" in L:
                     r = act(h, w, cin)

@@ -90,10 +90,50 @@ def headline(ref):
 
 
 @torch.no_grad()
+def sampler2(ref):
+    """tests/golden/sampler2.npz (`--sampler2`): sampler surfaces the first fixtures did not reach -- interpolate() between two noise
+    endpoints (:538-560; the random-endpoint branch of generate_linear_noise raises in the reference, :247-252 unpack a 1-element
+    tensor into two names), the "non_repeat" noise strategy (:62-77), q_sample with per-sample timesteps (:271-294) and inpainting
+    with a per-channel [B,C,H,W] mask as inpaint_with_text.py:229-231 passes it -- all on the toy model, height 16."""
+    g = {}
+    B, Hh = 3, 16
+    cond, uncond = W.synthetic_conditions(B, 16, seed=91)
+    draws = cases.randn((12, B, 4, Hh, 64), 92)
+    e0, e1 = cases.randn((4, Hh, 64), 93), cases.randn((4, Hh, 64), 94)
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B, height=Hh), draws)
+    S.activate_classifier_free_guidance(3, uncond)
+    S.respace(list(np.linspace(0, 999, 6, dtype=np.int32)))
+    imgs, init = S.interpolate(cases.toy_model, (B, 4, Hh, 64), 1.0, first_endpoint=e0, second_endpoint=e1, return_tensor=True,
+                               condition=cond, sampler="ddpm")
+    g["interp_init"], g["interp_last"] = init.numpy(), imgs[-1].numpy()
+    S = ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=2, height=Hh, max_width=96, noise_strategy="non_repeat")
+    S.respace(list(np.linspace(0, 999, 6, dtype=np.int32)))
+    big = cases.randn((2, 4, Hh, 96), 95)
+    imgs, init = S.sample(cases.toy_model, (2, 4, Hh, 40), return_tensor=True, condition=cond[:2], sampler="ddim", initial_noise=big)
+    g["nonrep_init"], g["nonrep_last"] = init.numpy(), imgs[-1].numpy()
+    S = ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B, height=Hh)
+    x0, nz = cases.randn((B, 4, Hh, 40), 96), cases.randn((B, 4, Hh, 40), 97)
+    g["qsample_t"] = np.array([3, 700, 999])
+    g["qsample_out"] = S.q_sample(x0, torch.tensor([3, 700, 999]), noise=nz).numpy()
+    mask = (cases.randn((B, 4, Hh, 40), 98) > 0).float()
+    guide = cases.randn((B, 4, Hh, 64), 99) * 0.5
+    S = ref_loader.feed_noise(ref.DiffSynthSampler(1000, device="cpu", mute=True, max_batchsize=B, height=Hh), draws)
+    S.activate_classifier_free_guidance(3, uncond)
+    S.respace(list(np.linspace(0, 999, 6, dtype=np.int32)))
+    imgs, _ = S.inpaint_sample(cases.toy_model, (B, 4, Hh, 40), 1.0, guide, mask, return_tensor=True, condition=cond, initial_noise=draws[0])
+    g["inpaint_cmask_last"] = imgs[-1].numpy()
+    np.savez_compressed(os.path.join(OUT, "sampler2.npz"), **g)
+
+
+@torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--sampler2" in sys.argv:
+        sampler2(ref)
+        print("sampler2.npz", os.path.getsize(os.path.join(OUT, "sampler2.npz")))
+        return
     if "--headline" in sys.argv:
         headline(ref)
         print("headline.npz", os.path.getsize(os.path.join(OUT, "headline.npz")))

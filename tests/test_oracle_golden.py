@@ -224,3 +224,27 @@ def test_headline_modify20_oracle_matches_reference(golden):
     assert np.linalg.norm(final - g["modify20_final"]) / np.linalg.norm(g["modify20_final"]) < 1e-4
     for k in range(sub.shape[0]):
         assert np.linalg.norm(sub[k] - g["modify20_sub"][k]) / np.linalg.norm(g["modify20_sub"][k]) < 1e-4, k
+
+
+def test_sampler2_oracle_matches_reference(golden):
+    """interpolate() between endpoints, per-sample q_sample and inpainting with a per-channel mask: oracle vs the reference's own
+    results (tests/golden/sampler2.npz)."""
+    g = golden["sampler2"]
+    B, Hh = 3, 16
+    cond, uncond = W.synthetic_conditions(B, 16, seed=91)
+    draws = cases.randn((12, B, 4, Hh, 64), 92)
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, 6, dtype=np.int32)))
+    mask = (cases.randn((B, 4, Hh, 40), 98) > 0).float()
+    guide = cases.randn((B, 4, Hh, 64), 99) * 0.5
+    imgs = O.sample_loop(cases.toy_model, sch, (B, 4, Hh, 40), cond, uncond, 3, draws, guide=guide, mask=mask, inpaint=True)
+    assert np.abs(imgs[-1].numpy() - g["inpaint_cmask_last"]).max() < 1e-5
+    e0, e1 = cases.randn((4, Hh, 64), 93), cases.randn((4, Hh, 64), 94)
+    lin = torch.stack([(i / (B - 1)) * e1 + (1 - i / (B - 1)) * e0 for i in range(B)])          # generate_linear_noise case 3 (:239-243)
+    assert np.abs(lin.numpy() - g["interp_init"]).max() < 1e-6
+    imgs = O.sample_loop(cases.toy_model, sch, (B, 4, Hh, 64), cond, uncond, 3, torch.cat([lin[None], draws[1:]]), sampler="ddpm")
+    assert np.abs(imgs[-1].numpy() - g["interp_last"]).max() < 1e-4
+    full = O.Schedule(1000)
+    x0, nz = cases.randn((B, 4, Hh, 40), 96), cases.randn((B, 4, Hh, 40), 97)
+    q = torch.stack([O.q_sample(full, x0[i], int(t), nz[i]) for i, t in enumerate(g["qsample_t"])])
+    assert np.abs(q.numpy() - g["qsample_out"]).max() < 1e-6

@@ -226,3 +226,101 @@ def all_gather_waveforms(local: torch.Tensor, total: int, world: int) -> torch.T
     out = local.new_empty((world * per,) + tuple(local.shape[1:]))
     dist.all_gather_into_tensor(out, local.contiguous())
     return out[:total]
+
+
+class ChunkGatherer:
+    """The collective half of the sharded job: rank-local result chunks [chunk, L] are all-gathered one by one (NCCL on a side
+    stream on GPUs, so that chunk k travels while chunk k+1 is computed; gloo / plain copies on CPU tensors in the host tests) into
+    the rank-major result [world, per_pad, L]; ``finish()`` returns the first ``total`` rows in prompt order."""
+
+    def __init__(self, total: int, rank: int, world: int, chunk: int, L: int, device, dtype=torch.float32):
+        self.total, self.rank, self.world, self.chunk, self.L = total, rank, world, chunk, L
+        self.per = -(-total // world)
+        self.n_chunks = -(-self.per // chunk)
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.out = torch.zeros((world, self.n_chunks * chunk, L), dtype=dtype, device=self.device)
+        self.stage = [torch.empty((world, chunk, L), dtype=dtype, device=self.device) for _ in range(2)]
+        self._exposed = None
+
+    def submit(self, k: int, w: torch.Tensor) -> None:
+        """Chunk k of this rank (rows past the rank's share zero-padded by the caller to [chunk, L])."""
+        import torch.distributed as dist
+        assert tuple(w.shape) == (self.chunk, self.L), tuple(w.shape)
+
+        def gather():
+            if self.world > 1:
+                st = self.stage[k % 2]
+                dist.all_gather_into_tensor(st.view(self.world * self.chunk, self.L), w.contiguous())
+                self.out[:, k * self.chunk:(k + 1) * self.chunk].copy_(st)
+            else:
+                self.out[0, k * self.chunk:(k + 1) * self.chunk].copy_(w)
+
+        if not self.cuda:
+            gather()
+            return
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            gather()
+            w.record_stream(self.comm)
+
+    def finish(self) -> torch.Tensor:
+        if self.cuda:
+            main = torch.cuda.current_stream(self.device)
+            t_main, t_comm = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_main.record(main)
+            t_comm.record(self.comm)
+            main.wait_stream(self.comm)
+            self._exposed = (t_main, t_comm)
+        return self.out[:, :self.per].reshape(self.world * self.per, self.L)[:self.total]
+
+    def exposed_ms(self) -> float:
+        """How long the side stream ran past the end of the last chunk's compute in the most recent job (synchronises)."""
+        if self._exposed is None:
+            return 0.0
+        t_main, t_comm = self._exposed
+        t_comm.synchronize()
+        return max(0.0, t_main.elapsed_time(t_comm))
+
+
+class ShardedGenerator:
+    """BASELINE configs[3] / SURVEY 8(e): ``total`` prompts split contiguously over ``world`` ranks; each rank samples its share in
+    chunks of ``chunk`` prompts through the text-to-timbre graph and the waveforms of chunk k are all-gathered on a side stream
+    while chunk k+1 is being sampled, so that only the last chunk's gather is exposed.  Every rank ends with all waveforms
+    [total, L] in prompt order."""
+
+    def __init__(self, pipe: TextToTimbre, total: int, rank: int, world: int, chunk: int = 64):
+        self.pipe, self.total, self.rank, self.world, self.chunk = pipe, total, rank, world, chunk
+        self.lo, self.hi = shard_range(total, rank, world)
+        self.gatherer: Optional[ChunkGatherer] = None
+        self.n_chunks = -(-(-(-total // world)) // chunk)
+        self.launches_per_job = 0
+
+    @torch.no_grad()
+    def run(self, cond: torch.Tensor, uncond: Optional[torch.Tensor], steps: int = 20, cfg_scale: float = 6, width: int = 64,
+            sampler: str = "ddim", seed: Optional[int] = None) -> torch.Tensor:
+        pipe, chunk = self.pipe, self.chunk
+        L = 256 * (4 * width - 1)
+        if self.gatherer is None or self.gatherer.L != L:
+            self.gatherer = ChunkGatherer(self.total, self.rank, self.world, chunk, L, pipe.device)
+        n_local = self.hi - self.lo
+        launches = 0
+        for k in range(self.n_chunks):
+            c = cond[k * chunk:min((k + 1) * chunk, n_local)]
+            if c.shape[0] > 0:
+                w = pipe.generate(c, uncond, steps=steps, cfg_scale=cfg_scale, width=width, sampler=sampler, seed=seed).waveforms
+                launches += pipe.last_launches
+                if w.shape[0] < chunk:
+                    w = torch.cat([w, w.new_zeros((chunk - w.shape[0], L))])
+            else:
+                w = torch.zeros((chunk, L), dtype=torch.float32, device=pipe.device)       # (a rank past the end of the prompt list)
+            self.gatherer.submit(k, w)
+        self.launches_per_job = launches
+        return self.gatherer.finish()
+
+    def exposed_gather_ms(self) -> float:
+        return self.gatherer.exposed_ms() if self.gatherer is not None else 0.0

@@ -90,6 +90,35 @@ print("rank", r, "ok")
         assert p.returncode == 0, out.decode()
 
 
+def test_two_rank_chunked_gather_gloo():
+    """configs[3] host logic on CPU: per-rank chunks submitted one by one, gathered into prompt order; uneven total (the last rank
+    owns fewer prompts and pads), world_size 2 over gloo."""
+    code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from diffusynth_b200.pipeline import shard_range, ChunkGatherer
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
+r = dist.get_rank()
+total, chunk, L = 9, 2, 3
+lo, hi = shard_range(total, r, 2)                       # rank 0: [0,5)  rank 1: [5,9)
+g = ChunkGatherer(total, r, 2, chunk, L, "cpu")
+assert g.n_chunks == 3 and g.per == 5
+for k in range(g.n_chunks):
+    ids = torch.arange(lo + k * chunk, min(lo + (k + 1) * chunk, hi)).float()
+    w = torch.zeros((chunk, L)); w[:ids.numel()] = ids.view(-1, 1) + 100.0
+    g.submit(k, w)
+out = g.finish()
+assert out.shape == (total, L) and torch.equal(out[:, 0], torch.arange(total).float() + 100.0), out
+print("rank", r, "ok")
+''' % ROOT
+    port = str(30500 + os.getpid() % 1000)
+    procs = [subprocess.Popen([sys.executable, "-c", code], env=dict(os.environ, RANK=str(r), PORT=port), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
+
+
 def test_shard_range_properties():
     from diffusynth_b200.pipeline import shard_range
     for total in (1, 5, 64, 1024, 1000):

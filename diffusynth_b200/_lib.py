@@ -66,6 +66,7 @@ _SIGNATURES = {
     "ds_attn_chunks": (_I, [_L]),
     "ds_attn_part_floats": (_L, [_I, _I, _L]),
     "ds_attn_ctx_partial": (_I, [_P, _P, _P, _I, _I, _L, _I, _F, _P]),
+    "ds_attn_qkv_ctx": (_I, [_P, _I, _I, _P, _I, _P, _P, _P, _P, _L, _P, _P, _I, _I, _L, _F, _P]),
     "ds_attn_finalize": (_I, [_P, _P, _P, _I, _I, _L, _I, _I, _P]),
     "ds_attn_finalize_cat": (_I, [_P, _P, _P, _L, _P, _P, _I, _I, _L, _I, _I, _P]),
     "ds_gn_apply_residual": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _L, _I, _P]),

@@ -1,0 +1,420 @@
+// Fused  PreNorm -> to_qkv -> (softmax_d(q) * scale,  online softmax_n(k),  partial context  S = P^T V)  for the U-Net's
+// LinearCrossAttentionAdd / LinearCrossAttention (model/diffusion_components.py:148-151,263,271-289 and :171-207):
+// the 1x1 to_qkv convolution runs on tcgen05 (TMA-fed, TMEM accumulator 128 pixels x 384 channels) and its epilogue keeps k
+// and v on chip -- they are never written to HBM: per 128-pixel tile the epilogue turns k into P = exp(k - m) (one running
+// maximum m per head; softmax over n is shift invariant per row, so any m >= max is exact), stages P and V as bf16 in shared
+// memory and contracts them over the pixels with warp-level MMAs into S[d][e] (+ Z[d] = sum_n P through a column of ones);
+// q is soft-maxed over its 32 head channels in registers and written as the only per-pixel output (q').
+// One partial (S[32][32], Z[32], m[32]) per (sample, head, 512-pixel chunk) leaves the kernel in the format
+// attn_reduce_kernel / attn_fold_kernel already consume (ds_attn_finalize).  Replaces a to_qkv launch (which wrote 384
+// channels per pixel) and an attn_ctx_partial launch (which read them back).
+//
+// CTA = 12 warps, persistent over (sample, chunk) items:  warp 0 activation TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator + weight TMA producer, warps 4-11 epilogue (thread = pixel row; warps 4-7 own k and q heads 0-1, warps 8-11 own
+// v and q heads 2-3; for the context MMAs warp w owns head w/2, d rows 16*(w%2)..+15).
+#include "common.cuh"
+#include "../../include/diffusynth_b200.h"
+#include "umma.cuh"
+
+namespace ds {
+
+static constexpr int AQ_THREADS = 384;
+static constexpr int AQ_BK = 32;                          // channels per K-block (64-byte rows, SWIZZLE_64B): divides every C
+static constexpr int AQ_STAGES = 4;
+static constexpr int AQ_HID = 128, AQ_HEADS = 4, AQ_DH = 32, AQ_NOUT = 3 * AQ_HID;
+static constexpr int AQ_TILE = 128;                       // pixels per MMA tile
+static constexpr int AQ_SUB = 4;                          // tiles per chunk (one partial per 512 pixels, as ds_attn_chunks)
+static constexpr int AQ_A_BYTES = AQ_TILE * AQ_BK * 2;    // 8 KB
+static constexpr int AQ_B_BYTES = AQ_NOUT * AQ_BK * 2;    // 24 KB
+static constexpr int AQ_STAGE_BYTES = AQ_A_BYTES + AQ_B_BYTES;
+static constexpr int AQ_PITCH = 2 * AQ_HID + 16;          // bytes per staged P / V row: 8 rows x 16 B hit 8 different bank groups
+static constexpr int AQ_PART = AQ_DH * AQ_DH + 2 * AQ_DH;
+static constexpr int AQ_SMEM = 1024 + AQ_STAGES * AQ_STAGE_BYTES + 2 * AQ_TILE * AQ_PITCH + AQ_NOUT * 4 + 256;
+
+struct AttnQkvDev {
+  int N, npix, C, num_kb, x_batch_mod, chunks, items;
+  const float2* stats_in; int stats_in_slots;
+  const float* e1; const float* e2; const float* sbias; long long sbias_stride;
+  act_t* qout; float* part; float scale;
+};
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void sts_128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(AQ_THREADS, 1)
+attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ AttnQkvDev P) {
+  extern __shared__ __align__(1024) uint8_t aq_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aq_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_p = smem + AQ_STAGES * AQ_STAGE_BYTES;                        // [128][AQ_PITCH] bf16 P rows
+  uint8_t* s_v = s_p + AQ_TILE * AQ_PITCH;                                 // [128][AQ_PITCH] bf16 V rows
+  float* s_t = reinterpret_cast<float*>(s_v + AQ_TILE * AQ_PITCH);         // [384] per-sample additive constants of the fold
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_t + AQ_NOUT);
+  uint64_t* empty_bar = full_bar + AQ_STAGES;
+  uint64_t* tmem_full = empty_bar + AQ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  float* s_wmax = reinterpret_cast<float*>(tmem_base_smem + 2);            // [4 lane groups][4 heads]
+  float* s_sc = s_wmax + 16;                                               // [4 heads] exp(m_old - m_new) of the current tile
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < AQ_STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) umma::tmem_alloc(tmem_base_smem, 512);
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  auto tiles_of = [&](int chunk) { const int left = P.npix - chunk * AQ_SUB * AQ_TILE; const int t = (left + AQ_TILE - 1) / AQ_TILE; return t < AQ_SUB ? t : AQ_SUB; };
+
+  if (warp == 0) {
+    // ================= activation producer =================
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int n = item / P.chunks, chunk = item - n * P.chunks;
+      const int nsrc = P.x_batch_mod > 0 ? n % P.x_batch_mod : n;
+      const int nt = tiles_of(chunk);
+      for (int sub = 0; sub < nt; ++sub) {
+        const int p0 = (chunk * AQ_SUB + sub) * AQ_TILE;
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
+          if (umma::elect_one()) {
+            mbar_expect_tx(&full_bar[stage], AQ_A_BYTES);
+            tma_load_3d(smem + stage * AQ_STAGE_BYTES, &map_a, &full_bar[stage], kb * AQ_BK, p0, nsrc);
+          }
+          __syncwarp();
+          if (++stage == AQ_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= weight producer (the 384 x C matrix streams once per tile; it stays L2 resident) =================
+    int stage = 0; uint32_t phase = 0;
+    for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int chunk = item % P.chunks;
+      const int nt = tiles_of(chunk);
+      for (int sub = 0; sub < nt; ++sub) {
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
+          if (umma::elect_one()) {
+            uint8_t* sb = smem + stage * AQ_STAGE_BYTES + AQ_A_BYTES;
+            mbar_expect_tx(&full_bar[stage], AQ_B_BYTES);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tma_load_3d(sb + j * (AQ_B_BYTES / 3), &map_b, &full_bar[stage], kb * AQ_BK, j * 128, 0);
+          }
+          __syncwarp();
+          if (++stage == AQ_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: D[128 x 384] = X[128 x C] W^T as an N = 128 (q) and an N = 256 (k | v) instruction per K step =================
+    const uint32_t idesc_q = umma::idesc_f16(128, 128), idesc_kv = umma::idesc_f16(128, 256);
+    int stage = 0; uint32_t phase = 0, acc_phase = 0;
+    for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int chunk = item % P.chunks;
+      const int nt = tiles_of(chunk);
+      for (int sub = 0; sub < nt; ++sub) {
+        mbar_wait_warp(tmem_empty, acc_phase ^ 1u);
+        umma::fence_after();
+        for (int kb = 0; kb < P.num_kb; ++kb) {
+          mbar_wait_warp(&full_bar[stage], phase);
+          umma::fence_after();
+          if (umma::elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * AQ_STAGE_BYTES);
+            const uint64_t adesc = umma::kmajor_desc<AQ_BK>(sa);
+            const uint64_t bq = umma::kmajor_desc<AQ_BK>(sa + AQ_A_BYTES);
+            const uint64_t bkv = umma::kmajor_desc<AQ_BK>(sa + AQ_A_BYTES + 128 * AQ_BK * 2);
+#pragma unroll
+            for (int k = 0; k < AQ_BK / 16; ++k) {
+              const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+              umma::mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bq + (uint64_t)(2 * k), idesc_q, accum);
+              umma::mma_f16(tmem_base + 128u, adesc + (uint64_t)(2 * k), bkv + (uint64_t)(2 * k), idesc_kv, accum);
+            }
+            umma::commit(&empty_bar[stage]);
+          }
+          __syncwarp();
+          if (++stage == AQ_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (umma::elect_one()) umma::commit(tmem_full);
+        __syncwarp();
+        acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int ew = warp - 4, lane_grp = warp & 3, half = ew >> 2;
+    const int row = lane_grp * 32 + lane;                       // pixel row of the tile = TMEM lane
+    const int etid = ew * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    const int hd = ew >> 1, mt = ew & 1;                        // context MMAs: head, 16-row half of d
+    const uint32_t sp_row = smem_u32(s_p) + (uint32_t)(row * AQ_PITCH), sv_row = smem_u32(s_v) + (uint32_t)(row * AQ_PITCH);
+    const int lr = lane & 7, lmat = lane >> 3;
+    uint32_t acc_phase = 0;
+    constexpr float kLog2e = 1.4426950408889634f;
+
+    for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
+      const int n = item / P.chunks, chunk = item - n * P.chunks;
+      const int nsrc = P.x_batch_mod > 0 ? n % P.x_batch_mod : n;
+      float mean = 0.f, rstd = 1.f;
+      if (P.stats_in != nullptr) { const float2 mr = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc)); mean = mr.x; rstd = mr.y; }
+      // additive constants of the GroupNorm fold + bias for this sample:  value = rstd * acc + t[col]
+      for (int col = etid; col < AQ_NOUT; col += 256) {
+        float t = __ldg(P.e2 + col);
+        if (P.e1 != nullptr) t = fmaf(-mean * rstd, __ldg(P.e1 + col), t);
+        if (P.sbias != nullptr) t += __ldg(P.sbias + (size_t)n * P.sbias_stride + col);
+        s_t[col] = t;
+      }
+      float runM[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float c[4][4], cz[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cz[i] = 0.f; for (int j = 0; j < 4; ++j) c[i][j] = 0.f; }
+      umma::named_bar_sync(2, 256);                              // s_t visible; the previous item's staging reads are done
+
+      const int nt = tiles_of(chunk);
+      for (int sub = 0; sub < nt; ++sub) {
+        const int p0 = (chunk * AQ_SUB + sub) * AQ_TILE;
+        const bool valid = p0 + row < P.npix;
+        mbar_wait_warp(tmem_full, acc_phase);
+        umma::fence_after();
+        if (half == 0) {
+          // ---- k: tile maximum per head, then P = exp(k - m) as bf16 rows ----
+          float mx[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t ra[16], rb[16];
+            umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32), ra);
+            umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32 + 16), rb);
+            umma::ld_wait16(ra);
+            umma::ld_wait16(rb);
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              m = fmaxf(m, fmaf(__uint_as_float(ra[j]), rstd, s_t[AQ_HID + h * 32 + j]));
+              m = fmaxf(m, fmaf(__uint_as_float(rb[j]), rstd, s_t[AQ_HID + h * 32 + 16 + j]));
+            }
+            mx[h] = valid ? m : -INFINITY;
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
+          if (lane < 4) s_wmax[lane_grp * 4 + lane] = lane == 0 ? mx[0] : lane == 1 ? mx[1] : lane == 2 ? mx[2] : mx[3];
+          umma::named_bar_sync(1, 128);
+          float newM[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float tm = fmaxf(fmaxf(s_wmax[h], s_wmax[4 + h]), fmaxf(s_wmax[8 + h], s_wmax[12 + h]));
+            newM[h] = fmaxf(runM[h], tm);
+          }
+          if (ew == 0 && lane < 4) {
+            const float o = lane == 0 ? runM[0] : lane == 1 ? runM[1] : lane == 2 ? runM[2] : runM[3];
+            const float nw = lane == 0 ? newM[0] : lane == 1 ? newM[1] : lane == 2 ? newM[2] : newM[3];
+            s_sc[lane] = __expf(o - nw);                          // 0 for the first tile (o = -inf)
+          }
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            runM[h] = newM[h];
+            const float mneg = -newM[h] * kLog2e;
+#pragma unroll
+            for (int q16 = 0; q16 < 2; ++q16) {
+              uint32_t r[16];
+              umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32 + q16 * 16), r);
+              umma::ld_wait16(r);
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float k0 = fmaf(__uint_as_float(r[2 * j]), rstd, s_t[AQ_HID + h * 32 + q16 * 16 + 2 * j]);
+                const float k1 = fmaf(__uint_as_float(r[2 * j + 1]), rstd, s_t[AQ_HID + h * 32 + q16 * 16 + 2 * j + 1]);
+                float e0, e1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(k0, kLog2e, mneg)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(k1, kLog2e, mneg)));
+                o[j] = valid ? pack_bf16(e0, e1) : 0u;
+              }
+              const uint32_t dst = sp_row + (uint32_t)((h * 32 + q16 * 16) * 2);
+              sts_128(dst, o[0], o[1], o[2], o[3]);
+              sts_128(dst + 16u, o[4], o[5], o[6], o[7]);
+            }
+          }
+        } else {
+          // ---- v as bf16 rows ----
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            uint32_t r[16];
+            umma::ld_32x32b_x16(t_row + (uint32_t)(2 * AQ_HID + c16 * 16), r);
+            umma::ld_wait16(r);
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v0 = fmaf(__uint_as_float(r[2 * j]), rstd, s_t[2 * AQ_HID + c16 * 16 + 2 * j]);
+              const float v1 = fmaf(__uint_as_float(r[2 * j + 1]), rstd, s_t[2 * AQ_HID + c16 * 16 + 2 * j + 1]);
+              o[j] = valid ? pack_bf16(v0, v1) : 0u;
+            }
+            const uint32_t dst = sv_row + (uint32_t)(c16 * 32);
+            sts_128(dst, o[0], o[1], o[2], o[3]);
+            sts_128(dst + 16u, o[4], o[5], o[6], o[7]);
+          }
+        }
+        umma::named_bar_sync(2, 256);                            // P, V and the rescale factors are staged
+
+        // ---- context: S[d][e] += sum_pix P[pix][d] V[pix][e] (and Z[d] through a column of ones), head hd, d rows 16*mt.. ----
+        {
+          const float sc = s_sc[hd];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { cz[i] *= sc; for (int j = 0; j < 4; ++j) c[i][j] *= sc; }
+          const uint32_t ones = ((lane >> 2) == 0) ? 0x3F803F80u : 0u;       // B fragment of the ones column: n = 0 for every k
+          const uint32_t pa = smem_u32(s_p) + (uint32_t)((lr + ((lmat >> 1) & 1) * 8) * AQ_PITCH + (hd * 32 + mt * 16 + (lmat & 1) * 8) * 2);
+          const uint32_t vb = smem_u32(s_v) + (uint32_t)((lr + (lmat & 1) * 8) * AQ_PITCH + (hd * 32 + (lmat >> 1) * 8) * 2);
+#pragma unroll
+          for (int ks = 0; ks < AQ_TILE / 16; ++ks) {
+            uint32_t a[4], b01[4], b23[4];
+            ldsm_x4_trans(a, pa + (uint32_t)(ks * 16 * AQ_PITCH));
+            ldsm_x4_trans(b01, vb + (uint32_t)(ks * 16 * AQ_PITCH));
+            ldsm_x4_trans(b23, vb + (uint32_t)(ks * 16 * AQ_PITCH + 32));
+            mma_bf16(c[0], a, b01[0], b01[1]);
+            mma_bf16(c[1], a, b01[2], b01[3]);
+            mma_bf16(c[2], a, b23[0], b23[1]);
+            mma_bf16(c[3], a, b23[2], b23[3]);
+            mma_bf16(cz, a, ones, ones);
+          }
+        }
+        // ---- q: softmax over the 32 channels of a head, scaled; this thread's two heads ----
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int h = half * 2 + hh;
+          uint32_t ra[16], rb[16];
+          umma::ld_32x32b_x16(t_row + (uint32_t)(h * 32), ra);
+          umma::ld_32x32b_x16(t_row + (uint32_t)(h * 32 + 16), rb);
+          umma::ld_wait16(ra);
+          umma::ld_wait16(rb);
+          float f[32];
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[j] = fmaf(__uint_as_float(ra[j]), rstd, s_t[h * 32 + j]);
+            f[16 + j] = fmaf(__uint_as_float(rb[j]), rstd, s_t[h * 32 + 16 + j]);
+            m = fmaxf(m, fmaxf(f[j], f[16 + j]));
+          }
+          float sum = 0.f;
+          const float mneg = -m * kLog2e;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f[j]) : "f"(fmaf(f[j], kLog2e, mneg))); sum += f[j]; }
+          const float inv = P.scale / sum;
+          if (valid) {
+            act_t* dst = P.qout + ((size_t)n * P.npix + p0 + row) * AQ_HID + h * 32;
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              uint4 a, b;
+              a.x = pack16(f[16 * v + 0] * inv, f[16 * v + 1] * inv);   a.y = pack16(f[16 * v + 2] * inv, f[16 * v + 3] * inv);
+              a.z = pack16(f[16 * v + 4] * inv, f[16 * v + 5] * inv);   a.w = pack16(f[16 * v + 6] * inv, f[16 * v + 7] * inv);
+              b.x = pack16(f[16 * v + 8] * inv, f[16 * v + 9] * inv);   b.y = pack16(f[16 * v + 10] * inv, f[16 * v + 11] * inv);
+              b.z = pack16(f[16 * v + 12] * inv, f[16 * v + 13] * inv); b.w = pack16(f[16 * v + 14] * inv, f[16 * v + 15] * inv);
+              stg_256(dst + 16 * v, a, b);
+            }
+          }
+        }
+        // ---- release the accumulator; the staging buffers are free once every warp is past its context MMAs ----
+        umma::fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+        acc_phase ^= 1u;
+        umma::named_bar_sync(2, 256);
+      }
+      // ---- one partial per (sample, head, chunk): S rows d = 16 mt + {g, g + 8}, Z from the ones column, m = the running maximum ----
+      {
+        float* po = P.part + (((size_t)n * AQ_HEADS + hd) * P.chunks + chunk) * AQ_PART;
+        const int g = lane >> 2, q = lane & 3;
+        const int d = mt * 16 + g;
+#pragma unroll
+        for (int nt8 = 0; nt8 < 4; ++nt8) {
+          *reinterpret_cast<float2*>(po + d * AQ_DH + nt8 * 8 + q * 2) = make_float2(c[nt8][0], c[nt8][1]);
+          *reinterpret_cast<float2*>(po + (d + 8) * AQ_DH + nt8 * 8 + q * 2) = make_float2(c[nt8][2], c[nt8][3]);
+        }
+        if (q == 0) { po[AQ_DH * AQ_DH + d] = cz[0]; po[AQ_DH * AQ_DH + d + 8] = cz[2]; }
+        // every epilogue thread carries the same running maxima only in the k warps; the others read them back from the
+        // rescale bookkeeping: the maximum of head hd after the last tile is broadcast through shared memory below
+      }
+      if (half == 0 && ew == 0 && lane < 4) s_wmax[lane] = lane == 0 ? runM[0] : lane == 1 ? runM[1] : lane == 2 ? runM[2] : runM[3];
+      umma::named_bar_sync(2, 256);
+      if (lane < 16) {
+        float* po = P.part + (((size_t)n * AQ_HEADS + hd) * P.chunks + chunk) * AQ_PART;
+        po[AQ_DH * AQ_DH + AQ_DH + mt * 16 + lane] = s_wmax[hd];
+      }
+    }
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 2) { umma::fence_after(); umma::tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace ds
+
+using namespace ds;
+
+extern "C" {
+
+/* Fused PreNorm + to_qkv + q soft-max + partial linear-attention context of the U-Net attention (hidden = 4 heads x 32).
+   d_x act16 NHWC [x_batch_mod or N][npix][C]; d_weight act16 [384][C] (rows q | k | v, GroupNorm gamma folded in);
+   d_e1 / d_e2 fp32 [384] (the fold's tables, e1 nullable), d_stats_in the statistics buffer of x (nullable: no norm);
+   d_sbias fp32 [N][sbias_stride] (label_query | label_key | 0; nullable).  Outputs: d_q_out act16 [N][npix][128] = softmax_d(q) * scale,
+   d_part = chunk partials in the layout of ds_attn_ctx_partial (ds_attn_part_floats floats; ds_attn_finalize merges them). */
+int ds_attn_qkv_ctx(const void* d_x, int C, int x_batch_mod, const void* d_stats_in, int stats_in_slots, const void* d_weight,
+                    const float* d_e1, const float* d_e2, const float* d_sbias, long long sbias_stride, void* d_q_out, float* d_part,
+                    int N, int heads, long long npix, float scale, void* stream) {
+  DS_REQUIRE(d_x && d_weight && d_e2 && d_q_out && d_part && N > 0 && npix > 0, "ds_attn_qkv_ctx: bad arguments");
+  DS_REQUIRE(heads == AQ_HEADS, "ds_attn_qkv_ctx: heads=%d (only the U-Net's 4 heads x 32 are built)", heads);
+  DS_REQUIRE(C > 0 && C % AQ_BK == 0, "ds_attn_qkv_ctx: C=%d must be a multiple of %d", C, AQ_BK);
+  DS_REQUIRE(!d_stats_in || d_e1, "ds_attn_qkv_ctx: stats_in needs e1");
+  DS_REQUIRE(npix < (1ll << 30) && (long long)N * ds_attn_chunks(npix) < (1ll << 30), "ds_attn_qkv_ctx: problem too large");
+  EncodeTiledFn encode = get_encode_fn();
+  DS_REQUIRE(encode != nullptr, "ds_attn_qkv_ctx: cuTensorMapEncodeTiled entry point not available");
+  const CUtensorMapDataType dt = kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap map_a, map_b;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)npix, (cuuint64_t)(x_batch_mod > 0 ? x_batch_mod : N)};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)npix * C * 2};
+    const cuuint32_t box[3] = {AQ_BK, AQ_TILE, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(&map_a, dt, 3, const_cast<void*>(d_x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DS_REQUIRE(r == CUDA_SUCCESS, "ds_attn_qkv_ctx: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)AQ_NOUT, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)AQ_NOUT * C * 2};
+    const cuuint32_t box[3] = {AQ_BK, 128, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(&map_b, dt, 3, const_cast<void*>(d_weight), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DS_REQUIRE(r == CUDA_SUCCESS, "ds_attn_qkv_ctx: cuTensorMapEncodeTiled(weight) failed with %d", (int)r);
+  }
+  AttnQkvDev P;
+  memset(&P, 0, sizeof(P));
+  P.N = N; P.npix = (int)npix; P.C = C; P.num_kb = C / AQ_BK; P.x_batch_mod = x_batch_mod;
+  P.chunks = ds_attn_chunks(npix);
+  P.items = N * P.chunks;
+  P.stats_in = reinterpret_cast<const float2*>(d_stats_in); P.stats_in_slots = stats_in_slots;
+  P.e1 = d_e1; P.e2 = d_e2; P.sbias = d_sbias; P.sbias_stride = sbias_stride;
+  P.qout = reinterpret_cast<act_t*>(d_q_out); P.part = d_part; P.scale = scale;
+  DS_CHECK_CUDA(cudaFuncSetAttribute(attn_qkv_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
+  const int grid = P.items < num_sms() ? P.items : num_sms();
+  attn_qkv_ctx_kernel<<<grid, AQ_THREADS, AQ_SMEM, (cudaStream_t)stream>>>(map_a, map_b, P);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+}  // extern "C"

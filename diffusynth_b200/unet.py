@@ -22,6 +22,9 @@ from .ops import PackedConv, Stats, conv_args, pack_conv_down, pack_conv_s1, pac
 
 HEADS, DHEAD = W.ATTN_HEADS, W.ATTN_DIM_HEAD
 HID = HEADS * DHEAD
+# to_qkv + q soft-max + partial context as ONE tcgen05 kernel that keeps k and v on chip (ds_attn_qkv_ctx); False builds the
+# plan from the separate ds_conv_gemm(to_qkv) + ds_attn_ctx_partial launches (kept for the A/B parity test).
+FUSED_ATTN = True
 
 
 class _Block:
@@ -398,16 +401,25 @@ class _Plan:
             """x_mod > 0: x (and its statistics) hold x_mod samples shared by the guidance halves."""
             a = net.attns[p]
             npix = h * w
-            qkv = scr("qkv", N, h, w, 3 * HID)
             sb = self.sbias[:, a.c_off:a.c_off + 3 * HID]
             cat = cfg["attn_type"] == "linear_cat"
-            conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=None if cat else sb, src_batch_mod=x_mod)
             qp = scr("qp", N, h, w, HID)
             part = torch.empty((lib.ds_attn_part_floats(N, HEADS, npix),), **f32)
             M = torch.empty((N, a.out.cout_pad, HID), dtype=ops.ACT, device=dev)
-            add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
-                                                                  float(DHEAD ** -0.5), stream()), "attn_ctx_partial"),
-                "attn_ctx", 2.0 * N * HEADS * DHEAD * DHEAD * npix, N * npix * (3 * HID + HID) * 2.0)
+            if FUSED_ATTN:
+                n_in = x_mod if x_mod > 0 else N
+                add(p + "qkv_ctx", lambda: check(lib.ds_attn_qkv_ctx(
+                    x.data_ptr(), a.dim, x_mod, st_x.buf.data_ptr(), st_x.slots, a.qkv.weight.data_ptr(), a.qkv.e1.data_ptr(), a.qkv.e2.data_ptr(),
+                    None if cat else sb.data_ptr(), self.sbias.stride(0), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, float(DHEAD ** -0.5),
+                    stream()), "attn_qkv_ctx"),
+                    "attn_qkv_ctx", 2.0 * N * npix * a.dim * 3 * HID + 2.0 * N * HEADS * DHEAD * DHEAD * npix,
+                    (n_in * npix * a.dim + N * npix * HID + 3 * HID * a.dim) * 2.0)
+            else:
+                qkv = scr("qkv", N, h, w, 3 * HID)
+                conv(p + "to_qkv", a.qkv, x, None, h, w, out=qkv, stats_in=st_x, sbias=None if cat else sb, src_batch_mod=x_mod)
+                add(p + "ctx", lambda: check(lib.ds_attn_ctx_partial(qkv.data_ptr(), qp.data_ptr(), part.data_ptr(), N, HEADS, npix, 0,
+                                                                      float(DHEAD ** -0.5), stream()), "attn_ctx_partial"),
+                    "attn_ctx", 2.0 * N * HEADS * DHEAD * DHEAD * npix, N * npix * (3 * HID + HID) * 2.0)
             if cat:
                 lk, lv = sb[:, :HID], sb[:, HID:2 * HID]
                 add(p + "fin", lambda: check(lib.ds_attn_finalize_cat(part.data_ptr(), lk.data_ptr(), lv.data_ptr(), self.sbias.stride(0),

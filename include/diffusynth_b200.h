@@ -157,6 +157,14 @@ int ds_attn_chunks(long long npix);
 long long ds_attn_part_floats(int N, int heads, long long npix);
 int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, int heads, long long npix,
                         int q_mode, float scale, void* stream);
+/* Fused PreNorm (folded GroupNorm(1,C)) + to_qkv + q soft-max + partial context of the U-Net attention (:148-151,263,271-289):
+   the to_qkv GEMM on tcgen05 with k and v kept on chip (P = exp(k - m) and S = P^T V in the epilogue); writes only
+   q' = softmax_d(q) * scale (act16 [N][npix][128]) and the chunk partials ds_attn_finalize consumes.  heads must be 4 (x 32).
+   d_x act16 NHWC [x_batch_mod or N][npix][C]; d_weight act16 [384][C] (q | k | v rows, gamma folded); d_e1 (nullable) / d_e2 fp32 [384];
+   d_stats_in statistics buffer of x (nullable); d_sbias fp32 [N][sbias_stride] = label_query | label_key | 0 (nullable). */
+int ds_attn_qkv_ctx(const void* d_x, int C, int x_batch_mod, const void* d_stats_in, int stats_in_slots, const void* d_weight,
+                    const float* d_e1, const float* d_e2, const float* d_sbias, long long sbias_stride, void* d_q_out, float* d_part,
+                    int N, int heads, long long npix, float scale, void* stream);
 int ds_attn_finalize(const float* d_part, const float* d_wout, void* d_M, int N, int heads, long long npix,
                      int C, int Cout_pad, void* stream);
 /* LinearCrossAttention ("linear_cat", diffusion_components.py:171-207): the condition contributes one extra key / value token,

@@ -330,6 +330,9 @@ def run_b200(args):
         plan = loop.plan
         # ---- per-kernel rooflines of one U-Net evaluation (CFG-doubled batch) and of the tail, measured here with CUDA events ----
         unet_ms = timed_ops(plan.ops)
+        if os.environ.get("DS_DUMP_OPS"):
+            with open(os.environ["DS_DUMP_OPS"], "w") as f:
+                json.dump([dict(op=k, ms=round(v, 4), **plan.meta.get(k, {})) for k, v in unet_ms.items()], f, indent=0)
         unet_fams = family_rooflines(unet_ms, plan.meta, pk)
         conv_keys = [k for k in unet_fams if k.startswith("conv")]
         conv_ms = sum(unet_fams[k]["ms"] for k in conv_keys)

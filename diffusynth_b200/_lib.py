@@ -81,6 +81,8 @@ _SIGNATURES = {
     "ds_istft_length": (_L, [_I]),
     "ds_stft_decode_istft": (_I, [_P, _P, _P, _I, _I, _P]),
     "ds_stft_encode": (_I, [_P, _L, _P, _I, _I, _P]),
+    "ds_decode_stft": (_I, [_P, _P, _L, _I, _P]),
+    "ds_encode_stft": (_I, [_P, _P, _L, _I, _P]),
     "ds_griffinlim_update": (_I, [_P, _P, _P, _F, _I, _I, _I, _P]),
     "ds_spec_images": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ds_latent_image": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -28,12 +28,82 @@ def spectrogram_to_waveform(spec: torch.Tensor) -> torch.Tensor:
     return wave
 
 
-def adjust_audio_length(audio: torch.Tensor, desired_length: int) -> torch.Tensor:
-    """Crop or zero-pad the last axis (tools.py:126-151, without the resampling branch)."""
+def adjust_audio_length(audio, desired_length: int, original_sample_rate: Optional[int] = None, target_sample_rate: Optional[int] = None):
+    """tools.adjust_audio_length (tools.py:126-151): resample when the rates differ, then crop or zero-pad the last axis.
+    Tensors stay tensors (the batched path of TextToTimbre.encode_audio), numpy arrays stay numpy arrays (drop-in use).
+    The reference resamples with ``librosa.core.resample`` (absent from this image, un-pinned in requirements.txt:3; its default
+    ``res_type`` is a band-limited sinc method): here a polyphase FIR resampler (``scipy.signal.resample_poly``) on the host
+    -- parity of this branch is UNPINNED by necessity; it is one clip of host-side preprocessing, not part of the device path."""
+    is_np = isinstance(audio, np.ndarray)
+    if original_sample_rate is not None and target_sample_rate is not None and original_sample_rate != target_sample_rate:
+        from math import gcd
+        from scipy.signal import resample_poly
+        g = gcd(int(original_sample_rate), int(target_sample_rate))
+        a = audio if is_np else audio.detach().cpu().numpy()
+        a = resample_poly(a, int(target_sample_rate) // g, int(original_sample_rate) // g, axis=-1)
+        audio = a if is_np else torch.from_numpy(np.ascontiguousarray(a)).to(audio.device, audio.dtype)
     L = audio.shape[-1]
     if L >= desired_length:
         return audio[..., :desired_length]
+    if is_np:
+        out = np.zeros(audio.shape[:-1] + (desired_length,))          # the reference pads into np.zeros (float64), :146-148
+        out[..., :L] = audio
+        return out
     return torch.nn.functional.pad(audio, (0, desired_length - L))
+
+
+# ---- numpy drop-ins of the reference's STFT+ helpers (tools.py:170-191, 320-345) ------------------------------------------------------
+def pad_STFT(D: np.ndarray, time_resolution: Optional[int] = 256) -> np.ndarray:
+    """tools.pad_STFT (:170-182): drop the DC row, zero-pad (never crop) the time axis to ``time_resolution``."""
+    D = D[1:, :]
+    if time_resolution is None:
+        return D
+    pad = time_resolution - D.shape[1]
+    return np.pad(D, ((0, 0), (0, pad)), "constant") if pad > 0 else D
+
+
+def depad_STFT(D_padded: np.ndarray) -> np.ndarray:
+    """tools.depad_STFT (:185-191): prepend a zero DC row (float64 zeros, so complex64 input is promoted like the reference's)."""
+    return np.concatenate([np.zeros((1, D_padded.shape[1])), D_padded], axis=0)
+
+
+def _device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def decode_stft(encoded_D: np.ndarray) -> np.ndarray:
+    """tools.decode_stft (:334-345): [3, F, T] (log1p magnitude, cos, sin) -> complex [F, T], evaluated by ds_decode_stft in the
+    precision of the input (float32 -> complex64, float64 -> complex128), like numpy."""
+    enc = np.ascontiguousarray(encoded_D)
+    dbl = enc.dtype == np.float64
+    if not dbl:
+        enc = enc.astype(np.float32, copy=False)
+    t = torch.from_numpy(enc).to(_device())
+    plane = int(np.prod(enc.shape[1:]))
+    out = torch.empty(tuple(enc.shape[1:]) + (2,), dtype=t.dtype, device=t.device)
+    check(_lib.load().ds_decode_stft(t.data_ptr(), out.data_ptr(), plane, 1 if dbl else 0, ops._stream()), "ds_decode_stft")
+    return torch.view_as_complex(out).cpu().numpy()
+
+
+def encode_stft(D: np.ndarray) -> np.ndarray:
+    """tools.encode_stft (:320-331): complex [F, T] -> [3, F, T] (log1p|D|, cos angle, sin angle) by ds_encode_stft."""
+    Dc = np.ascontiguousarray(D)
+    dbl = Dc.dtype == np.complex128
+    if not dbl:
+        Dc = Dc.astype(np.complex64, copy=False)
+    t = torch.view_as_real(torch.from_numpy(Dc)).contiguous().to(_device())
+    plane = int(np.prod(Dc.shape))
+    out = torch.empty((3,) + tuple(Dc.shape), dtype=t.dtype, device=t.device)
+    check(_lib.load().ds_encode_stft(t.data_ptr(), out.data_ptr(), plane, 1 if dbl else 0, ops._stream()), "ds_encode_stft")
+    return out.cpu().numpy()
+
+
+def istft(D: np.ndarray, hop_length: int = 256, win_length: int = 1024) -> np.ndarray:
+    """``librosa.istft(D, hop_length=256, win_length=1024)`` as the reference calls it (utils.py:184,241,260) for one complex
+    [513, T] matrix (DC row ignored: depad_STFT made it zero), on the device through the fused decode + iSTFT kernel."""
+    assert hop_length == 256 and win_length == 1024 and D.shape[0] == 513, "the path's iSTFT is fixed at n_fft 1024 / hop 256"
+    enc = encode_stft(np.asarray(D)[1:].astype(np.complex64))
+    return spectrogram_to_waveform(torch.from_numpy(enc)[None].to(_device()))[0].cpu().numpy()
 
 
 @torch.no_grad()

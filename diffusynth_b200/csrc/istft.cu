@@ -207,6 +207,32 @@ __global__ void griffinlim_update_kernel(const float* __restrict__ rebuilt, floa
   }
 }
 
+// ---- tools.decode_stft / tools.encode_stft as stand-alone elementwise kernels (the numpy drop-ins of codec.py; the sampling path
+// uses the fused forms above).  T = float or double: numpy computes in the precision of its input. ----
+template <typename T>
+__global__ void decode_stft_kernel(const T* __restrict__ enc, T* __restrict__ out, long long plane) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+    const T mag = expm1(enc[i]);                                  // tools.py:340
+    const T ph = atan2(enc[2 * plane + i], enc[plane + i]);       // :342
+    T s, c;
+    sincos(ph, &s, &c);
+    out[2 * i] = mag * c;                                          // :344  magnitude * (cos(phase) + 1j * sin(phase))
+    out[2 * i + 1] = mag * s;
+  }
+}
+template <typename T>
+__global__ void encode_stft_kernel(const T* __restrict__ D, T* __restrict__ out, long long plane) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < plane; i += (long long)gridDim.x * blockDim.x) {
+    const T re = D[2 * i], im = D[2 * i + 1];
+    const T ph = atan2(im, re);                                    // np.angle, tools.py:323
+    T s, c;
+    sincos(ph, &s, &c);
+    out[i] = log1p(hypot(re, im));                                 // :322,325
+    out[plane + i] = c;                                            // :327
+    out[2 * plane + i] = s;                                        // :328
+  }
+}
+
 __global__ void twiddle_init_kernel(float2* tw512, float2* tw1024) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 256) { double s, c; sincospi((double)i / 256.0, &s, &c); tw512[i] = make_float2((float)c, (float)s); }
@@ -280,6 +306,29 @@ int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int T
   const size_t smem = FR * XS_PITCH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(stft_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   stft_encode_kernel<<<dim3((Tpad + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_wave, L, d_spec, T, Tpad, tw512, tw1024);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+/* tools.decode_stft (tools.py:334-345): d_enc [3, plane] (log1p magnitude, cos, sin) -> d_out [plane] complex (re, im interleaved);
+   tools.encode_stft (:320-331): the inverse mapping.  is_double selects float64 (numpy computes in the precision of its input). */
+int ds_decode_stft(const void* d_enc, void* d_out, long long plane, int is_double, void* stream) {
+  DS_REQUIRE(d_enc && d_out && plane > 0, "ds_decode_stft: bad arguments");
+  long long blocks = (plane + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (is_double) decode_stft_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)d_enc, (double*)d_out, plane);
+  else decode_stft_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)d_enc, (float*)d_out, plane);
+  DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+int ds_encode_stft(const void* d_D, void* d_out, long long plane, int is_double, void* stream) {
+  DS_REQUIRE(d_D && d_out && plane > 0, "ds_encode_stft: bad arguments");
+  long long blocks = (plane + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (is_double) encode_stft_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const double*)d_D, (double*)d_out, plane);
+  else encode_stft_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)d_D, (float*)d_out, plane);
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

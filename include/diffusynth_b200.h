@@ -198,6 +198,10 @@ long long ds_istft_length(int T);
 int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, int B, int T, void* stream);
 /* librosa.stft(n_fft 1024, hop 256) + pad_STFT + encode_stft (sound2sound_with_text.py:85-94; tools.py:170-182,320-331). */
 int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int Tpad, void* stream);
+/* tools.decode_stft / tools.encode_stft (tools.py:334-345, 320-331) as stand-alone elementwise kernels behind the numpy drop-ins of
+   diffusynth_b200.codec: d_enc [3][plane] real <-> d_D [plane] complex (re, im interleaved); is_double: float64 instead of float32. */
+int ds_decode_stft(const void* d_enc, void* d_D, long long plane, int is_double, void* stream);
+int ds_encode_stft(const void* d_D, void* d_enc, long long plane, int is_double, void* stream);
 /* Griffin-Lim phase update (the loop body of librosa.griffinlim as called by tools.py:63-76,194-223: hop 256, win 1024,
    momentum 0.99): d_rebuilt = ds_stft_encode(ds_stft_decode_istft(d_spec)) as [B,3,512,T]; d_tprev fp32 [B,512,T,2] holds the
    previous rebuilt STFT (ignored and initialised when first != 0); channels 1, 2 (cos, sin) of d_spec are overwritten. */

@@ -305,3 +305,28 @@ def test_griffinlim_matches_oracle_and_converges():
     assert e32 < e8 < e0 and e32 < 0.25 * e0
     rnd = codec.griffinlim(mag, n_iter=4, generator=torch.Generator(device="cuda").manual_seed(1))     # random start like librosa's default
     assert torch.isfinite(rnd).all()
+
+
+def test_numpy_dropins_of_tools_stft_helpers(golden):
+    """codec.decode_stft / depad_STFT / encode_stft / pad_STFT (numpy in, numpy out) against the reference's own outputs
+    (tests/golden/codec.npz, minted from tools.py:170-191,320-345), and codec.istft against the float64 oracle."""
+    from diffusynth_b200 import codec
+    g = golden["codec"]
+    D = codec.decode_stft(g["decode_in"])
+    assert D.dtype == g["decode_out"].dtype and D.shape == g["decode_out"].shape
+    assert np.abs(D - g["decode_out"]).max() <= 2e-6 * np.abs(g["decode_out"]).max()
+    dp = codec.depad_STFT(g["decode_out"])
+    assert dp.dtype == g["depad_out"].dtype and np.array_equal(dp, g["depad_out"])
+    pad = codec.pad_STFT(g["encode_in"], 8)
+    assert np.array_equal(pad, g["pad_out"]) and codec.pad_STFT(g["encode_in"], None).shape == (512, 5) and codec.pad_STFT(g["encode_in"], 3).shape == (512, 5)
+    enc = codec.encode_stft(g["pad_out"])
+    assert enc.dtype == g["encode_out"].dtype and enc.shape == g["encode_out"].shape
+    assert np.abs(enc - g["encode_out"]).max() < 1e-12 if enc.dtype == np.float64 else np.abs(enc - g["encode_out"]).max() < 2e-6
+    Dc = (cases.randn((513, 12), 44) + 1j * cases.randn((513, 12), 45)).numpy()
+    Dc[0] = 0
+    w = codec.istft(Dc)
+    ref = O.istft(Dc)
+    assert w.shape == ref.shape and rel(torch.from_numpy(w), torch.from_numpy(ref)) < 1e-5
+    a = codec.adjust_audio_length(np.ones(10), 16)
+    assert a.dtype == np.float64 and a.shape == (16,) and a[:10].sum() == 10 and a[10:].sum() == 0
+    assert codec.adjust_audio_length(np.ones(32000), 16000, 32000, 16000).shape == (16000,)

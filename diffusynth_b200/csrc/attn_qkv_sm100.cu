@@ -10,11 +10,17 @@
 // channels per pixel) and an attn_ctx_partial launch (which read them back).
 //
 // CTA = 12 warps, persistent over (sample, chunk) items:  warp 0 activation TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator + weight TMA producer, warps 4-11 epilogue (thread = pixel row; warps 4-7 own k and q heads 0-1, warps 8-11 own
-// v and q heads 2-3; for the context MMAs warp w owns head w/2, d rows 16*(w%2)..+15).
+// allocator + weight TMA producer, warps 4-11 epilogue (thread = pixel row; warps 4-7 own heads 0-1 of q, k and v, warps 8-11
+// heads 2-3; for the context MMAs warp w owns head w/2, d rows 16*(w%2)..+15).
 #include "common.cuh"
 #include "../../include/diffusynth_b200.h"
 #include "umma.cuh"
+
+// AQ_DBG (tools_dev/ab_attn.py builds): 1 = no MMA issue, 2 = no weight TMA loads, 4 = no activation TMA loads, 8 = no epilogue work,
+// 16 = no TMEM loads, 32 = no MUFU, 64 = no context MMAs, 128 = no q' stores, 256 = no P / V staging stores
+#ifndef AQ_DBG
+#define AQ_DBG 0
+#endif
 
 namespace ds {
 
@@ -63,11 +69,13 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   float* s_t = reinterpret_cast<float*>(s_v + AQ_TILE * AQ_PITCH);         // [384] per-sample additive constants of the fold
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_t + AQ_NOUT);
   uint64_t* empty_bar = full_bar + AQ_STAGES;
+  // one accumulator (columns q [0,128) | k [128,256) | v [256,384)): the epilogue pulls its whole share into registers first and
+  // releases it, so the next tile's MMAs run under this tile's exponentials, context MMAs and stores
   uint64_t* tmem_full = empty_bar + AQ_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  float* s_wmax = reinterpret_cast<float*>(tmem_base_smem + 2);            // [4 lane groups][4 heads]
-  float* s_sc = s_wmax + 16;                                               // [4 heads] exp(m_old - m_new) of the current tile
+  float* s_wmax = reinterpret_cast<float*>(tmem_base_smem + 2);            // [2 tile parities][4 lane groups][4 heads], log2 domain
+  float* s_sc = s_wmax + 32;                                               // [4 heads] exp2(m_old - m_new) of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -97,8 +105,11 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = 0; kb < P.num_kb; ++kb) {
           mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
           if (umma::elect_one()) {
-            mbar_expect_tx(&full_bar[stage], AQ_A_BYTES);
-            tma_load_3d(smem + stage * AQ_STAGE_BYTES, &map_a, &full_bar[stage], kb * AQ_BK, p0, nsrc);
+            if (AQ_DBG & 4) { mbar_arrive(&full_bar[stage]); }
+            else {
+              mbar_expect_tx(&full_bar[stage], AQ_A_BYTES);
+              tma_load_3d(smem + stage * AQ_STAGE_BYTES, &map_a, &full_bar[stage], kb * AQ_BK, p0, nsrc);
+            }
           }
           __syncwarp();
           if (++stage == AQ_STAGES) { stage = 0; phase ^= 1u; }
@@ -116,9 +127,12 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait_warp(&empty_bar[stage], phase ^ 1u);
           if (umma::elect_one()) {
             uint8_t* sb = smem + stage * AQ_STAGE_BYTES + AQ_A_BYTES;
-            mbar_expect_tx(&full_bar[stage], AQ_B_BYTES);
+            if (AQ_DBG & 2) { mbar_arrive(&full_bar[stage]); }
+            else {
+              mbar_expect_tx(&full_bar[stage], AQ_B_BYTES);
 #pragma unroll
-            for (int j = 0; j < 3; ++j) tma_load_3d(sb + j * (AQ_B_BYTES / 3), &map_b, &full_bar[stage], kb * AQ_BK, j * 128, 0);
+              for (int j = 0; j < 3; ++j) tma_load_3d(sb + j * (AQ_B_BYTES / 3), &map_b, &full_bar[stage], kb * AQ_BK, j * 128, 0);
+            }
           }
           __syncwarp();
           if (++stage == AQ_STAGES) { stage = 0; phase ^= 1u; }
@@ -146,6 +160,7 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int k = 0; k < AQ_BK / 16; ++k) {
               const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+              if (AQ_DBG & 1) continue;
               umma::mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bq + (uint64_t)(2 * k), idesc_q, accum);
               umma::mma_f16(tmem_base + 128u, adesc + (uint64_t)(2 * k), bkv + (uint64_t)(2 * k), idesc_kv, accum);
             }
@@ -161,29 +176,36 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
+    // thread = pixel row (TMEM lane); warps 4-7 own heads 0-1 of q, k and v, warps 8-11 heads 2-3 (64 columns of each).
     const int ew = warp - 4, lane_grp = warp & 3, half = ew >> 2;
-    const int row = lane_grp * 32 + lane;                       // pixel row of the tile = TMEM lane
+    const int row = lane_grp * 32 + lane;
     const int etid = ew * 32 + lane;
-    const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+    const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(half * 64);
     const int hd = ew >> 1, mt = ew & 1;                        // context MMAs: head, 16-row half of d
-    const uint32_t sp_row = smem_u32(s_p) + (uint32_t)(row * AQ_PITCH), sv_row = smem_u32(s_v) + (uint32_t)(row * AQ_PITCH);
+    const uint32_t sp_row = smem_u32(s_p) + (uint32_t)(row * AQ_PITCH + half * 128), sv_row = smem_u32(s_v) + (uint32_t)(row * AQ_PITCH + half * 128);
     const int lr = lane & 7, lmat = lane >> 3;
     uint32_t acc_phase = 0;
-    constexpr float kLog2e = 1.4426950408889634f;
+    int tile_par = 0;
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    const float* tq = s_t + half * 64;                           // this thread's 64 columns of the q / k / v constants
+    const float* tk = s_t + AQ_HID + half * 64;
+    const float* tv = s_t + 2 * AQ_HID + half * 64;
 
     for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = item / P.chunks, chunk = item - n * P.chunks;
       const int nsrc = P.x_batch_mod > 0 ? n % P.x_batch_mod : n;
       float mean = 0.f, rstd = 1.f;
       if (P.stats_in != nullptr) { const float2 mr = __ldg(stats_sample(P.stats_in, P.stats_in_slots, nsrc)); mean = mr.x; rstd = mr.y; }
-      // additive constants of the GroupNorm fold + bias for this sample:  value = rstd * acc + t[col]
+      const float rl2 = rstd * kLog2e;
+      // additive constants of the GroupNorm fold + bias for this sample: value = rstd * acc + t[col]; q and k work in the log2
+      // domain (their only consumers are exponentials): value * log2(e) = (rstd log2 e) * acc + t[col] log2 e
       for (int col = etid; col < AQ_NOUT; col += 256) {
         float t = __ldg(P.e2 + col);
         if (P.e1 != nullptr) t = fmaf(-mean * rstd, __ldg(P.e1 + col), t);
         if (P.sbias != nullptr) t += __ldg(P.sbias + (size_t)n * P.sbias_stride + col);
-        s_t[col] = t;
+        s_t[col] = col < 2 * AQ_HID ? t * kLog2e : t;
       }
-      float runM[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float runM[2] = {-INFINITY, -INFINITY};                    // log2 domain, heads 2*half + {0, 1}; identical in the 4 warps of a half
       float c[4][4], cz[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { cz[i] = 0.f; for (int j = 0; j < 4; ++j) c[i][j] = 0.f; }
@@ -195,83 +217,101 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const bool valid = p0 + row < P.npix;
         mbar_wait_warp(tmem_full, acc_phase);
         umma::fence_after();
-        if (half == 0) {
-          // ---- k: tile maximum per head, then P = exp(k - m) as bf16 rows ----
-          float mx[4];
+        if (AQ_DBG & 8) {
+          umma::fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty);
+          acc_phase ^= 1u;
+          continue;
+        }
+        // ---- pull this thread's 64 columns of k, v and q out of TMEM: k first, v and q while k / v are being processed ----
+        uint32_t k0[32], k1[32];
+#define AQ_LD(addr, r) do { if (AQ_DBG & 16) { _Pragma("unroll") for (int z_ = 0; z_ < 32; ++z_) r[z_] = 0x3f000000u + z_ + lane; } else umma::ld_32x32b_x32(addr, r); } while (0)
+        AQ_LD(t_row + (uint32_t)AQ_HID, k0);
+        AQ_LD(t_row + (uint32_t)(AQ_HID + 32), k1);
+        umma::ld_wait32(k0);
+        umma::ld_wait32(k1);
+        uint32_t v0[32], v1[32];
+        AQ_LD(t_row + (uint32_t)(2 * AQ_HID), v0);
+        AQ_LD(t_row + (uint32_t)(2 * AQ_HID + 32), v1);
+        // ---- k -> P = exp(k - m) as bf16 rows.  m (one per head) only has to be the SAME for every pixel of the chunk's partial
+        // and keep the exponentials finite: the first tile of an item measures its own maximum, later tiles use the running
+        // maximum of the tiles before them (their own maximum is collected on the way for the next tile); bf16 has the fp32
+        // exponent range, so P > 1 is harmless, and the exponent is clamped far below overflow.
+        float kf0[32], kf1[32];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            uint32_t ra[16], rb[16];
-            umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32), ra);
-            umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32 + 16), rb);
-            umma::ld_wait16(ra);
-            umma::ld_wait16(rb);
-            float m = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              m = fmaxf(m, fmaf(__uint_as_float(ra[j]), rstd, s_t[AQ_HID + h * 32 + j]));
-              m = fmaxf(m, fmaf(__uint_as_float(rb[j]), rstd, s_t[AQ_HID + h * 32 + 16 + j]));
-            }
-            mx[h] = valid ? m : -INFINITY;
+        for (int j = 0; j < 32; ++j) {
+          kf0[j] = fmaf(__uint_as_float(k0[j]), rl2, tk[j]);
+          kf1[j] = fmaf(__uint_as_float(k1[j]), rl2, tk[32 + j]);
+          mx0 = fmaxf(mx0, kf0[j]);
+          mx1 = fmaxf(mx1, kf1[j]);
+        }
+        mx0 = warp_max(valid ? mx0 : -INFINITY);
+        mx1 = warp_max(valid ? mx1 : -INFINITY);
+        if (lane < 2) s_wmax[tile_par * 16 + lane_grp * 4 + half * 2 + lane] = lane == 0 ? mx0 : mx1;
+        if (sub == 0) umma::named_bar_sync(1 + 2 * half, 128);  // first tile: its own maxima, exchanged among the 4 warps of this half
+        {
+          const int rd = (sub == 0 ? tile_par : tile_par ^ 1) * 16 + half * 2;
+          const float t0 = fmaxf(fmaxf(s_wmax[rd], s_wmax[rd + 4]), fmaxf(s_wmax[rd + 8], s_wmax[rd + 12]));
+          const float t1 = fmaxf(fmaxf(s_wmax[rd + 1], s_wmax[rd + 5]), fmaxf(s_wmax[rd + 9], s_wmax[rd + 13]));
+          const float n0 = fmaxf(runM[0], t0), n1 = fmaxf(runM[1], t1);
+          if ((ew & 3) == 0 && lane < 2) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((lane == 0 ? runM[0] : runM[1]) - (lane == 0 ? n0 : n1)));      // 0 on the first tile
+            s_sc[half * 2 + lane] = e;
           }
+          runM[0] = n0; runM[1] = n1;
+        }
 #pragma unroll
-          for (int h = 0; h < 4; ++h) mx[h] = warp_max(mx[h]);
-          if (lane < 4) s_wmax[lane_grp * 4 + lane] = lane == 0 ? mx[0] : lane == 1 ? mx[1] : lane == 2 ? mx[2] : mx[3];
-          umma::named_bar_sync(1, 128);
-          float newM[4];
+        for (int hh = 0; hh < 2; ++hh) {
+          const float mh = runM[hh];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float tm = fmaxf(fmaxf(s_wmax[h], s_wmax[4 + h]), fmaxf(s_wmax[8 + h], s_wmax[12 + h]));
-            newM[h] = fmaxf(runM[h], tm);
-          }
-          if (ew == 0 && lane < 4) {
-            const float o = lane == 0 ? runM[0] : lane == 1 ? runM[1] : lane == 2 ? runM[2] : runM[3];
-            const float nw = lane == 0 ? newM[0] : lane == 1 ? newM[1] : lane == 2 ? newM[2] : newM[3];
-            s_sc[lane] = __expf(o - nw);                          // 0 for the first tile (o = -inf)
-          }
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t o[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            runM[h] = newM[h];
-            const float mneg = -newM[h] * kLog2e;
-#pragma unroll
-            for (int q16 = 0; q16 < 2; ++q16) {
-              uint32_t r[16];
-              umma::ld_32x32b_x16(t_row + (uint32_t)(AQ_HID + h * 32 + q16 * 16), r);
-              umma::ld_wait16(r);
-              uint32_t o[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float k0 = fmaf(__uint_as_float(r[2 * j]), rstd, s_t[AQ_HID + h * 32 + q16 * 16 + 2 * j]);
-                const float k1 = fmaf(__uint_as_float(r[2 * j + 1]), rstd, s_t[AQ_HID + h * 32 + q16 * 16 + 2 * j + 1]);
-                float e0, e1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(k0, kLog2e, mneg)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(k1, kLog2e, mneg)));
-                o[j] = valid ? pack_bf16(e0, e1) : 0u;
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = hh == 0 ? kf0[q8 * 8 + 2 * j] : kf1[q8 * 8 + 2 * j], a1 = hh == 0 ? kf0[q8 * 8 + 2 * j + 1] : kf1[q8 * 8 + 2 * j + 1];
+              float e0, e1;
+              if (AQ_DBG & 32) { e0 = fminf(a0 - mh, 100.0f) * 0.5f; e1 = fminf(a1 - mh, 100.0f) * 0.5f; }
+              else {
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(a0 - mh, 100.0f)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(a1 - mh, 100.0f)));
               }
-              const uint32_t dst = sp_row + (uint32_t)((h * 32 + q16 * 16) * 2);
-              sts_128(dst, o[0], o[1], o[2], o[3]);
-              sts_128(dst + 16u, o[4], o[5], o[6], o[7]);
+              o[j] = valid ? pack_bf16(e0, e1) : 0u;
             }
-          }
-        } else {
-          // ---- v as bf16 rows ----
-#pragma unroll
-          for (int c16 = 0; c16 < 8; ++c16) {
-            uint32_t r[16];
-            umma::ld_32x32b_x16(t_row + (uint32_t)(2 * AQ_HID + c16 * 16), r);
-            umma::ld_wait16(r);
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v0 = fmaf(__uint_as_float(r[2 * j]), rstd, s_t[2 * AQ_HID + c16 * 16 + 2 * j]);
-              const float v1 = fmaf(__uint_as_float(r[2 * j + 1]), rstd, s_t[2 * AQ_HID + c16 * 16 + 2 * j + 1]);
-              o[j] = valid ? pack_bf16(v0, v1) : 0u;
-            }
-            const uint32_t dst = sv_row + (uint32_t)(c16 * 32);
-            sts_128(dst, o[0], o[1], o[2], o[3]);
-            sts_128(dst + 16u, o[4], o[5], o[6], o[7]);
+            if (!((AQ_DBG & 256) && o[0] != 0x12345u)) sts_128(sp_row + (uint32_t)(hh * 64 + q8 * 16), o[0], o[1], o[2], o[3]);
           }
         }
-        umma::named_bar_sync(2, 256);                            // P, V and the rescale factors are staged
+        // ---- v as bf16 rows; q loads in flight ----
+        umma::ld_wait32(v0);
+        umma::ld_wait32(v1);
+        uint32_t q0[32], q1[32];
+        AQ_LD(t_row, q0);
+        AQ_LD(t_row + 32u, q1);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t r0 = hh == 0 ? v0[q8 * 8 + 2 * j] : v1[q8 * 8 + 2 * j], r1 = hh == 0 ? v0[q8 * 8 + 2 * j + 1] : v1[q8 * 8 + 2 * j + 1];
+              const float a0 = fmaf(__uint_as_float(r0), rstd, tv[hh * 32 + q8 * 8 + 2 * j]);
+              const float a1 = fmaf(__uint_as_float(r1), rstd, tv[hh * 32 + q8 * 8 + 2 * j + 1]);
+              o[j] = valid ? pack_bf16(a0, a1) : 0u;
+            }
+            if (!((AQ_DBG & 256) && o[0] != 0x12345u)) sts_128(sv_row + (uint32_t)(hh * 64 + q8 * 16), o[0], o[1], o[2], o[3]);
+          }
+        }
+        umma::ld_wait32(q0);
+        umma::ld_wait32(q1);
+        // everything this thread needs from the accumulator is in registers: the next tile's MMAs may start
+        umma::fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty);
+        acc_phase ^= 1u;
+        umma::named_bar_sync(2, 256);                            // P, V, the rescale factors and this tile's maxima are staged
 
         // ---- context: S[d][e] += sum_pix P[pix][d] V[pix][e] (and Z[d] through a column of ones), head hd, d rows 16*mt.. ----
         {
@@ -282,7 +322,7 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const uint32_t pa = smem_u32(s_p) + (uint32_t)((lr + ((lmat >> 1) & 1) * 8) * AQ_PITCH + (hd * 32 + mt * 16 + (lmat & 1) * 8) * 2);
           const uint32_t vb = smem_u32(s_v) + (uint32_t)((lr + (lmat & 1) * 8) * AQ_PITCH + (hd * 32 + (lmat >> 1) * 8) * 2);
 #pragma unroll
-          for (int ks = 0; ks < AQ_TILE / 16; ++ks) {
+          for (int ks = 0; ks < ((AQ_DBG & 64) ? 0 : AQ_TILE / 16); ++ks) {
             uint32_t a[4], b01[4], b23[4];
             ldsm_x4_trans(a, pa + (uint32_t)(ks * 16 * AQ_PITCH));
             ldsm_x4_trans(b01, vb + (uint32_t)(ks * 16 * AQ_PITCH));
@@ -294,30 +334,25 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mma_bf16(cz, a, ones, ones);
           }
         }
-        // ---- q: softmax over the 32 channels of a head, scaled; this thread's two heads ----
+        // ---- q: softmax over the 32 channels of a head, scaled; this thread's two heads, from registers ----
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int h = half * 2 + hh;
-          uint32_t ra[16], rb[16];
-          umma::ld_32x32b_x16(t_row + (uint32_t)(h * 32), ra);
-          umma::ld_32x32b_x16(t_row + (uint32_t)(h * 32 + 16), rb);
-          umma::ld_wait16(ra);
-          umma::ld_wait16(rb);
           float f[32];
           float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[j] = fmaf(__uint_as_float(ra[j]), rstd, s_t[h * 32 + j]);
-            f[16 + j] = fmaf(__uint_as_float(rb[j]), rstd, s_t[h * 32 + 16 + j]);
-            m = fmaxf(m, fmaxf(f[j], f[16 + j]));
+          for (int j = 0; j < 32; ++j) {
+            f[j] = fmaf(__uint_as_float(hh == 0 ? q0[j] : q1[j]), rl2, tq[hh * 32 + j]);
+            m = fmaxf(m, f[j]);
           }
           float sum = 0.f;
-          const float mneg = -m * kLog2e;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f[j]) : "f"(fmaf(f[j], kLog2e, mneg))); sum += f[j]; }
+          for (int j = 0; j < 32; ++j) {
+            if (AQ_DBG & 32) f[j] = (f[j] - m) * 0.5f; else asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(f[j]) : "f"(f[j] - m));
+            sum += f[j];
+          }
           const float inv = P.scale / sum;
-          if (valid) {
-            act_t* dst = P.qout + ((size_t)n * P.npix + p0 + row) * AQ_HID + h * 32;
+          if (valid && !((AQ_DBG & 128) && sum != 1234.5f)) {
+            act_t* dst = P.qout + ((size_t)n * P.npix + p0 + row) * AQ_HID + (half * 2 + hh) * 32;
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               uint4 a, b;
@@ -329,12 +364,8 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
-        // ---- release the accumulator; the staging buffers are free once every warp is past its context MMAs ----
-        umma::fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);
-        acc_phase ^= 1u;
-        umma::named_bar_sync(2, 256);
+        tile_par ^= 1;
+        umma::named_bar_sync(2, 256);                            // every warp is past its context MMAs: the staging rows are free
       }
       // ---- one partial per (sample, head, chunk): S rows d = 16 mt + {g, g + 8}, Z from the ones column, m = the running maximum ----
       {
@@ -347,14 +378,13 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           *reinterpret_cast<float2*>(po + (d + 8) * AQ_DH + nt8 * 8 + q * 2) = make_float2(c[nt8][2], c[nt8][3]);
         }
         if (q == 0) { po[AQ_DH * AQ_DH + d] = cz[0]; po[AQ_DH * AQ_DH + d + 8] = cz[2]; }
-        // every epilogue thread carries the same running maxima only in the k warps; the others read them back from the
-        // rescale bookkeeping: the maximum of head hd after the last tile is broadcast through shared memory below
       }
-      if (half == 0 && ew == 0 && lane < 4) s_wmax[lane] = lane == 0 ? runM[0] : lane == 1 ? runM[1] : lane == 2 ? runM[2] : runM[3];
+      // the running maxima (natural-log units, as attn_reduce_kernel expects) reach the warps that write them through shared memory
+      if ((ew & 3) == 0 && lane < 2) s_sc[half * 2 + lane] = (lane == 0 ? runM[0] : runM[1]) * kLn2;
       umma::named_bar_sync(2, 256);
       if (lane < 16) {
         float* po = P.part + (((size_t)n * AQ_HEADS + hd) * P.chunks + chunk) * AQ_PART;
-        po[AQ_DH * AQ_DH + AQ_DH + mt * 16 + lane] = s_wmax[hd];
+        po[AQ_DH * AQ_DH + AQ_DH + mt * 16 + lane] = s_sc[hd];
       }
     }
   }

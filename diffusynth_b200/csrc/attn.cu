@@ -51,6 +51,7 @@ static constexpr int AT_SUB = 4;         // 128-pixel sub-chunks per block: one 
 __global__ void __launch_bounds__(256)
 attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int q_mode, float scale,
                         act_t* __restrict__ qout /* [N, n, hidden] */, float* __restrict__ part, int chunks) {
+  pdl_enter();
   __shared__ __align__(16) __half s_k[AT_PIX][AT_PITCH];     // k, then p = exp(k - m), as IEEE half
   __shared__ __align__(16) __half s_v[AT_PIX][AT_PITCH];
   __shared__ float s_red[8][AT_D];
@@ -182,6 +183,7 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
 __global__ void __launch_bounds__(256)
 attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ ctx, const float* __restrict__ label_k,
                    const float* __restrict__ label_v, long long label_stride) {
+  pdl_enter();
   __shared__ float s_M[AT_D], s_Zinv[AT_D], s_lw[AT_D];
   const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
   const float* pb = part + ((size_t)n * gridDim.x + head) * chunks * AT_PART;
@@ -218,6 +220,7 @@ attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad, int hidden,
                  act_t* __restrict__ M) {
+  pdl_enter();
   __shared__ __align__(16) float s_w[64][AT_D];
   const int c0 = blockIdx.x * 64, head = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
   const int warp = tid >> 5, d = tid & 31;
@@ -267,8 +270,8 @@ int ds_attn_ctx_partial(const void* d_qkv, void* d_q_out, float* d_part, int N, 
   DS_REQUIRE(d_qkv && d_q_out && d_part && N > 0 && heads > 0 && npix > 0, "ds_attn_ctx_partial: bad arguments");
   const int chunks = ds_attn_chunks(npix);
   DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_ctx_partial: grid too large");
-  attn_ctx_partial_kernel<<<dim3(chunks, heads, N), 256, 0, (cudaStream_t)stream>>>((const act_t*)d_qkv, heads * AT_D, (int)npix,
-                                                                                   q_mode, scale, (act_t*)d_q_out, d_part, chunks);
+  DS_CHECK_CUDA(launch_pdl(attn_ctx_partial_kernel, dim3(dim3(chunks, heads, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const act_t*)d_qkv, heads * AT_D, (int)npix,
+                                                                                   q_mode, scale, (act_t*)d_q_out, d_part, chunks));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -281,8 +284,8 @@ static int attn_finalize_impl(const float* d_part, const float* d_label_k, const
   const int chunks = ds_attn_chunks(npix);
   float* ctx = const_cast<float*>(d_part) + (size_t)N * heads * chunks * AT_PART;
   DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_finalize: grid too large");
-  attn_reduce_kernel<<<dim3(heads, N), 256, 0, (cudaStream_t)stream>>>(d_part, chunks, ctx, d_label_k, d_label_v, label_stride);
-  attn_fold_kernel<<<dim3((Cout_pad + 63) / 64, heads, N), 256, 0, (cudaStream_t)stream>>>(ctx, d_wout, C, Cout_pad, heads * AT_D, (act_t*)d_M);
+  DS_CHECK_CUDA(launch_pdl(attn_reduce_kernel, dim3(dim3(heads, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_part, chunks, ctx, d_label_k, d_label_v, label_stride));
+  DS_CHECK_CUDA(launch_pdl(attn_fold_kernel, dim3(dim3((Cout_pad + 63) / 64, heads, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, ctx, d_wout, C, Cout_pad, heads * AT_D, (act_t*)d_M));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -86,6 +86,8 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) umma::tmem_alloc(tmem_base_smem, 512);
+  pdl_launch_dependents();
+  pdl_wait();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
@@ -187,9 +189,10 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t acc_phase = 0;
     int tile_par = 0;
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-    const float* tq = s_t + half * 64;                           // this thread's 64 columns of the q / k / v constants
-    const float* tk = s_t + AQ_HID + half * 64;
-    const float* tv = s_t + 2 * AQ_HID + half * 64;
+    // this thread's 64 columns of the q / k / v constants, read as LDS.128 through shared-space addresses (a generic pointer
+    // makes every read an LD with a long-scoreboard wait)
+    const uint32_t tq_s = smem_u32(s_t + half * 64), tk_s = smem_u32(s_t + AQ_HID + half * 64), tv_s = smem_u32(s_t + 2 * AQ_HID + half * 64);
+    auto lds4 = [](uint32_t addr) { float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory"); return v; };
 
     for (int item = blockIdx.x; item < P.items; item += gridDim.x) {
       const int n = item / P.chunks, chunk = item - n * P.chunks;
@@ -241,11 +244,17 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         float kf0[32], kf1[32];
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          kf0[j] = fmaf(__uint_as_float(k0[j]), rl2, tk[j]);
-          kf1[j] = fmaf(__uint_as_float(k1[j]), rl2, tk[32 + j]);
-          mx0 = fmaxf(mx0, kf0[j]);
-          mx1 = fmaxf(mx1, kf1[j]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 a = lds4(tk_s + 16u * j4), b = lds4(tk_s + 128u + 16u * j4);
+          const float ta[4] = {a.x, a.y, a.z, a.w}, tb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = 4 * j4 + i;
+            kf0[j] = fmaf(__uint_as_float(k0[j]), rl2, ta[i]);
+            kf1[j] = fmaf(__uint_as_float(k1[j]), rl2, tb[i]);
+            mx0 = fmaxf(mx0, kf0[j]);
+            mx1 = fmaxf(mx1, kf1[j]);
+          }
         }
         mx0 = warp_max(valid ? mx0 : -INFINITY);
         mx1 = warp_max(valid ? mx1 : -INFINITY);
@@ -294,11 +303,13 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
           for (int q8 = 0; q8 < 4; ++q8) {
             uint32_t o[4];
+            const float4 ta = lds4(tv_s + (uint32_t)(hh * 32 + q8 * 8) * 4u), tb = lds4(tv_s + (uint32_t)(hh * 32 + q8 * 8 + 4) * 4u);
+            const float tvv[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t r0 = hh == 0 ? v0[q8 * 8 + 2 * j] : v1[q8 * 8 + 2 * j], r1 = hh == 0 ? v0[q8 * 8 + 2 * j + 1] : v1[q8 * 8 + 2 * j + 1];
-              const float a0 = fmaf(__uint_as_float(r0), rstd, tv[hh * 32 + q8 * 8 + 2 * j]);
-              const float a1 = fmaf(__uint_as_float(r1), rstd, tv[hh * 32 + q8 * 8 + 2 * j + 1]);
+              const float a0 = fmaf(__uint_as_float(r0), rstd, tvv[2 * j]);
+              const float a1 = fmaf(__uint_as_float(r1), rstd, tvv[2 * j + 1]);
               o[j] = valid ? pack_bf16(a0, a1) : 0u;
             }
             if (!((AQ_DBG & 256) && o[0] != 0x12345u)) sts_128(sv_row + (uint32_t)(hh * 64 + q8 * 16), o[0], o[1], o[2], o[3]);
@@ -340,9 +351,15 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           float f[32];
           float m = -INFINITY;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = fmaf(__uint_as_float(hh == 0 ? q0[j] : q1[j]), rl2, tq[hh * 32 + j]);
-            m = fmaxf(m, f[j]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 a = lds4(tq_s + (uint32_t)(hh * 32 + 4 * j4) * 4u);
+            const float ta[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = 4 * j4 + i;
+              f[j] = fmaf(__uint_as_float(hh == 0 ? q0[j] : q1[j]), rl2, ta[i]);
+              m = fmaxf(m, f[j]);
+            }
           }
           float sum = 0.f;
 #pragma unroll
@@ -442,7 +459,7 @@ int ds_attn_qkv_ctx(const void* d_x, int C, int x_batch_mod, const void* d_stats
   P.qout = reinterpret_cast<act_t*>(d_q_out); P.part = d_part; P.scale = scale;
   DS_CHECK_CUDA(cudaFuncSetAttribute(attn_qkv_ctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AQ_SMEM));
   const int grid = P.items < num_sms() ? P.items : num_sms();
-  attn_qkv_ctx_kernel<<<grid, AQ_THREADS, AQ_SMEM, (cudaStream_t)stream>>>(map_a, map_b, P);
+  DS_CHECK_CUDA(launch_pdl(attn_qkv_ctx_kernel, dim3(grid), dim3(AQ_THREADS), (size_t)(AQ_SMEM), (cudaStream_t)stream, map_a, map_b, P));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

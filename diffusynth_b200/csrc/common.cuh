@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace ds {
 
@@ -46,7 +47,32 @@ inline int num_sms() {
   return n;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------------------
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its blocks may be scheduled while
+// the previous kernel of the stream is still draining, run their prologue (barrier init, tensor-memory allocation, weight
+// tables), and block in griddepcontrol.wait until that kernel has completed and its writes are visible.  A kernel touches
+// activations (reads OR writes) only after pdl_wait(); since every kernel waits, the ordering is transitive along the stream.
+// DS_PDL=0 (read once) launches everything with plain stream serialisation (A/B timing).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("DS_PDL"); return !e || atoi(e) != 0; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
 // 16-bit storage / tensor-core operand type of activations and weights.
 // Default: IEEE fp16 (tcgen05 kind::f16 with f16 inputs, fp32 accumulate).  bf16 activations cannot hold the
 // classifier-free-guidance difference eps_c - eps_u (0.5% of |eps| at random init, below bf16 resolution), see

@@ -269,7 +269,8 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 // reads its per-K-block coordinates (tensor map, channel offset, tap shift) from a table built once in shared memory.
 // EPI specialises the epilogue so that every instantiation carries only the code it runs (the generic kernel is ~9000 SASS
 // instructions and the role warps evict each other from the instruction cache): 0 = everything (fp32 / ragged outputs),
-// 1 = 16-bit output with full chunks, no activation, no residual (the 1x1 convolutions), 2 = + GELU (conv1), 3 = + residual (conv2).
+// 1 = 16-bit output with full chunks, no activation, no residual (the 1x1 convolutions), 2 = + GELU (conv1), 3 = + residual (conv2),
+// 4 = as 1 without GroupNorm fold and per-sample bias (to_out, res_conv: value = acc + e2[col]; a third of the instructions of 1).
 template <int BK, int CG, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
@@ -328,6 +329,9 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
     const int src = cb < P.cblocks0 ? 0 : 1;
     s_kbt[i] = make_int4((src * 4 + tp.view) * (int)sizeof(CUtensorMap), (src == 0 ? cb : cb - P.cblocks0) * BK, tp.dx, tp.dy);
   }
+  // (everything above reads only launch parameters and weight tables: it overlaps the tail of the previous kernel)
+  pdl_launch_dependents();
+  pdl_wait();
   tcgen05_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is signalled across the pair
@@ -504,7 +508,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
       for (int i = 0; i < 4; ++i) sb_next[i] = (lane + 32 * i < sb_cols) ? __ldg(src + lane + 32 * i) : 0.f;
     };
-    fetch_sbias(w_first);
+    if (EPI != 4) fetch_sbias(w_first);
     const bool epi_timed = (DS_DBG(P) & 64) != 0;
     long long epi_wait = 0;
     const long long epi_begin = clock64();
@@ -518,16 +522,16 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const float nmr = -mean * rstd;
       const bool valid = (h < P.H) && (w < P.W);
       const int col0 = t.nt * P.BN + chunk_lo * 16;        // first global output channel of this warp's column range
-      if (P.sbias != nullptr) {
+      if (EPI != 4 && P.sbias != nullptr) {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) my_sb[lane + 32 * i] = sb_next[i];
         __syncwarp();
       }
-      fetch_sbias(tile + w_step);
+      if (EPI != 4) fetch_sbias(tile + w_step);
       int cls = 0;
       if (P.ncls == 9) cls = (h == 0 ? 0 : (h == P.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == P.W - 1 ? 2 : 1));
-      const bool use_e1 = P.e1 != nullptr, use_sb = P.sbias != nullptr, do_stats = P.stats_out != nullptr;
+      const bool use_e1 = EPI != 4 && P.e1 != nullptr, use_sb = EPI != 4 && P.sbias != nullptr, do_stats = P.stats_out != nullptr;
       // running addresses, advanced by one 16-column chunk at a time: 32-bit shared-space addresses for the tables (so the
       // loads are LDS with immediate offsets, not generic LD), element pointers for the tensors
       uint32_t e2_s = smem_u32(s_e2) + (uint32_t)(cls * P.Cout_pad + col0) * 4u;
@@ -649,6 +653,13 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) tb[q4] = use_sb ? lds_f4_volatile(sb_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
           float v[16];
+          if (EPI == 4) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) + t2[q4].x; v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) + t2[q4].y;
+              v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) + t2[q4].z; v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) + t2[q4].w;
+            }
+          } else
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             v[4 * q4 + 0] = fmaf(__uint_as_float(r[4 * q4 + 0]), rstd, fmaf(nmr, t1[q4].x, t2[q4].x) + tb[q4].x);
@@ -925,7 +936,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   // epilogue specialisation (see the kernel): the main path needs a 16-bit output whose every chunk is full
   int epi = 0;
   if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !knobs().generic_epi) {
-    if (a->act == 0) epi = a->d_residual ? 3 : 1;
+    if (a->act == 0) epi = a->d_residual ? 3 : (!a->d_e1 && !a->d_sbias && !a->d_stats_in) ? 4 : 1;
     else if (!a->d_residual) epi = 2;
   }
 #define DS_LAUNCH_CONV(BKV, CGV, EPIV)                                                                                                \
@@ -934,16 +945,26 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     cudaLaunchConfig_t cfg;                                                                                                           \
     memset(&cfg, 0, sizeof(cfg));                                                                                                     \
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;                    \
-    cudaLaunchAttribute attr[1];                                                                                                      \
-    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                                 \
-    attr[0].val.clusterDim.x = CGV; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;                                      \
-    cfg.attrs = attr; cfg.numAttrs = (CGV == 2) ? 1 : 0;                                                                              \
+    cudaLaunchAttribute attr[2];                                                                                                      \
+    int na = 0;                                                                                                                       \
+    if (CGV == 2) {                                                                                                                   \
+      attr[na].id = cudaLaunchAttributeClusterDimension;                                                                              \
+      attr[na].val.clusterDim.x = CGV; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;                                 \
+      ++na;                                                                                                                           \
+    }                                                                                                                                 \
+    if (pdl_enabled()) {                                                                                                              \
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                               \
+      attr[na].val.programmaticStreamSerializationAllowed = 1;                                                                        \
+      ++na;                                                                                                                           \
+    }                                                                                                                                 \
+    cfg.attrs = attr; cfg.numAttrs = na;                                                                                              \
     DS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BKV, CGV, EPIV>, maps, P));                                               \
   } while (0)
 #define DS_LAUNCH_CONV_E(BKV, CGV)                                                                                  \
   do {                                                                                                              \
     if (epi == 1) DS_LAUNCH_CONV(BKV, CGV, 1); else if (epi == 2) DS_LAUNCH_CONV(BKV, CGV, 2);                     \
-    else if (epi == 3) DS_LAUNCH_CONV(BKV, CGV, 3); else DS_LAUNCH_CONV(BKV, CGV, 0);                              \
+    else if (epi == 3) DS_LAUNCH_CONV(BKV, CGV, 3); else if (epi == 4) DS_LAUNCH_CONV(BKV, CGV, 4);                \
+    else DS_LAUNCH_CONV(BKV, CGV, 0);                                                                              \
   } while (0)
   if (a->BK == 64) { if (P.cg == 2) DS_LAUNCH_CONV_E(64, 2); else DS_LAUNCH_CONV_E(64, 1); }
   else             { if (P.cg == 2) DS_LAUNCH_CONV_E(32, 2); else DS_LAUNCH_CONV_E(32, 1); }

@@ -28,6 +28,7 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
                const float* __restrict__ weight,   // [49][C] (tap-major)
                const float* __restrict__ tbias, long long tbias_stride,   // [N or 1][>=C]: conv bias + time projection
                act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w, int tiles) {
+  pdl_enter();
   constexpr int TH = 8 * R, HH = TH + 6;
   extern __shared__ __align__(16) float2 dw_smem[];
   float2* s_in = dw_smem;                                   // [HH][DW_PITCH][16] fp32 channel pairs (converted once at staging)
@@ -429,6 +430,8 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       bfr[ci][dy] = pack16(w0, w1);
     }
   }
+  pdl_launch_dependents();
+  pdl_wait();
   __syncthreads();
 
   auto issue = [&](int item, int stage) {
@@ -643,6 +646,7 @@ stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __r
 // One thread per (pixel, ky): 64 contiguous output bytes.
 // ---------------------------------------------------------------------------------------------
 __global__ void stem_im2col_kernel(const float* __restrict__ x, act_t* __restrict__ col, int Cin, int H, int W, long long total /* N*H*W*7 */) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % W);
     long long r = i / W;
@@ -739,9 +743,9 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
       int gm = 2 * num_sms() / cblks;
       if (gm > work) gm = (int)work;
       if (gm < 1) gm = 1;
-      dwconv7_mma_kernel<<<dim3(gm, cblks), 256, DM_SMEM_BYTES, (cudaStream_t)stream>>>(
+      DS_CHECK_CUDA(launch_pdl(dwconv7_mma_kernel, dim3(dim3(gm, cblks)), dim3(256), (size_t)(DM_SMEM_BYTES), (cudaStream_t)stream, 
           maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
-          H, W, tiles_w, tiles, N, dw_dbg);
+          H, W, tiles_w, tiles, N, dw_dbg));
       DS_CHECK_CUDA(cudaGetLastError());
       return DS_OK;
     }
@@ -752,13 +756,13 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
         maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
         H, W, tiles_w, tiles, N);
   } else if (R == 2)
-    dwconv7_kernel<2><<<grid, 256, dw_smem_bytes(2), (cudaStream_t)stream>>>(
+    DS_CHECK_CUDA(launch_pdl((dwconv7_kernel<2>), dim3(grid), dim3(256), (size_t)(dw_smem_bytes(2)), (cudaStream_t)stream, 
         (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles);
+        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles));
   else
-    dwconv7_kernel<1><<<grid, 256, dw_smem_bytes(1), (cudaStream_t)stream>>>(
+    DS_CHECK_CUDA(launch_pdl((dwconv7_kernel<1>), dim3(grid), dim3(256), (size_t)(dw_smem_bytes(1)), (cudaStream_t)stream, 
         (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles);
+        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -794,7 +798,7 @@ int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, 
   const long long total = (long long)N * H * W * 7;
   long long g = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
-  stem_im2col_kernel<<<(int)(g < cap ? g : cap), 256, 0, (cudaStream_t)stream>>>(d_x, (act_t*)d_col, Cin, H, W, total);
+  DS_CHECK_CUDA(launch_pdl(stem_im2col_kernel, dim3((int)(g < cap ? g : cap)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_x, (act_t*)d_col, Cin, H, W, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

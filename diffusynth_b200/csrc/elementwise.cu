@@ -14,6 +14,7 @@ namespace ds {
 __global__ void ddim_step_kernel(const float4* __restrict__ eps_u, const float4* __restrict__ eps_c,
                                  const float4* __restrict__ x, const float4* __restrict__ z,
                                  const float* __restrict__ coef, float4* __restrict__ out, long long n4) {
+  pdl_enter();
   const float c0 = coef[0], c1 = coef[1], c2 = coef[2], c3 = coef[3], c4 = coef[4], s = coef[5];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 ec = __ldg(eps_c + i), xv = __ldg(x + i);
@@ -41,6 +42,7 @@ __global__ void ddim_step_kernel(const float4* __restrict__ eps_u, const float4*
 // per_sample4 > 0 (= float4 vectors per sample: the reference gathers the coefficients per batch element, :17-22,290-293)
 __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __restrict__ noise, const float* __restrict__ coef,
                                 float4* __restrict__ out, long long n4, long long per_sample4) {
+  pdl_enter();
   float a = coef[0], b = coef[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     if (per_sample4 > 0) { const long long n = i / per_sample4; a = __ldg(coef + 2 * n); b = __ldg(coef + 2 * n + 1); }
@@ -55,6 +57,7 @@ __global__ void q_sample_kernel(const float4* __restrict__ x0, const float4* __r
 // its mask over the channels, inpaint_with_text.py:229-231); coef = {a, b} (a=1,b=0 reproduces the i==0 branch).
 __global__ void mask_blend_kernel(const float* __restrict__ guide, const float* __restrict__ noise, const float* __restrict__ mask,
                                   const float* __restrict__ coef, float* __restrict__ img, int C, int mask_c, long long hw, long long total) {
+  pdl_enter();
   const float a = coef[0], b = coef[1];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / (C * hw), p = i % hw;
@@ -67,6 +70,7 @@ __global__ void mask_blend_kernel(const float* __restrict__ guide, const float* 
 // fp32 NCHW -> bf16 NHWC with the channel count padded to Cp (zeros); and back.
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, act_t* __restrict__ out, int C, int Cp,
                                              long long hw, long long total_pix) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_pix * Cp; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cp);
     const long long pix = i / Cp, n = pix / hw, p = pix % hw;
@@ -77,6 +81,7 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ in, act_t
 // plane) and each thread writes its pixel's Cp channels as 16-byte vectors, so a warp writes one contiguous 32*Cp*2-byte span.
 __global__ void __launch_bounds__(256)
 nchw_f32_to_nhwc_vec_kernel(const float* __restrict__ in, uint4* __restrict__ out, int C, int Cp8, long long hw, long long total_pix) {
+  pdl_enter();
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total_pix; pix += (long long)gridDim.x * blockDim.x) {
     const long long n = pix / hw, p = pix % hw;
     const float* src = in + n * C * hw + p;
@@ -90,6 +95,7 @@ nchw_f32_to_nhwc_vec_kernel(const float* __restrict__ in, uint4* __restrict__ ou
 }
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const act_t* __restrict__ in, float* __restrict__ out, int C, int Cp,
                                              long long hw, long long total) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i % hw, r = i / hw;
     const int c = (int)(r % C);
@@ -111,6 +117,7 @@ gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ 
                          const float2* __restrict__ stats, int slots,
                          const float* __restrict__ gamma, const float* __restrict__ beta, int C8,
                          long long vec_per_sample, int x_batch_mod) {
+  pdl_enter();
   const int n = blockIdx.y;
   const float2 mr = __ldg(stats_sample(stats, slots, n));
   const float mean = mr.x, rstd = mr.y;
@@ -157,6 +164,7 @@ gn_apply_residual_kernel(const uint4* __restrict__ y, const uint4* __restrict__ 
 // 16-byte (8-channel) accesses: the host picks blockDim.x as a multiple of Cp/8, so a thread always meets the same 8 channels.
 __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restrict__ part, int C, int Cp, int G,
                                    long long hw, int chunks) {
+  pdl_enter();
   extern __shared__ float s_acc[];   // [pixel lanes][Cp][2]: per-thread (sum, sumsq) of every channel, summed in fixed order (deterministic)
   const int n = blockIdx.y, chunk = blockIdx.x, cpg = C / G, C8 = Cp / 8;
   const long long per = (hw + chunks - 1) / chunks;
@@ -204,6 +212,7 @@ __global__ void group_stats_kernel(const act_t* __restrict__ x, float2* __restri
 __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ out, const float2* __restrict__ part,
                               int chunks, const float* __restrict__ gamma, const float* __restrict__ beta, int C, int Cp, int G,
                               long long hw, float eps, int act) {
+  pdl_enter();
   extern __shared__ float s_ab[];   // per channel scale, shift  [2*Cp]
   const int n = blockIdx.y, cpg = C / G, C8 = Cp / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -254,6 +263,7 @@ __global__ void gn_act_kernel(const act_t* __restrict__ x, act_t* __restrict__ o
 // (diffusion_components.py:97-100).  bias_stride 0 = one row for all samples.
 __global__ void add_channel_bias_kernel(act_t* __restrict__ x, const float* __restrict__ bias, long long bias_stride, int C, long long per_sample /* hw*C/2 */,
                                         long long total) {
+  pdl_enter();
   uint32_t* xv = reinterpret_cast<uint32_t*>(x);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / per_sample;
@@ -266,6 +276,7 @@ __global__ void add_channel_bias_kernel(act_t* __restrict__ x, const float* __re
 
 // out = a + b (bf16 NHWC), used for the VQGAN residual adds that are not fused into a conv epilogue
 __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, long long n8) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     const uint4 x = __ldg(a + i), y = __ldg(b + i);
     const uint32_t xx[4] = {x.x, x.y, x.z, x.w}, yy[4] = {y.x, y.y, y.z, y.w};
@@ -279,6 +290,7 @@ __global__ void add_bf16_kernel(const uint4* __restrict__ a, const uint4* __rest
 // VQGAN decoder head (model/VQGAN.py:394-398): ch0 softplus, ch1/ch2 tanh on (a + b); fp32 NCHW [N,3,H,W] in and out
 // (a = final ResnetBlock conv, b = its nin_shortcut; both written as fp32 by the conv epilogue).
 __global__ void decoder_head_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long long hw, long long total) {
+  pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)((i / hw) % 3);
     const float v = a[i] + (b ? b[i] : 0.f);
@@ -294,6 +306,7 @@ __global__ void decoder_head_kernel(const float* __restrict__ a, const float* __
 // ---------------------------------------------------------------------------------------------
 __global__ void linear_kernel(const float* __restrict__ in, long long in_stride, const float* __restrict__ W, const float* __restrict__ bias,
                               float* __restrict__ out, long long out_stride, int N, int K, int O, int act_in, int act_out) {
+  pdl_enter();
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= O) return;
@@ -318,6 +331,7 @@ __global__ void linear_kernel(const float* __restrict__ in, long long in_stride,
 }
 
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __restrict__ out, int N, int dim) {
+  pdl_enter();
   const int half = dim / 2;
   const float k = logf(10000.0f) / (float)(half - 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * half; i += gridDim.x * blockDim.x) {
@@ -346,8 +360,8 @@ extern "C" {
 int ds_ddim_step(const float* d_eps_u, const float* d_eps_c, const float* d_x, const float* d_z, const float* d_coef,
                  float* d_out, long long n, void* stream) {
   DS_REQUIRE(d_eps_c && d_x && d_coef && d_out && n > 0 && n % 4 == 0, "ds_ddim_step: bad arguments (n=%lld must be a positive multiple of 4)", n);
-  ddim_step_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)d_eps_u, (const float4*)d_eps_c, (const float4*)d_x, (const float4*)d_z, d_coef, (float4*)d_out, n / 4);
+  DS_CHECK_CUDA(launch_pdl(ddim_step_kernel, dim3(grid_for(n / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+      (const float4*)d_eps_u, (const float4*)d_eps_c, (const float4*)d_x, (const float4*)d_z, d_coef, (float4*)d_out, n / 4));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -356,8 +370,8 @@ int ds_q_sample(const float* d_x0, const float* d_noise, const float* d_coef, fl
                 void* stream) {
   DS_REQUIRE(d_x0 && d_noise && d_coef && d_out && n > 0 && n % 4 == 0, "ds_q_sample: bad arguments");
   DS_REQUIRE(per_sample >= 0 && per_sample % 4 == 0 && (per_sample == 0 || n % per_sample == 0), "ds_q_sample: per_sample=%lld must divide n=%lld and be a multiple of 4", per_sample, n);
-  q_sample_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_x0, (const float4*)d_noise, d_coef,
-                                                                          (float4*)d_out, n / 4, per_sample / 4);
+  DS_CHECK_CUDA(launch_pdl(q_sample_kernel, dim3(grid_for(n / 4, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float4*)d_x0, (const float4*)d_noise, d_coef,
+                                                                          (float4*)d_out, n / 4, per_sample / 4));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -367,7 +381,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
   DS_REQUIRE(d_guide && d_noise && d_mask && d_coef && d_img && B > 0 && C > 0 && hw > 0, "ds_mask_blend: bad arguments");
   DS_REQUIRE(mask_channels == 1 || mask_channels == C, "ds_mask_blend: mask_channels=%d must be 1 or C=%d", mask_channels, C);
   const long long total = (long long)B * C * hw;
-  mask_blend_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_guide, d_noise, d_mask, d_coef, d_img, C, mask_channels, hw, total);
+  DS_CHECK_CUDA(launch_pdl(mask_blend_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_guide, d_noise, d_mask, d_coef, d_img, C, mask_channels, hw, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -375,7 +389,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
 int ds_add_channel_bias(void* d_x, const float* d_bias, long long bias_stride, int N, int C, long long hw, void* stream) {
   DS_REQUIRE(d_x && d_bias && N > 0 && C > 0 && C % 2 == 0 && hw > 0 && bias_stride >= 0, "ds_add_channel_bias: bad arguments");
   const long long per = hw * C / 2, total = per * N;
-  add_channel_bias_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((act_t*)d_x, d_bias, bias_stride, C, per, total);
+  DS_CHECK_CUDA(launch_pdl(add_channel_bias_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (act_t*)d_x, d_bias, bias_stride, C, per, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -383,10 +397,10 @@ int ds_add_channel_bias(void* d_x, const float* d_bias, long long bias_stride, i
 int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int Cp, long long hw, void* stream) {
   DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nchw_f32_to_nhwc_bf16: bad arguments");
   if (Cp % 8 == 0 && reinterpret_cast<uintptr_t>(d_out) % 16 == 0)
-    nchw_f32_to_nhwc_vec_kernel<<<grid_for((long long)N * hw, 256), 256, 0, (cudaStream_t)stream>>>(d_in, (uint4*)d_out, C, Cp / 8, hw, (long long)N * hw);
+    DS_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_vec_kernel, dim3(grid_for((long long)N * hw, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_in, (uint4*)d_out, C, Cp / 8, hw, (long long)N * hw));
   else
-    nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)N * hw * Cp, 256), 256, 0, (cudaStream_t)stream>>>(
-        d_in, (act_t*)d_out, C, Cp, hw, (long long)N * hw);
+    DS_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_bf16_kernel, dim3(grid_for((long long)N * hw * Cp, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+        d_in, (act_t*)d_out, C, Cp, hw, (long long)N * hw));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -394,7 +408,7 @@ int ds_nchw_f32_to_nhwc_bf16(const float* d_in, void* d_out, int N, int C, int C
 int ds_nhwc_bf16_to_nchw_f32(const void* d_in, float* d_out, int N, int C, int Cp, long long hw, void* stream) {
   DS_REQUIRE(d_in && d_out && N > 0 && C > 0 && Cp >= C && hw > 0, "ds_nhwc_bf16_to_nchw_f32: bad arguments");
   const long long total = (long long)N * C * hw;
-  nhwc_bf16_to_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const act_t*)d_in, d_out, C, Cp, hw, total);
+  DS_CHECK_CUDA(launch_pdl(nhwc_bf16_to_nchw_f32_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const act_t*)d_in, d_out, C, Cp, hw, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -413,9 +427,9 @@ int ds_gn_apply_residual(const void* d_y, const void* d_x, void* d_out, const vo
   if (gx > cap) gx = cap;
   gx = (gx + m - 1) / m * m;
   if (gx < m) gx = m;
-  gn_apply_residual_kernel<<<dim3(gx, N), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
+  DS_CHECK_CUDA(launch_pdl(gn_apply_residual_kernel, dim3(dim3(gx, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const uint4*)d_y, (const uint4*)d_x, (uint4*)d_out,
                                                                           (const float2*)d_stats, slots, d_gamma,
-                                                                          d_beta, C / 8, vps, x_batch_mod);
+                                                                          d_beta, C / 8, vps, x_batch_mod));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -425,8 +439,8 @@ int ds_group_stats(const void* d_x, void* d_part, int N, int C, int Cp, int G, l
   DS_REQUIRE(Cp % 8 == 0, "ds_group_stats: Cp must be a multiple of 8");
   const int C8 = Cp / 8;
   const int block = C8 * 8;                    // 8 pixel lanes x Cp/8 channel vectors: few colliding shared atomics at the end
-  group_stats_kernel<<<dim3(chunks, N), block, (size_t)8 * Cp * 2 * sizeof(float), (cudaStream_t)stream>>>((const act_t*)d_x, (float2*)d_part,
-                                                                                              C, Cp, G, hw, chunks);
+  DS_CHECK_CUDA(launch_pdl(group_stats_kernel, dim3(dim3(chunks, N)), dim3(block), (size_t)((size_t)8 * Cp * 2 * sizeof(float)), (cudaStream_t)stream, (const act_t*)d_x, (float2*)d_part,
+                                                                                              C, Cp, G, hw, chunks));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -445,15 +459,15 @@ int ds_gn_act(const void* d_x, void* d_out, const void* d_part, int chunks, cons
   if (gx > cap) gx = cap;
   gx = (gx + m - 1) / m * m;
   if (gx < m) gx = m;
-  gn_act_kernel<<<dim3(gx, N), 256, (2 * Cp + 4) * sizeof(float), (cudaStream_t)stream>>>(
-      (const act_t*)d_x, (act_t*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act);
+  DS_CHECK_CUDA(launch_pdl(gn_act_kernel, dim3(dim3(gx, N)), dim3(256), (size_t)((2 * Cp + 4) * sizeof(float)), (cudaStream_t)stream, 
+      (const act_t*)d_x, (act_t*)d_out, (const float2*)d_part, chunks, d_gamma, d_beta, C, Cp, G, hw, eps, act));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
 
 int ds_add_bf16(const void* d_a, const void* d_b, void* d_out, long long n, void* stream) {
   DS_REQUIRE(d_a && d_b && d_out && n > 0 && n % 8 == 0, "ds_add_bf16: bad arguments");
-  add_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n / 8);
+  DS_CHECK_CUDA(launch_pdl(add_bf16_kernel, dim3(grid_for(n / 8, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const uint4*)d_a, (const uint4*)d_b, (uint4*)d_out, n / 8));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -461,7 +475,7 @@ int ds_add_bf16(const void* d_a, const void* d_b, void* d_out, long long n, void
 int ds_decoder_head(const float* d_a, const float* d_b, float* d_out, int N, long long hw, void* stream) {
   DS_REQUIRE(d_a && d_out && N > 0 && hw > 0, "ds_decoder_head: bad arguments");
   const long long total = (long long)N * 3 * hw;
-  decoder_head_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(d_a, d_b, d_out, hw, total);
+  DS_CHECK_CUDA(launch_pdl(decoder_head_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_a, d_b, d_out, hw, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -471,15 +485,15 @@ int ds_linear(const float* d_in, long long in_stride, const float* d_w, const fl
   DS_REQUIRE(d_in && d_w && d_out && N > 0 && K > 0 && O > 0, "ds_linear: bad arguments");
   const int wpb = 8;
   int gy = N < 16 ? N : 16;
-  linear_kernel<<<dim3((O + wpb - 1) / wpb, gy), wpb * 32, 0, (cudaStream_t)stream>>>(d_in, in_stride, d_w, d_bias, d_out, out_stride, N, K,
-                                                                                      O, act_in, act_out);
+  DS_CHECK_CUDA(launch_pdl(linear_kernel, dim3(dim3((O + wpb - 1) / wpb, gy)), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, d_in, in_stride, d_w, d_bias, d_out, out_stride, N, K,
+                                                                                      O, act_in, act_out));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
 
 int ds_sinusoidal_embedding(const long long* d_t, float* d_out, int N, int dim, void* stream) {
   DS_REQUIRE(d_t && d_out && N > 0 && dim >= 4 && dim % 2 == 0, "ds_sinusoidal_embedding: bad arguments");
-  sinusoidal_kernel<<<grid_for((long long)N * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(d_t, d_out, N, dim);
+  DS_CHECK_CUDA(launch_pdl(sinusoidal_kernel, dim3(grid_for((long long)N * dim / 2, 128)), dim3(128), (size_t)(0), (cudaStream_t)stream, d_t, d_out, N, dim));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -69,6 +69,7 @@ __device__ __forceinline__ void store_bitrev(float2* __restrict__ xs, const floa
 __global__ void __launch_bounds__(256)
 istft_frames_kernel(const float* __restrict__ spec, float* __restrict__ frames, int T, const float2* __restrict__ tw512,
                     const float2* __restrict__ tw1024 /* e^{+2 pi i k/1024}, k<512 */) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t is_smem[];
   float2 (*X)[NH + 1] = reinterpret_cast<float2 (*)[NH + 1]>(is_smem);                                        // [FR][513]
   float2 (*xs)[XS_PITCH] = reinterpret_cast<float2 (*)[XS_PITCH]>(is_smem + FR * (NH + 1) * sizeof(float2));   // [FR][544]
@@ -118,6 +119,7 @@ istft_frames_kernel(const float* __restrict__ spec, float* __restrict__ frames, 
 
 // ---- overlap-add, window-sum-square normalisation, centre trim: wave [B][256*(T-1)] --------------
 __global__ void istft_ola_kernel(const float* __restrict__ frames, float* __restrict__ wave, int T, long long out_len) {
+  pdl_enter();
   const int b = blockIdx.y;
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < out_len; j += (long long)gridDim.x * blockDim.x) {
     const long long jj = j + NFFT / 2;
@@ -138,6 +140,7 @@ __global__ void istft_ola_kernel(const float* __restrict__ frames, float* __rest
 __global__ void __launch_bounds__(256)
 stft_encode_kernel(const float* __restrict__ wave, long long L, float* __restrict__ spec, int T, int Tpad, const float2* __restrict__ tw512,
                    const float2* __restrict__ tw1024) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t st_smem[];
   float2 (*xs)[XS_PITCH] = reinterpret_cast<float2 (*)[XS_PITCH]>(st_smem);      // [FR][544]
   const int b = blockIdx.y, t0 = blockIdx.x * FR;
@@ -287,10 +290,10 @@ int ds_stft_decode_istft(const float* d_spec, float* d_frames, float* d_wave, in
   if (rc) return rc;
   const size_t smem = FR * (NH + 1) * sizeof(float2) + FR * XS_PITCH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(istft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  istft_frames_kernel<<<dim3((T + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_spec, d_frames, T, tw512, tw1024);
+  DS_CHECK_CUDA(launch_pdl(istft_frames_kernel, dim3(dim3((T + FR - 1) / FR, B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, d_spec, d_frames, T, tw512, tw1024));
   DS_CHECK_CUDA(cudaGetLastError());
   const long long out_len = ds_istft_length(T);
-  istft_ola_kernel<<<dim3((unsigned)((out_len + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(d_frames, d_wave, T, out_len);
+  DS_CHECK_CUDA(launch_pdl(istft_ola_kernel, dim3(dim3((unsigned)((out_len + 255) / 256), B)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_frames, d_wave, T, out_len));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }
@@ -305,7 +308,7 @@ int ds_stft_encode(const float* d_wave, long long L, float* d_spec, int B, int T
   if (rc) return rc;
   const size_t smem = FR * XS_PITCH * sizeof(float2);
   DS_CHECK_CUDA(cudaFuncSetAttribute(stft_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stft_encode_kernel<<<dim3((Tpad + FR - 1) / FR, B), 256, smem, (cudaStream_t)stream>>>(d_wave, L, d_spec, T, Tpad, tw512, tw1024);
+  DS_CHECK_CUDA(launch_pdl(stft_encode_kernel, dim3(dim3((Tpad + FR - 1) / FR, B)), dim3(256), (size_t)(smem), (cudaStream_t)stream, d_wave, L, d_spec, T, Tpad, tw512, tw1024));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

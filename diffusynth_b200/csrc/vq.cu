@@ -14,6 +14,7 @@ static constexpr int VQ_PPT = 4;   // positions per thread
 __global__ void __launch_bounds__(256)
 vq_kernel(const float* __restrict__ x /* [B,4,H,W] */, const float4* __restrict__ codebook, int K, float* __restrict__ out,
           long long* __restrict__ idx_out, long long hw, long long total /* B*hw */) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t vq_smem[];
   float4* s_code = reinterpret_cast<float4*>(vq_smem);
   float* s_se = reinterpret_cast<float*>(s_code + K);
@@ -84,7 +85,7 @@ int ds_vq_quantize(const float* d_x, const float* d_codebook, int K, float* d_ou
   const long long total = (long long)B * hw;
   long long want = (total + 256 * VQ_PPT - 1) / (256 * VQ_PPT);
   int grid = (int)(want < num_sms() ? want : num_sms());
-  vq_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, (const float4*)d_codebook, K, d_out, d_idx, hw, total);
+  DS_CHECK_CUDA(launch_pdl(vq_kernel, dim3(grid), dim3(256), (size_t)(smem), (cudaStream_t)stream, d_x, (const float4*)d_codebook, K, d_out, d_idx, hw, total));
   DS_CHECK_CUDA(cudaGetLastError());
   return DS_OK;
 }

@@ -17,8 +17,8 @@ for kid, d in sorted(per.items()):
     a['n'] += 1; a['us'] += d.get('gpu__time_duration.sum', 0); a['rd'] += d.get('dram__bytes_read.sum', 0); a['wr'] += d.get('dram__bytes_write.sum', 0)
     a['tens'] += d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0) * d.get('gpu__time_duration.sum', 0)
 tot = sum(a['us'] for a in agg.values())
-lines = ["# ncu per-kernel summary of ONE U-Net evaluation (CFG-doubled batch 64 = 128 samples, 128x64 latents), final round-1 code\n",
-         "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none python tools_dev/unet_once.py` (REPS=1; after the same command exited 0 without ncu; summarised by tools_dev/summarize_traffic.py). Raw CSV: r01_unet_eval_traffic.csv. ncu times are cold-cache and serialised: compare shares, not absolutes. The at:: fill kernels belong to the one-time buffer allocation of the plan, not to the evaluation.\n",
+lines = ["# ncu per-kernel summary of ONE U-Net evaluation (CFG-doubled batch 64 = 128 samples, 128x64 latents), round-2 code\n",
+         "Command: `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --clock-control none python tools_dev/unet_once.py` (REPS=1; after the same command exited 0 without ncu; summarised by tools_dev/summarize_traffic.py). Raw CSV: r02_unet_eval_traffic.csv. ncu times are cold-cache and serialised: compare shares, not absolutes. The at:: fill kernels belong to the one-time buffer allocation of the plan, not to the evaluation.\n",
          "| kernel | launches | ms | share | DRAM read GB | DRAM write GB | avg DRAM GB/s | tensor-pipe active (time-weighted) |", "|---|---|---|---|---|---|---|---|"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
     if a['us'] / tot < 0.0005: continue
@@ -28,10 +28,10 @@ conv = [d for d in per.values() if 'conv_gemm' in d['name']]
 tr = sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in conv) / len(conv)
 cshare = sum(d.get('gpu__time_duration.sum', 0) for d in conv) / tot
 lines.append(f"\nconv_gemm_kernel: {len(conv)} launches per evaluation = {100*cshare:.1f} % of the kernel time, average DRAM traffic per launch {tr/1e6:.1f} MB (total {tr*len(conv)/1e9:.1f} GB; every operand moved about once, no re-read waste).\n")
-open('profiles/r01_unet_eval_ncu_summary.md', 'w').write("\n".join(lines))
-json.dump(dict(avg_dram_bytes_per_conv_launch=tr, conv_launches=len(conv)), open('profiles/r01_conv_traffic.json', 'w'))
-with open('profiles/r01_launches_unet_eval_b64.csv', 'w') as f:
+open('profiles/r02_unet_eval_ncu_summary.md', 'w').write("\n".join(lines))
+json.dump(dict(avg_dram_bytes_per_conv_launch=tr, conv_launches=len(conv)), open('profiles/r02_conv_traffic.json', 'w'))
+with open('profiles/r02_launches_unet_eval_b64.csv', 'w') as f:
     f.write("id,kernel,grid,us\n")
     for kid, d in sorted(per.items()): f.write(f"{kid},{d['name']},{d['grid']},{d.get('gpu__time_duration.sum',0):.3f}\n")
-shutil.copy(src, 'profiles/r01_unet_eval_traffic.csv')
+shutil.copy(src, 'profiles/r02_unet_eval_traffic.csv')
 print("\n".join(lines[2:]))

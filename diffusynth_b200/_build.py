@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart", "-ldl"])
     return LIB
 
 

@@ -86,6 +86,30 @@ _SIGNATURES = {
     "ds_griffinlim_update": (_I, [_P, _P, _P, _F, _I, _I, _I, _P]),
     "ds_spec_images": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ds_latent_image": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    # module-level entry points (csrc/engine.cu, csrc/comm.cu; structures in diffusynth_b200/engine.py)
+    "ds_unet_create": (_I, [_P, _P]),
+    "ds_unet_destroy": (None, [_P]),
+    "ds_unet_load": (_I, [_P, C.c_char_p, _P, _P, _I]),
+    "ds_unet_finalize": (_I, [_P]),
+    "ds_unet_forward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "ds_unet_plan_get": (_I, [_P, _I, _I, _I, _I, _I, _P]),
+    "ds_unet_plan_run_cond": (_I, [_P, _I, _P]),
+    "ds_unet_plan_run": (_I, [_P, _I, _P, _P, _P]),
+    "ds_vqgan_create": (_I, [_P, _P]),
+    "ds_vqgan_destroy": (None, [_P]),
+    "ds_vqgan_load": (_I, [_P, C.c_char_p, _P, _P, _I]),
+    "ds_vqgan_finalize": (_I, [_P]),
+    "ds_vqgan_quantize": (_I, [_P, _P, _P, _P, _I, _L, _P]),
+    "ds_vqgan_decode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "ds_vqgan_encode": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "ds_sample_graph_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ds_sample_graph_run": (_I, [_P, _P]),
+    "ds_sample_graph_launches": (_I, [_P]),
+    "ds_sample_graph_destroy": (None, [_P]),
+    "ds_comm_unique_id": (_I, [_P]),
+    "ds_comm_init": (_I, [_I, _I, _P, _P]),
+    "ds_allgather": (_I, [_P, _P, _P, _L, _I, _P]),
+    "ds_comm_destroy": (None, [_P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -88,9 +88,10 @@ def _border_tables(wk_fold_bf16: torch.Tensor, w_raw: torch.Tensor, beta: Option
     """e1[cls][o] = sum over taps valid in border class cls, and channels, of the (bf16-rounded, gamma-folded)
     weights; e2[cls][o] = bias[o] + sum_valid sum_c W[o,c,tap]*beta[c].  cls = rowclass*3 + colclass."""
     O = w_raw.shape[0]
-    wf = wk_fold_bf16.float()                       # [O, k, k, C]
+    # sums in float64, rounded once (csrc/engine.cu packs the same tables the same way: the two paths agree bit for bit)
+    wf = wk_fold_bf16.double()                      # [O, k, k, C]
     s1 = wf.sum(dim=3)                              # [O, k, k]
-    s2 = (w_raw.permute(0, 2, 3, 1) * beta).sum(dim=3) if beta is not None else torch.zeros_like(s1)
+    s2 = (w_raw.permute(0, 2, 3, 1) * beta).double().sum(dim=3) if beta is not None else torch.zeros_like(s1)
     ncls = 9 if ksize == 3 else 1
     e1 = torch.zeros(ncls, cout_pad)
     e2 = torch.zeros(ncls, cout_pad)
@@ -98,8 +99,8 @@ def _border_tables(wk_fold_bf16: torch.Tensor, w_raw: torch.Tensor, beta: Option
         rc, cc = (cls // 3, cls % 3) if ksize == 3 else (1, 1)
         ky = [k for k in range(ksize) if not (ksize == 3 and ((rc == 0 and k == 0) or (rc == 2 and k == 2)))]
         kx = [k for k in range(ksize) if not (ksize == 3 and ((cc == 0 and k == 0) or (cc == 2 and k == 2)))]
-        e1[cls, :O] = s1[:, ky][:, :, kx].sum(dim=(1, 2))
-        e2[cls, :O] = s2[:, ky][:, :, kx].sum(dim=(1, 2))
+        e1[cls, :O] = s1[:, ky][:, :, kx].sum(dim=(1, 2)).float()
+        e2[cls, :O] = s2[:, ky][:, :, kx].sum(dim=(1, 2)).float()
         if bias is not None:
             e2[cls, :O] += bias
     return e1, e2, ncls

@@ -58,6 +58,34 @@ class _Tail:
             fn()
 
 
+class _TailBuffers:
+    """Result buffers of the tail when it runs inside the library's sampling graph (ds_sample_graph_build): the same attributes
+    _Tail exposes (q, idx, spec, wave), no launch list."""
+
+    def __init__(self, src: torch.Tensor):
+        B, Cc, H, Wd = src.shape
+        dev = src.device
+        self.src = src
+        self.q = torch.empty((B, Cc, H, Wd), dtype=torch.float32, device=dev)
+        self.idx = torch.empty((B * H * Wd,), dtype=torch.long, device=dev)
+        self.spec = torch.empty((B, 3, 4 * H, 4 * Wd), dtype=torch.float32, device=dev)
+        self.wave = torch.empty((B, _lib.load().ds_istft_length(4 * Wd)), dtype=torch.float32, device=dev)
+
+
+class _TailFactory:
+    """What the sampler needs to put the tail into its graph: the VQGAN (its module-level handle for the library's graph), the
+    result buffers, or -- for the operator-level path and bench.py's per-kernel timings -- the Python launch list."""
+
+    def __init__(self, vqgan: VQGAN):
+        self.vqgan = vqgan
+
+    def __call__(self, src: torch.Tensor) -> _Tail:
+        return _Tail(self.vqgan, src)
+
+    def buffers(self, src: torch.Tensor) -> _TailBuffers:
+        return _TailBuffers(src)
+
+
 class TextToTimbre:
     def __init__(self, unet: ConditionedUnet, vqgan: VQGAN, timesteps: int = 1000, height: int = 128, channels: int = 4,
                  noise_strategy: str = "repeat", device=None):
@@ -65,15 +93,16 @@ class TextToTimbre:
         self.timesteps, self.height, self.channels, self.noise_strategy = timesteps, height, channels, noise_strategy
         self.device = torch.device(device if device is not None else unet.device)
         self._samplers = {}
-        self._tail_factory = lambda src: _Tail(self.vqgan, src)      # one object: its id() is part of the samplers' graph keys
+        self._tail_factory = _TailFactory(self.vqgan)                # one object: its id() is part of the samplers' graph keys
         self.last_launches = 0
         self._last_tail: Optional[_Tail] = None
 
     def tail_for(self, batch: int, width: int) -> _Tail:
-        """The tail captured with the most recent graph of this batch / width (bench.py times its launches one by one)."""
+        """The tail of the most recent generate() of this batch / width as an operator-level launch list on the same final-latent
+        buffer (bench.py times its launches one by one)."""
         t = self._last_tail
         assert t is not None and t.src.shape[0] == batch and t.src.shape[3] == width, "no generate() call with this shape yet"
-        return t
+        return t if isinstance(t, _Tail) else _Tail(self.vqgan, t.src)
 
     def _decode(self, s: DiffSynthSampler, latents: torch.Tensor) -> Timbres:
         """Results of the tail that ran inside the sampler's graph (copied out of its static buffers)."""

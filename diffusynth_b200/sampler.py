@@ -22,7 +22,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops
+from . import engine, ops
 from .unet import ConditionedUnet
 
 
@@ -351,9 +351,9 @@ class DiffSynthSampler:
         cond = condition.to(self.device, torch.float32)
         if cfg_on:
             u = self.unconditional_condition.to(self.device, torch.float32).reshape(1, -1).expand(B, -1)
-            loop.plan.cond.copy_(torch.cat([u, cond]))
+            loop.cond.copy_(torch.cat([u, cond]))
         else:
-            loop.plan.cond.copy_(cond)
+            loop.cond.copy_(cond)
         if eta > 0 or self.faithful_rng:
             for k in range(n_iter):
                 z, _ = self.get_deterministic_noise_tensor(B, Wd)
@@ -373,9 +373,8 @@ class DiffSynthSampler:
             loop.blend_coef.copy_(torch.tensor(ab, dtype=torch.float32))
             loop.guide.copy_(guide_img)
             loop.init_noise.copy_(initial_noise)
-        loop.plan.run_cond()        # condition projections are step-invariant: once per call, outside the graph
-        loop.launch()
-        self.last_graph_launches = loop.launches + len(loop.plan.cond_ops)
+        loop.launch()               # (the step-invariant condition projections run once per call, ahead of the graph)
+        self.last_graph_launches = loop.launches
         self.last_tail = loop.tail
         if self.final_only:         # (pipeline use: only imgs[0] and imgs[-1] are read)
             first, last = loop.imgs[0].clone(), loop.imgs[n_iter].clone()
@@ -439,27 +438,62 @@ class _GraphLoop:
             self.guide = torch.zeros((B, Cc, H, Wd), **f32)
             self.init_noise = torch.zeros((B, Cc, H, Wd), **f32)
         N = 2 * B if cfg_on else B
-        self.plan = model.plan(N, H, Wd, x_batch_mod=B if cfg_on else 0, uniform_time=True)
-        self.tail = tail_factory(self.imgs[n_iter]) if tail_factory is not None else None
-        self.has_tail = self.tail is not None
-        self.launches = n_iter * (self.plan.num_launches() + 1 + (1 if inpaint else 0)) + (self.tail.num_launches if self.tail else 0)
+        self.N, self.shape = N, (B, Cc, H, Wd)
         self.inpaint = inpaint
         self.B = B
+        self._plan = None
+        self.sgraph = None
+        self.graph = None
+        use_graph = os.environ.get("DS_NO_GRAPH", "0") != "1"      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
+        if getattr(model, "_engine", None) is not None and model.use_engine:
+            # module-level C ABI: the plan, the capture and the replay live in the library (ds_sample_graph_build / _run)
+            self.cond = torch.zeros((N, model.cfg["label_emb_dim"]), **f32)
+            self.tail = tail_factory.buffers(self.imgs[n_iter]) if tail_factory is not None else None
+            b = engine.SampleBuffers()
+            b.d_imgs, b.d_coef, b.d_ttab, b.d_cond = self.imgs.data_ptr(), self.coef.data_ptr(), self.ttab.data_ptr(), self.cond.data_ptr()
+            b.d_noise = self.noise.data_ptr() if self.noise is not None else None
+            if inpaint:
+                b.d_guide, b.d_init_noise = self.guide.data_ptr(), self.init_noise.data_ptr()
+                b.d_masks, b.d_blend_coef = self.masks.data_ptr(), self.blend_coef.data_ptr()
+            if self.tail is not None:
+                t = self.tail
+                b.d_quantized, b.d_indices, b.d_spec, b.d_wave = t.q.data_ptr(), t.idx.data_ptr(), t.spec.data_ptr(), t.wave.data_ptr()
+            self.sgraph = engine.SampleGraph(model._engine, tail_factory.vqgan._engine if self.tail is not None else None, b, B, H, Wd,
+                                             n_iter, cfg_on, use_graph=use_graph)
+            self.launches = self.sgraph.launches
+            self.has_tail = self.tail is not None
+            return
+        # operator-level path (the other U-Net variants; A/B against the library's graph): Python plan + torch.cuda.graph
+        self._plan = model.plan(N, H, Wd, x_batch_mod=B if cfg_on else 0, uniform_time=True)
+        self.cond = self._plan.cond
+        self.tail = tail_factory(self.imgs[n_iter]) if tail_factory is not None else None
+        self.has_tail = self.tail is not None
+        self.launches = n_iter * (self._plan.num_launches() + 1 + (1 if inpaint else 0)) + (self.tail.num_launches if self.tail else 0) \
+            + len(self._plan.cond_ops)
         # warm-up run outside capture (lazy one-time initialisations, kernel attribute sets), then capture
+        self._plan.run_cond()
         self._body(first_only=True)
         if self.tail is not None:
             self.tail.run()
         torch.cuda.synchronize()
-        self.graph = None
-        if os.environ.get("DS_NO_GRAPH", "0") != "1":      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
+        if use_graph:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._body()
                 if self.tail is not None:
                     self.tail.run()
 
+    @property
+    def plan(self):
+        """The operator-level plan of this loop's U-Net shape (bench.py times its launches one by one); built on demand when the
+        loop itself runs through the library's graph."""
+        if self._plan is None:
+            B = self.B
+            self._plan = self.model.plan(self.N, self.shape[2], self.shape[3], x_batch_mod=B if self.cfg_on else 0, uniform_time=True)
+        return self._plan
+
     def _body(self, first_only: bool = False):
-        pl, B = self.plan, self.B
+        pl, B = self._plan, self.B
         for k in range(1 if first_only else self.n_iter):
             pl.x.copy_(self.imgs[k])
             pl.t[:1].copy_(self.ttab[k:k + 1])
@@ -471,6 +505,10 @@ class _GraphLoop:
                 ops.mask_blend(self.guide, self.init_noise, self.masks[k], self.blend_coef[k], self.imgs[k + 1])
 
     def launch(self):
+        if self.sgraph is not None:
+            self.sgraph.run()
+            return
+        self._plan.run_cond()        # condition projections are step-invariant: once per call, outside the graph
         if self.graph is not None:
             self.graph.replay()
         else:

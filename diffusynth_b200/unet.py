@@ -16,7 +16,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
-from . import _lib, ops, weights as W
+from . import _lib, engine, ops, weights as W
 from ._lib import check
 from .ops import PackedConv, Stats, conv_args, pack_conv_down, pack_conv_s1, pack_conv_up, run_conv
 
@@ -128,6 +128,8 @@ class ConditionedUnet:
         self._sd: Optional[OrderedDict] = None
         self._plans: Dict[Tuple, "_Plan"] = {}
         self.weights_version = 0      # bumped by every repack; graph caches key on it (sampler._run_graph_loop)
+        self._engine = None
+        self.use_engine = True        # False: route forward() / the sampling graph through the operator-level Python plan (A/B tests)
         self.training = False
 
     # ---- nn.Module-like surface ------------------------------------------------------------
@@ -172,6 +174,10 @@ class ConditionedUnet:
         dd, ud, td, L = cfg["down_dims"], cfg["up_dims"], cfg["time_dim"], cfg["label_emb_dim"]
         self.weights_version += 1
         self._probe = torch.zeros(1, device=dev)
+        # the module-level C ABI handle (ds_unet_*): forward() and the sampling graph run through it for the deployed family;
+        # the operator-level plan below stays for the other variants, the per-layer taps of the parity tests and bench.py's
+        # per-kernel timings
+        self._engine = engine.UnetEngine(cfg, sd, dev) if engine.unet_supported(cfg) else None
         self.blocks: "OrderedDict[str, _Block]" = OrderedDict()
         self.attns: "OrderedDict[str, _Attn]" = OrderedDict()
         self.samplers: Dict[str, PackedConv] = {}
@@ -268,6 +274,9 @@ class ConditionedUnet:
         n_stage = len(self.cfg["down_dims"]) - 1
         if (H >> n_stage) < 1 or (Wd >> n_stage) < 1:
             raise RuntimeError(f"H={H}, W={Wd}: the map vanishes after {n_stage} stride-2 stages")      # torch: "Output size is too small"
+        if self._engine is not None and taps is None and self.use_engine:
+            return self._engine.forward(x.to(self.device, torch.float32).contiguous(), time.to(self.device, torch.long).contiguous(),
+                                        condition.to(self.device, torch.float32).contiguous())
         pl = self.plan(N, H, Wd)
         pl.x.copy_(x.to(self.device, torch.float32))
         pl.t.copy_(time.to(self.device, torch.long))

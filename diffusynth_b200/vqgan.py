@@ -15,7 +15,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
-from . import _lib, ops, weights as W
+from . import _lib, engine, ops, weights as W
 from ._lib import check
 from .ops import PackedConv, conv_args, pack_conv_down, pack_conv_s1, pack_conv_up, run_conv
 
@@ -255,8 +255,10 @@ class _StackPlan:
 
 
 class _StackModule:
-    def __init__(self, stack: _Stack):
+    def __init__(self, stack: _Stack, eng: Optional["engine.VqganEngine"] = None):
         self._stack = stack
+        self._engine = eng            # module-level C ABI handle (ds_vqgan_decode / ds_vqgan_encode); the stack plan stays for taps / timings
+        self.use_engine = True
         self._probe = torch.zeros(1, device=stack.device)
 
     def parameters(self):
@@ -269,6 +271,8 @@ class _StackModule:
     def forward(self, x):
         x = x.to(self._stack.device, torch.float32)
         B, Cc, H, Wd = x.shape
+        if self._engine is not None and self.use_engine:
+            return (self._engine.decode if self._stack.is_decoder else self._engine.encode)(x.contiguous())
         pl = self._stack.plan(B, H, Wd)
         pl.inp.copy_(x)
         pl.run()
@@ -300,6 +304,7 @@ class VQGAN:
         self._encoder: Optional[Encoder] = None
         self._decoder: Optional[Decoder] = None
         self._sd = None
+        self._engine = None
 
     def load_state_dict(self, state_dict, strict=True):
         spec = W.vqgan_param_spec(self.cfg)
@@ -313,8 +318,9 @@ class VQGAN:
         self._sd = sd
         enc_plan, dec_plan = W.vqgan_layer_plan(self.cfg)
         self._vq_vae.load_codebook(sd["_vq_vae._embedding.weight"])
-        self._encoder = Encoder(_Stack(sd, "_encoder._layers.", enc_plan, self.cfg, self.device, is_decoder=False))
-        self._decoder = Decoder(_Stack(sd, "_decoder._layers.", dec_plan, self.cfg, self.device, is_decoder=True))
+        self._engine = engine.VqganEngine(self.cfg, sd, self.device)
+        self._encoder = Encoder(_Stack(sd, "_encoder._layers.", enc_plan, self.cfg, self.device, is_decoder=False), self._engine)
+        self._decoder = Decoder(_Stack(sd, "_decoder._layers.", dec_plan, self.cfg, self.device, is_decoder=True), self._engine)
         return self
 
     def state_dict(self):

@@ -220,6 +220,110 @@ int ds_spec_images(const float* d_spec, void* d_mag_img, void* d_phase_img, void
 int ds_latent_image(const float* d_lat, void* d_img, void* d_minmax /* scratch: 32 bytes per sample */, int B, int H, int W,
                     void* stream);
 
+/* ========================================================================================
+ * Module-level entry points: the network plans, the weight packing and the sampling graph live behind
+ * opaque handles inside the library, so a host in any language loads a reference checkpoint by its state_dict names and runs
+ * whole modules; the Python classes of diffusynth_b200/ are thin hosts over exactly these calls.  A handle belongs to one
+ * device (the current device of the creating thread) and to one host thread at a time; distinct handles are independent.
+ * ====================================================================================== */
+#define DS_MAX_LEVELS 8
+
+/* ---- ConditionedUnet (model/diffusion.py:21-258; ctor arguments :22-33) ---- */
+typedef struct ds_unet_config {
+  int32_t in_dim, out_dim;                 /* out_dim <= 0: in_dim (diffusion.py:35) */
+  int32_t n_levels;                        /* len(down_dims) == len(up_dims) */
+  int32_t down_dims[DS_MAX_LEVELS], up_dims[DS_MAX_LEVELS];
+  int32_t mid_depth;                       /* <= 0: 3 */
+  int32_t with_time_emb;                   /* must be 1 */
+  int32_t time_dim;                        /* <= 0: 4 * down_dims[0] (diffusion.py:99) */
+  int32_t use_convnext;                    /* must be 1 (the ResNet-block variant runs through the operator-level entries) */
+  int32_t convnext_mult;                   /* <= 0: 2 */
+  int32_t attn_type;                       /* 0 = "linear_add" (deployed, app.py:40) */
+  int32_t condition_type;                  /* 0 = "natural_language_prompt" */
+  int32_t label_emb_dim;
+} ds_unet_config;
+typedef struct ds_unet ds_unet;
+int ds_unet_create(const ds_unet_config* cfg, ds_unet** out);       /* -4 for a variant outside the deployed family */
+void ds_unet_destroy(ds_unet* h);
+/* One parameter by its reference state_dict name (e.g. "downs.0.0.net.1.weight"); fp32, `data` may be host or device memory. */
+int ds_unet_load(ds_unet* h, const char* name, const float* data, const long long* shape, int ndim);
+/* Pack the loaded parameters for the device (fails naming the first missing / mis-shaped parameter).  Invalidates earlier plans. */
+int ds_unet_finalize(ds_unet* h);
+/* model(x, time, condition) (diffusion.py:187-258): d_x fp32 [N,in_dim,H,W], d_t int64 [N], d_cond fp32 [N,label_emb_dim]
+   -> d_out fp32 [N,out_dim,H,W].  The call sequence of a given (N, H, W) is built on first use and replayed afterwards. */
+int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const float* d_cond, float* d_out, int N, int H, int W,
+                    void* stream);
+/* The plan of one evaluation shape, for hosts that drive the sampling loop themselves (generic sampler loops, per-step probes):
+   x_batch_mod > 0 with uniform_time = the guidance-doubled batch of DiffSynthSampler.ddim_sample (:307-319): N = 2 * x_batch_mod
+   samples read x_batch_mod latents and ONE timestep (d_t[0]).  d_cond / d_eps are the plan's own device buffers. */
+typedef struct ds_unet_plan_io {
+  int32_t plan;                            /* plan id for ds_unet_plan_run* */
+  float* d_cond;                           /* [N][label_emb_dim]: write the conditions here, then ds_unet_plan_run_cond */
+  float* d_eps;                            /* [N][out_dim][H][W]: result of ds_unet_plan_run */
+  int32_t launches, cond_launches;         /* kernels per ds_unet_plan_run / ds_unet_plan_run_cond */
+} ds_unet_plan_io;
+int ds_unet_plan_get(ds_unet* h, int N, int H, int W, int x_batch_mod, int uniform_time, ds_unet_plan_io* io);
+int ds_unet_plan_run_cond(ds_unet* h, int plan, void* stream);      /* label_embedding + label_query / label_key: step-invariant */
+int ds_unet_plan_run(ds_unet* h, int plan, const float* d_x, const long long* d_t, void* stream);
+
+/* ---- VQGAN (model/VQGAN.py:403-458; ctor arguments :404-418) ---- */
+typedef struct ds_vqgan_config {
+  int32_t in_channels, out_channels, embedding_dim;      /* embedding_dim must be 4 */
+  int32_t n_hidden, hidden_channels[DS_MAX_LEVELS];
+  int32_t block_depth;
+  int32_t n_attn_pos, attn_pos[DS_MAX_LEVELS];
+  int32_t attn_with_skip;
+  int32_t act_relu;                        /* 1: act_type == "relu", 0: swish (decoder ResnetBlocks; the encoder's are always swish, :441) */
+  int32_t num_embeddings, num_groups;
+} ds_vqgan_config;
+typedef struct ds_vqgan ds_vqgan;
+int ds_vqgan_create(const ds_vqgan_config* cfg, ds_vqgan** out);
+void ds_vqgan_destroy(ds_vqgan* h);
+int ds_vqgan_load(ds_vqgan* h, const char* name, const float* data, const long long* shape, int ndim);   /* "_decoder._layers.0.weight", ... */
+int ds_vqgan_finalize(ds_vqgan* h);
+/* VectorQuantizerEMA.forward eval (:98-146) with the handle's codebook; Decoder.forward (:390-400): d_latent fp32 [B,4,H,W] ->
+   d_spec fp32 [B,out_channels,4H,4W]; Encoder.forward (:323-326): d_spec fp32 [B,in_channels,H,W] -> d_latent fp32 [B,4,H/4,W/4]. */
+int ds_vqgan_quantize(ds_vqgan* h, const float* d_x, float* d_out, long long* d_idx, int B, long long hw, void* stream);
+int ds_vqgan_decode(ds_vqgan* h, const float* d_latent, float* d_spec, int B, int H, int W, void* stream);
+int ds_vqgan_encode(ds_vqgan* h, const float* d_spec, float* d_latent, int B, int H, int W, void* stream);
+
+/* ---- the sampling loop as ONE CUDA graph (model/DiffSynthSampler.py:425-517 p_sample_loop; tail = text2sound.py:128-134,
+   utils.py:224-241): n_iter x [ U-Net on the (guidance-doubled) batch, fused CFG + DDIM/DDPM update, optional inpaint blend ],
+   then quantiser -> decoder -> STFT+ decode + iSTFT.  All buffers are caller-owned device memory at fixed addresses; the
+   step-dependent scalars live in the tables, so one graph serves every schedule / seed / prompt of its shape. ---- */
+typedef struct ds_sample_buffers {
+  float* d_imgs;                 /* [n_iter+1][B,C,H,W]: [0] = start latent (input), [k+1] = latent after step k */
+  const float* d_coef;           /* [n_iter][8]: ds_ddim_step coefficients of step k */
+  const long long* d_ttab;       /* [n_iter]: timestep fed to the U-Net at step k (timestep_map of the respaced schedule) */
+  const float* d_noise;          /* [n_iter][B,C,H,W] per-step noise (ddpm), or NULL (ddim, sigma = 0) */
+  const float* d_cond;           /* [N][label_emb_dim], N = 2B with guidance ([uncond x B | cond]) else B; read at every run */
+  const float* d_guide;          /* inpainting (:499-510), all four or none: guide latent [B,C,H,W] */
+  const float* d_init_noise;     /*   the noise q_sample mixes into the guide [B,C,H,W] */
+  const float* d_masks;          /*   [n_iter][B,C,H,W] */
+  const float* d_blend_coef;     /*   [n_iter][2] */
+  float* d_quantized;            /* tail outputs (with a ds_vqgan): [B,C,H,W] */
+  long long* d_indices;          /*   [B*H*W] codebook indices */
+  float* d_spec;                 /*   [B,3,4H,4W] or NULL */
+  float* d_wave;                 /*   [B, ds_istft_length(4W)] or NULL */
+} ds_sample_buffers;
+typedef struct ds_sample_graph ds_sample_graph;
+/* cfg_on: classifier-free guidance (CFG != 1.0, :307-319); vqgan NULL: no tail; use_graph 0 replays the launches eagerly
+   (profilers that cannot follow a captured graph).  Runs one warm-up step on `stream` before capturing. */
+int ds_sample_graph_build(ds_unet* unet, ds_vqgan* vqgan, const ds_sample_buffers* bufs, int B, int H, int W, int n_iter, int cfg_on,
+                          int use_graph, void* stream, ds_sample_graph** out);
+int ds_sample_graph_run(ds_sample_graph* g, void* stream);
+int ds_sample_graph_launches(const ds_sample_graph* g);     /* kernels per ds_sample_graph_run */
+void ds_sample_graph_destroy(ds_sample_graph* g);
+
+/* ---- the one collective of the sharded job: an all-gather of the rank-local waveforms over NCCL.  The library binds
+   libnccl.so.2 at run time (the copy already loaded in the process, e.g. PyTorch's, else the system one). ---- */
+typedef struct ds_comm ds_comm;
+int ds_comm_unique_id(void* id128);                                        /* rank 0: 128 bytes to hand to every rank */
+int ds_comm_init(int rank, int world, const void* id128, ds_comm** out);  /* -3 on any NCCL failure */
+/* dtype: 0 = fp32, 1 = act16, 2 = int64; count = elements contributed per rank; d_recv holds world * count. */
+int ds_allgather(ds_comm* c, const void* d_send, void* d_recv, long long count, int dtype, void* stream);
+void ds_comm_destroy(ds_comm* c);
+
 #ifdef __cplusplus
 }
 #endif

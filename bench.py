@@ -452,7 +452,16 @@ def run_sharded1024(args):
     from diffusynth_b200.pipeline import ShardedGenerator
     pipe = TextToTimbre.random_init(device=dev, seed=0)
     cond_all, uncond = W.synthetic_conditions(SHARDED_TOTAL, 512)
-    gen = ShardedGenerator(pipe, SHARDED_TOTAL, rank, world, chunk=BATCH)
+    comm = None
+    if world > 1:          # the job's one collective runs on the library's own communicator (ds_comm_init / ds_allgather)
+        from diffusynth_b200.engine import Comm
+
+        def bootstrap(ident):
+            buf = ident.to(dev)
+            dist.broadcast(buf, src=0)
+            return buf.cpu()
+        comm = Comm(rank, world, bootstrap)
+    gen = ShardedGenerator(pipe, SHARDED_TOTAL, rank, world, chunk=BATCH, comm=comm)
     cond_host = cond_all[gen.lo:gen.hi].contiguous().pin_memory()
     uncond_dev = uncond.to(dev)
     result_host = torch.empty((SHARDED_TOTAL, 256 * (4 * WIDTH - 1)), dtype=torch.float32).pin_memory() if rank == 0 else None
@@ -479,7 +488,7 @@ def run_sharded1024(args):
                     e2e=dict(value=v, unit="timbres/s", h2d_bytes_per_step=int(cond_host.numel() * 4), d2h_bytes_per_step=int(result_host.numel() * 4), ms_per_step=ms),
                     gpu_launches=int(gen.launches_per_job * args.steps), validated=ok,
                     validation=dict(finite=ok, note="output checked finite and complete; parity of this path: tests/test_gpu_headline.py, tests/test_gpu_fullsize.py"),
-                    chunks_per_rank=gen.n_chunks, gather=dict(bytes_total=int(SHARDED_TOTAL * 256 * (4 * WIDTH - 1) * 4), overlapped=world > 1,
+                    chunks_per_rank=gen.n_chunks, gather=dict(bytes_total=int(SHARDED_TOTAL * 256 * (4 * WIDTH - 1) * 4), overlapped=world > 1, collective="ds_allgather (library NCCL communicator)" if comm is not None else "none (1 rank)",
                                                              ms_exposed_after_last_chunk=gen.exposed_gather_ms()))
         emit(json.dumps(line))
     if world > 1:

@@ -159,3 +159,38 @@ class SampleGraph:
                 self.lib.ds_sample_graph_destroy(h)
             except Exception:
                 pass
+
+
+class Comm:
+    """ds_comm handle: the job's one collective (all-gather of rank-local results) on the library's own NCCL communicator.
+    ``bootstrap(buf)`` must broadcast the 128-byte id tensor from rank 0 to every rank (e.g. torch.distributed.broadcast on any
+    backend): that exchange is the only thing the host contributes."""
+
+    def __init__(self, rank: int, world: int, bootstrap=None):
+        self.lib = _lib.load()
+        self.rank, self.world = rank, world
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            check(self.lib.ds_comm_unique_id(ident.data_ptr()), "ds_comm_unique_id")
+        if world > 1:
+            assert bootstrap is not None, "a bootstrap broadcast is required for world > 1"
+            ident = bootstrap(ident)
+        self.h = C.c_void_p()
+        check(self.lib.ds_comm_init(rank, world, ident.cpu().contiguous().data_ptr(), C.byref(self.h)), "ds_comm_init")
+
+    def all_gather(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        send = send.contiguous()
+        dt = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 1, torch.int64: 2}[send.dtype]
+        if recv is None:
+            recv = send.new_empty((self.world * send.shape[0],) + tuple(send.shape[1:]))
+        assert recv.is_contiguous() and recv.numel() == self.world * send.numel() and recv.dtype == send.dtype
+        check(self.lib.ds_allgather(self.h, send.data_ptr(), recv.data_ptr(), send.numel(), dt, _stream()), "ds_allgather")
+        return recv
+
+    def __del__(self):
+        h, self.h = getattr(self, "h", None), None
+        if h:
+            try:
+                self.lib.ds_comm_destroy(h)
+            except Exception:
+                pass

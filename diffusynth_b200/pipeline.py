@@ -262,8 +262,9 @@ class ChunkGatherer:
     stream on GPUs, so that chunk k travels while chunk k+1 is computed; gloo / plain copies on CPU tensors in the host tests) into
     the rank-major result [world, per_pad, L]; ``finish()`` returns the first ``total`` rows in prompt order."""
 
-    def __init__(self, total: int, rank: int, world: int, chunk: int, L: int, device, dtype=torch.float32):
+    def __init__(self, total: int, rank: int, world: int, chunk: int, L: int, device, dtype=torch.float32, comm=None):
         self.total, self.rank, self.world, self.chunk, self.L = total, rank, world, chunk, L
+        self.comm_handle = comm      # engine.Comm (the library's own NCCL communicator, ds_allgather) or None = torch.distributed
         self.per = -(-total // world)
         self.n_chunks = -(-self.per // chunk)
         self.device = torch.device(device)
@@ -281,7 +282,10 @@ class ChunkGatherer:
         def gather():
             if self.world > 1:
                 st = self.stage[k % 2]
-                dist.all_gather_into_tensor(st.view(self.world * self.chunk, self.L), w.contiguous())
+                if self.comm_handle is not None:
+                    self.comm_handle.all_gather(w, recv=st.view(self.world * self.chunk, self.L))
+                else:
+                    dist.all_gather_into_tensor(st.view(self.world * self.chunk, self.L), w.contiguous())
                 self.out[:, k * self.chunk:(k + 1) * self.chunk].copy_(st)
             else:
                 self.out[0, k * self.chunk:(k + 1) * self.chunk].copy_(w)
@@ -322,8 +326,9 @@ class ShardedGenerator:
     while chunk k+1 is being sampled, so that only the last chunk's gather is exposed.  Every rank ends with all waveforms
     [total, L] in prompt order."""
 
-    def __init__(self, pipe: TextToTimbre, total: int, rank: int, world: int, chunk: int = 64):
+    def __init__(self, pipe: TextToTimbre, total: int, rank: int, world: int, chunk: int = 64, comm=None):
         self.pipe, self.total, self.rank, self.world, self.chunk = pipe, total, rank, world, chunk
+        self.comm = comm
         self.lo, self.hi = shard_range(total, rank, world)
         self.gatherer: Optional[ChunkGatherer] = None
         self.n_chunks = -(-(-(-total // world)) // chunk)
@@ -335,7 +340,7 @@ class ShardedGenerator:
         pipe, chunk = self.pipe, self.chunk
         L = 256 * (4 * width - 1)
         if self.gatherer is None or self.gatherer.L != L:
-            self.gatherer = ChunkGatherer(self.total, self.rank, self.world, chunk, L, pipe.device)
+            self.gatherer = ChunkGatherer(self.total, self.rank, self.world, chunk, L, pipe.device, comm=self.comm)
         n_local = self.hi - self.lo
         launches = 0
         for k in range(self.n_chunks):

@@ -7,7 +7,7 @@ Importing the compute classes needs a CUDA build of torch; there is no CPU fallb
 from . import weights  # noqa: F401  (pure-python parameter inventory; safe everywhere)
 
 __all__ = ["weights", "DiffSynthSampler", "ConditionedUnet", "VQGAN", "VectorQuantizerEMA", "Decoder", "Encoder",
-           "TextToTimbre", "spectrogram_to_waveform", "waveform_to_spectrogram"]
+           "TextToTimbre", "TextEncoder", "spectrogram_to_waveform", "waveform_to_spectrogram"]
 
 
 def __getattr__(name):
@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ("VQGAN", "VectorQuantizerEMA", "Decoder", "Encoder"):
         from . import vqgan
         return getattr(vqgan, name)
+    if name == "TextEncoder":
+        from .text import TextEncoder
+        return TextEncoder
     if name == "TextToTimbre":
         from .pipeline import TextToTimbre
         return TextToTimbre

@@ -86,6 +86,12 @@ _SIGNATURES = {
     "ds_griffinlim_update": (_I, [_P, _P, _P, _F, _I, _I, _I, _P]),
     "ds_spec_images": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "ds_latent_image": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "ds_text_embed_ln": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P]),
+    "ds_layernorm_rows": (_I, [_P, _P, _P, _I, _I, _F, _P]),
+    "ds_text_attention": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
+    "ds_cls_gather": (_I, [_P, _P, _I, _I, _I, _P]),
+    "ds_l2_normalize_rows": (_I, [_P, _I, _I, _P]),
+    "ds_add_layernorm_rows_f32": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     # module-level entry points (csrc/engine.cu, csrc/comm.cu; structures in diffusynth_b200/engine.py)
     "ds_unet_create": (_I, [_P, _P]),
     "ds_unet_destroy": (None, [_P]),

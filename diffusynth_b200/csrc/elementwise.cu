@@ -300,7 +300,7 @@ __global__ void decoder_head_kernel(const float* __restrict__ a, const float* __
 
 // ---------------------------------------------------------------------------------------------
 // Tiny linears (time MLP, per-block time projections, condition projections):
-//   out[n][o] = bias[o] + sum_k act(in[n][k]) * W[o][k]        act_in: 0 none, 1 GELU(erf), 2 SiLU
+//   out[n][o] = act_out(bias[o] + sum_k act_in(in[n][k]) * W[o][k])        act: 0 none, 1 GELU(erf), 2 SiLU (in), 3 tanh (out), 4 ReLU (out)
 // One warp per output feature, looping over samples (the weight row stays in registers/L1).
 // SinusoidalPositionEmbeddings (diffusion_components.py:42-56) is a separate small kernel.
 // ---------------------------------------------------------------------------------------------
@@ -325,6 +325,8 @@ __global__ void linear_kernel(const float* __restrict__ in, long long in_stride,
     if (lane == 0) {
       float r = acc + b;
       if (act_out == 1) r = gelu_erf(r);
+      else if (act_out == 3) r = tanhf(r);                 // ClapTextPooler
+      else if (act_out == 4) r = fmaxf(r, 0.f);            // ClapProjectionLayer (projection_hidden_act = relu)
       out[(size_t)n * out_stride + o] = r;
     }
   }

@@ -134,6 +134,16 @@ class TextToTimbre:
         return s
 
     @torch.no_grad()
+    def generate_from_tokens(self, text_encoder, input_ids: torch.Tensor, attention_mask: torch.Tensor, negative_ids: torch.Tensor,
+                             negative_mask: torch.Tensor, **kw) -> Timbres:
+        """text2sound.py:89-134 with the text front end on the device: ``text_encoder`` (diffusynth_b200.TextEncoder) turns the
+        tokenizer's output for B DISTINCT prompts and for the one negative prompt into the condition / unconditional vectors
+        (the reference encodes a single prompt on the CPU and repeats it, :89-91,109)."""
+        cond = text_encoder.get_text_features(input_ids, attention_mask)
+        uncond = text_encoder.get_text_features(negative_ids[:1], negative_mask[:1])[0]
+        return self.generate(cond, uncond, **kw)
+
+    @torch.no_grad()
     def generate(self, cond: torch.Tensor, uncond: Optional[torch.Tensor], steps: int = 20, cfg_scale: float = 6, width: int = 64,
                  sampler: str = "ddim", seed: Optional[int] = None, noise_feed: Optional[torch.Tensor] = None,
                  decode: bool = True) -> Timbres:

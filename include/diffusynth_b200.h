@@ -148,7 +148,8 @@ int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, cons
 /* init_conv as a tensor-core GEMM: 7x7xCin patches -> act16 [N, H, W, 224] (k = ky*32 + kx*4 + ci), then ds_conv_gemm 1x1. */
 int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, void* stream);
 /* SinusoidalPositionEmbeddings (:42-56) and the small Linear layers (time_mlp, per-block mlp,
-   label_embedding, label_key/label_query): out = act_out(bias + W . act_in(in)); act 1 = GELU(erf). */
+   label_embedding, label_key/label_query, the text tower's pooler / projections): out = act_out(bias + W . act_in(in));
+   act 0 none, 1 GELU(erf), 2 SiLU (act_in only), 3 tanh, 4 ReLU (act_out only). */
 int ds_sinusoidal_embedding(const long long* d_t, float* d_out, int N, int dim, void* stream);
 int ds_linear(const float* d_in, long long in_stride, const float* d_w, const float* d_bias, float* d_out,
               long long out_stride, int N, int K, int O, int act_in, int act_out, void* stream);
@@ -219,6 +220,24 @@ int ds_spec_images(const float* d_spec, void* d_mag_img, void* d_phase_img, void
                    int B, int T, void* stream);
 int ds_latent_image(const float* d_lat, void* d_img, void* d_minmax /* scratch: 32 bytes per sample */, int B, int H, int W,
                     void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Text-conditioning front end (text2sound.py:89-109 -> multi_modal_model.get_text_features, model/multimodal_model.py:114-116):
+ * transformers' ClapTextModel (RoBERTa-base) + ClapProjectionLayer + L2 normalisation, then ProjectionHead (:14-47).  The dense
+ * layers are ds_conv_gemm calls over the token axis; these are the remaining pieces (diffusynth_b200/text.py is the host).
+ * -------------------------------------------------------------------------------------- */
+/* ClapTextEmbeddings: LayerNorm(word[ids] + position[cumsum(ids != pad) * (ids != pad) + pad] + token_type[0]) -> act16 [B*L][D]. */
+int ds_text_embed_ln(const long long* d_ids, const float* d_word, const float* d_pos, const float* d_type0, const float* d_gamma, const float* d_beta,
+                     void* d_out, int B, int L, int D, int pad_idx, float eps, void* stream);
+/* LayerNorm over the rows of act16 [T][D], in place (post-LN blocks: the residual is added by the producing GEMM's epilogue). */
+int ds_layernorm_rows(void* d_x, const float* d_gamma, const float* d_beta, int T, int D, float eps, void* stream);
+/* softmax(q k^T * scale + mask) v per (sample, head), head size 64: d_qkv act16 [B][L][3*heads*64] (q | k | v), d_mask int64 [B][L],
+   d_out act16 [B][L][heads*64]. */
+int ds_text_attention(const void* d_qkv, const long long* d_mask, void* d_out, int B, int L, int heads, float scale, void* stream);
+int ds_cls_gather(const void* d_x, float* d_out, int B, int L, int D, void* stream);                 /* fp32 out[b] = x[b][0][:] */
+int ds_l2_normalize_rows(float* d_x, int B, int D, void* stream);                                     /* F.normalize(x, dim=-1) in place */
+/* ProjectionLayer tail (multimodal_model.py:28-31): x = LayerNorm(x + y) * gamma + beta, fp32 rows, in place on x. */
+int ds_add_layernorm_rows_f32(float* d_x, const float* d_y, const float* d_gamma, const float* d_beta, int B, int D, float eps, void* stream);
 
 /* ========================================================================================
  * Module-level entry points: the network plans, the weight packing and the sampling graph live behind

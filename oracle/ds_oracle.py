@@ -643,3 +643,53 @@ def griffinlim(S: np.ndarray, init_phase: np.ndarray, n_iter: int = 32, momentum
         angles = angles * S
         tprev = rebuilt
     return istft(angles)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Text-conditioning front end.  The text tower is THIRD-PARTY code: transformers' ClapModel
+# (requirements.txt:5, unpinned; app.py:44 loads "laion/clap-htsat-unfused") -- models/clap/modeling_clap.py: ClapTextEmbeddings
+# (word + token-type + position embeddings with RoBERTa's padding-aware position ids, LayerNorm), 12 x ClapTextLayer (self
+# attention, post-LayerNorm residual blocks, GELU(erf) feed-forward), ClapTextPooler (tanh dense on token 0),
+# ClapProjectionLayer (linear, ReLU, linear) and F.normalize in ClapModel.get_text_features.  The restatement is pinned against
+# the installed transformers (5.5) ClapModel in tests/test_oracle_text.py.  ProjectionHead is the reference's own code
+# (model/multimodal_model.py:14-47), applied by multi_modal_model.get_text_features (:114-116).
+# ---------------------------------------------------------------------------------------------------------------------
+def clap_text_features(sd: SD, input_ids: Tensor, attention_mask: Tensor, heads: int = 12, pad_idx: int = 1, eps: float = 1e-12,
+                       num_projection_layers: int = 2, taps: Optional[dict] = None) -> Tensor:
+    t = "text_encoder.text_model."
+    mask = input_ids.ne(pad_idx).long()
+    pos_ids = torch.cumsum(mask, dim=1) * mask + pad_idx                                   # create_position_ids_from_input_ids
+    x = sd[t + "embeddings.word_embeddings.weight"][input_ids] + sd[t + "embeddings.token_type_embeddings.weight"][0] \
+        + sd[t + "embeddings.position_embeddings.weight"][pos_ids]
+    D = x.shape[-1]
+    x = F.layer_norm(x, (D,), sd[t + "embeddings.LayerNorm.weight"], sd[t + "embeddings.LayerNorm.bias"], eps)
+    B, L, _ = x.shape
+    dh = D // heads
+    bias = (1.0 - attention_mask[:, None, None, :].to(x.dtype)) * torch.finfo(x.dtype).min  # additive key mask
+    i = 0
+    while f"{t}encoder.layer.{i}.attention.self.query.weight" in sd:
+        p = f"{t}encoder.layer.{i}."
+        q, k, v = (F.linear(x, sd[p + f"attention.self.{n}.weight"], sd[p + f"attention.self.{n}.bias"]).view(B, L, heads, dh).transpose(1, 2)
+                   for n in ("query", "key", "value"))
+        a = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5 + bias, dim=-1) @ v
+        a = a.transpose(1, 2).reshape(B, L, D)
+        x = F.layer_norm(F.linear(a, sd[p + "attention.output.dense.weight"], sd[p + "attention.output.dense.bias"]) + x, (D,),
+                         sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"], eps)
+        f = F.gelu(F.linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))
+        x = F.layer_norm(F.linear(f, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"]) + x, (D,),
+                         sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)
+        i += 1
+    if taps is not None:
+        taps["last_hidden_state"] = x
+    pooled = torch.tanh(F.linear(x[:, 0], sd[t + "pooler.dense.weight"], sd[t + "pooler.dense.bias"]))
+    y = F.linear(F.relu(F.linear(pooled, sd["text_encoder.text_projection.linear1.weight"], sd["text_encoder.text_projection.linear1.bias"])),
+                 sd["text_encoder.text_projection.linear2.weight"], sd["text_encoder.text_projection.linear2.bias"])
+    y = F.normalize(y, dim=-1)
+    if taps is not None:
+        taps["clap_text_features"] = y
+    for j in range(num_projection_layers):                                                 # ProjectionHead, multimodal_model.py:25-32,44-47
+        p = f"text_projection.layers.{j}."
+        projected = F.linear(y, sd[p + "projection.weight"], sd[p + "projection.bias"])
+        y = F.linear(F.gelu(projected), sd[p + "fc.weight"], sd[p + "fc.bias"]) + projected
+        y = F.layer_norm(y, (y.shape[-1],), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], 1e-5)
+    return y

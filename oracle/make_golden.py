@@ -126,6 +126,30 @@ def sampler2(ref):
 
 
 @torch.no_grad()
+
+def text_head():
+    """tests/golden/text.npz: the reference's ProjectionHead (model/multimodal_model.py:35-47) on unit-norm features, with the
+    synthetic head weights of tests/test_oracle_text.py::_head_sd.  `python -m oracle.make_golden --text`."""
+    import importlib.util
+    import types
+    ref_loader.load()
+    m = types.ModuleType("model.timbre_encoder_pretrain")
+    m.get_timbre_encoder = lambda *a, **k: None
+    sys.modules["model.timbre_encoder_pretrain"] = m
+    from model.multimodal_model import ProjectionHead
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_tt", os.path.join(here, "tests", "test_oracle_text.py"))
+    tt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tt)
+    head = ProjectionHead(embedding_dim=64, projection_dim=64, dropout=0.1, num_layers=2).eval()
+    sd = tt._head_sd()
+    head.load_state_dict({k.replace("text_projection.", ""): v for k, v in sd.items()})
+    y = torch.nn.functional.normalize(torch.randn((5, 64), generator=torch.Generator().manual_seed(2)), dim=-1)
+    with torch.no_grad():
+        out = head(y)
+    np.savez(os.path.join(here, "tests", "golden", "text.npz"), features=y.numpy(), head_out=out.numpy())
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
@@ -139,6 +163,9 @@ def main():
         print("headline.npz", os.path.getsize(os.path.join(OUT, "headline.npz")))
         return
     extra(ref)
+    if "--text" in sys.argv:
+        text_head()
+        return
     if "--extra" in sys.argv:
         print("extra.npz", os.path.getsize(os.path.join(OUT, "extra.npz")))
         return

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "ds_stem_conv7": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ds_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ds_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _P]),
+    "ds_embedding_gather": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "ds_linear": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "ds_attn_chunks": (_I, [_L]),
     "ds_attn_part_floats": (_L, [_I, _I, _L]),

@@ -332,6 +332,17 @@ __global__ void linear_kernel(const float* __restrict__ in, long long in_stride,
   }
 }
 
+// nn.Embedding lookup (ConditionalEmbedding with condition_type "instrument_family", diffusion_components.py:161,167)
+__global__ void embedding_gather_kernel(const float* __restrict__ table, const long long* __restrict__ ids, float* __restrict__ out, int N, int D, int rows) {
+  pdl_enter();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * D; i += gridDim.x * blockDim.x) {
+    const int n = i / D, c = i - n * D;
+    long long r = ids[n];
+    r = r < 0 ? 0 : (r >= rows ? rows - 1 : r);
+    out[i] = table[(size_t)r * D + c];
+  }
+}
+
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, float* __restrict__ out, int N, int dim) {
   pdl_enter();
   const int half = dim / 2;
@@ -490,6 +501,12 @@ int ds_linear(const float* d_in, long long in_stride, const float* d_w, const fl
   DS_CHECK_CUDA(launch_pdl(linear_kernel, dim3(dim3((O + wpb - 1) / wpb, gy)), dim3(wpb * 32), (size_t)(0), (cudaStream_t)stream, d_in, in_stride, d_w, d_bias, d_out, out_stride, N, K,
                                                                                       O, act_in, act_out));
   DS_CHECK_CUDA(cudaGetLastError());
+  return DS_OK;
+}
+
+int ds_embedding_gather(const float* d_table, const long long* d_ids, float* d_out, int N, int D, int rows, void* stream) {
+  DS_REQUIRE(d_table && d_ids && d_out && N > 0 && D > 0 && rows > 0, "ds_embedding_gather: bad arguments");
+  DS_CHECK_CUDA(launch_pdl(embedding_gather_kernel, dim3(grid_for((long long)N * D, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, d_table, d_ids, d_out, N, D, rows));
   return DS_OK;
 }
 

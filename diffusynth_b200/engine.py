@@ -56,7 +56,7 @@ def _load_params(fn, handle, state_dict) -> None:
 def unet_supported(cfg: dict) -> bool:
     """The variants the module-level entry points implement (the deployed family); the others keep the operator-level plan."""
     return bool(cfg.get("use_convnext", True)) and cfg["attn_type"] == "linear_add" and cfg["condition_type"] == "natural_language_prompt" \
-        and cfg["in_dim"] <= 4 and len(cfg["down_dims"]) <= DS_MAX_LEVELS
+        and cfg.get("with_time_emb", True) and cfg["in_dim"] <= 4 and len(cfg["down_dims"]) <= DS_MAX_LEVELS
 
 
 class UnetEngine:

@@ -213,6 +213,45 @@ class TextToTimbre:
 
 
     # ---- per-note synthesis for arrangements (track_maker.py:228-283) ---------------------------------------------------
+    @staticmethod
+    def note_width(duration_sec: float, time_resolution: int = 256, vae_scale: int = 4) -> int:
+        return int(time_resolution * ((duration_sec + 1) / 4) / vae_scale)                                    # track_maker.py:245
+
+    @torch.no_grad()
+    def _synthesize_group(self, instrument_latent, condition, width: int, B: int, sample_steps, noising_strength, attack, before_release,
+                          sampler, time_resolution, vae_scale, noise_feed) -> Timbres:
+        """B notes of one width as ONE batched inpainting run (one graph launch): every note is an independent sample of the batch
+        (own noise rows), exactly what B separate calls of the reference's per-note closure compute."""
+        # the reference builds a fresh sampler per note (:248-249); here it is cached per (step count, batch) so that the captured
+        # graph of a (width, steps, batch) triple is reused by every later group of that shape instead of being re-captured
+        key = ("note", sample_steps, B)
+        s = self._samplers.get(key)
+        if s is None:
+            s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy="repeat", mute=True,
+                                 device=str(self.device), max_batchsize=B)                                     # :248
+            s.respace(list(np.linspace(0, self.timesteps - 1, sample_steps, dtype=np.int32)))                  # :249
+            self._samplers[key] = s
+        s.activate_classifier_free_guidance(1.0, None)
+        s.noise_feed = None
+        s.graph_tail, s.final_only = self._tail_factory, True
+        mask = torch.zeros((B, 1, self.height, width), dtype=torch.float32, device=self.device)                # :252-254
+        mask[:, :, :, :int(time_resolution * (attack / 4) / vae_scale)] = 1.0
+        mask[:, :, :, -int(time_resolution * ((before_release + 1) / 4) / vae_scale):] = 1.0
+        init = None
+        if noise_feed is not None:
+            init = noise_feed[0][:B].to(self.device, torch.float32)
+            s.noise_feed = noise_feed[1:]
+        guide = instrument_latent.to(self.device, torch.float32)
+        if guide.shape[0] == 1 and B > 1:
+            guide = guide.repeat(B, 1, 1, 1)
+        cond = condition.to(self.device)
+        if cond.shape[0] == 1 and B > 1:
+            cond = cond.repeat(B, 1)
+        imgs, _ = s.inpaint_sample(self.unet, (B, self.channels, self.height, width), noising_strength, guide, mask, return_tensor=True,
+                                   condition=cond, sampler=sampler, initial_noise=init,
+                                   use_dynamic_mask=True, end_noise_level_ratio=0.0, mask_flexivity=1.0)       # :257-269
+        return self._decode(s, imgs[-1])       # quantiser :275, decoder + iSTFT :277-283, inside the group's graph
+
     @torch.no_grad()
     def synthesize_note(self, instrument_latent: torch.Tensor, condition: torch.Tensor, duration_sec: float, sample_steps: int = 20,
                         noising_strength: float = 1.0, attack: float = 0.5, before_release: float = 0.5, sampler: str = "ddim",
@@ -222,31 +261,27 @@ class TextToTimbre:
         ``condition`` [1,512] the empty-prompt embedding the reference passes (:231-233; no classifier-free guidance here);
         attack and tail are frozen by a mask that shrinks over the steps (``use_dynamic_mask``, mask_flexivity 1.0).
         The width ``int(256 * ((duration + 1) / 4) / 4)`` is arbitrary, odd levels included (pad_to_match)."""
-        width = int(time_resolution * ((duration_sec + 1) / 4) / vae_scale)                                   # :245
-        # the reference builds a fresh sampler per note (:248-249); here it is cached per step count so that the captured graph
-        # of a (width, steps) pair is reused by every later note of that duration instead of being re-captured
-        key = ("note", sample_steps)
-        s = self._samplers.get(key)
-        if s is None:
-            s = DiffSynthSampler(self.timesteps, height=self.height, channels=self.channels, noise_strategy="repeat", mute=True,
-                                 device=str(self.device), max_batchsize=1)                                     # :248
-            s.respace(list(np.linspace(0, self.timesteps - 1, sample_steps, dtype=np.int32)))                  # :249
-            self._samplers[key] = s
-        s.activate_classifier_free_guidance(1.0, None)
-        s.noise_feed = None
-        s.graph_tail, s.final_only = self._tail_factory, True
-        mask = torch.zeros((1, 1, self.height, width), dtype=torch.float32, device=self.device)                # :252-254
-        mask[:, :, :, :int(time_resolution * (attack / 4) / vae_scale)] = 1.0
-        mask[:, :, :, -int(time_resolution * ((before_release + 1) / 4) / vae_scale):] = 1.0
-        init = None
-        if noise_feed is not None:
-            init = noise_feed[0][:1].to(self.device, torch.float32)
-            s.noise_feed = noise_feed[1:]
-        imgs, _ = s.inpaint_sample(self.unet, (1, self.channels, self.height, width), noising_strength,
-                                   instrument_latent.to(self.device, torch.float32), mask, return_tensor=True,
-                                   condition=condition.to(self.device), sampler=sampler, initial_noise=init,
-                                   use_dynamic_mask=True, end_noise_level_ratio=0.0, mask_flexivity=1.0)       # :257-269
-        return self._decode(s, imgs[-1])       # quantiser :275, decoder + iSTFT :277-283, inside the note's graph
+        width = self.note_width(duration_sec, time_resolution, vae_scale)
+        return self._synthesize_group(instrument_latent, condition, width, 1, sample_steps, noising_strength, attack, before_release,
+                                      sampler, time_resolution, vae_scale, noise_feed)
+
+    @torch.no_grad()
+    def synthesize_notes(self, instrument_latent: torch.Tensor, condition: torch.Tensor, durations_sec, sample_steps: int = 20,
+                         noising_strength: float = 1.0, attack: float = 0.5, before_release: float = 0.5, sampler: str = "ddim",
+                         time_resolution: int = 256, vae_scale: int = 4, noise_feeds=None) -> list:
+        """The notes of a track (track_maker.py:285-330 calls the per-note closure once per distinct duration): notes of equal
+        duration -- hence equal latent width -- are batched into ONE graph launch.  Returns one ``Timbres`` per
+        note, in input order.  ``noise_feeds`` (tests): per note a host noise tensor [count, 1, C, H, 64]."""
+        widths = [self.note_width(d, time_resolution, vae_scale) for d in durations_sec]
+        out = [None] * len(widths)
+        for w in sorted(set(widths)):
+            idx = [i for i, ww in enumerate(widths) if ww == w]
+            feed = torch.cat([noise_feeds[i] for i in idx], dim=1) if noise_feeds is not None else None
+            t = self._synthesize_group(instrument_latent, condition, w, len(idx), sample_steps, noising_strength, attack, before_release,
+                                       sampler, time_resolution, vae_scale, feed)
+            for b, i in enumerate(idx):
+                out[i] = Timbres(t.latents[b:b + 1], t.quantized[b:b + 1], t.spectrograms[b:b + 1], t.waveforms[b:b + 1])
+        return out
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

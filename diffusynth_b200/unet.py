@@ -108,9 +108,6 @@ class ConditionedUnet:
             raise NotImplementedError()                       # diffusion.py:96
         if condition_type not in ("instrument_family", "natural_language_prompt"):
             raise NotImplementedError()                       # diffusion_components.py:165
-        if condition_type != "natural_language_prompt" or not with_time_emb:
-            raise NotImplementedError("diffusynth_b200 implements condition_type='natural_language_prompt' with with_time_emb=True "
-                                      "(ConvNeXt or ResNet blocks, attn_type 'linear_add' = deployed, app.py:40, or 'linear_cat')")
         if up_dims is None:
             up_dims = [128, 128, 64, 32]
         if down_dims is None:
@@ -120,7 +117,8 @@ class ConditionedUnet:
         assert up_dims[0] == down_dims[-1], "up_dims[0] != down_dims[-1]"
         self.cfg = W.unet_config(in_dim=in_dim, out_dim=out_dim, down_dims=list(down_dims), up_dims=list(up_dims), mid_depth=mid_depth,
                                  time_dim=time_dim, convnext_mult=convnext_mult, attn_type=attn_type, condition_type=condition_type,
-                                 label_emb_dim=label_emb_dim, use_convnext=bool(use_convnext), resnet_block_groups=int(resnet_block_groups))
+                                 label_emb_dim=label_emb_dim, use_convnext=bool(use_convnext), resnet_block_groups=int(resnet_block_groups),
+                                 with_time_emb=bool(with_time_emb), n_label_class=int(n_label_class))
         for d in set(self.cfg["down_dims"] + self.cfg["up_dims"]):
             if d % 32:
                 raise NotImplementedError(f"channel widths must be multiples of 32 (got {d})")
@@ -183,7 +181,7 @@ class ConditionedUnet:
         self.samplers: Dict[str, PackedConv] = {}
 
         def blk(p, dim, dim_out, has_time=True):
-            self.blocks[p] = (_Block if cfg["use_convnext"] else _ResBlock)(sd, p, dim, dim_out, has_time)
+            self.blocks[p] = (_Block if cfg["use_convnext"] else _ResBlock)(sd, p, dim, dim_out, has_time and cfg["with_time_emb"])
 
         def att(p, dim):
             self.attns[p] = _Attn(sd, p, dim)
@@ -234,10 +232,11 @@ class ConditionedUnet:
             off += 3 * HID
         self.c_total = off
         self.c_w, self.c_b = torch.cat(rows).contiguous().to(dev), torch.cat(biases).contiguous().to(dev)
-        self.lab_w = sd["label_embedding.embedding.weight"].float().contiguous().to(dev)
-        self.lab_b = sd["label_embedding.embedding.bias"].float().contiguous().to(dev)
-        self.tm1_w, self.tm1_b = sd["time_mlp.1.weight"].float().contiguous().to(dev), sd["time_mlp.1.bias"].float().contiguous().to(dev)
-        self.tm3_w, self.tm3_b = sd["time_mlp.3.weight"].float().contiguous().to(dev), sd["time_mlp.3.bias"].float().contiguous().to(dev)
+        self.lab_w = sd["label_embedding.embedding.weight"].float().contiguous().to(dev)      # Linear weight, or the nn.Embedding table
+        self.lab_b = sd["label_embedding.embedding.bias"].float().contiguous().to(dev) if "label_embedding.embedding.bias" in sd else None
+        if cfg["with_time_emb"]:
+            self.tm1_w, self.tm1_b = sd["time_mlp.1.weight"].float().contiguous().to(dev), sd["time_mlp.1.bias"].float().contiguous().to(dev)
+            self.tm3_w, self.tm3_b = sd["time_mlp.3.weight"].float().contiguous().to(dev), sd["time_mlp.3.bias"].float().contiguous().to(dev)
         # stem as a GEMM over im2col patches: [Cout, Cin, 7, 7] -> [Cout, ky*32 + kx*4 + ci] (8th pixel slot and ci >= Cin are zero)
         w0 = sd["init_conv.weight"].float()
         wst = torch.zeros(dd[0], 7, 8, 4)
@@ -267,21 +266,24 @@ class ConditionedUnet:
     @torch.no_grad()
     def forward(self, x, time, condition=None, taps: Optional[dict] = None):
         """x [N,4,H,W] fp32, time [N] int64, condition [N, label_emb_dim] fp32 -> eps [N,4,H,W] fp32 (diffusion.py:187-258)."""
-        if condition is None:
-            raise NotImplementedError("unconditional call (condition=None) is not implemented; the sampling path always conditions")
+        if condition is None and self.cfg["attn_type"] != "linear_add":
+            raise NotImplementedError("condition=None with attn_type='linear_cat' (the extra key / value token is part of the plan)")
         N, Cin, H, Wd = x.shape
         assert Cin == self.cfg["in_dim"]
         n_stage = len(self.cfg["down_dims"]) - 1
         if (H >> n_stage) < 1 or (Wd >> n_stage) < 1:
             raise RuntimeError(f"H={H}, W={Wd}: the map vanishes after {n_stage} stride-2 stages")      # torch: "Output size is too small"
-        if self._engine is not None and taps is None and self.use_engine:
+        if self._engine is not None and taps is None and self.use_engine and condition is not None:
             return self._engine.forward(x.to(self.device, torch.float32).contiguous(), time.to(self.device, torch.long).contiguous(),
                                         condition.to(self.device, torch.float32).contiguous())
         pl = self.plan(N, H, Wd)
         pl.x.copy_(x.to(self.device, torch.float32))
         pl.t.copy_(time.to(self.device, torch.long))
-        pl.cond.copy_(condition.to(self.device, torch.float32))
-        pl.run_cond()
+        if condition is None:
+            pl.sbias.zero_()          # diffusion.py:199-202, diffusion_components.py:279-283: no label_query / label_key terms at all
+        else:
+            pl.cond.copy_(condition.to(self.device, pl.cond.dtype).reshape(pl.cond.shape))
+            pl.run_cond()
         pl.run()
         if taps is not None:
             pl.export_taps(taps)
@@ -303,7 +305,8 @@ class _Plan:
         nb = x_batch_mod if x_batch_mod > 0 else N
         self.x = torch.zeros((nb, cfg["in_dim"], H, Wd), **f32)
         self.t = torch.zeros((N,), dtype=torch.long, device=dev)
-        self.cond = torch.zeros((N, cfg["label_emb_dim"]), **f32)
+        labels = cfg["condition_type"] == "instrument_family"       # integer class labels through nn.Embedding (diffusion_components.py:161)
+        self.cond = torch.zeros((N,), dtype=torch.long, device=dev) if labels else torch.zeros((N, cfg["label_emb_dim"]), **f32)
         self.eps = torch.zeros((N, cfg["out_dim"], H, Wd), **f32)
         dd, td = cfg["down_dims"], cfg["time_dim"]
         self.uniform_time = uniform_time
@@ -331,18 +334,28 @@ class _Plan:
         # ---- condition path (step-invariant: run once per sample() call) ----
         cemb = torch.empty((N, cfg["label_emb_dim"]), **f32)
         self.sbias = torch.empty((N, net.c_total), **f32)
-        self.cond_ops.append(("label_embedding", lambda: ops.linear(self.cond, net.lab_w, net.lab_b, cemb)))
+        if labels:
+            self.cond_ops.append(("label_embedding", lambda: check(lib.ds_embedding_gather(net.lab_w.data_ptr(), self.cond.data_ptr(), cemb.data_ptr(), N,
+                                                                                           cfg["label_emb_dim"], net.lab_w.shape[0], stream()), "embedding_gather")))
+        else:
+            self.cond_ops.append(("label_embedding", lambda: ops.linear(self.cond, net.lab_w, net.lab_b, cemb)))
         self.cond_ops.append(("label_qk", lambda: ops.linear(cemb, net.c_w, net.c_b, self.sbias)))
         # ---- time path ----
         sin = torch.empty((NT, dd[0]), **f32)
         t1 = torch.empty((NT, td), **f32)
         temb = torch.empty((NT, td), **f32)
         self.tbias = torch.empty((NT, net.t_total), **f32)
-        add("time_sin", lambda: check(lib.ds_sinusoidal_embedding(self.t.data_ptr(), sin.data_ptr(), NT, dd[0], stream()), "sinusoidal"))
-        add("time_mlp1", lambda: ops.linear(sin, net.tm1_w, net.tm1_b, t1, act_out=1))
-        add("time_mlp3", lambda: ops.linear(t1, net.tm3_w, net.tm3_b, temb))
-        add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1 if cfg["use_convnext"] else 2))
-        self.named["time_emb"] = (temb, -1)
+        if cfg["with_time_emb"]:
+            add("time_sin", lambda: check(lib.ds_sinusoidal_embedding(self.t.data_ptr(), sin.data_ptr(), NT, dd[0], stream()), "sinusoidal"))
+            add("time_mlp1", lambda: ops.linear(sin, net.tm1_w, net.tm1_b, t1, act_out=1))
+            add("time_mlp3", lambda: ops.linear(t1, net.tm3_w, net.tm3_b, temb))
+            add("time_proj", lambda: ops.linear(temb, net.t_w, net.t_b, self.tbias, act_in=1 if cfg["use_convnext"] else 2))
+            self.named["time_emb"] = (temb, -1)
+        else:
+            # with_time_emb=False (diffusion.py:107-109,211): no time terms; the per-channel bias of each block's first conv is all
+            # the fused buffer carries (one row, read with stride 0)
+            self.tbias = net.t_b.reshape(1, -1).clone()
+            self.t_stride = 0
 
         def conv(name, pc, s0, s1, h, w, n=None, **kw):
             a, st, keep = conv_args(pc, s0, s1, N if n is None else n, h, w, **kw)

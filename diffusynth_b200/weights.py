@@ -47,6 +47,8 @@ def unet_config(**overrides) -> dict:
         cfg["time_dim"] = int(cfg["down_dims"][0] * 4)
     cfg.setdefault("use_convnext", True)
     cfg.setdefault("resnet_block_groups", 8)
+    cfg.setdefault("with_time_emb", True)
+    cfg.setdefault("n_label_class", 11)
     return cfg
 
 
@@ -95,8 +97,10 @@ def unet_param_spec(cfg: dict) -> Spec:
     cfg = unet_config(**cfg)
     dd, ud = cfg["down_dims"], cfg["up_dims"]
     L, td, mult = cfg["label_emb_dim"], cfg["time_dim"], cfg["convnext_mult"]
-    assert cfg["attn_type"] in ("linear_add", "linear_cat") and cfg["condition_type"] == "natural_language_prompt"
+    assert cfg["attn_type"] in ("linear_add", "linear_cat") and cfg["condition_type"] in ("natural_language_prompt", "instrument_family")
     at = cfg["attn_type"]
+    if not cfg["with_time_emb"]:
+        td = None                                          # diffusion.py:107-109: no time_mlp, blocks built without their mlp
 
     def _blk(spec, p, dim, dim_out, mult, time_dim):      # block_klass (diffusion.py:83-87)
         if cfg["use_convnext"]:
@@ -104,10 +108,14 @@ def unet_param_spec(cfg: dict) -> Spec:
         else:
             _resnet(spec, p, dim, dim_out, time_dim)
 
-    spec: Spec = [("label_embedding.embedding.weight", (L, L)), ("label_embedding.embedding.bias", (L,)),
-                  ("init_conv.weight", (dd[0], cfg["in_dim"], 7, 7)), ("init_conv.bias", (dd[0],)),
-                  ("time_mlp.1.weight", (td, dd[0])), ("time_mlp.1.bias", (td,)),
-                  ("time_mlp.3.weight", (td, td)), ("time_mlp.3.bias", (td,))]
+    if cfg["condition_type"] == "natural_language_prompt":   # ConditionalEmbedding, diffusion_components.py:155-168
+        spec: Spec = [("label_embedding.embedding.weight", (L, L)), ("label_embedding.embedding.bias", (L,))]
+    else:                                                     # nn.Embedding(n_label_class + 1, label_emb_dim)
+        spec = [("label_embedding.embedding.weight", (cfg["n_label_class"] + 1, L))]      # one extra token (diffusion.py:63-64)
+    spec += [("init_conv.weight", (dd[0], cfg["in_dim"], 7, 7)), ("init_conv.bias", (dd[0],))]
+    if td is not None:
+        spec += [("time_mlp.1.weight", (td, dd[0])), ("time_mlp.1.bias", (td,)),
+                 ("time_mlp.3.weight", (td, td)), ("time_mlp.3.bias", (td,))]
     skips = []
     for i, (cin, cout) in enumerate(zip(dd[:-1], dd[1:])):
         p = f"downs.{i}."

@@ -151,6 +151,8 @@ int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, 
    label_embedding, label_key/label_query, the text tower's pooler / projections): out = act_out(bias + W . act_in(in));
    act 0 none, 1 GELU(erf), 2 SiLU (act_in only), 3 tanh, 4 ReLU (act_out only). */
 int ds_sinusoidal_embedding(const long long* d_t, float* d_out, int N, int dim, void* stream);
+/* ConditionalEmbedding for condition_type "instrument_family" (diffusion_components.py:161,167): out[n] = table[ids[n]], fp32. */
+int ds_embedding_gather(const float* d_table, const long long* d_ids, float* d_out, int N, int D, int rows, void* stream);
 int ds_linear(const float* d_in, long long in_stride, const float* d_w, const float* d_bias, float* d_out,
               long long out_stride, int N, int K, int O, int act_in, int act_out, void* stream);
 /* Linear attention core (LinearCrossAttentionAdd.forward :271-293; VQGAN LinearAttention :261-272). */

@@ -13,6 +13,8 @@ SMALL_UNET = dict(in_dim=4, down_dims=[32, 32, 64], up_dims=[64, 64, 32], mid_de
 
 SMALL_UNET_CAT = dict(SMALL_UNET, attn_type="linear_cat")
 SMALL_UNET_RESNET = dict(SMALL_UNET, use_convnext=False, resnet_block_groups=8)
+SMALL_UNET_FAMILY = dict(SMALL_UNET, condition_type="instrument_family", n_label_class=11)      # integer labels through nn.Embedding
+SMALL_UNET_NOTIME = dict(SMALL_UNET, with_time_emb=False)
 
 
 def randn(shape, seed):
@@ -36,6 +38,12 @@ def unet_case(name: str):
         cfg, B, Wd = SMALL_UNET_RESNET, 2, 16
     elif name == "small_cat_w16":       # attn_type="linear_cat" (LinearCrossAttention: the condition is an extra key / value token)
         cfg, B, Wd = SMALL_UNET_CAT, 2, 16
+    elif name == "small_family_w16":    # condition_type="instrument_family" (diffusion_components.py:160-161)
+        cfg, B, Wd = SMALL_UNET_FAMILY, 2, 16
+    elif name == "small_notime_w16":    # with_time_emb=False (diffusion.py:107-109)
+        cfg, B, Wd = SMALL_UNET_NOTIME, 2, 16
+    elif name == "small_nocond_w16":    # condition=None (diffusion.py:199-202)
+        cfg, B, Wd = SMALL_UNET, 2, 16
     else:
         raise KeyError(name)
     sd = W.unet_random_state_dict(cfg, seed=0)
@@ -43,6 +51,10 @@ def unet_case(name: str):
     x = randn((B, 4, H, Wd), 11) * 1.5
     t = torch.tensor([947, 52][:B], dtype=torch.long)
     cond = randn((B, W.unet_config(**cfg)["label_emb_dim"]), 12)
+    if name == "small_family_w16":
+        cond = torch.tensor([7, 2][:B], dtype=torch.long)
+    elif name == "small_nocond_w16":
+        cond = None
     return cfg, sd, x, t, cond
 
 

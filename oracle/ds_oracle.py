@@ -337,11 +337,14 @@ def unet_forward(sd: SD, x: Tensor, t: Tensor, cond: Optional[Tensor], taps: Opt
 
     cemb = None
     if cond is not None:
-        cemb = F.linear(cond, sd["label_embedding.embedding.weight"], sd["label_embedding.embedding.bias"])
+        if "label_embedding.embedding.bias" in sd:      # condition_type "natural_language_prompt": nn.Linear (diffusion_components.py:163)
+            cemb = F.linear(cond, sd["label_embedding.embedding.weight"], sd["label_embedding.embedding.bias"])
+        else:                                           # "instrument_family": nn.Embedding over integer labels (:161)
+            cemb = sd["label_embedding.embedding.weight"][cond.long()]
     hs = []
     x = tap("init_conv", F.conv2d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=3))
     hs.append(x)
-    temb = tap("time_emb", time_embedding(sd, t, dim0))
+    temb = tap("time_emb", time_embedding(sd, t, dim0)) if "time_mlp.1.weight" in sd else None      # with_time_emb=False: diffusion.py:107-109,211
     for i in range(n_stage):
         p = f"downs.{i}."
         x = tap(p + "0", _block(sd, p + "0.", x, temb))

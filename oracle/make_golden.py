@@ -150,10 +150,31 @@ def text_head():
     np.savez(os.path.join(here, "tests", "golden", "text.npz"), features=y.numpy(), head_out=out.numpy())
 
 
+
+VARIANTS = ("small_family_w16", "small_notime_w16", "small_nocond_w16")
+
+
+def variants(ref):
+    """tests/golden/variants.npz: the reference U-Net's own outputs for condition_type="instrument_family", with_time_emb=False and
+    condition=None (diffusion_components.py:155-168; diffusion.py:107-109,199-202,211).  `python -m oracle.make_golden --variants`."""
+    out = {}
+    for name in VARIANTS:
+        cfg, sd, x, t, cond = cases.unet_case(name)
+        net = ref.ConditionedUnet(**cfg).eval()
+        net.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out[f"{name}_eps"] = net(x, t, cond).numpy()
+    np.savez(os.path.join(OUT, "variants.npz"), **out)
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--variants" in sys.argv:
+        variants(ref)
+        print("variants.npz", os.path.getsize(os.path.join(OUT, "variants.npz")))
+        return
     if "--sampler2" in sys.argv:
         sampler2(ref)
         print("sampler2.npz", os.path.getsize(os.path.join(OUT, "sampler2.npz")))

@@ -30,4 +30,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
     d = os.path.join(ROOT, "tests", "golden")
-    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("sampler", "unet", "vqgan", "codec", "extra", "headline", "sampler2")}
+    return {n: np.load(os.path.join(d, n + ".npz")) for n in ("sampler", "unet", "vqgan", "codec", "extra", "headline", "sampler2", "variants")}

@@ -54,6 +54,20 @@ def test_unet_forward_parity(name, golden):
     assert rel(eps, torch.from_numpy(golden["unet"][f"{name}_eps"])) < BF16_TOL       # the reference's own output
 
 
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+def test_unet_conditioning_variants_parity(name, golden):
+    """condition_type="instrument_family" (integer labels, ds_embedding_gather), with_time_emb=False and condition=None
+    (diffusion_components.py:155-168; diffusion.py:107-109,199-202,211)."""
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    net = _unet(cfg, sd)
+    eps = net.forward(x.cuda(), t.cuda(), None if cond is None else cond.cuda()).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, x, t, cond)
+    print(f"\n[{name}] eps rel-L2 {rel(eps, ref):.3e}")
+    assert rel(eps, ref) < BF16_TOL
+    assert rel(eps, torch.from_numpy(golden["variants"][f"{name}_eps"])) < BF16_TOL       # the reference's own output
+
+
 def test_unet_rejects_unsupported_variants():
     from diffusynth_b200 import ConditionedUnet
     with pytest.raises(NotImplementedError):
@@ -322,3 +336,28 @@ def test_note_synthesis_odd_width_parity():
     assert tuple(out.spectrograms.shape) == (1, 3, 512, 4 * Wd) and tuple(out.waveforms.shape) == (1, 256 * (4 * Wd - 1))
     assert torch.equal(q_same, out.quantized.cpu())
     assert e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL
+
+
+def test_batched_notes_equal_single_notes():
+    """notes of equal duration go through ONE batched graph launch (TextToTimbre.synthesize_notes); every note of
+    the batch equals the same note synthesised on its own with the same noise (the path has no cross-sample operation)."""
+    from diffusynth_b200 import TextToTimbre
+    pipe = TextToTimbre.random_init(device="cuda", seed=0)
+    steps = 3
+    durs = [0.9, 2.0, 0.9, 0.9]                       # widths 30, 48, 30, 30 -> two groups (batch 3 and batch 1)
+    feeds = [W.host_noise(40 + i, 1 + steps, 1) for i in range(len(durs))]
+    cond, _ = W.synthetic_conditions(1, 512)
+    inst = cases.vq_latents(B=1, seed=22)
+    notes = pipe.synthesize_notes(inst.cuda(), cond.cuda(), durs, sample_steps=steps, noise_feeds=feeds)
+    n_graphs = sum(len(s._graphs) for k, s in pipe._samplers.items() if k[0] == "note")
+    assert n_graphs == 2 and [n.waveforms.shape[1] for n in notes] == [256 * (4 * TextToTimbre.note_width(d) - 1) for d in durs]
+    worst = 0.0
+    for i in (0, 2, 1):
+        one = pipe.synthesize_note(inst.cuda(), cond.cuda(), durs[i], sample_steps=steps, noise_feed=feeds[i])
+        worst = max(worst, rel(notes[i].latents, one.latents), rel(notes[i].waveforms, one.waveforms))
+        assert torch.equal(notes[i].quantized, one.quantized)
+    print(f"\nbatched notes vs single notes: worst rel-L2 {worst:.2e}")
+    assert worst < 1e-6
+    # a second track with the same durations reuses both graphs
+    pipe.synthesize_notes(inst.cuda(), cond.cuda(), durs, sample_steps=steps)
+    assert sum(len(s._graphs) for k, s in pipe._samplers.items() if k[0] == "note") == 3      # (+ the single-note graph of width 30 / 48)

@@ -169,6 +169,16 @@ def test_unet_odd_width_matches_reference(golden, name):
     assert rel(eps.numpy(), golden["extra"][f"{name}_eps"]) < 2e-6
 
 
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+def test_unet_conditioning_variants_match_reference(golden, name):
+    """condition_type="instrument_family" (nn.Embedding over integer labels), with_time_emb=False and condition=None
+    (diffusion_components.py:155-168; diffusion.py:107-109,199-202,211) against the reference's own outputs."""
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    with torch.no_grad():
+        eps = O.unet_forward(sd, x, t, cond)
+    assert rel(eps.numpy(), golden["variants"][f"{name}_eps"]) < 2e-6
+
+
 def _dynmask_loop():
     B, Wd, Hh = 2, 150, 16
     draws = cases.randn((10, B, 4, Hh, 64), 71)

@@ -33,6 +33,17 @@ def test_unet_small_live(ref):
 
 
 @torch.no_grad()
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+def test_unet_conditioning_variants_live(ref, name):
+    cfg, sd, x, t, cond = cases.unet_case(name)
+    net = ref.ConditionedUnet(**cfg).eval()
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == W.unet_param_spec(cfg)
+    net.load_state_dict(sd, strict=True)
+    a, b = net(x, t, cond), O.unet_forward(sd, x, t, cond)
+    assert (a - b).norm() / a.norm() < 2e-6
+
+
+@torch.no_grad()
 def test_full_sample_live(ref):
     """Reference sample() with CFG on the small U-Net vs the oracle loop, same host noise."""
     cfg, sd, _, _, _ = cases.unet_case("small_w16")

@@ -59,7 +59,6 @@ _SIGNATURES = {
     "ds_mask_blend": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _L, _P]),
     "ds_dwconv7": (_I, [_P, _P, _I, _I, _I, _P, _P, _L, _P, _P, _F, _I, _I, _I, _P]),
     "ds_dwconv7_stats_slots": (_I, [_I, _I, _I]),
-    "ds_stem_conv7": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ds_stem_im2col": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "ds_sinusoidal_embedding": (_I, [_P, _P, _I, _I, _P]),
     "ds_embedding_gather": (_I, [_P, _P, _P, _I, _I, _I, _P]),

@@ -215,15 +215,18 @@ def encodeBatch2GradioOutput_STFT(decoder, latent_vector_batch, resolution=(512,
 @torch.no_grad()
 def InputBatch2Encode_STFT(encoder, STFT_batch, resolution=(512, 256), quantizer=None, squared=True):
     """utils.py:131-191: encode a batch of spectral representations (and quantise), and render the INPUT batch back to
-    images / signals.  Only the VQ path exists (the reference's ``quantizer=None`` branch expects a VAE encoder returning
-    (mu, logvar, z), which the deployed VQGAN encoder is not)."""
-    if quantizer is None:
-        raise NotImplementedError("InputBatch2Encode_STFT without a quantizer (VAE encoder variant)")
+    images / signals.  ``quantizer=None`` is the reference's VAE branch (:162-164): the encoder must then return
+    ``(mu, logvar, z)`` and there is no quantised batch; the deployed VQGAN encoder returns a single tensor, so -- exactly as
+    in the reference -- that combination fails at the unpacking."""
     device = next(encoder.parameters()).device
     if isinstance(STFT_batch, np.ndarray):
         STFT_batch = torch.from_numpy(STFT_batch)
     spec = STFT_batch.to(device, torch.float32)
-    latents = encoder(spec)
-    quantized, _loss, (_, _, _) = quantizer(latents)
+    if quantizer is not None:
+        latents = encoder(spec)
+        quantized, _loss, (_, _, _) = quantizer(latents)
+    else:
+        _mu, _logvar, latents = encoder(spec)          # (a tensor [3, ...] would be split along dim 0, as in the reference)
+        quantized = None
     imgs, phases, signals = _decode_lists(spec)
     return imgs, phases, signals, latents, quantized

@@ -129,201 +129,10 @@ dwconv7_kernel(const act_t* __restrict__ src0, const act_t* __restrict__ src1, i
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// dwconv7, TMA-staged: the same arithmetic as dwconv7_kernel<2> (tile 16 rows x 16 cols x 32 channels, thread = 2 rows x
-// 8 cols x 2 channels, fp32 FFMA2 accumulation) but the 22 x 22 halo tile arrives as ONE cp.async.bulk.tensor box whose
-// out-of-range rows/columns are zero-filled by the TMA unit (= the conv padding), into a 3-deep ring, while the block
-// computes the previous tiles: there is no load->convert->store staging phase and no bounds logic.  The tile stays 16-bit
-// in shared memory (31 KB per stage) and is widened at use (HADD2.F32).  A block is persistent over the (sample, tile)
-// pairs of ONE 32-channel slice, so its 49 x 32 weights are staged once.
-// ---------------------------------------------------------------------------------------------
+// halo tile of the tensor-core kernel below: one cp.async.bulk.tensor box of 22 x 22 pixels x 32 channels (out-of-range rows and
+// columns zero-filled by the TMA unit = the conv padding), two stages
 static constexpr int DT_HALO = 22, DT_STAGES = 2;
-static constexpr bool DW_HACC_DEFAULT = false;
-static constexpr bool DW_MMA_DEFAULT = true;
 static constexpr int DT_TILE_BYTES = DT_HALO * DT_HALO * DW_CB * 2;     // 30976, a multiple of 128
-static constexpr int DT_SMEM_BYTES = DT_STAGES * DT_TILE_BYTES + 49 * (DW_CB / 2) * 8 + DT_STAGES * 8 + 128;
-
-// HACC (fp16 operands only): the taps of TWO input rows (<= 14 products per output) are accumulated with packed HFMA2 directly on
-// the staged 16-bit pairs and folded into the fp32 accumulators with FHADD (add.f32.f16) after every second input row: the FMA
-// pipe sees 1 HFMA2 (rt 2) per two MACs instead of 1 FFMA2 (rt 4) and the 16->32-bit widening of every staged value disappears.
-// Rounding: each fp16 partial sum carries <= 14 roundings of 2^-11 relative to its running value, the 49-tap total stays fp32.
-__device__ __forceinline__ void hfma2_acc(uint32_t& acc, uint32_t a, uint32_t b) {
-  asm("fma.rn.f16x2 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(b));
-}
-__device__ __forceinline__ void fold16(float2& acc, uint32_t& h) {
-  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}"
-      : "+f"(acc.x), "+f"(acc.y) : "r"(h));
-  h = 0u;
-}
-
-template <bool HACC>
-__global__ void __launch_bounds__(256, 3)
-dwconv7_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, int C0, int C1, int src_batch_mod,
-                   const float* __restrict__ weight, const float* __restrict__ tbias, long long tbias_stride,
-                   act_t* __restrict__ out, float2* __restrict__ stats, float stats_inv_count, float eps, int H, int W, int tiles_w,
-                   int tiles, int N) {
-  extern __shared__ uint8_t dt_smem_raw[];
-  uint8_t* smem = dt_smem_raw + ((128u - (smem_u32(dt_smem_raw) & 127u)) & 127u);   // offset on the shared array keeps LDS addressing
-  float2* s_w = reinterpret_cast<float2*>(smem + DT_STAGES * DT_TILE_BYTES);             // [49][16]
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_w + 49 * (DW_CB / 2));
-  __shared__ float s_red[2][16];   // per-warp (sum, sumsq) of a tile, double-buffered over iterations
-  const int C = C0 + C1;
-  const int cblk = blockIdx.y, c0 = cblk * DW_CB;
-  const CUtensorMap* map = c0 < C0 ? &map0 : &map1;
-  const int cs0 = c0 < C0 ? c0 : c0 - C0;
-  const int total = N * tiles;
-
-  if (threadIdx.x == 0) {
-    prefetch_tmap(map);
-    for (int s = 0; s < DT_STAGES; ++s) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  uint32_t* s_wh = reinterpret_cast<uint32_t*>(s_w);      // HACC: the same table as 16-bit pairs
-  for (int i = threadIdx.x; i < 49 * (DW_CB / 2); i += 256) {
-    const int tap = i / (DW_CB / 2), cp = i % (DW_CB / 2);
-    const float w0 = __ldg(weight + (size_t)tap * C + c0 + 2 * cp), w1 = __ldg(weight + (size_t)tap * C + c0 + 2 * cp + 1);
-    if (HACC) s_wh[i] = pack16(w0, w1);
-    else s_w[i] = make_float2(w0, w1);
-  }
-  __syncthreads();
-
-  auto issue = [&](int item, int stage) {
-    const int n = item / tiles, t = item - n * tiles;
-    const int th = t / tiles_w, tw = t - th * tiles_w;
-    const int nsrc = (src_batch_mod > 0 && c0 < C0) ? n % src_batch_mod : n;
-    mbar_expect_tx(&full[stage], DT_TILE_BYTES);
-    tma_load_4d(smem + stage * DT_TILE_BYTES, map, &full[stage], cs0, tw * DW_TW - 3, th * 16 - 3, nsrc);
-  };
-  // contiguous run of (sample, tile) items per block; statistics slots are announced once per run (see stats_arrive_run)
-  const int per_block = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int item0 = blockIdx.x * per_block, item1 = min(item0 + per_block, total);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < DT_STAGES - 1; ++k)
-      if (item0 + k < item1) issue(item0 + k, k);
-  int run_len = 0;
-
-  const int cp = threadIdx.x & 15, pt = threadIdx.x >> 4;
-  const int row0 = (pt & 7) * 2, col0 = (pt >> 3) * 8;
-  const int c = c0 + 2 * cp;
-  int it = 0;
-  for (int item = item0; item < item1; ++item, ++it) {
-    const int stage = it % DT_STAGES;
-    if (threadIdx.x == 0) {
-      const int nxt = item + (DT_STAGES - 1);      // its stage was released by the barrier that ended iteration it-1
-      if (nxt < item1) issue(nxt, (it + DT_STAGES - 1) % DT_STAGES);
-    }
-    const int n = item / tiles, t = item - n * tiles;
-    const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
-    const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
-    const float b0 = __ldg(tb + c), b1 = __ldg(tb + c + 1);
-    mbar_wait(&full[stage], (uint32_t)(it / DT_STAGES) & 1u);
-    const uint32_t* s_in = reinterpret_cast<const uint32_t*>(smem + stage * DT_TILE_BYTES);   // [22][22][16] channel pairs
-
-    float2 acc[2][8];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
-    if (HACC) {
-      uint32_t acc16[2][8], wh[2][7];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc16[i][j] = 0u;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (r < 7) {
-#pragma unroll
-          for (int kx = 0; kx < 7; ++kx) wh[r % 2][kx] = s_wh[(r * 7 + kx) * (DW_CB / 2) + cp];
-        }
-        const uint32_t* rowp = s_in + ((row0 + r) * DT_HALO + col0) * (DW_CB / 2) + cp;
-#pragma unroll
-        for (int j = 0; j < 14; ++j) {
-          const uint32_t in = rowp[j * (DW_CB / 2)];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int ky = r - i;
-            if (ky >= 0 && ky < 7) {
-#pragma unroll
-              for (int kx = 0; kx < 7; ++kx) {
-                const int ow = j - kx;
-                if (ow >= 0 && ow < 8) hfma2_acc(acc16[i][ow], in, wh[ky % 2][kx]);
-              }
-            }
-          }
-        }
-        if (r & 1) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) fold16(acc[i][j], acc16[i][j]);
-        }
-      }
-    } else {
-    float2 wbuf[2][7];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      if (r < 7) {
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx) wbuf[r % 2][kx] = s_w[(r * 7 + kx) * (DW_CB / 2) + cp];
-      }
-      const uint32_t* rowp = s_in + ((row0 + r) * DT_HALO + col0) * (DW_CB / 2) + cp;
-#pragma unroll
-      for (int j = 0; j < 14; ++j) {
-        const float2 in = cvt16x2(rowp[j * (DW_CB / 2)]);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int ky = r - i;
-          if (ky >= 0 && ky < 7) {
-#pragma unroll
-            for (int kx = 0; kx < 7; ++kx) {
-              const int ow = j - kx;
-              if (ow >= 0 && ow < 8) ffma2(acc[i][ow], in, wbuf[ky % 2][kx]);
-            }
-          }
-        }
-      }
-    }
-    }
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int y = h0 + row0 + i;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int x = w0 + col0 + j;
-        if (y < H && x < W) {
-          const float v0 = acc[i][j].x + b0, v1 = acc[i][j].y + b1;
-          s += v0 + v1;
-          q = fmaf(v0, v0, fmaf(v1, v1, q));
-          *reinterpret_cast<uint32_t*>(out + (((size_t)n * H + y) * W + x) * C + c) = pack16(v0, v1);
-        }
-      }
-    }
-    float* red = s_red[it & 1];
-    if (stats != nullptr) {
-      s = warp_sum(s);
-      q = warp_sum(q);
-      const int warp = threadIdx.x >> 5;
-      if ((threadIdx.x & 31) == 0) { red[warp] = s; red[8 + warp] = q; }
-    }
-    __syncthreads();     // every thread is done with this stage before it is refilled; the per-warp partials are visible
-    if (stats != nullptr && threadIdx.x < 32) {     // warp 0 writes the tile's slot while the others start the next tile (which uses the other s_red)
-      const int slots = tiles * gridDim.y;
-      float2* sb = stats_sample(stats, slots, n);
-      if (threadIdx.x == 0) {
-        float ts = 0.f, tq = 0.f;
-        for (int i = 0; i < 8; ++i) { ts += red[i]; tq += red[8 + i]; }
-        sb[2 + cblk * tiles + t] = make_float2(ts, tq);
-      }
-      ++run_len;
-      if (t == tiles - 1 || item + 1 == item1) {
-        stats_arrive_run(sb, slots, run_len, stats_inv_count, eps, threadIdx.x);
-        run_len = 0;
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // dwconv7 on the warp-level tensor cores (mma.sync.m16n8k16, fp32 accumulate), Toeplitz formulation.
@@ -570,75 +379,8 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   }
 }
 
-static inline int dw_rows_per_thread(int H) {
-  static const int forced = [] { const char* e = getenv("DS_DWCONV_R"); return e ? atoi(e) : 0; }();
-  if (forced == 1 || forced == 2) return forced;
-  return H >= 16 ? 2 : 1;
-}
+static inline int dw_rows_per_thread(int H) { return H >= 16 ? 2 : 1; }      // 16-row tiles (tensor-core kernel) or 8-row tiles
 static inline size_t dw_smem_bytes(int R) { return (size_t)((8 * R + 6) * DW_PITCH + 49) * (DW_CB / 2) * sizeof(float2); }
-
-// ---------------------------------------------------------------------------------------------
-// Stem: 7x7 conv, Cin (<=4) -> Cout (multiple of 32, <= 128), fp32 NCHW in, bf16 NHWC out.
-// block = 256 threads; tile = 4 rows x 32 cols; thread = (pixel, half of the output channels).
-// Weights live in shared memory as [tap*Cin + ci][Cout] fp32 and are read as broadcast float4.
-// ---------------------------------------------------------------------------------------------
-static constexpr int ST_TH = 4, ST_TW = 32;
-
-template <int CO_PER_THREAD>
-__global__ void __launch_bounds__(256)
-stem_conv7_kernel(const float* __restrict__ x, int x_batch_mod, const float* __restrict__ weight /* [49*Cin][Cout] */,
-                  const float* __restrict__ bias, act_t* __restrict__ out, int N, int Cin, int Cout, int H, int W,
-                  int tiles_w, int tiles_per_sample, int total_tiles) {
-  extern __shared__ __align__(16) float s_mem[];
-  float* s_w = s_mem;                                   // [49*Cin][Cout]
-  float* s_in = s_mem + 49 * Cin * Cout;                // [Cin][ST_TH+6][ST_TW+6 (+1 pad)]
-  const int IW = ST_TW + 7;
-  for (int i = threadIdx.x; i < 49 * Cin * Cout; i += 256) s_w[i] = __ldg(weight + i);
-  const int p = threadIdx.x & 127, half = threadIdx.x >> 7;
-  const int pr = p / ST_TW, pc = p % ST_TW;
-  const int co0 = half * CO_PER_THREAD;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int n = tile / tiles_per_sample, t = tile % tiles_per_sample;
-    const int h0 = (t / tiles_w) * ST_TH, w0 = (t % tiles_w) * ST_TW;
-    const int nsrc = x_batch_mod > 0 ? n % x_batch_mod : n;
-    __syncthreads();
-    for (int i = threadIdx.x; i < Cin * (ST_TH + 6) * (ST_TW + 6); i += 256) {
-      const int cc = i % (ST_TW + 6), r = (i / (ST_TW + 6)) % (ST_TH + 6), ci = i / ((ST_TW + 6) * (ST_TH + 6));
-      const int y = h0 + r - 3, xx = w0 + cc - 3;
-      float v = 0.f;
-      if (y >= 0 && y < H && xx >= 0 && xx < W) v = __ldg(x + (((size_t)nsrc * Cin + ci) * H + y) * W + xx);
-      s_in[(ci * (ST_TH + 6) + r) * IW + cc] = v;
-    }
-    __syncthreads();
-    float2 acc2[CO_PER_THREAD / 2];
-#pragma unroll
-    for (int j = 0; j < CO_PER_THREAD / 2; ++j) acc2[j] = make_float2(__ldg(bias + co0 + 2 * j), __ldg(bias + co0 + 2 * j + 1));
-    for (int ky = 0; ky < 7; ++ky)
-      for (int kx = 0; kx < 7; ++kx)
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float v = s_in[(ci * (ST_TH + 6) + pr + ky) * IW + pc + kx];
-          const float2 vv = make_float2(v, v);
-          const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 7 + kx) * Cin + ci) * Cout + co0);
-#pragma unroll
-          for (int j = 0; j < CO_PER_THREAD / 4; ++j) {
-            const float4 w4 = wr[j];
-            ffma2(acc2[2 * j], vv, make_float2(w4.x, w4.y));
-            ffma2(acc2[2 * j + 1], vv, make_float2(w4.z, w4.w));
-          }
-        }
-    float acc[CO_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < CO_PER_THREAD / 2; ++j) { acc[2 * j] = acc2[j].x; acc[2 * j + 1] = acc2[j].y; }
-    const int y = h0 + pr, xx = w0 + pc;
-    if (y < H && xx < W) {
-      uint4* op = reinterpret_cast<uint4*>(out + (((size_t)n * H + y) * W + xx) * Cout + co0);
-#pragma unroll
-      for (int j = 0; j < CO_PER_THREAD / 8; ++j)
-        op[j] = make_uint4(pack16(acc[8 * j], acc[8 * j + 1]), pack16(acc[8 * j + 2], acc[8 * j + 3]),
-                           pack16(acc[8 * j + 4], acc[8 * j + 5]), pack16(acc[8 * j + 6], acc[8 * j + 7]));
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Stem as a GEMM: im2col of the 7x7xCin (Cin <= 4) patches into a 16-bit [N, H, W, 224] matrix (k = ky*32 + kx*4 + ci,
@@ -691,105 +433,53 @@ int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_b
   const int R = dw_rows_per_thread(H);
   const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + 8 * R - 1) / (8 * R);
   const int tiles = tiles_w * tiles_h;
-  DS_REQUIRE(N <= 65535 && (C0 + C1) / DW_CB <= 65535, "ds_dwconv7: grid too large");
-  static bool attr_set = false;
-  if (!attr_set) {
-    DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(1)));
-    DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(2)));
-    attr_set = true;
-  }
-  const dim3 grid(tiles, (C0 + C1) / DW_CB, N);
+  const int cblks = (C0 + C1) / DW_CB;
+  DS_REQUIRE(N <= 65535 && cblks <= 65535, "ds_dwconv7: grid too large");
   const float inv_count = 1.0f / ((float)H * (float)W * (float)(C0 + C1));
-  static const bool use_tma = [] { const char* e = getenv("DS_DWCONV_TMA"); return !e || atoi(e) != 0; }();
-  if (R == 2 && use_tma) {
-    EncodeTiledFn encode = get_encode_fn();
-    DS_REQUIRE(encode != nullptr, "ds_dwconv7: cuTensorMapEncodeTiled entry point not available");
-    static bool tma_attr_set = false;
-    if (!tma_attr_set) {
-      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
-      DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
-      tma_attr_set = true;
-    }
-    // DS_DWCONV_MMA=0/1: Toeplitz formulation on mma.sync (dwconv7_mma_kernel; its halo tile is staged with the 64-byte swizzle)
-    static const bool use_mma = [] { const char* e = getenv("DS_DWCONV_MMA"); return e ? atoi(e) != 0 : DW_MMA_DEFAULT; }();
-    CUtensorMap maps[2];
-    for (int sidx = 0; sidx < 2; ++sidx) {
-      const int nsamp = (sidx == 0 && src_batch_mod > 0) ? src_batch_mod : N;
-      const int Cs = sidx == 0 ? C0 : C1;
-      const void* base = sidx == 0 ? d_src0 : d_src1;
-      if (Cs == 0) { maps[1] = maps[0]; break; }
-      const cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nsamp};
-      const cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
-      const cuuint32_t box[4] = {(cuuint32_t)DW_CB, (cuuint32_t)DT_HALO, (cuuint32_t)DT_HALO, 1};
-      const cuuint32_t estr[4] = {1, 1, 1, 1};
-      const CUresult r = encode(&maps[sidx], kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                                4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                use_mma ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      DS_REQUIRE(r == CUDA_SUCCESS, "ds_dwconv7: cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d)", (int)r, Cs, W, H);
-    }
-    const int cblks = (C0 + C1) / DW_CB;
-    long long work = (long long)N * tiles;
-    int gx = 3 * num_sms() / cblks;      // never more blocks than resident slots: a straggler wave would cost a whole pass
-    if (gx > work) gx = (int)work;
-    if (gx < 1) gx = 1;
-    if (use_mma) {
-      static const int dw_dbg = [] { const char* e = getenv("DS_DW_DBG"); return e ? atoi(e) : 0; }();
-      static bool mma_attr_set = false;
-      if (!mma_attr_set) {
-        DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
-        mma_attr_set = true;
-      }
-      int gm = 2 * num_sms() / cblks;
-      if (gm > work) gm = (int)work;
-      if (gm < 1) gm = 1;
-      DS_CHECK_CUDA(launch_pdl(dwconv7_mma_kernel, dim3(dim3(gm, cblks)), dim3(256), (size_t)(DM_SMEM_BYTES), (cudaStream_t)stream, 
-          maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
-          H, W, tiles_w, tiles, N, dw_dbg));
-      DS_CHECK_CUDA(cudaGetLastError());
-      return DS_OK;
-    }
-    // DS_DWCONV_HACC=1: packed fp16 accumulation over pairs of input rows (see hfma2_acc); fp16 operand builds only
-    static const bool hacc = [] { const char* e = getenv("DS_DWCONV_HACC"); return kOperandIsFp16 && (e ? atoi(e) != 0 : DW_HACC_DEFAULT); }();
-    auto kern = hacc ? dwconv7_tma_kernel<true> : dwconv7_tma_kernel<false>;
-    kern<<<dim3(gx, cblks), 256, DT_SMEM_BYTES, (cudaStream_t)stream>>>(
-        maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
-        H, W, tiles_w, tiles, N);
-  } else if (R == 2)
-    DS_CHECK_CUDA(launch_pdl((dwconv7_kernel<2>), dim3(grid), dim3(256), (size_t)(dw_smem_bytes(2)), (cudaStream_t)stream, 
+  if (R == 1) {
+    // maps shorter than 16 rows (the deepest levels of narrow / low configurations): direct FFMA2 kernel on 8-row tiles
+    DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem_bytes(1)));
+    DS_CHECK_CUDA(launch_pdl((dwconv7_kernel<1>), dim3(tiles, cblks, N), dim3(256), dw_smem_bytes(1), (cudaStream_t)stream,
         (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
         (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles));
-  else
-    DS_CHECK_CUDA(launch_pdl((dwconv7_kernel<1>), dim3(grid), dim3(256), (size_t)(dw_smem_bytes(1)), (cudaStream_t)stream, 
-        (const act_t*)d_src0, (const act_t*)d_src1, C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride,
-        (act_t*)d_out, (float2*)d_stats, inv_count, eps, H, W, tiles_w, tiles));
-  DS_CHECK_CUDA(cudaGetLastError());
+    return DS_OK;
+  }
+  EncodeTiledFn encode = get_encode_fn();
+  DS_REQUIRE(encode != nullptr, "ds_dwconv7: cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap maps[2];      // per call: host threads may launch concurrently
+  for (int sidx = 0; sidx < 2; ++sidx) {
+    const int nsamp = (sidx == 0 && src_batch_mod > 0) ? src_batch_mod : N;
+    const int Cs = sidx == 0 ? C0 : C1;
+    const void* base = sidx == 0 ? d_src0 : d_src1;
+    if (Cs == 0) { maps[1] = maps[0]; break; }
+    const cuuint64_t dims[4] = {(cuuint64_t)Cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nsamp};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cs * 2, (cuuint64_t)W * Cs * 2, (cuuint64_t)H * W * Cs * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)DW_CB, (cuuint32_t)DT_HALO, (cuuint32_t)DT_HALO, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode(&maps[sidx], kOperandIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                              4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DS_REQUIRE(r == CUDA_SUCCESS, "ds_dwconv7: cuTensorMapEncodeTiled failed with %d (C=%d W=%d H=%d)", (int)r, Cs, W, H);
+  }
+  const long long work = (long long)N * tiles;
+  int gm = 2 * num_sms() / cblks;      // never more blocks than resident slots (2 per SM): a straggler wave would cost a whole pass
+  if (gm > work) gm = (int)work;
+  if (gm < 1) gm = 1;
+#ifdef DS_CONV_DEBUG
+  static const int dw_dbg = [] { const char* e = getenv("DS_DW_DBG"); return e ? atoi(e) : 0; }();      // phase switches (tools_dev/ab_dwconv.py)
+#else
+  const int dw_dbg = 0;
+#endif
+  DS_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM_BYTES));
+  DS_CHECK_CUDA(launch_pdl(dwconv7_mma_kernel, dim3(gm, cblks), dim3(256), (size_t)DM_SMEM_BYTES, (cudaStream_t)stream,
+      maps[0], maps[1], C0, C1, src_batch_mod, d_weight, d_tbias, tbias_stride, (act_t*)d_out, (float2*)d_stats, inv_count, eps,
+      H, W, tiles_w, tiles, N, dw_dbg));
   return DS_OK;
 }
 
 int ds_dwconv7_stats_slots(int C, int H, int W) {
   const int R = dw_rows_per_thread(H);
   return ((W + DW_TW - 1) / DW_TW) * ((H + 8 * R - 1) / (8 * R)) * (C / DW_CB);
-}
-
-/* Stem 7x7 conv (init_conv).  d_x fp32 NCHW [x_batch_mod or N, Cin, H, W]; d_weight fp32 [49*Cin][Cout]
-   ((ky,kx,ci)-major); output bf16 NHWC [N,H,W,Cout]. */
-int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out, int N, int Cin, int Cout,
-                  int H, int W, void* stream) {
-  DS_REQUIRE(d_x && d_weight && d_bias && d_out && N > 0 && Cin > 0 && Cin <= 4 && H > 0 && W > 0, "ds_stem_conv7: bad arguments");
-  DS_REQUIRE(Cout == 96 || Cout == 64 || Cout == 32 || Cout == 128, "ds_stem_conv7: Cout=%d unsupported (32/64/96/128)", Cout);
-  const int tiles_w = (W + ST_TW - 1) / ST_TW, tiles_h = (H + ST_TH - 1) / ST_TH;
-  const int tps = tiles_w * tiles_h, total = tps * N;
-  const size_t smem = (size_t)(49 * Cin * Cout + Cin * (ST_TH + 6) * (ST_TW + 7)) * sizeof(float);
-  int grid = total < 2 * num_sms() ? total : 2 * num_sms();
-#define LAUNCH_STEM(CPT)                                                                                                    \
-  DS_CHECK_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-  stem_conv7_kernel<CPT><<<grid, 256, smem, (cudaStream_t)stream>>>(d_x, x_batch_mod, d_weight, d_bias, (act_t*)d_out, N, \
-                                                                     Cin, Cout, H, W, tiles_w, tps, total);
-  if (Cout == 96) { LAUNCH_STEM(48) } else if (Cout == 64) { LAUNCH_STEM(32) } else if (Cout == 32) { LAUNCH_STEM(16) } else { LAUNCH_STEM(64) }
-#undef LAUNCH_STEM
-  DS_CHECK_CUDA(cudaGetLastError());
-  return DS_OK;
 }
 
 /* im2col for the stem (init_conv as a GEMM): d_x fp32 NCHW [N, Cin<=4, H, W] -> d_col act16 [N, H, W, 224]. */

@@ -3,7 +3,7 @@
 
 Same constructor arguments, same ``state_dict`` key names, same call signature and result
 (fp32 NCHW epsilon).  The forward pass is a fixed sequence of calls into the C ABI
-(ds_stem_conv7, ds_dwconv7, ds_conv_gemm, ds_attn_*, ds_gn_apply_residual, ds_linear ...);
+(ds_stem_im2col, ds_dwconv7, ds_conv_gemm, ds_attn_*, ds_gn_apply_residual, ds_linear ...);
 activations live in HBM as bf16 NHWC and GroupNorm(1,C) never runs as its own pass -- its
 statistics come out of the producing kernel's epilogue and its affine is folded into the
 consuming convolution.  The call sequence for a given (N, H, W) is built once
@@ -531,8 +531,8 @@ class _Plan:
             fn()
 
     def num_launches(self) -> int:
-        """Kernels launched by one run(): one per op, two for the attention finalize (reduce + fold)."""
-        return len(self.ops) + sum(1 for name, _ in self.ops if name.endswith("fin"))
+        """Kernels launched by one run(): one per op (linear_cat's finalize is two: reduce + fold)."""
+        return len(self.ops) + (sum(1 for name, _ in self.ops if name.endswith("fin")) if self.net.cfg["attn_type"] == "linear_cat" else 0)
 
     def export_taps(self, taps: dict):
         """Named intermediates as fp32 NCHW (for per-layer parity tests)."""

@@ -142,10 +142,7 @@ int ds_mask_blend(const float* d_guide, const float* d_noise, const float* d_mas
 int ds_dwconv7(const void* d_src0, const void* d_src1, int C0, int C1, int src_batch_mod, const float* d_weight,
                const float* d_tbias, long long tbias_stride, void* d_out, void* d_stats, float eps, int N, int H, int W, void* stream);
 int ds_dwconv7_stats_slots(int C, int H, int W);
-/* init_conv 7x7 (model/diffusion.py:82,208): fp32 NCHW in, act16 NHWC out. */
-int ds_stem_conv7(const float* d_x, int x_batch_mod, const float* d_weight, const float* d_bias, void* d_out,
-                  int N, int Cin, int Cout, int H, int W, void* stream);
-/* init_conv as a tensor-core GEMM: 7x7xCin patches -> act16 [N, H, W, 224] (k = ky*32 + kx*4 + ci), then ds_conv_gemm 1x1. */
+/* init_conv 7x7 (model/diffusion.py:82,208) as a tensor-core GEMM: 7x7xCin patches of the fp32 NCHW input -> act16 [N, H, W, 224] (k = ky*32 + kx*4 + ci), then ds_conv_gemm 1x1. */
 int ds_stem_im2col(const float* d_x, void* d_col, int N, int Cin, int H, int W, void* stream);
 /* SinusoidalPositionEmbeddings (:42-56) and the small Linear layers (time_mlp, per-block mlp,
    label_embedding, label_key/label_query, the text tower's pooler / projections): out = act_out(bias + W . act_in(in));

@@ -95,14 +95,18 @@ def test_dwconv7(C0, C1, H, W, N):
     assert torch.allclose(buf[:, 0, 1], (ref.double().var(dim=(1, 2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=1e-3)
 
 
-def test_stem_conv7():
-    x = cases.randn((2, 4, 128, 64), 12) * 3
-    w, b = cases.randn((96, 4, 7, 7), 13) * 0.07, cases.randn((96,), 14)
-    out = torch.zeros((4, 128, 64, 96), dtype=ops.ACT, device="cuda")
-    xd, wd, bd = x.cuda(), w.permute(2, 3, 1, 0).reshape(-1, 96).contiguous().cuda(), b.cuda()
-    assert lib().ds_stem_conv7(xd.data_ptr(), 2, wd.data_ptr(), bd.data_ptr(), out.data_ptr(), 4, 4, 96, 128, 64, S()) == 0
-    ref = F.conv2d(x, w, b, padding=3)
-    assert rel(nchw(out)[:2], ref) < EPS16 and torch.equal(out[:2], out[2:])
+def test_stem_im2col():
+    """init_conv as im2col + GEMM (diffusion.py:82): col[n, h, w, ky*32 + kx*4 + ci] = x[n, ci, h + ky - 3, w + kx - 3] (zero padded,
+    8th pixel slot of every kernel row zero); the GEMM itself is covered by the init_conv tap of tests/test_gpu_model.py."""
+    x = cases.randn((2, 4, 32, 24), 12) * 3
+    col = torch.full((2, 32, 24, 224), 7.0, dtype=ops.ACT, device="cuda")
+    assert lib().ds_stem_im2col(x.cuda().data_ptr(), col.data_ptr(), 2, 4, 32, 24, S()) == 0
+    xp = F.pad(x, (3, 3, 3, 3))
+    ref = torch.zeros((2, 32, 24, 7, 8, 4))
+    for ky in range(7):
+        for kx in range(7):
+            ref[:, :, :, ky, kx, :] = xp[:, :, ky:ky + 32, kx:kx + 24].permute(0, 2, 3, 1)
+    assert torch.equal(col.float().cpu(), ref.reshape(2, 32, 24, 224).to(ops.ACT).float())
 
 
 def test_time_and_condition_linears():
@@ -272,8 +276,17 @@ def test_input_batch_encode_glue():
     d = _circ(imgs[0], m_ref)
     assert d.max() <= 1 and (d != 0).mean() < 5e-3
     assert rel(torch.from_numpy(signals[0]), torch.from_numpy(s_ref)) < 1e-5
-    with pytest.raises(NotImplementedError):
-        codec.InputBatch2Encode_STFT(vq._encoder, spec)
+    # quantizer=None is the reference's VAE branch (utils.py:162-164): the encoder returns (mu, logvar, z), no quantised batch
+    class _VaeEncoder:
+        def parameters(self):
+            return vq._encoder.parameters()
+
+        def __call__(self, x):
+            z = vq._encoder(x)
+            return z * 0.5, z * 0.0, z
+
+    imgs2, _, signals2, lat2, q2 = codec.InputBatch2Encode_STFT(_VaeEncoder(), spec)
+    assert q2 is None and torch.equal(lat2, lat) and np.array_equal(imgs2[0], imgs[0]) and np.array_equal(signals2[0], signals[0])
 
 
 def test_griffinlim_matches_oracle_and_converges():

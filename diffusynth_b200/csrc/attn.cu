@@ -255,59 +255,6 @@ attn_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout /
   }
 }
 
-// attn_finalize (fused reduce + fold, no label token): grid = (N, splits), block = 256.  Warp w works on head w & 3; lane d first
-// rebuilds row d of that head's merged context exactly as attn_reduce_kernel does (same operation order), keeps it in registers, and
-// then walks the rows c = first + (w >> 2), +2, ... of this block's share of Wout, producing M[n][c][head*32 + d] like attn_fold_kernel.
-// One launch of N x splits blocks replaces a 512-block reduce and a (Cout/64 x heads x N)-block fold whose few microseconds of work
-// each were dominated by launch and block-scheduling latency.
-__global__ void __launch_bounds__(256)
-attn_finalize_kernel(const float* __restrict__ part, int chunks, const float* __restrict__ wout /* [C][hidden] */, int C, int Cout_pad, int heads,
-                     act_t* __restrict__ M) {
-  pdl_enter();
-  const int n = blockIdx.x, warp = threadIdx.x >> 5, d = threadIdx.x & 31;
-  const int head = warp & 3, sub = warp >> 2, hidden = heads * AT_D;
-  const float* pb = part + ((size_t)n * heads + head) * chunks * AT_PART;
-  float mx = -INFINITY;
-  for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d));
-  float z = 0.f;
-  for (int c = 0; c < chunks; ++c)
-    z += __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + d) * __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d) - mx);
-  const float zinv = 1.0f / z;
-  float cr[AT_D];
-#pragma unroll
-  for (int e = 0; e < AT_D; ++e) cr[e] = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    const float wgt = __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d) - mx);
-    const float4* row = reinterpret_cast<const float4*>(pb + (size_t)c * AT_PART + d * AT_D);
-#pragma unroll
-    for (int e4 = 0; e4 < AT_D / 4; ++e4) {
-      const float4 v = __ldg(row + e4);
-      cr[4 * e4] = fmaf(v.x, wgt, cr[4 * e4]); cr[4 * e4 + 1] = fmaf(v.y, wgt, cr[4 * e4 + 1]);
-      cr[4 * e4 + 2] = fmaf(v.z, wgt, cr[4 * e4 + 2]); cr[4 * e4 + 3] = fmaf(v.w, wgt, cr[4 * e4 + 3]);
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < AT_D; ++e) cr[e] *= zinv;
-  // this block's rows of Wout
-  const int per = (Cout_pad + (int)gridDim.y - 1) / (int)gridDim.y;
-  const int c_lo = blockIdx.y * per, c_hi = min(c_lo + per, Cout_pad);
-  act_t* Mn = M + (size_t)n * Cout_pad * hidden + head * AT_D + d;
-#pragma unroll 2
-  for (int c = c_lo + sub; c < c_hi; c += 2) {
-    float acc = 0.f;
-    if (c < C) {
-      const float4* wr = reinterpret_cast<const float4*>(wout + (size_t)c * hidden + head * AT_D);      // one address per warp: broadcast
-#pragma unroll
-      for (int e4 = 0; e4 < AT_D / 4; ++e4) {
-        const float4 w4 = __ldg(wr + e4);
-        acc = fmaf(w4.x, cr[4 * e4], acc); acc = fmaf(w4.y, cr[4 * e4 + 1], acc);
-        acc = fmaf(w4.z, cr[4 * e4 + 2], acc); acc = fmaf(w4.w, cr[4 * e4 + 3], acc);
-      }
-    }
-    Mn[(size_t)c * hidden] = f2act(acc);
-  }
-}
-
 }  // namespace ds
 
 using namespace ds;
@@ -337,14 +284,6 @@ static int attn_finalize_impl(const float* d_part, const float* d_label_k, const
   const int chunks = ds_attn_chunks(npix);
   float* ctx = const_cast<float*>(d_part) + (size_t)N * heads * chunks * AT_PART;
   DS_REQUIRE(N <= 65535 && heads <= 65535, "ds_attn_finalize: grid too large");
-  if (d_label_k == nullptr && heads == 4) {
-    // fused reduce + fold (the U-Net's 4-head attention): one launch, N x splits blocks
-    int splits = (2 * num_sms() + N - 1) / N;
-    if (splits < 1) splits = 1;
-    if (splits > Cout_pad / 16) splits = Cout_pad / 16 > 0 ? Cout_pad / 16 : 1;
-    DS_CHECK_CUDA(launch_pdl(attn_finalize_kernel, dim3(N, splits), dim3(256), (size_t)0, (cudaStream_t)stream, d_part, chunks, d_wout, C, Cout_pad, heads, (act_t*)d_M));
-    return DS_OK;
-  }
   DS_CHECK_CUDA(launch_pdl(attn_reduce_kernel, dim3(dim3(heads, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, d_part, chunks, ctx, d_label_k, d_label_v, label_stride));
   DS_CHECK_CUDA(launch_pdl(attn_fold_kernel, dim3(dim3((Cout_pad + 63) / 64, heads, N)), dim3(256), (size_t)(0), (cudaStream_t)stream, ctx, d_wout, C, Cout_pad, heads * AT_D, (act_t*)d_M));
   DS_CHECK_CUDA(cudaGetLastError());

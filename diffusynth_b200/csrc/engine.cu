@@ -611,7 +611,7 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
       add([=](const Run& r) { ENG_CALL(ds_attn_qkv_ctx(xp, dim, x_mod, sx.buf, sx.slots, qkv.weight, qkv.e1, qkv.e2, sb, c_total, qp, part, Nn, HEADS, npix,
                                                        1.0f / sqrtf((float)DHEAD), r.s)); });
       const float* wout = a.wout; const int cop = a.out.cout_pad;
-      add([=](const Run& r) { ENG_CALL(ds_attn_finalize(part, wout, M, Nn, HEADS, npix, dim, cop, r.s)); });
+      add([=](const Run& r) { ENG_CALL(ds_attn_finalize(part, wout, M, Nn, HEADS, npix, dim, cop, r.s)); }, 2);
     }
     act_t* y = scr("atty", Nn, h, w, a.dim);
     Stats st_y;

@@ -531,8 +531,8 @@ class _Plan:
             fn()
 
     def num_launches(self) -> int:
-        """Kernels launched by one run(): one per op (linear_cat's finalize is two: reduce + fold)."""
-        return len(self.ops) + (sum(1 for name, _ in self.ops if name.endswith("fin")) if self.net.cfg["attn_type"] == "linear_cat" else 0)
+        """Kernels launched by one run(): one per op, two for the attention finalize (reduce + fold)."""
+        return len(self.ops) + sum(1 for name, _ in self.ops if name.endswith("fin"))
 
     def export_taps(self, taps: dict):
         """Named intermediates as fp32 NCHW (for per-layer parity tests)."""

@@ -74,8 +74,7 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + AQ_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  float* s_wmax = reinterpret_cast<float*>(tmem_base_smem + 2);            // [2 tile parities][4 lane groups][4 heads], log2 domain
-  float* s_sc = s_wmax + 32;                                               // [4 heads] exp2(m_old - m_new) of the current tile
+  float* s_wmax = reinterpret_cast<float*>(tmem_base_smem + 2);            // [4 lane groups][4 heads]: per-warp maxima of an item's first tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -187,7 +186,6 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t sp_row = smem_u32(s_p) + (uint32_t)(row * AQ_PITCH + half * 128), sv_row = smem_u32(s_v) + (uint32_t)(row * AQ_PITCH + half * 128);
     const int lr = lane & 7, lmat = lane >> 3;
     uint32_t acc_phase = 0;
-    int tile_par = 0;
     constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
     // this thread's 64 columns of the q / k / v constants, read as LDS.128 through shared-space addresses (a generic pointer
     // makes every read an LD with a long-scoreboard wait)
@@ -208,16 +206,22 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (P.sbias != nullptr) t += __ldg(P.sbias + (size_t)n * P.sbias_stride + col);
         s_t[col] = col < 2 * AQ_HID ? t * kLog2e : t;
       }
-      float runM[2] = {-INFINITY, -INFINITY};                    // log2 domain, heads 2*half + {0, 1}; identical in the 4 warps of a half
+      // Stabiliser of the exponentials, one per head (log2 domain, of the bare product rl2 * acc): soft-max over n is shift invariant
+      // per row d, so ANY reference that is the same for every pixel of this partial is exact; the first tile of the item measures
+      // its own maximum and the later tiles keep it (P = exp2(rl2 acc - mh) may exceed 1 there: bf16 / fp32 have the exponent range).
+      // The per-column constant tk[d] never enters the inner loop: exp2(k - (mh + tk[d])) = exp2(rl2 acc - mh), so the partial
+      // simply reports m[d] = mh + tk[d].
+      float mh[2] = {0.f, 0.f};
       float c[4][4], cz[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { cz[i] = 0.f; for (int j = 0; j < 4; ++j) c[i][j] = 0.f; }
       umma::named_bar_sync(2, 256);                              // s_t visible; the previous item's staging reads are done
+      const float tk_d = lane < 16 ? s_t[AQ_HID + hd * AQ_DH + mt * 16 + lane] : 0.f;      // (s_t is rewritten by the next item's prologue)
 
       const int nt = tiles_of(chunk);
       for (int sub = 0; sub < nt; ++sub) {
         const int p0 = (chunk * AQ_SUB + sub) * AQ_TILE;
-        const bool valid = p0 + row < P.npix;
+        const bool valid = p0 + row < P.npix;                    // (false only in the ragged last tile of a sample)
         mbar_wait_warp(tmem_full, acc_phase);
         umma::fence_after();
         if (AQ_DBG & 8) {
@@ -237,55 +241,35 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         uint32_t v0[32], v1[32];
         AQ_LD(t_row + (uint32_t)(2 * AQ_HID), v0);
         AQ_LD(t_row + (uint32_t)(2 * AQ_HID + 32), v1);
-        // ---- k -> P = exp(k - m) as bf16 rows.  m (one per head) only has to be the SAME for every pixel of the chunk's partial
-        // and keep the exponentials finite: the first tile of an item measures its own maximum, later tiles use the running
-        // maximum of the tiles before them (their own maximum is collected on the way for the next tile); bf16 has the fp32
-        // exponent range, so P > 1 is harmless, and the exponent is clamped far below overflow.
-        float kf0[32], kf1[32];
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (sub == 0) {
+          // first tile: maximum of the accumulator per head over the tile's pixels (rl2 > 0: max(rl2 acc) = rl2 max(acc))
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 a = lds4(tk_s + 16u * j4), b = lds4(tk_s + 128u + 16u * j4);
-          const float ta[4] = {a.x, a.y, a.z, a.w}, tb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * j4 + i;
-            kf0[j] = fmaf(__uint_as_float(k0[j]), rl2, ta[i]);
-            kf1[j] = fmaf(__uint_as_float(k1[j]), rl2, tb[i]);
-            mx0 = fmaxf(mx0, kf0[j]);
-            mx1 = fmaxf(mx1, kf1[j]);
-          }
+          for (int j = 0; j < 32; ++j) { mx0 = fmaxf(mx0, __uint_as_float(k0[j])); mx1 = fmaxf(mx1, __uint_as_float(k1[j])); }
+          mx0 = warp_max(valid ? mx0 : -INFINITY);
+          mx1 = warp_max(valid ? mx1 : -INFINITY);
+          if (lane < 2) s_wmax[lane_grp * 4 + half * 2 + lane] = lane == 0 ? mx0 : mx1;
+          umma::named_bar_sync(1 + 2 * half, 128);                // exchanged among the 4 warps of this half
+          const int rd = half * 2;
+          mh[0] = rl2 * fmaxf(fmaxf(s_wmax[rd], s_wmax[rd + 4]), fmaxf(s_wmax[rd + 8], s_wmax[rd + 12]));
+          mh[1] = rl2 * fmaxf(fmaxf(s_wmax[rd + 1], s_wmax[rd + 5]), fmaxf(s_wmax[rd + 9], s_wmax[rd + 13]));
         }
-        mx0 = warp_max(valid ? mx0 : -INFINITY);
-        mx1 = warp_max(valid ? mx1 : -INFINITY);
-        if (lane < 2) s_wmax[tile_par * 16 + lane_grp * 4 + half * 2 + lane] = lane == 0 ? mx0 : mx1;
-        if (sub == 0) umma::named_bar_sync(1 + 2 * half, 128);  // first tile: its own maxima, exchanged among the 4 warps of this half
-        {
-          const int rd = (sub == 0 ? tile_par : tile_par ^ 1) * 16 + half * 2;
-          const float t0 = fmaxf(fmaxf(s_wmax[rd], s_wmax[rd + 4]), fmaxf(s_wmax[rd + 8], s_wmax[rd + 12]));
-          const float t1 = fmaxf(fmaxf(s_wmax[rd + 1], s_wmax[rd + 5]), fmaxf(s_wmax[rd + 9], s_wmax[rd + 13]));
-          const float n0 = fmaxf(runM[0], t0), n1 = fmaxf(runM[1], t1);
-          if ((ew & 3) == 0 && lane < 2) {
-            float e;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((lane == 0 ? runM[0] : runM[1]) - (lane == 0 ? n0 : n1)));      // 0 on the first tile
-            s_sc[half * 2 + lane] = e;
-          }
-          runM[0] = n0; runM[1] = n1;
-        }
+        // ---- k -> P = exp2(rl2 acc - mh) as bf16 rows ----
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const float mh = runM[hh];
+          const float nm = -mh[hh];
 #pragma unroll
           for (int q8 = 0; q8 < 4; ++q8) {
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float a0 = hh == 0 ? kf0[q8 * 8 + 2 * j] : kf1[q8 * 8 + 2 * j], a1 = hh == 0 ? kf0[q8 * 8 + 2 * j + 1] : kf1[q8 * 8 + 2 * j + 1];
+              const uint32_t r0 = hh == 0 ? k0[q8 * 8 + 2 * j] : k1[q8 * 8 + 2 * j], r1 = hh == 0 ? k0[q8 * 8 + 2 * j + 1] : k1[q8 * 8 + 2 * j + 1];
+              const float a0 = fmaf(__uint_as_float(r0), rl2, nm), a1 = fmaf(__uint_as_float(r1), rl2, nm);
               float e0, e1;
-              if (AQ_DBG & 32) { e0 = fminf(a0 - mh, 100.0f) * 0.5f; e1 = fminf(a1 - mh, 100.0f) * 0.5f; }
+              if (AQ_DBG & 32) { e0 = a0 * 0.5f; e1 = a1 * 0.5f; }
               else {
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(a0 - mh, 100.0f)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(a1 - mh, 100.0f)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
               }
               o[j] = valid ? pack_bf16(e0, e1) : 0u;
             }
@@ -310,7 +294,7 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               const uint32_t r0 = hh == 0 ? v0[q8 * 8 + 2 * j] : v1[q8 * 8 + 2 * j], r1 = hh == 0 ? v0[q8 * 8 + 2 * j + 1] : v1[q8 * 8 + 2 * j + 1];
               const float a0 = fmaf(__uint_as_float(r0), rstd, tvv[2 * j]);
               const float a1 = fmaf(__uint_as_float(r1), rstd, tvv[2 * j + 1]);
-              o[j] = valid ? pack_bf16(a0, a1) : 0u;
+              o[j] = pack_bf16(a0, a1);                           // (rows past the end of the sample meet P = 0)
             }
             if (!((AQ_DBG & 256) && o[0] != 0x12345u)) sts_128(sv_row + (uint32_t)(hh * 64 + q8 * 16), o[0], o[1], o[2], o[3]);
           }
@@ -322,13 +306,10 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(tmem_empty);
         acc_phase ^= 1u;
-        umma::named_bar_sync(2, 256);                            // P, V, the rescale factors and this tile's maxima are staged
+        umma::named_bar_sync(2, 256);                            // P and V of this tile are staged
 
         // ---- context: S[d][e] += sum_pix P[pix][d] V[pix][e] (and Z[d] through a column of ones), head hd, d rows 16*mt.. ----
         {
-          const float sc = s_sc[hd];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { cz[i] *= sc; for (int j = 0; j < 4; ++j) c[i][j] *= sc; }
           const uint32_t ones = ((lane >> 2) == 0) ? 0x3F803F80u : 0u;       // B fragment of the ones column: n = 0 for every k
           const uint32_t pa = smem_u32(s_p) + (uint32_t)((lr + ((lmat >> 1) & 1) * 8) * AQ_PITCH + (hd * 32 + mt * 16 + (lmat & 1) * 8) * 2);
           const uint32_t vb = smem_u32(s_v) + (uint32_t)((lr + (lmat & 1) * 8) * AQ_PITCH + (hd * 32 + (lmat >> 1) * 8) * 2);
@@ -381,10 +362,10 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           }
         }
-        tile_par ^= 1;
         umma::named_bar_sync(2, 256);                            // every warp is past its context MMAs: the staging rows are free
       }
-      // ---- one partial per (sample, head, chunk): S rows d = 16 mt + {g, g + 8}, Z from the ones column, m = the running maximum ----
+      // ---- one partial per (sample, head, chunk): S rows d = 16 mt + {g, g + 8}, Z from the ones column,
+      //      m[d] = (mh + tk[d]) ln 2 in natural-log units as attn_reduce_kernel expects ----
       {
         float* po = P.part + (((size_t)n * AQ_HEADS + hd) * P.chunks + chunk) * AQ_PART;
         const int g = lane >> 2, q = lane & 3;
@@ -395,13 +376,7 @@ attn_qkv_ctx_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           *reinterpret_cast<float2*>(po + (d + 8) * AQ_DH + nt8 * 8 + q * 2) = make_float2(c[nt8][2], c[nt8][3]);
         }
         if (q == 0) { po[AQ_DH * AQ_DH + d] = cz[0]; po[AQ_DH * AQ_DH + d + 8] = cz[2]; }
-      }
-      // the running maxima (natural-log units, as attn_reduce_kernel expects) reach the warps that write them through shared memory
-      if ((ew & 3) == 0 && lane < 2) s_sc[half * 2 + lane] = (lane == 0 ? runM[0] : runM[1]) * kLn2;
-      umma::named_bar_sync(2, 256);
-      if (lane < 16) {
-        float* po = P.part + (((size_t)n * AQ_HEADS + hd) * P.chunks + chunk) * AQ_PART;
-        po[AQ_DH * AQ_DH + AQ_DH + mt * 16 + lane] = s_sc[hd];
+        if (lane < 16) po[AQ_DH * AQ_DH + AQ_DH + mt * 16 + lane] = (mh[(ew >> 1) & 1] + tk_d) * kLn2;
       }
     }
   }

@@ -628,6 +628,8 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
   // ---- network (diffusion.py:187-258) ----
   const int n_stage = cfg.n_levels - 1;
   ENG_REQUIRE((H >> n_stage) >= 1 && (W >> n_stage) >= 1, "H=%d, W=%d: the map vanishes after %d stride-2 stages", H, W, n_stage);
+  // the GroupNorm fold's border classes assume every level is >= 2 pixels in both directions
+  if ((H >> n_stage) < 2 || (W >> n_stage) < 2) fail(DS_ERR_UNSUPPORTED, "H=%d, W=%d: a level of the U-Net is 1 pixel wide or high (minimum input %d x %d)", H, W, 2 << n_stage, 2 << n_stage);
   int h = H, w = W;
   // Classifier-free guidance inside the sampling loop: both halves of the doubled batch share the latent and the timestep and
   // differ only through the condition, which first enters in downs.0.1: init_conv and downs.0.0 are evaluated once for the nb

@@ -273,6 +273,10 @@ class ConditionedUnet:
         n_stage = len(self.cfg["down_dims"]) - 1
         if (H >> n_stage) < 1 or (Wd >> n_stage) < 1:
             raise RuntimeError(f"H={H}, W={Wd}: the map vanishes after {n_stage} stride-2 stages")      # torch: "Output size is too small"
+        if (H >> n_stage) < 2 or (Wd >> n_stage) < 2:
+            # the GroupNorm fold's border classes (top / middle / bottom x left / middle / right) assume every level is >= 2 pixels
+            # in both directions: a 1-pixel level is at the same time a first and a last row / column
+            raise NotImplementedError(f"H={H}, W={Wd}: a level of the U-Net is 1 pixel wide or high (minimum input {2 << n_stage} x {2 << n_stage})")
         if self._engine is not None and taps is None and self.use_engine and condition is not None:
             return self._engine.forward(x.to(self.device, torch.float32).contiguous(), time.to(self.device, torch.long).contiguous(),
                                         condition.to(self.device, torch.float32).contiguous())

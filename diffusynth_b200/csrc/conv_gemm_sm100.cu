@@ -271,8 +271,11 @@ __device__ __forceinline__ uint32_t pack16_epi(float lo, float hi) {   // one F2
 // instructions and the role warps evict each other from the instruction cache): 0 = everything (fp32 / ragged outputs),
 // 1 = 16-bit output with full chunks, no activation, no residual (the 1x1 convolutions), 2 = + GELU (conv1), 3 = + residual (conv2),
 // 4 = as 1 without GroupNorm fold and per-sample bias (to_out, res_conv: value = acc + e2[col]; a third of the instructions of 1).
+// EPI = 4 with one CTA per MMA (the plain 1x1 convolutions to_out / res_conv: short K loops, latency-bound epilogues) is compiled for
+// TWO resident CTAs per SM (<= 80 registers; the launcher then gives each CTA half of the shared memory and at most 256 TMEM columns):
+// while one CTA waits for its accumulator or its stores, the other one runs.
 template <int BK, int CG, int EPI>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, (EPI == 4 && CG == 1) ? 2 : 1)
 conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ ConvGemmDev P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x sps x (A | B)] | barriers | stats partials | sbias | tables e2, e1 | K-block table
@@ -902,15 +905,23 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     DS_REQUIRE(r == CUDA_SUCCESS, "ds_conv_gemm: cuTensorMapEncodeTiled(B) failed with %d (K=%lld Cout_pad=%d)", (int)r, K, a->Cout_pad);
   }
 
+  // epilogue specialisation (see the kernel): the main path needs a 16-bit output whose every chunk is full
+  int epi = 0;
+  if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !knobs().generic_epi) {
+    if (a->act == 0) epi = a->d_residual ? 3 : (!a->d_e1 && !a->d_sbias && !a->d_stats_in) ? 4 : 1;
+    else if (!a->d_residual) epi = 2;
+  }
+  // two resident CTAs per SM for the plain 1x1 convolutions whose accumulator pair fits half of the tensor memory (see the kernel)
+  const bool two_per_sm = epi == 4 && P.cg == 1 && 2 * a->BN <= 256;
   const size_t fixed_bytes = smem_fixed_bytes(a);
-  const size_t budget = smem_budget(a);
+  const size_t budget = two_per_sm ? (fixed_bytes < 111 * 1024 ? 111 * 1024 - fixed_bytes : 0) : smem_budget(a);
   // K-blocks per stage: one barrier round trip per stage costs a few hundred cycles on the single MMA-issuing thread, so every
   // stage should carry >= ~384 cycles of tensor work (BK/16 MMAs of BN/2 cycles each per K-block) while >= 4 stages still fit.
   P.sps = 1;
   {
     const size_t sub = (size_t)P.stage_a_bytes + P.stage_b_bytes;
     const int cyc = (a->BK / 16) * (a->BN / 2);
-    const int max_sps = knobs().max_sps;          // 4: the producer keeps at most 4 table entries in registers
+    const int max_sps = two_per_sm ? 1 : knobs().max_sps;          // 4: the producer keeps at most 4 table entries in registers
     const int min_stages = knobs().min_stages;    // 3: three stages already saturate the pipeline (measured); deeper rings buy nothing
     const int cyc_target = knobs().sps_cyc;       // 768: measured, two barrier round trips per ~768 MMA cycles keep the single issuing thread off the critical path
     while (P.sps < max_sps && P.sps * cyc < cyc_target && P.sps < P.num_kb && (size_t)(P.sps + 1) * sub * min_stages <= budget) ++P.sps;
@@ -924,7 +935,8 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   P.stages = stages;
   const size_t smem = fixed_bytes + stages * stage_bytes;
 
-  int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  const int slots = two_per_sm ? 2 * num_sms() : num_sms();
+  int grid = P.num_tiles < slots ? P.num_tiles : slots;
   if (P.cg == 2) { const int pairs = num_sms() / 2; grid = 2 * (P.num_tiles < pairs ? P.num_tiles : pairs); }
   static unsigned long long* dbg_buf = nullptr;
   P.dbg_buf = nullptr;
@@ -932,12 +944,6 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     if (!dbg_buf) DS_CHECK_CUDA(cudaMalloc(&dbg_buf, sizeof(unsigned long long) * 16 * 1024));
     DS_CHECK_CUDA(cudaMemsetAsync(dbg_buf, 0, sizeof(unsigned long long) * 16 * 1024, stream));
     P.dbg_buf = dbg_buf;
-  }
-  // epilogue specialisation (see the kernel): the main path needs a 16-bit output whose every chunk is full
-  int epi = 0;
-  if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !knobs().generic_epi) {
-    if (a->act == 0) epi = a->d_residual ? 3 : (!a->d_e1 && !a->d_sbias && !a->d_stats_in) ? 4 : 1;
-    else if (!a->d_residual) epi = 2;
   }
 #define DS_LAUNCH_CONV(BKV, CGV, EPIV)                                                                                                \
   do {                                                                                                                                \

@@ -40,6 +40,7 @@ struct __align__(16) ConvGemmDev {
   float inv_n_tiles_n, inv_tiles_m, inv_groups, inv_tiles_w, inv_Wb;   // reciprocals for fast_divmod
   unsigned long long* dbg_buf;      // DS_CONV_DBG & 64: per-CTA wait-cycle counters [grid][8]
   int dbg;                          // DS_CONV_DBG bitmask (profiling experiments): 1 = no global stores, 2 = no TMEM loads, 4 = no MMA issue
+  int nacc;                         // accumulators in tensor memory: 2 (double-buffered) or 1 (two CTAs per SM, BN > 128)
   int sps;                          // K-blocks per pipeline stage (generic mode): keeps >= ~384 MMA cycles behind every barrier round trip
   unsigned stage_a_bytes, stage_b_bytes;
   int Cout, Cout_pad;
@@ -300,7 +301,8 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
   const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;           // 0 = leader of the pair
   const int w_first = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int w_step = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const uint32_t tmem_cols = (2 * P.BN <= 32) ? 32u : (2 * P.BN <= 64) ? 64u : (2 * P.BN <= 128) ? 128u : (2 * P.BN <= 256) ? 256u : 512u;
+  const int acc_cols = P.nacc * P.BN;      // nacc accumulators of BN columns (2 = double-buffered; 1 = two CTAs per SM share the tensor memory)
+  const uint32_t tmem_cols = (acc_cols <= 32) ? 32u : (acc_cols <= 64) ? 64u : (acc_cols <= 128) ? 128u : (acc_cols <= 256) ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2; ++s)
@@ -451,7 +453,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       }
       if (elect_one_sync()) { if (CG == 2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]); }       // accumulator complete
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == P.nacc) { acc = 0; acc_phase ^= 1u; }
     }
     if (timed && lane == 0) {
       P.dbg_buf[blockIdx.x * 16 + 2] = (unsigned long long)w_full; P.dbg_buf[blockIdx.x * 16 + 3] = (unsigned long long)w_tmem;
@@ -477,7 +479,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(&stats_empty[acc]);
         stats_publish(stats_sample(P.stats_out, P.stats_slots, t.n), P.stats_slots, t.slot, s, q, P.out_inv_count, P.eps, lane);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == P.nacc) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -728,7 +730,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
         __syncwarp();
       }
       if (epi_timed) e_tail += clock64() - te2;
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == P.nacc) { acc = 0; acc_phase ^= 1u; }
     }
     if (epi_timed && ew == 0 && lane == 0) {
       P.dbg_buf[blockIdx.x * 16 + 11] = (unsigned long long)e_pro; P.dbg_buf[blockIdx.x * 16 + 12] = (unsigned long long)e_chunks;
@@ -912,9 +914,13 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
     else if (!a->d_residual) epi = 2;
   }
   // two resident CTAs per SM for the plain 1x1 convolutions whose accumulator pair fits half of the tensor memory (see the kernel)
-  const bool two_per_sm = epi == 4 && P.cg == 1 && 2 * a->BN <= 256;
+  // (BN <= 128: each CTA keeps its double-buffered accumulator in half of the tensor memory; BN <= 256: a single accumulator per CTA,
+  // the other CTA's work covers the wait between a tile's MMAs and its epilogue)
   const size_t fixed_bytes = smem_fixed_bytes(a);
-  const size_t budget = two_per_sm ? (fixed_bytes < 111 * 1024 ? 111 * 1024 - fixed_bytes : 0) : smem_budget(a);
+  const size_t half_budget = fixed_bytes < 111 * 1024 ? 111 * 1024 - fixed_bytes : 0;
+  const bool two_per_sm = epi == 4 && P.cg == 1 && a->ntaps == 1 && half_budget >= 2 * ((size_t)P.stage_a_bytes + P.stage_b_bytes);
+  P.nacc = (two_per_sm && 2 * a->BN > 256) ? 1 : 2;
+  const size_t budget = two_per_sm ? half_budget : smem_budget(a);
   // K-blocks per stage: one barrier round trip per stage costs a few hundred cycles on the single MMA-issuing thread, so every
   // stage should carry >= ~384 cycles of tensor work (BK/16 MMAs of BN/2 cycles each per K-block) while >= 4 stages still fit.
   P.sps = 1;

@@ -1,6 +1,12 @@
-# multi-GPU check: torchrun bench at N ranks (run under gpurun --gpus N)
-N=${1:-2}
+# usage: bash tools_dev/run_multi_gpu.sh N [workloads...]   (on the GPU box, through gpurun --gpus N): one JSON line per workload into gpurun_out/
+N=$1; shift
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/smi_multi.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 2 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
-echo "rc=$?"; tail -c 1500 gpurun_out/bench_n$N.json; tail -3 gpurun_out/bench_n$N.err
+nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
+for w in "${@:-text2timbre sharded1024 modify}"; do
+  for wl in $w; do
+    extra=""; [ "$wl" = "text2timbre" ] && extra="--warmup 3"
+    timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 200)) bench.py --gpus $N --workload $wl --steps 2 $extra \
+      > gpurun_out/bench_${wl}_n$N.json 2> gpurun_out/bench_${wl}_n$N.err
+    echo "$wl n=$N rc=$?"; head -c 400 gpurun_out/bench_${wl}_n$N.json; echo; tail -n 2 gpurun_out/bench_${wl}_n$N.err | cut -c1-300
+  done
+done

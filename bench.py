@@ -355,6 +355,18 @@ def run_b200(args):
         step_ms = (graph_ms - (sum(tail_ms.values()) if loop.has_tail else 0.0)) / loop.n_iter
         algo_step_tflop = 2 * BATCH * 136.70e9 / 1e12
         launches = pipe.last_launches
+        # ---- latency of the batch-1 per-note path (track_maker.py:228-283): one 2-second note (width 48), same step count, cached graph ----
+        inst = (torch.randn((1, 4, 128, 64), generator=torch.Generator().manual_seed(22)) * 0.9).to(dev)      # synthetic instrument latent
+        note = lambda: pipe.synthesize_note(inst, cond_all[:1].to(dev), 2.0, sample_steps=args.sample_steps)
+        note(); note()
+        lat = []
+        for _ in range(5):
+            torch.cuda.synchronize()
+            e0.record(); note(); e1.record()
+            torch.cuda.synchronize()
+            lat.append(e0.elapsed_time(e1))
+        note_latency = dict(ms=float(np.median(lat)), batch=1, width=48, sample_steps=args.sample_steps,
+                            what="TextToTimbre.synthesize_note: dynamic-mask inpainting + VQ + decoder + iSTFT, one cached graph launch")
         # ---- CPU baseline doubling as the validation reference: the same prompt + host noise on the GPU ----
         cpu, validation = None, dict(finite=all_finite)
         if world == 1:
@@ -403,7 +415,8 @@ def run_b200(args):
                              "(64 timbres); frac = max(algorithmic FLOPs / sustained bf16 peak, algorithmic bytes / HBM copy peak) / measured time",
                         peaks=dict(tensor_tflops=pk["tf_sustained"], hbm_gbs=pk["hbm"], source=pk["source"]),
                         unet_eval=unet_fams, tail=tail_fams),
-                    unet_eval_ms_eager=sum(unet_ms.values()), tail_ms_eager=sum(tail_ms.values()), sampling_graph_ms=graph_ms)
+                    unet_eval_ms_eager=sum(unet_ms.values()), tail_ms_eager=sum(tail_ms.values()), sampling_graph_ms=graph_ms,
+                    note_latency=note_latency)
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "s_per_timbre", "s_per_unet_step", "split_s")}
         emit(json.dumps(line))

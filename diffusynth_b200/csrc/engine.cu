@@ -370,6 +370,7 @@ struct UnetPlan {
   int launches = 0;
   float* cond = nullptr;      // [N][L] input
   float* eps = nullptr;       // [N][out_dim][H][W] output
+  size_t cond_bytes = 0;      // N * L floats, or N int64 labels (condition_type "instrument_family")
   float* sbias = nullptr;     // [N][c_total]
   float* tbias = nullptr;
   std::map<std::string, void*> scratch;
@@ -390,7 +391,8 @@ void Unet::pack() {
 
   auto blk = [&](const std::string& p, int dim, int dim_out, bool has_time) {
     Block b;
-    b.p = p; b.dim = dim; b.dim_out = dim_out; b.has_time = has_time;
+    b.p = p; b.dim = dim; b.dim_out = dim_out; b.has_time = has_time && cfg.with_time_emb;
+    has_time = b.has_time;
     const HostTensor& dw = need(sd, p + "ds_conv.weight", {dim, 1, 7, 7});
     need(sd, p + "ds_conv.bias", {dim});
     std::vector<float> dwt((size_t)49 * dim);
@@ -490,10 +492,17 @@ void Unet::pack() {
     c_total = off;
     c_w = A.upload(w); c_b = A.upload(b);
   }
-  lab_w = A.upload(need(sd, "label_embedding.embedding.weight", {L, L}).v);
-  lab_b = A.upload(need(sd, "label_embedding.embedding.bias", {L}).v);
-  tm1_w = A.upload(need(sd, "time_mlp.1.weight", {td, dd[0]}).v); tm1_b = A.upload(need(sd, "time_mlp.1.bias", {td}).v);
-  tm3_w = A.upload(need(sd, "time_mlp.3.weight", {td, td}).v); tm3_b = A.upload(need(sd, "time_mlp.3.bias", {td}).v);
+  if (cfg.condition_type == 0) {            // ConditionalEmbedding: nn.Linear for text embeddings, nn.Embedding for class labels (diffusion_components.py:155-168)
+    lab_w = A.upload(need(sd, "label_embedding.embedding.weight", {L, L}).v);
+    lab_b = A.upload(need(sd, "label_embedding.embedding.bias", {L}).v);
+  } else {
+    lab_w = A.upload(need(sd, "label_embedding.embedding.weight", {cfg.n_label_class + 1, L}).v);
+    lab_b = nullptr;
+  }
+  if (cfg.with_time_emb) {
+    tm1_w = A.upload(need(sd, "time_mlp.1.weight", {td, dd[0]}).v); tm1_b = A.upload(need(sd, "time_mlp.1.bias", {td}).v);
+    tm3_w = A.upload(need(sd, "time_mlp.3.weight", {td, td}).v); tm3_b = A.upload(need(sd, "time_mlp.3.bias", {td}).v);
+  }
   // stem as a GEMM over im2col patches: [Cout, Cin, 7, 7] -> [Cout_pad][ky*32 + kx*4 + ci] (8th pixel slot and ci >= Cin are zero)
   {
     const HostTensor& w0 = need(sd, "init_conv.weight", {dd[0], cfg.in_dim, 7, 7});
@@ -518,8 +527,10 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
   const int td = cfg.time_dim, L = cfg.label_emb_dim;
   nb = x_batch_mod > 0 ? x_batch_mod : N;
   const int NT = uniform_time ? 1 : N;
-  const long long t_stride = uniform_time ? 0 : net->t_total;
-  cond = A.alloc<float>((size_t)N * L, true);
+  const long long t_stride = (uniform_time || !cfg.with_time_emb) ? 0 : net->t_total;
+  const bool labels = cfg.condition_type == 1;      // integer class labels [N] (int64) instead of embeddings [N][L]
+  cond = static_cast<float*>(A.raw(labels ? (size_t)N * sizeof(long long) : (size_t)N * L * sizeof(float), true));
+  cond_bytes = labels ? (size_t)N * sizeof(long long) : (size_t)N * L * sizeof(float);
   eps = A.alloc<float>((size_t)N * cfg.out_dim * H * W, true);
   float* cemb = A.alloc<float>((size_t)N * L);
   sbias = A.alloc<float>((size_t)N * net->c_total);
@@ -546,11 +557,19 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
   // ---- condition path (step-invariant: once per sampling call) ----
   {
     float* cnd = cond; float* sb = sbias;
-    cond_ops.push_back([=](const Run& r) { ENG_CALL(ds_linear(cnd, L, nt->lab_w, nt->lab_b, cemb, L, Nn, L, L, 0, 0, r.s)); });
+    if (labels) {
+      const int rows = cfg.n_label_class + 1;
+      cond_ops.push_back([=](const Run& r) { ENG_CALL(ds_embedding_gather(nt->lab_w, reinterpret_cast<const long long*>(cnd), cemb, Nn, L, rows, r.s)); });
+    } else {
+      cond_ops.push_back([=](const Run& r) { ENG_CALL(ds_linear(cnd, L, nt->lab_w, nt->lab_b, cemb, L, Nn, L, L, 0, 0, r.s)); });
+    }
     cond_ops.push_back([=](const Run& r) { ENG_CALL(ds_linear(cemb, L, nt->c_w, nt->c_b, sb, c_total, Nn, L, c_total, 0, 0, r.s)); });
   }
   // ---- time path ----
-  {
+  if (!cfg.with_time_emb) {
+    // diffusion.py:107-109,211: no time terms; one row of per-channel biases (ds_conv.bias of every block), read with stride 0
+    ENG_CUDA(cudaMemcpy(tbias, net->t_b, (size_t)net->t_total * sizeof(float), cudaMemcpyDeviceToDevice));
+  } else {
     const int d0 = dd[0];
     float* tb = tbias;
     add([=](const Run& r) { ENG_CALL(ds_sinusoidal_embedding(r.t, sin, NT, d0, r.s)); });
@@ -1027,9 +1046,10 @@ int ds_unet_create(const ds_unet_config* cfg, ds_unet** out) {
   return guarded([&] {
     ENG_REQUIRE(cfg && out, "ds_unet_create: null argument");
     ENG_REQUIRE(cfg->n_levels >= 2 && cfg->n_levels <= DS_MAX_LEVELS, "ds_unet_create: n_levels=%d", cfg->n_levels);
-    if (cfg->attn_type != 0 || cfg->condition_type != 0 || !cfg->use_convnext || !cfg->with_time_emb)
-      fail(DS_ERR_UNSUPPORTED, "ds_unet_create: the module-level entry points implement the deployed family (ConvNeXt blocks, attn_type 'linear_add', "
-                               "condition_type 'natural_language_prompt', with_time_emb); the other variants run through the operator-level entries");
+    if (cfg->attn_type != 0 || !cfg->use_convnext || cfg->condition_type < 0 || cfg->condition_type > 1)
+      fail(DS_ERR_UNSUPPORTED, "ds_unet_create: the module-level entry points implement ConvNeXt blocks with attn_type 'linear_add' (text or class-label "
+                               "conditioning, with or without time embedding); 'linear_cat' and the ResNet-block variant run through the operator-level entries");
+    ENG_REQUIRE(cfg->condition_type == 0 || cfg->n_label_class >= 1, "ds_unet_create: n_label_class=%d", cfg->n_label_class);
     ENG_REQUIRE(cfg->down_dims[0] == cfg->up_dims[cfg->n_levels - 1] && cfg->up_dims[0] == cfg->down_dims[cfg->n_levels - 1], "ds_unet_create: down_dims / up_dims do not mirror");
     for (int i = 0; i < cfg->n_levels; ++i)
       ENG_REQUIRE(cfg->down_dims[i] > 0 && cfg->down_dims[i] % 32 == 0 && cfg->up_dims[i] > 0 && cfg->up_dims[i] % 32 == 0, "ds_unet_create: channel widths must be multiples of 32");
@@ -1049,13 +1069,17 @@ int ds_unet_load(ds_unet* h, const char* name, const float* data, const long lon
 int ds_unet_finalize(ds_unet* h) {
   return guarded([&] { ENG_REQUIRE(h, "ds_unet_finalize: null handle"); h->u.pack(); });
 }
-int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const float* d_cond, float* d_out, int N, int H, int W, void* stream) {
+int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const void* d_cond, float* d_out, int N, int H, int W, void* stream) {
   return guarded([&] {
-    ENG_REQUIRE(h && d_x && d_t && d_cond && d_out && N > 0 && H > 0 && W > 0, "ds_unet_forward: bad arguments");
+    ENG_REQUIRE(h && d_x && d_t && d_out && N > 0 && H > 0 && W > 0, "ds_unet_forward: bad arguments");
     UnetPlan* p = get_plan(&h->u, N, H, W, 0, 0);
     cudaStream_t s = (cudaStream_t)stream;
-    ENG_CUDA(cudaMemcpyAsync(p->cond, d_cond, (size_t)N * h->u.cfg.label_emb_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    p->run_cond(s);
+    if (d_cond == nullptr) {      // condition=None (diffusion.py:199-202, diffusion_components.py:279-283): no label_query / label_key terms
+      ENG_CUDA(cudaMemsetAsync(p->sbias, 0, (size_t)N * h->u.c_total * sizeof(float), s));
+    } else {
+      ENG_CUDA(cudaMemcpyAsync(p->cond, d_cond, p->cond_bytes, cudaMemcpyDeviceToDevice, s));
+      p->run_cond(s);
+    }
     p->run(d_x, d_t, s);
     ENG_CUDA(cudaMemcpyAsync(d_out, p->eps, (size_t)N * h->u.cfg.out_dim * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
   });
@@ -1145,7 +1169,7 @@ int ds_sample_graph_build(ds_unet* unet, ds_vqgan* vqgan, const ds_sample_buffer
     }
     cudaStream_t s = (cudaStream_t)stream;
     // warm-up outside capture (lazy one-time initialisations: function attributes, twiddle tables), then capture
-    ENG_CUDA(cudaMemcpyAsync(g.plan->cond, bufs->d_cond, (size_t)g.N * unet->u.cfg.label_emb_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(g.plan->cond, bufs->d_cond, g.plan->cond_bytes, cudaMemcpyDeviceToDevice, s));
     g.plan->run_cond(s);
     g.body(s, 1);
     g.tail(s);
@@ -1177,7 +1201,7 @@ int ds_sample_graph_run(ds_sample_graph* h, void* stream) {
     SampleGraph& g = h->g;
     cudaStream_t s = (cudaStream_t)stream;
     // the condition projections are step-invariant: once per call, outside the graph
-    ENG_CUDA(cudaMemcpyAsync(g.plan->cond, g.b.d_cond, (size_t)g.N * g.unet->cfg.label_emb_dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    ENG_CUDA(cudaMemcpyAsync(g.plan->cond, g.b.d_cond, g.plan->cond_bytes, cudaMemcpyDeviceToDevice, s));
     g.plan->run_cond(s);
     if (g.exec) ENG_CUDA(cudaGraphLaunch(g.exec, s));
     else { g.body(s, g.n_iter); g.tail(s); }

@@ -348,9 +348,10 @@ class DiffSynthSampler:
         coef = [self._coef(i, eta) for i in steps]
         loop.coef.copy_(torch.tensor(coef, dtype=torch.float32))
         loop.ttab.copy_(torch.tensor([self.timestep_map[i] for i in steps], dtype=torch.long))
-        cond = condition.to(self.device, torch.float32)
+        cond = condition.to(self.device, loop.cond.dtype)          # fp32 [B, L] text conditions, or int64 [B] class labels
         if cfg_on:
-            u = self.unconditional_condition.to(self.device, torch.float32).reshape(1, -1).expand(B, -1)
+            u = self.unconditional_condition.to(self.device, loop.cond.dtype)
+            u = u.reshape(1, -1).expand(B, -1) if cond.dim() == 2 else u.reshape(1).expand(B)       # :313-314
             loop.cond.copy_(torch.cat([u, cond]))
         else:
             loop.cond.copy_(cond)
@@ -447,7 +448,8 @@ class _GraphLoop:
         use_graph = os.environ.get("DS_NO_GRAPH", "0") != "1"      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
         if getattr(model, "_engine", None) is not None and model.use_engine:
             # module-level C ABI: the plan, the capture and the replay live in the library (ds_sample_graph_build / _run)
-            self.cond = torch.zeros((N, model.cfg["label_emb_dim"]), **f32)
+            self.cond = torch.zeros((N,), dtype=torch.long, device=dev) if model.cfg["condition_type"] == "instrument_family" \
+                else torch.zeros((N, model.cfg["label_emb_dim"]), **f32)
             self.tail = tail_factory.buffers(self.imgs[n_iter]) if tail_factory is not None else None
             b = engine.SampleBuffers()
             b.d_imgs, b.d_coef, b.d_ttab, b.d_cond = self.imgs.data_ptr(), self.coef.data_ptr(), self.ttab.data_ptr(), self.cond.data_ptr()

@@ -277,9 +277,10 @@ class ConditionedUnet:
             # the GroupNorm fold's border classes (top / middle / bottom x left / middle / right) assume every level is >= 2 pixels
             # in both directions: a 1-pixel level is at the same time a first and a last row / column
             raise NotImplementedError(f"H={H}, W={Wd}: a level of the U-Net is 1 pixel wide or high (minimum input {2 << n_stage} x {2 << n_stage})")
-        if self._engine is not None and taps is None and self.use_engine and condition is not None:
+        if self._engine is not None and taps is None and self.use_engine:
+            cdt = torch.long if self.cfg["condition_type"] == "instrument_family" else torch.float32
             return self._engine.forward(x.to(self.device, torch.float32).contiguous(), time.to(self.device, torch.long).contiguous(),
-                                        condition.to(self.device, torch.float32).contiguous())
+                                        None if condition is None else condition.to(self.device, cdt).contiguous())
         pl = self.plan(N, H, Wd)
         pl.x.copy_(x.to(self.device, torch.float32))
         pl.t.copy_(time.to(self.device, torch.long))

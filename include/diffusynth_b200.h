@@ -252,13 +252,14 @@ typedef struct ds_unet_config {
   int32_t n_levels;                        /* len(down_dims) == len(up_dims) */
   int32_t down_dims[DS_MAX_LEVELS], up_dims[DS_MAX_LEVELS];
   int32_t mid_depth;                       /* <= 0: 3 */
-  int32_t with_time_emb;                   /* must be 1 */
+  int32_t with_time_emb;                   /* 0: no time_mlp, blocks without their mlp (diffusion.py:107-109) */
   int32_t time_dim;                        /* <= 0: 4 * down_dims[0] (diffusion.py:99) */
   int32_t use_convnext;                    /* must be 1 (the ResNet-block variant runs through the operator-level entries) */
   int32_t convnext_mult;                   /* <= 0: 2 */
   int32_t attn_type;                       /* 0 = "linear_add" (deployed, app.py:40) */
-  int32_t condition_type;                  /* 0 = "natural_language_prompt" */
+  int32_t condition_type;                  /* 0 = "natural_language_prompt" (d_cond fp32 [N][label_emb_dim]), 1 = "instrument_family" (d_cond int64 [N]) */
   int32_t label_emb_dim;
+  int32_t n_label_class;                   /* condition_type 1: the embedding table has n_label_class + 1 rows (diffusion.py:63-64) */
 } ds_unet_config;
 typedef struct ds_unet ds_unet;
 int ds_unet_create(const ds_unet_config* cfg, ds_unet** out);       /* -4 for a variant outside the deployed family */
@@ -267,16 +268,17 @@ void ds_unet_destroy(ds_unet* h);
 int ds_unet_load(ds_unet* h, const char* name, const float* data, const long long* shape, int ndim);
 /* Pack the loaded parameters for the device (fails naming the first missing / mis-shaped parameter).  Invalidates earlier plans. */
 int ds_unet_finalize(ds_unet* h);
-/* model(x, time, condition) (diffusion.py:187-258): d_x fp32 [N,in_dim,H,W], d_t int64 [N], d_cond fp32 [N,label_emb_dim]
-   -> d_out fp32 [N,out_dim,H,W].  The call sequence of a given (N, H, W) is built on first use and replayed afterwards. */
-int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const float* d_cond, float* d_out, int N, int H, int W,
+/* model(x, time, condition) (diffusion.py:187-258): d_x fp32 [N,in_dim,H,W], d_t int64 [N], d_cond fp32 [N,label_emb_dim] (or int64
+   [N] class labels; NULL = condition=None) -> d_out fp32 [N,out_dim,H,W].  The call sequence of a given (N, H, W) is built on first
+   use and replayed afterwards. */
+int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const void* d_cond, float* d_out, int N, int H, int W,
                     void* stream);
 /* The plan of one evaluation shape, for hosts that drive the sampling loop themselves (generic sampler loops, per-step probes):
    x_batch_mod > 0 with uniform_time = the guidance-doubled batch of DiffSynthSampler.ddim_sample (:307-319): N = 2 * x_batch_mod
    samples read x_batch_mod latents and ONE timestep (d_t[0]).  d_cond / d_eps are the plan's own device buffers. */
 typedef struct ds_unet_plan_io {
   int32_t plan;                            /* plan id for ds_unet_plan_run* */
-  float* d_cond;                           /* [N][label_emb_dim]: write the conditions here, then ds_unet_plan_run_cond */
+  float* d_cond;                           /* [N][label_emb_dim] (int64 [N] for class labels): write the conditions here, then ds_unet_plan_run_cond */
   float* d_eps;                            /* [N][out_dim][H][W]: result of ds_unet_plan_run */
   int32_t launches, cond_launches;         /* kernels per ds_unet_plan_run / ds_unet_plan_run_cond */
 } ds_unet_plan_io;

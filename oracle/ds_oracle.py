@@ -194,7 +194,7 @@ def sample_loop(model, sch: Schedule, shape, cond: Tensor, uncond: Optional[Tens
         if cfg_scale == 1.0:
             eps_u, eps_c = None, model(img, t_mapped, cond)
         else:
-            u = uncond.unsqueeze(0).repeat(B, 1)
+            u = uncond.unsqueeze(0).repeat(*([B] + [1] * uncond.dim()))      # :313-314 (a vector for text conditions, a scalar label for class conditions)
             out = model(torch.cat([img, img]), torch.cat([t_mapped, t_mapped]), torch.cat([u, cond]))
             eps_u, eps_c = out[:B], out[B:]
         z, _ = noise_layout_repeat(noise_draws[k], B, W, train_width)

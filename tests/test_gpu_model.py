@@ -240,6 +240,30 @@ def test_timbre_modification_pipeline_parity():
     assert e_guide < BF16_TOL and e_lat < BF16_TOL and e_spec < BF16_TOL and e_wave < 2 * BF16_TOL
 
 
+def test_graph_loop_class_label_conditioning():
+    """condition_type="instrument_family" through the library's sampling graph with classifier-free guidance: integer labels,
+    the unconditional condition is a scalar label (DiffSynthSampler.py:313-317 repeats it per sample)."""
+    from diffusynth_b200 import DiffSynthSampler
+    cfg, sd, _, _, _ = cases.unet_case("small_family_w16")
+    net = _unet(cfg, sd)
+    B, steps, Hh, Wd = 3, 4, 32, 32
+    draws = cases.randn((1 + steps, B, 4, Hh, 64), 64)
+    cond, uncond = torch.tensor([3, 0, 9]), torch.tensor(11)
+    s = DiffSynthSampler(1000, device="cuda", mute=True, max_batchsize=B, height=Hh)
+    s.noise_feed = draws[1:]
+    s.activate_classifier_free_guidance(4, uncond.cuda())
+    s.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    imgs, _ = s.sample(net, (B, 4, Hh, Wd), return_tensor=True, condition=cond.cuda(), initial_noise=draws[0].cuda())
+    assert s.last_graph_launches > 0 and next(iter(s._graphs.values())).sgraph is not None
+    sch = O.Schedule(1000)
+    sch.respace(list(np.linspace(0, 999, steps, dtype=np.int32)))
+    with torch.no_grad():
+        ref = O.sample_loop(lambda x, t, c: O.unet_forward(sd, x, t, c), sch, (B, 4, Hh, Wd), cond, uncond, 4, draws)
+    errs = [rel(a, b) for a, b in zip(imgs, ref)]
+    print(f"\n[class labels] latents rel-L2 per step: {[f'{e:.1e}' for e in errs]}")
+    assert max(errs) < BF16_TOL
+
+
 @pytest.mark.parametrize("mode", ["inpaint", "guided", "nocfg", "wide"])
 def test_graph_loop_variants_small_unet(mode):
     """The CUDA-graph loop with the B200 U-Net in its other modes (inpaint blend with a fixed mask, image-guided start,

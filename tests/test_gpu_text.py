@@ -62,3 +62,19 @@ def test_text_batch_of_distinct_prompts():
     torch.cuda.synchronize()
     print(f"\n64 prompts x 16 tokens: {e0.elapsed_time(e1) / 5:.2f} ms per batch ({enc.num_launches(64, 16)} launches); batched vs single rel-L2 {r:.2e}")
     assert r < 2e-3
+
+
+def test_generate_from_tokens():
+    """text2sound.py:89-134 with the text front end on the device: B distinct tokenised prompts + one negative prompt -> waveforms."""
+    from diffusynth_b200 import TextToTimbre
+    from diffusynth_b200.text import TextEncoder, text_random_state_dict
+    enc = TextEncoder(device="cuda").load_state_dict(text_random_state_dict(seed=7))
+    pipe = TextToTimbre.random_init(device="cuda", seed=0)
+    ids, mask = _prompts(3, 10, 5)
+    nid, nmask = _prompts(1, 4, 6)
+    out = pipe.generate_from_tokens(enc, ids, mask, nid, nmask, steps=2, cfg_scale=6.0, width=64, seed=3)
+    cond = enc.get_text_features(ids, mask)
+    uncond = enc.get_text_features(nid, nmask)[0]
+    ref = pipe.generate(cond, uncond, steps=2, cfg_scale=6.0, width=64, seed=3)
+    assert tuple(out.waveforms.shape) == (3, 65280) and torch.isfinite(out.waveforms).all()
+    assert torch.equal(out.waveforms, ref.waveforms)

@@ -1,5 +1,5 @@
 """Timing and accuracy of ds_dwconv7 on the level-0..2 shapes of the U-Net (same process, 20 launches each).
-DS_DWCONV_HACC=0/1 selects fp32 / paired-row fp16 accumulation (read once per process: run twice to compare).
+DS_LIB_PATH selects an A/B build.
 Error: relative L2 against an fp32 torch depthwise convolution of the same 16-bit inputs (first 4 samples)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +7,6 @@ import torch
 import torch.nn.functional as F
 from diffusynth_b200 import ops
 N = 128
-print("DS_DWCONV_HACC =", os.environ.get("DS_DWCONV_HACC", "(default)"))
 for C0, C1, H, W in [(96, 0, 128, 64), (96, 192, 128, 64), (192, 0, 64, 32), (384, 0, 32, 16), (384, 384, 16, 8)]:
     C = C0 + C1
     g = torch.Generator(device="cuda").manual_seed(1)

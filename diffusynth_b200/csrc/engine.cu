@@ -319,7 +319,7 @@ static ds_conv_gemm_args conv_args(Arena& A, const PackedConv& pc, const void* s
   return a;
 }
 
-struct Run { const float* x; const long long* t; cudaStream_t s; };
+struct Run { const float* x; const long long* t; cudaStream_t s; bool no_cond = false; };
 typedef std::function<void(const Run&)> Op;
 
 static const int HEADS = 4, DHEAD = 32, HID = HEADS * DHEAD;
@@ -331,8 +331,10 @@ struct Block {
   std::string p;
   int dim = 0, dim_out = 0, t_off = 0;
   bool has_time = true, has_res = false;
+  int t_dim = 0;                  // width of this block's slice of the fused time projection (dim for ConvNeXt, dim_out for ResNet blocks)
   float* dw = nullptr;            // [49][C]
   PackedConv conv1, conv2, res;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;      // ResNet-block GroupNorm(groups) affines
 };
 struct Attn {
   std::string p;
@@ -376,7 +378,7 @@ struct UnetPlan {
   std::map<std::string, void*> scratch;
   UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut);
   void run_cond(cudaStream_t s) { Run r{nullptr, nullptr, s}; for (auto& f : cond_ops) f(r); }
-  void run(const float* x, const long long* t, cudaStream_t s) { Run r{x, t, s}; for (auto& f : ops) f(r); }
+  void run(const float* x, const long long* t, cudaStream_t s, bool no_cond = false) { Run r{x, t, s, no_cond}; for (auto& f : ops) f(r); }
 };
 
 void Unet::pack() {
@@ -393,6 +395,32 @@ void Unet::pack() {
     Block b;
     b.p = p; b.dim = dim; b.dim_out = dim_out; b.has_time = has_time && cfg.with_time_emb;
     has_time = b.has_time;
+    if (!cfg.use_convnext) {
+      // ResnetBlock (diffusion_components.py:59-104): two (conv3x3 -> GroupNorm(groups) -> SiLU) blocks, the time embedding added in
+      // between; the residual projection is a 1x1 conv or -- where the reference uses nn.Identity -- an identity matrix, so that the
+      // residual add and the statistics of the block's output stay in the conv epilogue
+      b.t_dim = dim_out;
+      b.conv1 = pack_conv_s1(A, need(sd, p + "block1.proj.weight", {dim_out, dim, 3, 3}), need(sd, p + "block1.proj.bias", {dim_out}).v.data(), nullptr, nullptr);
+      b.conv2 = pack_conv_s1(A, need(sd, p + "block2.proj.weight", {dim_out, dim_out, 3, 3}), need(sd, p + "block2.proj.bias", {dim_out}).v.data(), nullptr, nullptr);
+      b.g1 = A.upload(need(sd, p + "block1.norm.weight", {dim_out}).v); b.b1 = A.upload(need(sd, p + "block1.norm.bias", {dim_out}).v);
+      b.g2 = A.upload(need(sd, p + "block2.norm.weight", {dim_out}).v); b.b2 = A.upload(need(sd, p + "block2.norm.bias", {dim_out}).v);
+      b.has_res = true;
+      if (dim != dim_out) {
+        b.res = pack_conv_s1(A, need(sd, p + "res_conv.weight", {dim_out, dim, 1, 1}), need(sd, p + "res_conv.bias", {dim_out}).v.data(), nullptr, nullptr);
+      } else {
+        HostTensor eye;
+        eye.shape = {dim, dim, 1, 1};
+        eye.v.assign((size_t)dim * dim, 0.f);
+        for (int c = 0; c < dim; ++c) eye.v[(size_t)c * dim + c] = 1.f;
+        std::vector<float> zero(dim, 0.f);
+        b.res = pack_conv_s1(A, eye, zero.data(), nullptr, nullptr);
+      }
+      if (has_time) { need(sd, p + "mlp.1.weight", {dim_out, td}); need(sd, p + "mlp.1.bias", {dim_out}); }
+      blocks[p] = b;
+      block_order.push_back(p);
+      return;
+    }
+    b.t_dim = dim;
     const HostTensor& dw = need(sd, p + "ds_conv.weight", {dim, 1, 7, 7});
     need(sd, p + "ds_conv.bias", {dim});
     std::vector<float> dwt((size_t)49 * dim);
@@ -419,7 +447,8 @@ void Unet::pack() {
     a.out = pack_bias_only(A, need(sd, p + "fn.fn.to_out.0.bias", {dim}).v.data(), HID, dim);
     a.gamma = A.upload(need(sd, p + "fn.fn.to_out.1.weight", {dim}).v);
     a.beta = A.upload(need(sd, p + "fn.fn.to_out.1.bias", {dim}).v);
-    need(sd, p + "fn.fn.label_query.weight", {HID, L}); need(sd, p + "fn.fn.label_query.bias", {HID});
+    const char* second = cfg.attn_type == 0 ? "label_query" : "label_value";      // LinearCrossAttentionAdd / LinearCrossAttention
+    need(sd, p + "fn.fn." + second + ".weight", {HID, L}); need(sd, p + "fn.fn." + second + ".bias", {HID});
     need(sd, p + "fn.fn.label_key.weight", {HID, L}); need(sd, p + "fn.fn.label_key.bias", {HID});
     attns[p] = a;
     attn_order.push_back(p);
@@ -457,17 +486,17 @@ void Unet::pack() {
     for (const std::string& p : block_order) {
       Block& bk = blocks[p];
       bk.t_off = off;
-      const std::vector<float>& dwb = sd[p + "ds_conv.bias"].v;
+      const std::vector<float> dwb = cfg.use_convnext ? sd[p + "ds_conv.bias"].v : std::vector<float>((size_t)bk.t_dim, 0.f);
       if (bk.has_time) {
         const std::vector<float>& mw = sd[p + "mlp.1.weight"].v;
         const std::vector<float>& mb = sd[p + "mlp.1.bias"].v;
         w.insert(w.end(), mw.begin(), mw.end());
-        for (int c = 0; c < bk.dim; ++c) b.push_back(mb[c] + dwb[c]);
+        for (int c = 0; c < bk.t_dim; ++c) b.push_back(mb[c] + dwb[c]);
       } else {
-        w.insert(w.end(), (size_t)bk.dim * td, 0.f);
+        w.insert(w.end(), (size_t)bk.t_dim * td, 0.f);
         b.insert(b.end(), dwb.begin(), dwb.end());
       }
-      off += bk.dim;
+      off += bk.t_dim;
     }
     t_total = off;
     t_w = A.upload(w); t_b = A.upload(b);
@@ -479,7 +508,11 @@ void Unet::pack() {
     for (const std::string& p : attn_order) {
       Attn& a = attns[p];
       a.c_off = off;
-      for (const char* nm : {"label_query", "label_key"}) {
+      // linear_add: [label_query | label_key | 0] added to q, k in the to_qkv epilogue; linear_cat: [label_key | label_value | 0] = the
+      // extra key / value token consumed by ds_attn_finalize_cat
+      const char* first_nm = cfg.attn_type == 0 ? "label_query" : "label_key";
+      const char* second_nm = cfg.attn_type == 0 ? "label_key" : "label_value";
+      for (const char* nm : {first_nm, second_nm}) {
         const std::vector<float>& lw = sd[p + "fn.fn." + nm + ".weight"].v;
         const std::vector<float>& lb = sd[p + "fn.fn." + nm + ".bias"].v;
         w.insert(w.end(), lw.begin(), lw.end());
@@ -575,7 +608,8 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
     add([=](const Run& r) { ENG_CALL(ds_sinusoidal_embedding(r.t, sin, NT, d0, r.s)); });
     add([=](const Run& r) { ENG_CALL(ds_linear(sin, d0, nt->tm1_w, nt->tm1_b, t1, td, NT, d0, td, 0, 1, r.s)); });
     add([=](const Run& r) { ENG_CALL(ds_linear(t1, td, nt->tm3_w, nt->tm3_b, temb, td, NT, td, td, 0, 0, r.s)); });
-    add([=](const Run& r) { ENG_CALL(ds_linear(temb, td, nt->t_w, nt->t_b, tb, t_total, NT, td, t_total, 1, 0, r.s)); });
+    const int act_in = cfg.use_convnext ? 1 : 2;      // per-block mlp: GELU (ConvNextBlock) or SiLU (ResnetBlock) on the time embedding
+    add([=](const Run& r) { ENG_CALL(ds_linear(temb, td, nt->t_w, nt->t_b, tb, t_total, NT, td, t_total, act_in, 0, r.s)); });
   }
 
   auto conv = [&](const PackedConv& pc, const void* s0, int C0, const void* s1, int C1, int n_, int h, int w, const ConvOpts& o, Stats* st_out) {
@@ -615,6 +649,38 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
       conv(b.conv2, y, b.conv1.cout, nullptr, 0, n_, h, w, o, st_o_out); }
     return Act{ob, b.dim_out};
   };
+  const int RG = cfg.resnet_block_groups > 0 ? cfg.resnet_block_groups : 8;
+  auto gn_silu = [&](const act_t* xin, int c, int h, int w, int n_, const float* gamma, const float* beta, const char* role) -> act_t* {
+    // GroupNorm(groups, eps 1e-5) + SiLU as statistics + apply passes (the VQGAN GroupNorm kernels)
+    float* part = A.alloc<float>((size_t)n_ * RG * 32 * 2);
+    act_t* out = scr(role, n_, h, w, c);
+    const long long hw = (long long)h * w;
+    add([=](const Run& r) { ENG_CALL(ds_group_stats(xin, part, n_, c, c, RG, hw, 32, r.s)); });
+    add([=](const Run& r) { ENG_CALL(ds_gn_act(xin, out, part, 32, gamma, beta, n_, c, c, RG, hw, 1e-5f, 2, r.s)); });
+    return out;
+  };
+  auto res_block = [&](const std::string& p, Act s0, Act s1, int h, int w, int n_, int s0_mod, Stats* st_o_out) -> Act {
+    const Block& b = net->blocks.at(p);
+    ENG_REQUIRE(s0.c + s1.c == b.dim, "block %s: %d + %d input channels, expected %d", p.c_str(), s0.c, s1.c, b.dim);
+    act_t* y1 = scr("rb_y1", n_, h, w, b.dim_out);
+    { ConvOpts o; o.out = y1; o.out_c = b.dim_out; o.src_batch_mod = s0_mod; conv(b.conv1, s0.p, s0.c, s1.p, s1.c, n_, h, w, o, nullptr); }
+    act_t* h1 = gn_silu(y1, b.dim_out, h, w, n_, b.g1, b.b1, "rb_h1");
+    if (b.has_time) {
+      const float* tb = tbias + b.t_off;
+      const int co = b.dim_out; const long long hw = (long long)h * w;
+      add([=](const Run& r) { ENG_CALL(ds_add_channel_bias(h1, tb, t_stride, n_, co, hw, r.s)); });
+    }
+    act_t* y2 = scr("rb_y2", n_, h, w, b.dim_out);
+    { ConvOpts o; o.out = y2; o.out_c = b.dim_out; conv(b.conv2, h1, b.dim_out, nullptr, 0, n_, h, w, o, nullptr); }
+    act_t* h2 = gn_silu(y2, b.dim_out, h, w, n_, b.g2, b.b2, "rb_h2");
+    act_t* ob = act(n_, h, w, b.dim_out);
+    { ConvOpts o; o.out = ob; o.out_c = b.dim_out; o.residual = h2; o.res_c = b.dim_out; o.want_stats = true; o.src_batch_mod = s0_mod;
+      conv(b.res, s0.p, s0.c, s1.p, s1.c, n_, h, w, o, st_o_out); }
+    return Act{ob, b.dim_out};
+  };
+  auto any_block = [&](const std::string& p, Act s0, Act s1, int h, int w, int n_, int s0_mod, Stats* st_o_out) -> Act {
+    return cfg.use_convnext ? block(p, s0, s1, h, w, n_, s0_mod, st_o_out) : res_block(p, s0, s1, h, w, n_, s0_mod, st_o_out);
+  };
   // Residual(PreNorm(LinearCrossAttentionAdd)); x_mod > 0: x (and its statistics) hold x_mod samples shared by the guidance halves.
   auto attn = [&](const std::string& p, Act x, const Stats& st_x, int h, int w, int x_mod) -> Act {
     const Attn& a = net->attns.at(p);
@@ -627,10 +693,15 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
       const act_t* xp = x.p; const int dim = a.dim;
       const Stats sx = st_x;
       const PackedConv qkv = a.qkv;
-      add([=](const Run& r) { ENG_CALL(ds_attn_qkv_ctx(xp, dim, x_mod, sx.buf, sx.slots, qkv.weight, qkv.e1, qkv.e2, sb, c_total, qp, part, Nn, HEADS, npix,
+      const bool cat = cfg.attn_type == 1;      // LinearCrossAttention: the condition is one extra key / value token, merged by the finalize
+      const float* sb_qk = cat ? nullptr : sb;
+      add([=](const Run& r) { ENG_CALL(ds_attn_qkv_ctx(xp, dim, x_mod, sx.buf, sx.slots, qkv.weight, qkv.e1, qkv.e2, sb_qk, c_total, qp, part, Nn, HEADS, npix,
                                                        1.0f / sqrtf((float)DHEAD), r.s)); });
       const float* wout = a.wout; const int cop = a.out.cout_pad;
-      add([=](const Run& r) { ENG_CALL(ds_attn_finalize(part, wout, M, Nn, HEADS, npix, dim, cop, r.s)); }, 2);
+      if (cat) add([=](const Run& r) {      // condition=None: no extra token (diffusion_components.py:195-200)
+        if (r.no_cond) ENG_CALL(ds_attn_finalize(part, wout, M, Nn, HEADS, npix, dim, cop, r.s));
+        else ENG_CALL(ds_attn_finalize_cat(part, sb, sb + HID, c_total, wout, M, Nn, HEADS, npix, dim, cop, r.s)); }, 2);
+      else add([=](const Run& r) { ENG_CALL(ds_attn_finalize(part, wout, M, Nn, HEADS, npix, dim, cop, r.s)); }, 2);
     }
     act_t* y = scr("atty", Nn, h, w, a.dim);
     Stats st_y;
@@ -672,13 +743,13 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
   for (int i = 0; i < n_stage; ++i) {
     const std::string p = "downs." + std::to_string(i) + ".";
     if (i == 0 && shared) {
-      x = block(p + "0.", x, none, h, w, shared, 0, &st);
+      x = any_block(p + "0.", x, none, h, w, shared, 0, &st);
       x = attn(p + "1.", x, st, h, w, shared); hs.push_back(x);
     } else {
-      x = block(p + "0.", x, none, h, w, N, 0, &st);
+      x = any_block(p + "0.", x, none, h, w, N, 0, &st);
       x = attn(p + "1.", x, st, h, w, 0); hs.push_back(x);
     }
-    x = block(p + "2.", x, none, h, w, N, 0, &st);
+    x = any_block(p + "2.", x, none, h, w, N, 0, &st);
     x = attn(p + "3.", x, st, h, w, 0); hs.push_back(x);
     const PackedConv& pc = net->samplers.at(p + "4.");
     act_t* d = act(N, h / 2, w / 2, pc.cout);
@@ -686,14 +757,14 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
     sizes.push_back({h, w});
     x = Act{d, pc.cout}; h /= 2; w /= 2; hs.push_back(x);
   }
-  for (int j = 0; j < cfg.mid_depth - 1; ++j) { x = block("mid_left." + std::to_string(j) + ".", x, none, h, w, N, 0, &st); hs.push_back(x); }
-  x = block("mid_mid.0.", x, none, h, w, N, 0, &st);
+  for (int j = 0; j < cfg.mid_depth - 1; ++j) { x = any_block("mid_left." + std::to_string(j) + ".", x, none, h, w, N, 0, &st); hs.push_back(x); }
+  x = any_block("mid_mid.0.", x, none, h, w, N, 0, &st);
   x = attn("mid_mid.1.", x, st, h, w, 0);
-  x = block("mid_mid.2.", x, none, h, w, N, 0, &st);
-  for (int j = 0; j < cfg.mid_depth - 1; ++j) { Act s = hs.back(); hs.pop_back(); x = block("mid_right." + std::to_string(j) + ".", s, x, h, w, N, 0, &st); }
+  x = any_block("mid_mid.2.", x, none, h, w, N, 0, &st);
+  for (int j = 0; j < cfg.mid_depth - 1; ++j) { Act s = hs.back(); hs.pop_back(); x = any_block("mid_right." + std::to_string(j) + ".", s, x, h, w, N, 0, &st); }
   for (int i = 0; i < n_stage; ++i) {
     const std::string p = "ups." + std::to_string(i) + ".";
-    { Act s = hs.back(); hs.pop_back(); x = block(p + "0.", s, x, h, w, N, 0, &st); }
+    { Act s = hs.back(); hs.pop_back(); x = any_block(p + "0.", s, x, h, w, N, 0, &st); }
     x = attn(p + "1.", x, st, h, w, 0);
     const PackedConv& pc = net->samplers.at(p + "2.");
     const int hp = sizes.back().first, wp = sizes.back().second;     // the skip's size: 2h / 2w, or one more where the level was odd (pad_to_match)
@@ -702,12 +773,12 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
     act_t* u = exact ? act(N, hp, wp, pc.cout) : A.alloc<act_t>((size_t)N * hp * wp * pc.cout, /*zero=*/true);     // the conv never writes the padding
     { ConvOpts o; o.out = u; o.out_c = pc.cout; o.out_hp = hp; o.out_wp = wp; conv(pc, x.p, x.c, nullptr, 0, N, h, w, o, nullptr); }
     x = Act{u, pc.cout}; h = hp; w = wp;
-    { Act s = hs.back(); hs.pop_back(); x = block(p + "3.", s, x, h, w, N, 0, &st); }
+    { Act s = hs.back(); hs.pop_back(); x = any_block(p + "3.", s, x, h, w, N, 0, &st); }
     x = attn(p + "4.", x, st, h, w, 0);
-    { Act s = hs.back(); hs.pop_back(); x = block(p + "5.", s, x, h, w, N, 0, &st); }
+    { Act s = hs.back(); hs.pop_back(); x = any_block(p + "5.", s, x, h, w, N, 0, &st); }
     x = attn(p + "6.", x, st, h, w, 0);
   }
-  { Act s = hs.back(); hs.pop_back(); x = block("final_conv.0.", s, x, h, w, N, shared, &st); }      // the last skip is init_conv's output
+  { Act s = hs.back(); hs.pop_back(); x = any_block("final_conv.0.", s, x, h, w, N, shared, &st); }      // the last skip is init_conv's output
   { ConvOpts o; o.out_f32 = eps; conv(net->final_conv, x.p, x.c, nullptr, 0, N, h, w, o, nullptr); }
 }
 
@@ -1046,9 +1117,8 @@ int ds_unet_create(const ds_unet_config* cfg, ds_unet** out) {
   return guarded([&] {
     ENG_REQUIRE(cfg && out, "ds_unet_create: null argument");
     ENG_REQUIRE(cfg->n_levels >= 2 && cfg->n_levels <= DS_MAX_LEVELS, "ds_unet_create: n_levels=%d", cfg->n_levels);
-    if (cfg->attn_type != 0 || !cfg->use_convnext || cfg->condition_type < 0 || cfg->condition_type > 1)
-      fail(DS_ERR_UNSUPPORTED, "ds_unet_create: the module-level entry points implement ConvNeXt blocks with attn_type 'linear_add' (text or class-label "
-                               "conditioning, with or without time embedding); 'linear_cat' and the ResNet-block variant run through the operator-level entries");
+    if (cfg->attn_type < 0 || cfg->attn_type > 1) fail(DS_ERR_UNSUPPORTED, "ds_unet_create: attn_type %d (0 = 'linear_add', 1 = 'linear_cat')", cfg->attn_type);      // diffusion.py:96
+    if (cfg->condition_type < 0 || cfg->condition_type > 1) fail(DS_ERR_UNSUPPORTED, "ds_unet_create: condition_type %d", cfg->condition_type);                // diffusion_components.py:165
     ENG_REQUIRE(cfg->condition_type == 0 || cfg->n_label_class >= 1, "ds_unet_create: n_label_class=%d", cfg->n_label_class);
     ENG_REQUIRE(cfg->down_dims[0] == cfg->up_dims[cfg->n_levels - 1] && cfg->up_dims[0] == cfg->down_dims[cfg->n_levels - 1], "ds_unet_create: down_dims / up_dims do not mirror");
     for (int i = 0; i < cfg->n_levels; ++i)
@@ -1080,7 +1150,7 @@ int ds_unet_forward(ds_unet* h, const float* d_x, const long long* d_t, const vo
       ENG_CUDA(cudaMemcpyAsync(p->cond, d_cond, p->cond_bytes, cudaMemcpyDeviceToDevice, s));
       p->run_cond(s);
     }
-    p->run(d_x, d_t, s);
+    p->run(d_x, d_t, s, d_cond == nullptr);
     ENG_CUDA(cudaMemcpyAsync(d_out, p->eps, (size_t)N * h->u.cfg.out_dim * H * W * sizeof(float), cudaMemcpyDeviceToDevice, s));
   });
 }

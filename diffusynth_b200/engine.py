@@ -19,7 +19,7 @@ class UnetConfig(C.Structure):
                 ("down_dims", C.c_int32 * DS_MAX_LEVELS), ("up_dims", C.c_int32 * DS_MAX_LEVELS),
                 ("mid_depth", C.c_int32), ("with_time_emb", C.c_int32), ("time_dim", C.c_int32), ("use_convnext", C.c_int32),
                 ("convnext_mult", C.c_int32), ("attn_type", C.c_int32), ("condition_type", C.c_int32), ("label_emb_dim", C.c_int32),
-                ("n_label_class", C.c_int32)]
+                ("n_label_class", C.c_int32), ("resnet_block_groups", C.c_int32)]
 
 
 class UnetPlanIO(C.Structure):
@@ -55,8 +55,8 @@ def _load_params(fn, handle, state_dict) -> None:
 
 
 def unet_supported(cfg: dict) -> bool:
-    """The variants the module-level entry points implement (the deployed family); the others keep the operator-level plan."""
-    return bool(cfg.get("use_convnext", True)) and cfg["attn_type"] == "linear_add" and cfg["in_dim"] <= 4 and len(cfg["down_dims"]) <= DS_MAX_LEVELS
+    """Every constructor variant of the reference runs through the module-level entry points (limits: in_dim <= 4, <= 8 levels)."""
+    return cfg["in_dim"] <= 4 and len(cfg["down_dims"]) <= DS_MAX_LEVELS
 
 
 class UnetEngine:
@@ -69,8 +69,9 @@ class UnetEngine:
         c.in_dim, c.out_dim, c.n_levels = cfg["in_dim"], cfg["out_dim"], len(cfg["down_dims"])
         for i, (d, u) in enumerate(zip(cfg["down_dims"], cfg["up_dims"])):
             c.down_dims[i], c.up_dims[i] = d, u
-        c.mid_depth, c.with_time_emb, c.time_dim, c.use_convnext = cfg["mid_depth"], int(cfg.get("with_time_emb", True)), cfg["time_dim"], 1
-        c.convnext_mult, c.attn_type, c.label_emb_dim = cfg["convnext_mult"], 0, cfg["label_emb_dim"]
+        c.mid_depth, c.with_time_emb, c.time_dim = cfg["mid_depth"], int(cfg.get("with_time_emb", True)), cfg["time_dim"]
+        c.use_convnext, c.resnet_block_groups = int(cfg.get("use_convnext", True)), int(cfg.get("resnet_block_groups", 8))
+        c.convnext_mult, c.attn_type, c.label_emb_dim = cfg["convnext_mult"], int(cfg["attn_type"] == "linear_cat"), cfg["label_emb_dim"]
         c.condition_type, c.n_label_class = int(cfg["condition_type"] == "instrument_family"), cfg.get("n_label_class", 11)
         self.h = C.c_void_p()
         with torch.cuda.device(device):

@@ -266,8 +266,6 @@ class ConditionedUnet:
     @torch.no_grad()
     def forward(self, x, time, condition=None, taps: Optional[dict] = None):
         """x [N,4,H,W] fp32, time [N] int64, condition [N, label_emb_dim] fp32 -> eps [N,4,H,W] fp32 (diffusion.py:187-258)."""
-        if condition is None and self.cfg["attn_type"] != "linear_add":
-            raise NotImplementedError("condition=None with attn_type='linear_cat' (the extra key / value token is part of the plan)")
         N, Cin, H, Wd = x.shape
         assert Cin == self.cfg["in_dim"]
         n_stage = len(self.cfg["down_dims"]) - 1
@@ -281,6 +279,9 @@ class ConditionedUnet:
             cdt = torch.long if self.cfg["condition_type"] == "instrument_family" else torch.float32
             return self._engine.forward(x.to(self.device, torch.float32).contiguous(), time.to(self.device, torch.long).contiguous(),
                                         None if condition is None else condition.to(self.device, cdt).contiguous())
+        if condition is None and self.cfg["attn_type"] != "linear_add":
+            raise NotImplementedError("condition=None with attn_type='linear_cat' runs through the module-level entry points only "
+                                      "(the operator-level plan used for per-layer taps has the extra key / value token built in)")
         pl = self.plan(N, H, Wd)
         pl.x.copy_(x.to(self.device, torch.float32))
         pl.t.copy_(time.to(self.device, torch.long))

@@ -254,15 +254,16 @@ typedef struct ds_unet_config {
   int32_t mid_depth;                       /* <= 0: 3 */
   int32_t with_time_emb;                   /* 0: no time_mlp, blocks without their mlp (diffusion.py:107-109) */
   int32_t time_dim;                        /* <= 0: 4 * down_dims[0] (diffusion.py:99) */
-  int32_t use_convnext;                    /* must be 1 (the ResNet-block variant runs through the operator-level entries) */
+  int32_t use_convnext;                    /* 1: ConvNextBlock (deployed); 0: ResnetBlock (diffusion_components.py:59-104) */
   int32_t convnext_mult;                   /* <= 0: 2 */
-  int32_t attn_type;                       /* 0 = "linear_add" (deployed, app.py:40) */
+  int32_t attn_type;                       /* 0 = "linear_add" (deployed, app.py:40), 1 = "linear_cat" */
   int32_t condition_type;                  /* 0 = "natural_language_prompt" (d_cond fp32 [N][label_emb_dim]), 1 = "instrument_family" (d_cond int64 [N]) */
   int32_t label_emb_dim;
   int32_t n_label_class;                   /* condition_type 1: the embedding table has n_label_class + 1 rows (diffusion.py:63-64) */
+  int32_t resnet_block_groups;             /* use_convnext 0: GroupNorm groups of the ResnetBlocks (<= 0: 8) */
 } ds_unet_config;
 typedef struct ds_unet ds_unet;
-int ds_unet_create(const ds_unet_config* cfg, ds_unet** out);       /* -4 for a variant outside the deployed family */
+int ds_unet_create(const ds_unet_config* cfg, ds_unet** out);       /* -4 for an unknown attn_type / condition_type */
 void ds_unet_destroy(ds_unet* h);
 /* One parameter by its reference state_dict name (e.g. "downs.0.0.net.1.weight"); fp32, `data` may be host or device memory. */
 int ds_unet_load(ds_unet* h, const char* name, const float* data, const long long* shape, int ndim);

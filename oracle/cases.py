@@ -44,6 +44,8 @@ def unet_case(name: str):
         cfg, B, Wd = SMALL_UNET_NOTIME, 2, 16
     elif name == "small_nocond_w16":    # condition=None (diffusion.py:199-202)
         cfg, B, Wd = SMALL_UNET, 2, 16
+    elif name == "small_cat_nocond_w16":    # condition=None with LinearCrossAttention: no extra token (diffusion_components.py:195-200)
+        cfg, B, Wd = SMALL_UNET_CAT, 2, 16
     else:
         raise KeyError(name)
     sd = W.unet_random_state_dict(cfg, seed=0)
@@ -53,7 +55,7 @@ def unet_case(name: str):
     cond = randn((B, W.unet_config(**cfg)["label_emb_dim"]), 12)
     if name == "small_family_w16":
         cond = torch.tensor([7, 2][:B], dtype=torch.long)
-    elif name == "small_nocond_w16":
+    elif name in ("small_nocond_w16", "small_cat_nocond_w16"):
         cond = None
     return cfg, sd, x, t, cond
 

@@ -151,7 +151,7 @@ def text_head():
 
 
 
-VARIANTS = ("small_family_w16", "small_notime_w16", "small_nocond_w16")
+VARIANTS = ("small_family_w16", "small_notime_w16", "small_nocond_w16", "small_cat_nocond_w16")
 
 
 def variants(ref):

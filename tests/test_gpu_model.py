@@ -54,7 +54,7 @@ def test_unet_forward_parity(name, golden):
     assert rel(eps, torch.from_numpy(golden["unet"][f"{name}_eps"])) < BF16_TOL       # the reference's own output
 
 
-@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16", "small_cat_nocond_w16"])
 def test_unet_conditioning_variants_parity(name, golden):
     """condition_type="instrument_family" (integer labels, ds_embedding_gather), with_time_emb=False and condition=None
     (diffusion_components.py:155-168; diffusion.py:107-109,199-202,211)."""

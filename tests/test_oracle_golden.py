@@ -169,7 +169,7 @@ def test_unet_odd_width_matches_reference(golden, name):
     assert rel(eps.numpy(), golden["extra"][f"{name}_eps"]) < 2e-6
 
 
-@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16", "small_cat_nocond_w16"])
 def test_unet_conditioning_variants_match_reference(golden, name):
     """condition_type="instrument_family" (nn.Embedding over integer labels), with_time_emb=False and condition=None
     (diffusion_components.py:155-168; diffusion.py:107-109,199-202,211) against the reference's own outputs."""

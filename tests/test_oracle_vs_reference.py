@@ -33,7 +33,7 @@ def test_unet_small_live(ref):
 
 
 @torch.no_grad()
-@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16"])
+@pytest.mark.parametrize("name", ["small_family_w16", "small_notime_w16", "small_nocond_w16", "small_cat_nocond_w16"])
 def test_unet_conditioning_variants_live(ref, name):
     cfg, sd, x, t, cond = cases.unet_case(name)
     net = ref.ConditionedUnet(**cfg).eval()

@@ -417,6 +417,12 @@ class DiffSynthSampler:
                                   mask_flexivity=mask_flexivity)
 
 
+def _profiler_attached() -> bool:
+    """True inside `ncu ...` (its injection library is named in the child's environment)."""
+    inj = os.environ.get("CUDA_INJECTION64_PATH", "") + os.environ.get("NV_COMPUTE_PROFILER_PERFWORKS_DIR", "")
+    return "nsight-compute" in inj.lower() or "nsight_compute" in inj.lower() or bool(os.environ.get("NV_COMPUTE_PROFILER_PERFWORKS_DIR"))
+
+
 class _GraphLoop:
     """All steps of one sampling call -- U-Net (CFG-doubled) + fused update (+ inpaint blend) -- captured in one CUDA graph.
     Step-dependent scalars (timestep, update coefficients, masks, noise) live in device tables the graph reads, so the
@@ -445,7 +451,11 @@ class _GraphLoop:
         self._plan = None
         self.sgraph = None
         self.graph = None
-        use_graph = os.environ.get("DS_NO_GRAPH", "0") != "1"      # (profilers that cannot follow stream capture set DS_NO_GRAPH=1)
+        # Nsight Compute dies on the first thread-block-cluster launch inside a stream capture (ncu exit code 9, seen on 2025.x with
+        # CUDA 12.9): under its injection library, or with DS_NO_GRAPH=1, the same launches run eagerly so that the profiler's launch
+        # list covers every kernel of the loop and the tail.  Results are identical (tests/test_gpu_abi_engine.py); timings are not
+        # bench values either way.
+        use_graph = os.environ.get("DS_NO_GRAPH", "0") != "1" and not _profiler_attached()
         if getattr(model, "_engine", None) is not None and model.use_engine:
             # module-level C ABI: the plan, the capture and the replay live in the library (ds_sample_graph_build / _run)
             self.cond = torch.zeros((N,), dtype=torch.long, device=dev) if model.cfg["condition_type"] == "instrument_family" \

@@ -232,10 +232,21 @@ static void choose_tile(int H, int W, int& Hb, int& Wb) {
     if (best < 0 || area < best) { best = area; Hb = hb; Wb = wb; }
   }
 }
-static int choose_bn(int cout_pad) {
-  for (int bn = 256; bn >= 16; bn -= 16)
-    if (cout_pad % bn == 0) return bn;
-  fail(DS_ERR_INVALID, "choose_bn(%d)", cout_pad);
+// N-tile width.  Large jobs: the widest divisor of Cout_pad (<= 256): fewest tcgen05.mma instructions per FLOP.  Jobs whose widest tiling
+// leaves more than half of the SMs idle (m_units = samples x groups x 128-pixel tiles: one-prompt sampling, the deep levels of small
+// batches) take the widest divisor <= 64 instead: one thread cannot issue tcgen05.mma faster than one per ~55 cycles
+// (profiles/r02_umma_rate.md), so a narrower tile costs the same per K-step while the K loop, the weight fetch and the epilogue
+// spread over 3-4x as many SMs.  Every output element keeps its K order: values do not depend on the choice (the statistics
+// partials are grouped per tile, their fixed-order double-precision merge differs in the last bits only).
+static int choose_bn(int cout_pad, long long m_units = 1 << 30) {
+  int wide = 0;
+  for (int bn = 256; bn >= 16 && !wide; bn -= 16)
+    if (cout_pad % bn == 0) wide = bn;
+  if (!wide) fail(DS_ERR_INVALID, "choose_bn(%d)", cout_pad);
+  if (m_units * (cout_pad / wide) > 74) return wide;
+  for (int bn = 64; bn >= 32; bn -= 32)
+    if (bn < wide && cout_pad % bn == 0) return bn;
+  return wide;
 }
 
 struct ConvOpts {
@@ -249,6 +260,7 @@ struct ConvOpts {
   int src_batch_mod = 0;
   const void* weight_override = nullptr; bool per_sample_weights = false;
   float eps = 1e-5f;
+  bool wide_tiles = false;      // batch-invariant tiling: always the widest N tile (ds_unet_config / ds_vqgan_config .batch_invariant)
 };
 
 // the argument block of one ds_conv_gemm call; src* 16-bit NHWC [N, Hin, Win, C]
@@ -280,7 +292,8 @@ static ds_conv_gemm_args conv_args(Arena& A, const PackedConv& pc, const void* s
   choose_tile(Hg, Wg, a.Hb, a.Wb);
   a.d_weight = o.weight_override ? o.weight_override : pc.weight;
   a.Cout_pad = pc.cout_pad; a.Cout = pc.cout;
-  a.BN = choose_bn(pc.cout_pad);
+  a.BN = o.wide_tiles ? choose_bn(pc.cout_pad)
+                      : choose_bn(pc.cout_pad, (long long)N * (long long)pc.taps.size() * ((Hg + a.Hb - 1) / a.Hb) * ((Wg + a.Wb - 1) / a.Wb));
   a.BK = (C0 % 64 == 0 && C1 % 64 == 0) ? 64 : 32;
   a.ntaps = (int)pc.taps[0].size(); a.groups = (int)pc.taps.size();
   a.per_sample_weights = o.per_sample_weights ? 1 : 0;
@@ -612,7 +625,9 @@ UnetPlan::UnetPlan(Unet* n, int N_, int H_, int W_, int mod, int ut) : net(n), N
     add([=](const Run& r) { ENG_CALL(ds_linear(temb, td, nt->t_w, nt->t_b, tb, t_total, NT, td, t_total, act_in, 0, r.s)); });
   }
 
-  auto conv = [&](const PackedConv& pc, const void* s0, int C0, const void* s1, int C1, int n_, int h, int w, const ConvOpts& o, Stats* st_out) {
+  const bool wide_tiles = cfg.batch_invariant != 0;
+  auto conv = [&](const PackedConv& pc, const void* s0, int C0, const void* s1, int C1, int n_, int h, int w, const ConvOpts& o_, Stats* st_out) {
+    ConvOpts o = o_; o.wide_tiles = wide_tiles;
     const ds_conv_gemm_args a = conv_args(A, pc, s0, C0, s1, C1, n_, h, w, o, st_out);
     add([a](const Run& r) { ENG_CALL(ds_conv_gemm(&a, r.s)); });
   };
@@ -806,7 +821,7 @@ static const int VQ_DH = 32, GN_CHUNKS = 64;
 struct StackPlan;
 struct Stack {
   std::string prefix;
-  bool is_decoder = false;
+  bool is_decoder = false, wide_tiles = false;
   int G = 16, res_act = 2;
   std::vector<Layer> layers;
   std::vector<std::unique_ptr<StackPlan>> plans;
@@ -887,7 +902,7 @@ void Vqgan::pack() {
   layer_plans(cfg, es, dsp);
   codebook = A.upload(need(sd, "_vq_vae._embedding.weight", {cfg.num_embeddings, cfg.embedding_dim}).v);
   auto build = [&](Stack& st, const std::string& prefix, const std::vector<LayerSpec>& specs, bool is_dec) {
-    st.prefix = prefix; st.is_decoder = is_dec; st.G = cfg.num_groups;
+    st.prefix = prefix; st.is_decoder = is_dec; st.G = cfg.num_groups; st.wide_tiles = cfg.batch_invariant != 0;
     // the encoder's ResnetBlocks get the literal string "act_type" (VQGAN.py:441) -> swish; decoder: the configured act_type
     st.res_act = (!is_dec || cfg.act_relu == 0) ? 2 : 1;
     for (const LayerSpec& s : specs) {
@@ -932,7 +947,9 @@ StackPlan::StackPlan(const Stack& st, int B_, int H_, int W_) : B(B_), H(H_), W(
   const int Bn = B;
   auto act = [&](int h, int w, int c) { return A.alloc<act_t>((size_t)Bn * h * w * pad32(c), /*zero=*/true); };     // padded channels stay zero
   auto add = [&](Op f, int nl = 1) { ops.push_back(std::move(f)); launches += nl; };
-  auto conv = [&](const PackedConv& pc, const act_t* src, int h, int w, const ConvOpts& o) {
+  const bool wide_tiles = st.wide_tiles;
+  auto conv = [&](const PackedConv& pc, const act_t* src, int h, int w, const ConvOpts& o_) {
+    ConvOpts o = o_; o.wide_tiles = wide_tiles;
     const ds_conv_gemm_args a = conv_args(A, pc, src, pc.cin, nullptr, 0, Bn, h, w, o, nullptr);
     add([a](const Run& r) { ENG_CALL(ds_conv_gemm(&a, r.s)); });
   };

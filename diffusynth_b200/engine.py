@@ -19,7 +19,7 @@ class UnetConfig(C.Structure):
                 ("down_dims", C.c_int32 * DS_MAX_LEVELS), ("up_dims", C.c_int32 * DS_MAX_LEVELS),
                 ("mid_depth", C.c_int32), ("with_time_emb", C.c_int32), ("time_dim", C.c_int32), ("use_convnext", C.c_int32),
                 ("convnext_mult", C.c_int32), ("attn_type", C.c_int32), ("condition_type", C.c_int32), ("label_emb_dim", C.c_int32),
-                ("n_label_class", C.c_int32), ("resnet_block_groups", C.c_int32)]
+                ("n_label_class", C.c_int32), ("resnet_block_groups", C.c_int32), ("batch_invariant", C.c_int32)]
 
 
 class UnetPlanIO(C.Structure):
@@ -30,7 +30,7 @@ class VqganConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("embedding_dim", C.c_int32),
                 ("n_hidden", C.c_int32), ("hidden_channels", C.c_int32 * DS_MAX_LEVELS), ("block_depth", C.c_int32),
                 ("n_attn_pos", C.c_int32), ("attn_pos", C.c_int32 * DS_MAX_LEVELS), ("attn_with_skip", C.c_int32),
-                ("act_relu", C.c_int32), ("num_embeddings", C.c_int32), ("num_groups", C.c_int32)]
+                ("act_relu", C.c_int32), ("num_embeddings", C.c_int32), ("num_groups", C.c_int32), ("batch_invariant", C.c_int32)]
 
 
 class SampleBuffers(C.Structure):
@@ -73,6 +73,7 @@ class UnetEngine:
         c.use_convnext, c.resnet_block_groups = int(cfg.get("use_convnext", True)), int(cfg.get("resnet_block_groups", 8))
         c.convnext_mult, c.attn_type, c.label_emb_dim = cfg["convnext_mult"], int(cfg["attn_type"] == "linear_cat"), cfg["label_emb_dim"]
         c.condition_type, c.n_label_class = int(cfg["condition_type"] == "instrument_family"), cfg.get("n_label_class", 11)
+        c.batch_invariant = int(bool(cfg.get("batch_invariant", False)))
         self.h = C.c_void_p()
         with torch.cuda.device(device):
             check(self.lib.ds_unet_create(C.byref(c), C.byref(self.h)), "ds_unet_create")
@@ -110,6 +111,7 @@ class VqganEngine:
             c.attn_pos[i] = v
         c.attn_with_skip, c.act_relu = int(bool(cfg["attn_with_skip"])), int(cfg["act_type"] == "relu")
         c.num_embeddings, c.num_groups = cfg["num_embeddings"], cfg["num_groups"]
+        c.batch_invariant = int(bool(cfg.get("batch_invariant", False)))
         self.h = C.c_void_p()
         with torch.cuda.device(device):
             check(self.lib.ds_vqgan_create(C.byref(c), C.byref(self.h)), "ds_vqgan_create")

@@ -47,11 +47,18 @@ def choose_tile(H: int, W: int) -> Tuple[int, int]:
     return best[1], best[2]
 
 
-def choose_bn(cout_pad: int) -> int:
-    for bn in range(256, 15, -16):
-        if cout_pad % bn == 0:
-            return bn
-    raise ValueError(cout_pad)
+NARROW_BELOW = 74      # CTAs of the widest tiling at or below which choose_bn narrows the N tile (half of the 148 SMs)
+
+
+def choose_bn(cout_pad: int, m_units: int = 1 << 30) -> int:
+    """N-tile width (the rule of csrc/engine.cu choose_bn): the widest divisor of Cout_pad (<= 256), or -- when that tiling would leave
+    more than half of the SMs idle (m_units = samples x groups x 128-pixel tiles) -- the widest divisor <= 64."""
+    wide = next((bn for bn in range(256, 15, -16) if cout_pad % bn == 0), None)
+    if wide is None:
+        raise ValueError(cout_pad)
+    if m_units * (cout_pad // wide) > NARROW_BELOW:
+        return wide
+    return next((bn for bn in (64, 32) if bn < wide and cout_pad % bn == 0), wide)
 
 
 def pad16(c: int) -> int:
@@ -197,7 +204,7 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
               stats_in: Optional[Stats] = None, eps: float = 1e-5, sbias: Optional[torch.Tensor] = None,
               act: int = 0, residual: Optional[torch.Tensor] = None, want_stats: bool = False,
               src_batch_mod: int = 0, weight_override: Optional[torch.Tensor] = None,
-              per_sample_weights: bool = False, device=None) -> Tuple[ConvGemmArgs, Optional[Stats], list]:
+              per_sample_weights: bool = False, device=None, wide_tiles: bool = False) -> Tuple[ConvGemmArgs, Optional[Stats], list]:
     """Build the argument block of one ds_conv_gemm call.  ``src*`` bf16 NHWC [N, Hin, Win, C].
     Returns (args, stats_out, keepalive)."""
     a = ConvGemmArgs()
@@ -228,7 +235,7 @@ def conv_args(pc: PackedConv, src0: torch.Tensor, src1: Optional[torch.Tensor], 
     w = weight_override if weight_override is not None else pc.weight
     a.d_weight = _ptr(w)
     a.Cout_pad, a.Cout = pc.cout_pad, pc.cout
-    a.BN = pc.bn or choose_bn(pc.cout_pad)
+    a.BN = pc.bn or (choose_bn(pc.cout_pad) if wide_tiles else choose_bn(pc.cout_pad, N * len(pc.taps) * (-(-Hg // a.Hb)) * (-(-Wg // a.Wb))))
     a.BK = 64 if (C0 % 64 == 0 and C1 % 64 == 0) else 32
     a.ntaps, a.groups = len(pc.taps[0]), len(pc.taps)
     a.per_sample_weights = 1 if per_sample_weights else 0

@@ -113,11 +113,12 @@ class TextToTimbre:
         return Timbres(latents, t.q.clone(), t.spec.clone(), t.wave.clone())
 
     @classmethod
-    def random_init(cls, device="cuda", seed: int = 0, perturb_norm: bool = False) -> "TextToTimbre":
+    def random_init(cls, device="cuda", seed: int = 0, perturb_norm: bool = False, batch_invariant: bool = False) -> "TextToTimbre":
         """Deployed architecture (app.py:32-40) with deterministic synthetic weights (no checkpoints offline)."""
-        unet = ConditionedUnet(**{k: v for k, v in W.UNET_DEPLOYED.items() if k not in ("out_dim", "time_dim")}, device=device)
+        unet = ConditionedUnet(**{k: v for k, v in W.UNET_DEPLOYED.items() if k not in ("out_dim", "time_dim")}, device=device,
+                               batch_invariant=batch_invariant)
         unet.load_state_dict(W.unet_random_state_dict(seed=seed, perturb_norm=perturb_norm))
-        vq = VQGAN(**W.VQGAN_DEPLOYED, device=device)
+        vq = VQGAN(**W.VQGAN_DEPLOYED, device=device, batch_invariant=batch_invariant)
         vq.load_state_dict(W.vqgan_random_state_dict(seed=seed + 1, perturb_norm=perturb_norm))
         return cls(unet, vq, device=device)
 

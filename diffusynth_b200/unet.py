@@ -103,7 +103,7 @@ class _Attn:
 class ConditionedUnet:
     def __init__(self, in_dim, out_dim=None, down_dims=None, up_dims=None, mid_depth=3, with_time_emb=True, time_dim=None,
                  resnet_block_groups=8, use_convnext=True, convnext_mult=2, attn_type="linear_cat", n_label_class=11,
-                 condition_type="instrument_family", label_emb_dim=128, device=None):
+                 condition_type="instrument_family", label_emb_dim=128, device=None, batch_invariant=False):
         if attn_type not in ("linear_cat", "linear_add"):
             raise NotImplementedError()                       # diffusion.py:96
         if condition_type not in ("instrument_family", "natural_language_prompt"):
@@ -119,6 +119,10 @@ class ConditionedUnet:
                                  time_dim=time_dim, convnext_mult=convnext_mult, attn_type=attn_type, condition_type=condition_type,
                                  label_emb_dim=label_emb_dim, use_convnext=bool(use_convnext), resnet_block_groups=int(resnet_block_groups),
                                  with_time_emb=bool(with_time_emb), n_label_class=int(n_label_class))
+        # (not a reference argument) False: jobs too small to fill the SMs run narrow N tiles -- lower latency, but a sample's low-order bits
+        # then depend on the batch it runs in (grouping of the GroupNorm partial sums); True: always the widest tiling, bit-identical
+        # samples whatever the batch / shard (ds_unet_config.batch_invariant)
+        self.cfg["batch_invariant"] = bool(batch_invariant)
         for d in set(self.cfg["down_dims"] + self.cfg["up_dims"]):
             if d % 32:
                 raise NotImplementedError(f"channel widths must be multiples of 32 (got {d})")
@@ -364,7 +368,7 @@ class _Plan:
             self.t_stride = 0
 
         def conv(name, pc, s0, s1, h, w, n=None, **kw):
-            a, st, keep = conv_args(pc, s0, s1, N if n is None else n, h, w, **kw)
+            a, st, keep = conv_args(pc, s0, s1, N if n is None else n, h, w, wide_tiles=cfg["batch_invariant"], **kw)
             self.keep += keep + [a]
             fam, fl, by = ops.conv_cost(a, pc)
             add(name, lambda a=a: run_conv(a), fam, fl, by)

@@ -151,7 +151,7 @@ class _StackPlan:
             self.meta[name] = dict(family=family, flops=float(flops), bytes=float(bytes))
 
         def conv(name, pc, src, h, w, **kw):
-            a, stt, keep = conv_args(pc, src, None, B, h, w, **kw)
+            a, stt, keep = conv_args(pc, src, None, B, h, w, wide_tiles=st.cfg.get("batch_invariant", False), **kw)
             self.keep += keep + [a]
             fam, fl, by = ops.conv_cost(a, pc)
             add(name, lambda a=a: run_conv(a), "vqgan_" + fam, fl, by)
@@ -291,14 +291,15 @@ class Encoder(_StackModule):
 
 class VQGAN:
     def __init__(self, in_channels, hidden_channels, embedding_dim, out_channels, block_depth=2, attn_pos=None, attn_with_skip=True,
-                 norm_type="groupnorm", act_type="relu", num_embeddings=1024, commitment_cost=0.25, decay=0.99, num_groups=32, device=None):
+                 norm_type="groupnorm", act_type="relu", num_embeddings=1024, commitment_cost=0.25, decay=0.99, num_groups=32, device=None, batch_invariant=False):
         if norm_type != "groupnorm":
             raise NotImplementedError("norm_type='batchnorm'")
         if not decay > 0.0:
             raise NotImplementedError("non-EMA VectorQuantizer (training-only variant)")
         self.cfg = dict(in_channels=in_channels, hidden_channels=list(hidden_channels), embedding_dim=embedding_dim, out_channels=out_channels,
                         block_depth=block_depth, attn_pos=list(attn_pos or []), attn_with_skip=attn_with_skip, norm_type=norm_type,
-                        act_type=act_type, num_embeddings=num_embeddings, commitment_cost=commitment_cost, decay=decay, num_groups=num_groups)
+                        act_type=act_type, num_embeddings=num_embeddings, commitment_cost=commitment_cost, decay=decay, num_groups=num_groups,
+                        batch_invariant=bool(batch_invariant))      # (see ConditionedUnet: tiling policy, not a reference argument)
         self.device = torch.device(device if device is not None else "cuda")
         self._vq_vae = VectorQuantizerEMA(num_embeddings, embedding_dim, commitment_cost, decay, device=self.device)
         self._encoder: Optional[Encoder] = None

@@ -261,6 +261,9 @@ typedef struct ds_unet_config {
   int32_t label_emb_dim;
   int32_t n_label_class;                   /* condition_type 1: the embedding table has n_label_class + 1 rows (diffusion.py:63-64) */
   int32_t resnet_block_groups;             /* use_convnext 0: GroupNorm groups of the ResnetBlocks (<= 0: 8) */
+  int32_t batch_invariant;                 /* 0: jobs too small to fill the SMs run narrow N tiles (lower latency; a sample's low-order bits then depend on the
+                                              batch it runs in, through the grouping of the GroupNorm partial sums); 1: always the widest tiling, every sample
+                                              bit-identical whatever the batch / shard it is part of */
 } ds_unet_config;
 typedef struct ds_unet ds_unet;
 int ds_unet_create(const ds_unet_config* cfg, ds_unet** out);       /* -4 for an unknown attn_type / condition_type */
@@ -296,6 +299,7 @@ typedef struct ds_vqgan_config {
   int32_t attn_with_skip;
   int32_t act_relu;                        /* 1: act_type == "relu", 0: swish (decoder ResnetBlocks; the encoder's are always swish, :441) */
   int32_t num_embeddings, num_groups;
+  int32_t batch_invariant;                 /* as ds_unet_config.batch_invariant */
 } ds_vqgan_config;
 typedef struct ds_vqgan ds_vqgan;
 int ds_vqgan_create(const ds_vqgan_config* cfg, ds_vqgan** out);

@@ -17,17 +17,29 @@ def pipe():
     return TextToTimbre.random_init(device="cuda", seed=0)
 
 
-def test_batch64_samples_are_independent_of_the_batch(pipe):
+@pytest.fixture(scope="module")
+def pipe_invariant():
+    from diffusynth_b200 import TextToTimbre
+    return TextToTimbre.random_init(device="cuda", seed=0, batch_invariant=True)
+
+
+def test_batch64_samples_are_independent_of_the_batch(pipe, pipe_invariant):
     """Sample k of a 64-prompt job equals the same prompt + noise run in a 2-prompt job (2 DDIM steps, CFG 6): nothing in the
-    CUDA path couples samples, and the prefix shared by the two guidance halves gives the same values as in the small job."""
+    CUDA path couples samples, and the prefix shared by the two guidance halves gives the same values as in the small job.
+    With batch_invariant=True (always the widest N tiling) the two jobs agree to the last bits; with the default tiling policy the
+    small job runs narrower N tiles on the deep levels, the GroupNorm partial sums are grouped differently, and the two results are
+    two equally accurate 16-bit roundings of the same trajectory: they agree within the parity tolerance (each is ~1e-3 from the
+    fp32 oracle, tests/test_gpu_headline.py)."""
     steps = 2
     draws = W.host_noise(11, 1 + steps, B)
     cond, uncond = W.synthetic_conditions(B, 512)
-    big = pipe.generate(cond.cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws, decode=False).latents
-    for k0 in (0, 41):
-        sl = slice(k0, k0 + 2)
-        small = pipe.generate(cond[sl].cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws[:, sl].contiguous(), decode=False).latents
-        assert rel(big[sl], small) < 1e-5, (k0, rel(big[sl], small))
+    for p, tol in ((pipe_invariant, 1e-5), (pipe, 1e-2)):
+        big = p.generate(cond.cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws, decode=False).latents
+        for k0 in (0, 41):
+            sl = slice(k0, k0 + 2)
+            small = p.generate(cond[sl].cuda(), uncond.cuda(), steps=steps, cfg_scale=6, noise_feed=draws[:, sl].contiguous(), decode=False).latents
+            print(f"\nbatch_invariant={p is pipe_invariant}: samples {k0}-{k0 + 1} of the batch-64 job vs the batch-2 job: rel-L2 {rel(big[sl], small):.2e}")
+            assert rel(big[sl], small) < tol, (k0, rel(big[sl], small))
 
 
 def test_vq_is_idempotent_at_full_size(pipe):

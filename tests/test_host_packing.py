@@ -99,6 +99,10 @@ def test_transposed_conv_as_four_phases():
 def test_tile_and_blocking_choices():
     assert ops.choose_tile(128, 64) == (2, 64) and ops.choose_tile(16, 8) == (16, 8) and ops.choose_tile(128, 24) == (16, 8)
     assert ops.choose_bn(768) == 256 and ops.choose_bn(384) == 192 and ops.choose_bn(96) == 96 and ops.choose_bn(16) == 16
+    # jobs too small to fill the SMs with the widest tiling take narrow N tiles (one-prompt sampling, deep levels of small batches);
+    # the batch-64 job (>= 128 M-tiles on every level) never does
+    assert ops.choose_bn(384, 2) == 64 and ops.choose_bn(768, 2) == 64 and ops.choose_bn(96, 32) == 32 and ops.choose_bn(16, 2) == 16
+    assert ops.choose_bn(384, 128) == 192 and ops.choose_bn(96, 128) == 96 and ops.choose_bn(192, 80) == 192 and ops.choose_bn(192, 32) == 64
     for hw in [(128, 64), (64, 32), (32, 16), (16, 8), (512, 256), (128, 144), (128, 24)]:
         hb, wb = ops.choose_tile(*hw)
         assert hb * wb == 128

@@ -130,8 +130,12 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {      // plain arrive on the leader CTA's copy of the barrier
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+// Plain arrive on the leader CTA's copy of the barrier.  RELAXED: the barrier only hands the tensor-memory accumulator back to the MMA
+// warp, and the epilogue's reads of it are complete (tcgen05.wait::ld) and ordered (tcgen05.fence::before_thread_sync) before the
+// arrive.  A .release.cluster arrive makes ptxas emit a cluster-scope memory barrier first, which waits for the tile's output stores
+// to be acknowledged by L2: ncu showed 25 % of the GELU epilogue's stall samples on that MEMBAR / ERRBAR pair.
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -251,6 +255,67 @@ __device__ __forceinline__ void gelu16(float (&v)[16]) {
     for (int j = 0; j < 8; ++j) p[j] = fmaf(p[j], t[j], 0.5f * 0.254829592f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[g + j] = fmaxf(v[g + j], 0.0f) - ax[j] * (p[j] * t[j] * e[j]);
+  }
+}
+
+// Packed fp32x2 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot).  The GELU epilogue is bound by
+// the issue slots of its two warps per scheduler (376 instructions per 16-column chunk, 68 % of the slots busy: measured
+// 1.1 k cycles per chunk), so the fold, the GELU polynomial and the statistics run on register pairs.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// gelu16 on 8 register pairs (same formula, same constants): per pair 2 abs/neg + 2 max + 4 MUFU stay scalar, the 10 multiply-adds are
+// packed.  Stage by stage over 4 pairs so that 8 independent chains interleave.
+__device__ __forceinline__ void gelu16_f2(f2_t (&v)[8]) {
+  const f2_t kP = f2_pack(-0.3275911f * 0.70710678118654752f, -0.3275911f * 0.70710678118654752f);      // times -|x|
+  const f2_t kOne = f2_pack(1.0f, 1.0f);
+  const f2_t kW = f2_pack(0.84932180028801904f, 0.84932180028801904f);
+  const f2_t a5 = f2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f), a4 = f2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f);
+  const f2_t a3 = f2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f), a2 = f2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f);
+  const f2_t a1 = f2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f);
+#pragma unroll
+  for (int g = 0; g < 8; g += 4) {
+    f2_t nax[4], relu[4], t[4], e[4], p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x0, x1;
+      f2_unpack(v[g + j], x0, x1);
+      nax[j] = f2_pack(-fabsf(x0), -fabsf(x1));
+      relu[j] = f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float d0, d1, t0, t1;
+      f2_unpack(f2_fma(kP, nax[j], kOne), d0, d1);
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+      t[j] = f2_pack(t0, t1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const f2_t w = f2_mul(nax[j], kW);
+      float q0, q1, e0, e1;
+      f2_unpack(f2_mul(w, w), q0, q1);
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-q0));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-q1));
+      e[j] = f2_pack(e0, e1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = f2_fma(a5, t[j], a4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = f2_fma(p[j], t[j], a3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = f2_fma(p[j], t[j], a2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = f2_fma(p[j], t[j], a1);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = f2_mul(f2_mul(p[j], t[j]), e[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[g + j] = f2_fma(nax[j], p[j], relu[j]);      // relu(x) - |x| * (0.5 poly(t) t e)
   }
 }
 
@@ -549,6 +614,7 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       const bool has_res = res_p != nullptr && valid;
       int cols_left = P.Cout - col0;                       // real (unpadded) output channels from col0 on
       float psum = 0.f, psq = 0.f;
+      f2_t psum2 = 0ull, psq2 = 0ull;      // EPI = 2: packed partial sums (even / odd columns), merged after the chunks
 
       // one 16-column chunk: folded-GroupNorm scalars, bias, activation, residual, statistics, store.
       // r = accumulator values, ra/rb = prefetched residual.  Advances the running addresses.
@@ -654,9 +720,36 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) t2[q4] = lds_f4(e2_s + 16u * q4);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) t1[q4] = use_e1 ? lds_f4(e1_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q4 = 0; q4 < 4; ++q4) t1[q4] = (EPI == 2 || use_e1) ? lds_f4(e1_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) tb[q4] = use_sb ? lds_f4_volatile(sb_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q4 = 0; q4 < 4; ++q4) tb[q4] = (EPI != 2 && use_sb) ? lds_f4_volatile(sb_s + 16u * q4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (EPI == 2) {
+            // GELU epilogue on register pairs: fold, GELU, statistics and the 16-bit pack (see gelu16_f2)
+            const f2_t rstd2 = f2_pack(rstd, rstd), nmr2 = f2_pack(nmr, nmr);
+            f2_t v2[8];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              // (the launcher selects EPI = 2 only for convolutions with a GroupNorm fold and without per-sample bias)
+              const f2_t c0 = f2_fma(nmr2, f2_pack(t1[q4].x, t1[q4].y), f2_pack(t2[q4].x, t2[q4].y));
+              const f2_t c1 = f2_fma(nmr2, f2_pack(t1[q4].z, t1[q4].w), f2_pack(t2[q4].z, t2[q4].w));
+              v2[2 * q4 + 0] = f2_fma(f2_pack(__uint_as_float(r[4 * q4 + 0]), __uint_as_float(r[4 * q4 + 1])), rstd2, c0);
+              v2[2 * q4 + 1] = f2_fma(f2_pack(__uint_as_float(r[4 * q4 + 2]), __uint_as_float(r[4 * q4 + 3])), rstd2, c1);
+            }
+            gelu16_f2(v2);
+            if (valid) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (do_stats) { psum2 = f2_add(psum2, v2[j]); psq2 = f2_fma(v2[j], v2[j], psq2); }
+                float lo, hi;
+                f2_unpack(v2[j], lo, hi);
+                pk[j] = pack16_epi(lo, hi);
+              }
+              stg_256(out_p, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            }
+            e2_s += 64u; e1_s += 64u; sb_s += 64u; out_p += 16;
+            return;
+          }
           float v[16];
           if (EPI == 4) {
 #pragma unroll
@@ -720,6 +813,11 @@ conv_gemm_kernel(const __grid_constant__ TmaMaps maps, const __grid_constant__ C
       if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       if (epi_timed) { te2 = clock64(); e_chunks += te2 - te1; }
       if (P.stats_out != nullptr) {
+        if (EPI == 2) {
+          float a, b, c, d;
+          f2_unpack(psum2, a, b); f2_unpack(psq2, c, d);
+          psum = a + b; psq = c + d;
+        }
         psum = warp_sum(psum);
         psq = warp_sum(psq);
         if (lane == 0) {
@@ -911,7 +1009,7 @@ static int conv_gemm_launch(const ds_conv_gemm_args* a, cudaStream_t stream) {
   int epi = 0;
   if (a->d_out && !a->d_out_f32_nchw && a->Cout == a->Cout_pad && !(P.dbg & 1) && !knobs().generic_epi) {
     if (a->act == 0) epi = a->d_residual ? 3 : (!a->d_e1 && !a->d_sbias && !a->d_stats_in) ? 4 : 1;
-    else if (!a->d_residual) epi = 2;
+    else if (!a->d_residual && a->d_e1 && a->d_stats_in && !a->d_sbias) epi = 2;      // ConvNeXt conv1: fold + GELU, no per-sample bias
   }
   // two resident CTAs per SM for the plain 1x1 convolutions whose accumulator pair fits half of the tensor memory (see the kernel)
   // (BN <= 128: each CTA keeps its double-buffered accumulator in half of the tensor memory; BN <= 256: a single accumulator per CTA,

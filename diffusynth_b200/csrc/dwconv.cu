@@ -269,6 +269,12 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     const int n = item / tiles, t = item - n * tiles;
     const int h0 = (t / tiles_w) * 16, w0 = (t % tiles_w) * DW_TW;
     const float* tb = tbias + (size_t)(tbias_stride ? n : 0) * tbias_stride;
+    // this warp's four bias values: requested before the wait for the tile so that the global-load latency hides behind the TMA wait and
+    // the transposes (issued at their first use, between two shared-memory phases, they showed up as long-scoreboard stalls on the
+    // accumulator initialisation)
+    float bias4[4];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) bias4[ci] = __ldg(tb + c0 + 4 * warp + ci);
     mbar_wait(&full[stage], (uint32_t)(it >> 1) & 1u);
     const uint32_t raw = s_raw + stage * DT_TILE_BYTES;
 
@@ -299,7 +305,7 @@ dwconv7_mma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
       float d[2][2][4];
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
-        const float bias = __ldg(tb + c0 + 4 * warp + 2 * cp + cc);
+        const float bias = bias4[2 * cp + cc];
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll

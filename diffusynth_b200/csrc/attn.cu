@@ -180,38 +180,68 @@ attn_ctx_partial_kernel(const act_t* __restrict__ qkv, int hidden, int npix, int
 // label_k / label_v (nullable, [N][label_stride], element head*32 + d): the extra key / value token of LinearCrossAttention
 // ("linear_cat", diffusion_components.py:187-195: k = cat([k, label_k]), v = cat([v, label_v]) along the sequence) joins the merge
 // like one more chunk with a single position: max candidate label_k[d], Z += exp(label_k[d] - M), S[d][e] += exp(.) * label_v[e].
+// All 256 threads take part in every phase and every phase's loads are independent of each other (the first version walked the chunks
+// with 32 threads in a load -> max / load -> exp -> add chain: 2 x chunks dependent global-memory round trips before the merge proper
+// started, 11-24 us per launch of pure latency).  Thread (d = tid & 31, slice = tid >> 5) covers chunks slice, slice + 8, ...; the
+// per-chunk weights exp(m_c[d] - M[d]) are kept in shared memory for the merge of S (up to AT_MAXW chunks; recomputed beyond that).
+static constexpr int AT_MAXW = 64;
 __global__ void __launch_bounds__(256)
 attn_reduce_kernel(const float* __restrict__ part, int chunks, float* __restrict__ ctx, const float* __restrict__ label_k,
                    const float* __restrict__ label_v, long long label_stride) {
   pdl_enter();
-  __shared__ float s_M[AT_D], s_Zinv[AT_D], s_lw[AT_D];
+  __shared__ float s_part[8][AT_D], s_M[AT_D], s_Zinv[AT_D], s_lw[AT_D];
+  __shared__ float s_w[AT_MAXW][AT_D];
   const int head = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const int d = tid & 31, sl = tid >> 5;
   const float* pb = part + ((size_t)n * gridDim.x + head) * chunks * AT_PART;
-  if (tid < AT_D) {
-    float mx = -INFINITY;
-    for (int c = 0; c < chunks; ++c) mx = fmaxf(mx, __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid));
-    const float lk = label_k ? __ldg(label_k + (size_t)n * label_stride + head * AT_D + tid) : -INFINITY;
-    mx = fmaxf(mx, lk);
-    float z = 0.f;
-    for (int c = 0; c < chunks; ++c)
-      z += __ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + tid) * __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + tid) - mx);
+  const float* pm = pb + AT_D * AT_D + AT_D + d;       // m_c[d] of chunk 0
+  const float* pz = pb + AT_D * AT_D + d;              // Z_c[d] of chunk 0
+  const float lk = label_k ? __ldg(label_k + (size_t)n * label_stride + head * AT_D + d) : -INFINITY;
+  float mx = -INFINITY;
+#pragma unroll 4
+  for (int c = sl; c < chunks; c += 8) mx = fmaxf(mx, __ldg(pm + (size_t)c * AT_PART));
+  s_part[sl][d] = mx;
+  __syncthreads();
+  mx = lk;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) mx = fmaxf(mx, s_part[w][d]);
+  __syncthreads();                                     // s_part is reused for the normaliser
+  float z = 0.f;
+#pragma unroll 4
+  for (int c = sl; c < chunks; c += 8) {
+    const float w = __expf(__ldg(pm + (size_t)c * AT_PART) - mx);
+    if (c < AT_MAXW) s_w[c][d] = w;
+    z = fmaf(__ldg(pz + (size_t)c * AT_PART), w, z);
+  }
+  s_part[sl][d] = z;
+  __syncthreads();
+  if (sl == 0) {
     const float lw = label_k ? __expf(lk - mx) : 0.f;
-    z += lw;
-    s_M[tid] = mx;
-    s_Zinv[tid] = 1.0f / z;
-    s_lw[tid] = lw;
+    z = lw;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) z += s_part[w][d];
+    s_M[d] = mx; s_Zinv[d] = 1.0f / z; s_lw[d] = lw;
   }
   __syncthreads();
-  float* co = ctx + ((size_t)n * gridDim.x + head) * AT_D * AT_D;
-  for (int i = tid; i < AT_D * AT_D; i += 256) {
-    const int d = i / AT_D;
-    const float M = s_M[d];
-    float s = 0.f;
+  // merge of S: element i = tid + 256 k of the 32 x 32 matrix (row i / 32 = 8 k + slice), chunks in order
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* ps = pb + tid;
 #pragma unroll 4
-    for (int c = 0; c < chunks; ++c)
-      s = fmaf(__ldg(pb + (size_t)c * AT_PART + i), __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + d) - M), s);
-    if (label_v) s = fmaf(s_lw[d], __ldg(label_v + (size_t)n * label_stride + head * AT_D + (i - d * AT_D)), s);
-    co[i] = s * s_Zinv[d];
+  for (int c = 0; c < chunks; ++c) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int dr = 8 * k + sl;
+      const float w = c < AT_MAXW ? s_w[c][dr] : __expf(__ldg(pb + (size_t)c * AT_PART + AT_D * AT_D + AT_D + dr) - s_M[dr]);
+      acc[k] = fmaf(__ldg(ps + (size_t)c * AT_PART + 256 * k), w, acc[k]);
+    }
+  }
+  float* co = ctx + ((size_t)n * gridDim.x + head) * AT_D * AT_D;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int dr = 8 * k + sl;
+    float sv = acc[k];
+    if (label_v) sv = fmaf(s_lw[dr], __ldg(label_v + (size_t)n * label_stride + head * AT_D + d), sv);
+    co[tid + 256 * k] = sv * s_Zinv[dr];
   }
 }
 

@@ -13,7 +13,12 @@ SHAPES = [
     ("l1 conv2 384->192", 384, 0, 192, 3, 64, 32, 0, 1),
     ("l2 conv1 768->768", 384, 384, 768, 3, 32, 16, 1, 0),
     ("l0 to_qkv 96->384", 96, 0, 384, 1, 128, 64, 0, 0),
+    ("l0 to_out 128->96", 128, 0, 96, 1, 128, 64, 0, 0),
+    ("l0 res_conv 288->96", 96, 192, 96, 1, 128, 64, 0, 0),
+    ("l1 to_out 128->192", 128, 0, 192, 1, 64, 32, 0, 0),
 ]
+if os.environ.get("ONLY"):
+    SHAPES = [s for s in SHAPES if os.environ["ONLY"] in s[0]]
 for name, c0, c1, cout, k, H, W, gelu, res in SHAPES:
     cin = c0 + c1
     w = torch.randn(cout, cin, k, k) * (1.0 / (cin * k * k) ** 0.5)

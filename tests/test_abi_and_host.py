@@ -42,6 +42,31 @@ def test_struct_layout_matches_header():
     assert got == [C.sizeof(A), A.taps.offset, A.d_e2.offset, A.out_goff.offset, A.d_stats_out.offset, A.view_off.offset]
 
 
+def test_module_level_struct_layouts_match_header():
+    """The ctypes mirrors of the module-level structs (diffusynth_b200/engine.py) against the header, field by field at the ends that
+    move when a field is added (ds_unet_config.batch_invariant, ds_vqgan_config.batch_invariant, the tail outputs of ds_sample_buffers)."""
+    from diffusynth_b200 import engine
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "diffusynth_b200.h"
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",
+       sizeof(ds_unet_config), offsetof(ds_unet_config, up_dims), offsetof(ds_unet_config, n_label_class), offsetof(ds_unet_config, batch_invariant),
+       sizeof(ds_vqgan_config), offsetof(ds_vqgan_config, attn_pos), offsetof(ds_vqgan_config, batch_invariant),
+       sizeof(ds_sample_buffers), offsetof(ds_sample_buffers, d_wave),
+       sizeof(ds_unet_plan_io), offsetof(ds_unet_plan_io, cond_launches)); return 0; }
+    '''
+    exe = "/tmp/ds_layout_check2"
+    with open(exe + ".c", "w") as f:
+        f.write(src)
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), exe + ".c", "-o", exe])
+    got = [int(v) for v in subprocess.check_output([exe]).split()]
+    U, V, S, P = engine.UnetConfig, engine.VqganConfig, engine.SampleBuffers, engine.UnetPlanIO
+    assert got == [C.sizeof(U), U.up_dims.offset, U.n_label_class.offset, U.batch_invariant.offset,
+                   C.sizeof(V), V.attn_pos.offset, V.batch_invariant.offset,
+                   C.sizeof(S), S.d_wave.offset, C.sizeof(P), P.cond_launches.offset]
+
+
 def test_invalid_arguments_fail_without_a_gpu():
     lib = _lib.load()
     assert lib.ds_ddim_step(None, None, None, None, None, None, 16, None) == -1

@@ -151,3 +151,14 @@ def test_shard_range_properties():
             spans = [shard_range(total, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_profiler_detection(monkeypatch):
+    """Under Nsight Compute (which sets NV_COMPUTE_PROFILER_PERFWORKS_DIR for its children) the sampler asks the library for the
+    eager form of the sampling graph: ncu 2025.2 dies on a cluster launch inside a stream capture."""
+    from diffusynth_b200 import sampler
+    monkeypatch.delenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR", raising=False)
+    monkeypatch.delenv("CUDA_INJECTION64_PATH", raising=False)
+    assert not sampler._profiler_attached()
+    monkeypatch.setenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR", "/opt/nvidia/nsight-compute/2025.2.1/target/linux-desktop-glibc_2_11_3-x64/.")
+    assert sampler._profiler_attached()
